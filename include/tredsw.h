@@ -1,0 +1,202 @@
+/*
+ * tredsw.h — C ABI of libtredsw.so, the sm_100a CUDA replacement for tredparse's native layer.
+ *
+ * Two groups of entry points:
+ *
+ *  (A) the six symbols of the reference's libssw.so, with identical signatures and the identical
+ *      s_align layout, so that the reference's own ctypes binding (src/ssw_wrap.py:69-83,274-280)
+ *      binds to this library unmodified;
+ *  (B) the batched entry points the hot path actually uses (one call = all reads x all templates of
+ *      many (sample, locus) problems; one call = many likelihood grids).
+ *
+ * All pointers are plain C pointers.  Unless TREDSW_DEVICE_PTRS is set in `flags` they are HOST
+ * pointers and the call performs its own host<->device copies on the context's stream and returns
+ * after the results are in the output buffers.  With TREDSW_DEVICE_PTRS every buffer pointer is a
+ * device pointer on the context's device, nothing is copied and the call only enqueues work on the
+ * stream (the caller synchronises).  No entry point prints or exits; errors are returned as negative
+ * codes and described by tredsw_last_error().  There is no CPU fallback: without a usable CUDA
+ * device every compute entry point fails with TREDSW_ERR_CUDA.
+ *
+ * Citations are into the reference tree (/root/reference at build time).
+ */
+#ifndef TREDSW_H
+#define TREDSW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * (A) libssw.so drop-in — replaces src/ssw.c behind src/ssw.h:72-182
+ * ---------------------------------------------------------------------------------------------- */
+struct _profile;
+typedef struct _profile s_profile;
+
+/* src/ssw.h:42-52 (== CAlignRes, src/ssw_wrap.py:43-51); 40 bytes on LP64 */
+typedef struct {
+    uint16_t score1;
+    uint16_t score2;
+    int32_t ref_begin1;
+    int32_t ref_end1;
+    int32_t read_begin1;
+    int32_t read_end1;
+    int32_t ref_end2;
+    uint32_t *cigar;
+    int32_t cigarLen;
+} s_align;
+
+/* src/ssw.h:72 / src/ssw.c:751-772.  `read` and `mat` are borrowed (must outlive the profile).
+ * Only n <= 5 (nucleotide matrices) is supported; otherwise NULL. */
+s_profile *ssw_init(const int8_t *read, const int32_t readLen, const int8_t *mat, const int32_t n,
+                    const int8_t score_size);
+/* src/ssw.h:77 / src/ssw.c:774-778 */
+void init_destroy(s_profile *p);
+/* src/ssw.h:112-120 / src/ssw.c:780-871.  One GPU launch per call — the compatibility path, not the
+ * fast one.  Returns NULL on error (never exits, never prints). */
+s_align *ssw_align(const s_profile *prof, const int8_t *ref, int32_t refLen, const uint8_t weight_gapO,
+                   const uint8_t weight_gapE, const uint8_t flag, const uint16_t filters,
+                   const int32_t filterd, const int32_t maskLen);
+/* src/ssw.h:125 / src/ssw.c:873-876 */
+void align_destroy(s_align *a);
+/* src/ssw.h:176,182 / src/ssw.c:878-904 */
+char cigar_int_to_op(uint32_t cigar_int);
+uint32_t cigar_int_to_len(uint32_t cigar_int);
+
+/* ------------------------------------------------------------------------------------------------
+ * (B) batched API
+ * ---------------------------------------------------------------------------------------------- */
+#define TREDSW_OK 0
+#define TREDSW_ERR_CUDA (-1)     /* CUDA runtime / driver error, or no device */
+#define TREDSW_ERR_ARG (-2)      /* invalid argument */
+#define TREDSW_ERR_UNSUPPORTED (-3)
+
+#define TREDSW_DEVICE_PTRS 1u    /* all buffer arguments are device pointers; enqueue only */
+#define TREDSW_SCORE2 2u         /* also produce score2 / ref_end2 exactly like ssw.c (ghost rows) */
+#define TREDSW_NO_BEGIN 4u       /* skip the reverse pass (ref_begin/query_begin = -1), flag==0 of ssw_align */
+#define TREDSW_CIGAR 8u          /* also produce CIGARs (banded_sw restatement) */
+#define TREDSW_FORCE_WORD 16u    /* behave like ssw_init(score_size=1): 16-bit kernel conventions only */
+
+typedef struct tredsw_ctx tredsw_ctx;
+
+int tredsw_version(void);
+int tredsw_device_count(void);
+const char *tredsw_last_error(void);            /* thread-local, never NULL */
+
+/* One context per (host thread, GPU).  stream == NULL: the context creates its own non-blocking
+ * stream; otherwise `stream` is a cudaStream_t the caller owns (e.g. torch's current stream). */
+tredsw_ctx *tredsw_create(int device, void *stream);
+void tredsw_destroy(tredsw_ctx *ctx);
+int tredsw_synchronize(tredsw_ctx *ctx);
+int tredsw_sm_count(tredsw_ctx *ctx);
+
+/* Tags of a classified read (tredparse/bam_parser.py:157-168). */
+enum { TREDSW_TAG_NONE = 0, TREDSW_TAG_FULL = 1, TREDSW_TAG_PREF = 2, TREDSW_TAG_POST = 3,
+       TREDSW_TAG_REPT = 4, TREDSW_TAG_HANG = 5 };
+
+/* Generic batch of independent (query, template) alignments == a batch of
+ * ssw_init -> ssw_align(flag=1) -> destroy calls (src/ssw_wrap.py:186-224).
+ * Sequences are int8 codes 0..4 (A,C,G,T,N) in flat buffers with offset arrays (nq+1 / nt+1 entries).
+ * mat25 is the 5x5 substitution matrix of src/ssw_wrap.py:154-167 (row = template code, col = query
+ * code).  out: npairs x 8 int32 = score, ref_begin, ref_end, query_begin, query_end, score2,
+ * ref_end2, cigar_len.  cigar_out (TREDSW_CIGAR): npairs x cigar_cap uint32 words (len<<4|op). */
+int tredsw_align_pairs(tredsw_ctx *ctx, const int8_t *qbuf, const int64_t *qoff, int32_t nq,
+                       const int8_t *tbuf, const int64_t *toff, int32_t nt, const int32_t *qidx,
+                       const int32_t *tidx, int64_t npairs, const int8_t *mat25, int gap_open,
+                       int gap_extend, uint32_t flags, int32_t *out, uint32_t *cigar_out,
+                       int32_t cigar_cap);
+
+/* A locus' template family (tredparse/bam_parser.py:84-100): templates prefix + repeat*u + suffix and
+ * their reverse complements for u = 1..max_units. */
+typedef struct {
+    int8_t prefix[32];          /* codes; prefix_len <= 32 */
+    int8_t suffix[32];
+    int8_t repeat[32];          /* period <= 32 */
+    int32_t prefix_len;
+    int32_t suffix_len;
+    int32_t period;
+    int32_t max_units;          /* ceil(READLEN / period) (bam_parser.py:73) */
+    int32_t clip;               /* bam_parser.py:154-155: per-read max_units when clipped reads are used */
+    int32_t reserved[3];
+} tredsw_family;
+
+/* The production path: every read against every template of its family, post-filter, classification
+ * and per-read arg-max fused (== BamParser._parseReadSW for a whole batch; bam_parser.py:123-182,
+ * src/ssw_wrap.py:213-220).  Reads are int8 codes, grouped by problem: read r belongs to family
+ * read_family[r].
+ * out: nreads x 8 int32 = tag, h (units), score, ref_begin, ref_end, query_begin, query_end, rank
+ * (rank = DB index of the winning template: 2*(units-1) + strand; -1 when tag == NONE).
+ * stats (optional, 4 x int64): [0] algorithmic forward cells (sum len(read)*len(template)),
+ * [1] executed forward cell updates, [2] executed second-phase cell updates, [3] alignments. */
+int tredsw_classify_reads(tredsw_ctx *ctx, const int8_t *rbuf, const int64_t *roff, int32_t nreads,
+                          const int32_t *read_family, const tredsw_family *families, int32_t nfamilies,
+                          const int8_t *mat25, int gap_open, int gap_extend, uint32_t flags,
+                          int32_t *out, int64_t *stats);
+
+/* One likelihood problem (tredparse/models.py:223-302 + 394-415); see SURVEY.md Appendix B. */
+typedef struct {
+    int32_t period;             /* K */
+    int32_t readlen;            /* L */
+    int32_t ploidy;
+    int32_t n_rept;             /* U */
+    int32_t max_partial;        /* mp (already raised to the largest partial key, models.py:241-242) */
+    int32_t run_pe;
+    int32_t pe_ref;             /* ref = repeat_end - repeat_start + 1 */
+    int32_t pe_minpe;
+    int32_t n_span;             /* K_s observed spanning keys */
+    int32_t n_part;             /* K_p observed partial keys */
+    int32_t n_target;           /* n_t target pair lengths */
+    int32_t n_h1;               /* candidate lists (bp), in reference order, duplicates kept (Q9) */
+    int32_t n_h2;
+    int32_t expansion;          /* PP rule: models.py:351-364 */
+    int32_t recessive;
+    int32_t cutoff_risk;
+    double half_depth;          /* D */
+    double stutter_x;           /* w0 + w1*K + w3*gc + w4*score  (models.py:79-84,156) */
+    double stutter_w2;          /* w2, multiplies h // K */
+    /* offsets into the shared arrays below */
+    int64_t off_span;           /* ipool: n_span keys (bp) followed by n_span counts */
+    int64_t off_part;           /* ipool: n_part keys (bp) followed by n_part counts */
+    int64_t off_target;
+    int64_t off_h1;
+    int64_t off_h2;
+    int64_t off_pdf;            /* 1000 doubles (normalised KDE), -1 when no PE model */
+    int64_t off_step;           /* 37 doubles: step PMF of this period */
+    int64_t off_surface;        /* n_h1*n_h2 doubles in `surface` (row-major, -inf where h1 > h2) */
+    int64_t off_ph1;            /* n_h1 doubles in `marg` */
+    int64_t off_ph2;            /* n_h2 doubles in `marg` */
+} tredsw_grid_problem;
+
+/* Per-problem reductions. */
+typedef struct {
+    double max_ml;              /* lik of the call */
+    double sum_all;             /* sum exp(ml - max_ml) over evaluated points (duplicates counted, Q9) */
+    double sum_path;            /* same over pathological points */
+    int32_t arg_i1;             /* indices into the h1/h2 candidate lists of the call (Q10) */
+    int32_t arg_i2;
+    int32_t n_points;
+    int32_t pad;
+} tredsw_grid_result;
+
+/* Evaluate the log-likelihood surface of `nproblems` problems and reduce it.
+ * ipool: int32 pool holding, per problem, the observed spanning / partial keys and counts, the target
+ * pair lengths (already wrapped into 0..999 like a numpy index) and the h1 / h2 candidate lists;
+ * dpool: double pool holding the KDE pdfs (1000 each) and step PMFs (37 each);
+ * surface / marg: output pools (surface may be NULL in host mode to skip copying it back).
+ * For ploidy 1 the caller passes n_h2 = 1 and the kernel evaluates h2 = h1 (models.py:261). */
+int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem *problems, int32_t nproblems,
+                           const int32_t *ipool, int64_t n_ipool, const double *dpool, int64_t n_dpool,
+                           double *surface, int64_t n_surface, double *marg, int64_t n_marg,
+                           tredsw_grid_result *results, uint32_t flags);
+
+/* Gaussian KDE of paired-end lengths on the grid 0..999, normalised to sum 1
+ * (tredparse/models.py:428-435: scipy gaussian_kde with Scott's factor, pdf / pdf.sum()).
+ * lens: int32 pool, off: nproblems+1 offsets; pdf_out: nproblems x 1000 doubles. */
+int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t *off, int32_t nproblems,
+                  double *pdf_out, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREDSW_H */

@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the oracle (gcc) once per session; the CUDA library only when nvcc is around and the
+    in-tree .so is stale or absent (on the GPU box the .so shipped with the snapshot is used)."""
+    from oracle import sw
+    sw.build()
+    from tredparse_b200 import build as b
+    try:
+        b.build()
+    except Exception as e:  # pragma: no cover
+        if not os.path.exists(b.OUT):
+            raise
+        sys.stderr.write("libtredsw.so rebuild skipped: {}\n".format(e))
+    yield

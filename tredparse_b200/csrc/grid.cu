@@ -1,0 +1,388 @@
+// grid.cu — the (h1, h2) log-likelihood surface of IntegratedCaller and its reductions, FP64.
+//
+// Replaces the double loop of tredparse/models.py:260-273 (evaluate_spanning / evaluate_partial /
+// evaluate_rept / PEMaxLikModel.evaluate at every candidate pair) and the reductions of
+// models.py:277-302, 342-368 (max, arg-max with key (ml, -h1), exp-normalised marginals, PP sums).
+//
+// The reference materialises length-1000 probability vectors per candidate allele and takes the log of
+// whole vectors at every grid point; only the entries at the observed keys are ever used.  Here each
+// thread evaluates one grid point from the closed forms of SURVEY.md Appendix B: per observed key one
+// mixture + log, a Poisson log-pmf, and per spanning pair one gather from the shifted KDE.
+//   PS(h)[k]  spanning pdf (models.py:149-168, quirks Q6/Q7)     PT(h)[k] partial pdf (:170-180, Q8)
+//   alpha     mixing weights (:182-190)                           R(h)[x]  rolled PE pdf (:441-458)
+// Arithmetic order follows the reference (sum over keys in the order given, ml1+ml2+ml3+ml4).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int SPAN = 1000;
+constexpr int NSTEP = 37;
+constexpr int DEV = 18;
+
+struct GridParams {
+    const tredsw_grid_problem *prob;
+    const int32_t *ipool;
+    const double *dpool;
+    double *surface;
+    double *marg;
+    tredsw_grid_result *res;
+    double small_value, really_small, log_small;
+};
+
+__device__ __forceinline__ double sigma_h(const tredsw_grid_problem &P, int h) {
+    const double z = P.stutter_x + P.stutter_w2 * (double)(h / P.period);
+    return 1.0 / (1.0 + exp(-1.0 * z));
+}
+
+// spanning pdf of allele h at key k given sig = sigma(h)
+__device__ __forceinline__ double pdf_span(const double *step, int h, double sig, int k) {
+    if (k < 0 || k >= SPAN) return 0.0;
+    int idx;
+    if (h + DEV + 1 <= SPAN) {
+        idx = k - h + DEV;                      // also covers the low-end clip (h < 18): tail of p
+    } else {
+        if (k < h - DEV) return 0.0;            // high-end clip copies the *tail* of p as well (Q6)
+        idx = k - (SPAN - NSTEP);
+    }
+    if (idx < 0 || idx >= NSTEP) return 0.0;
+    return idx == DEV ? (1.0 - sig) : step[idx] * sig;
+}
+
+__device__ __forceinline__ double pdf_part(const double *step, int hc, double sig_c, double c, int k) {
+    double v = (k < hc) ? c : 0.0;
+    return v + c * pdf_span(step, hc, sig_c, k);
+}
+
+__device__ __forceinline__ double pe_roll(const double *pdf, int h, int ref, int minpe, int x, double eps) {
+    if (x < minpe) return eps;
+    const int y = x + h - ref;
+    if (y < 0 || y >= SPAN) return eps;
+    return pdf[y];
+}
+
+__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2) {
+    const int32_t *skey = g.ipool + P.off_span, *scnt = skey + P.n_span;
+    const int32_t *pkey = g.ipool + P.off_part, *pcnt = pkey + P.n_part;
+    const double *step = g.dpool + P.off_step;
+    const double eps = g.small_value;
+    const int t1 = P.readlen - 9, t2 = P.readlen - 18;
+    double ml = 0.0;
+    // spanning
+    if (P.n_span > 0) {
+        const int s1 = max(0, t2 - h1), s2 = max(0, t2 - h2);
+        const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
+        const double sg1 = sigma_h(P, h1), sg2 = sigma_h(P, h2);
+        double acc = 0.0;
+        for (int i = 0; i < P.n_span; ++i) {
+            const int k = skey[i];
+            const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
+            double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            double l = (v < eps) ? g.log_small : log(v);
+            acc = __dadd_rn(acc, __dmul_rn(l, (double)scnt[i]));
+        }
+        ml = acc;
+    }
+    // partial
+    double ml2 = 0.0;
+    if (P.n_part > 0) {
+        const int s1 = min(h1, t1), s2 = min(h2, t1);
+        const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
+        const int hc1 = min(h1, P.max_partial), hc2 = min(h2, P.max_partial);
+        const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
+        const double sg1 = sigma_h(P, hc1), sg2 = sigma_h(P, hc2);
+        double acc = 0.0;
+        for (int i = 0; i < P.n_part; ++i) {
+            const int k = pkey[i];
+            const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
+            double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            double l = (v < eps) ? g.log_small : log(v);
+            acc = __dadd_rn(acc, __dmul_rn(l, (double)pcnt[i]));
+        }
+        ml2 = acc;
+    }
+    ml = __dadd_rn(ml, ml2);
+    // repeat-only reads: Poisson (scipy: exp(xlogy(k, mu) - gammaln(k + 1) - mu))
+    {
+        const int d1 = max(h1 - P.readlen, 1), d2 = max(h2 - P.readlen, 1);
+        const double mu = (double)(d1 + d2) * P.half_depth / (double)P.readlen;
+        const double kk = (double)P.n_rept;
+        const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
+        const double pk = xl - lgamma(kk + 1.0) - mu;
+        double prob = exp(pk);
+        if (!(prob > g.really_small)) prob = g.really_small;
+        ml = __dadd_rn(ml, log(prob));
+    }
+    // paired-end
+    double ml4 = 0.0;
+    if (P.run_pe) {
+        const double *pdf = g.dpool + P.off_pdf;
+        const int32_t *tl = g.ipool + P.off_target;
+        double acc = 0.0;
+        for (int i = 0; i < P.n_target; ++i) {
+            const int x = tl[i];
+            const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
+            const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
+            double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
+            double l = (v < eps) ? g.log_small : log(v);
+            acc = __dadd_rn(acc, l);
+        }
+        ml4 = acc;
+    }
+    ml = __dadd_rn(ml, ml4);
+    return ml;
+}
+
+// grid: x = tiles of points, y = problem
+__global__ void __launch_bounds__(256) grid_surface_kernel(GridParams g, int nproblems) {
+    for (int pi = blockIdx.y; pi < nproblems; pi += gridDim.y) {
+        const tredsw_grid_problem P = g.prob[pi];
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const long long total = (long long)P.n_h1 * P.n_h2;
+        double *surf = g.surface + P.off_surface;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+             t += (long long)gridDim.x * blockDim.x) {
+            const int i1 = (int)(t / P.n_h2), i2 = (int)(t % P.n_h2);
+            const int h1 = h1s[i1];
+            const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+            double ml = -INFINITY;
+            if (h1 <= h2) ml = point_ml(P, g, h1, h2);
+            surf[t] = ml;
+        }
+    }
+}
+
+struct ArgMax { double ml; int h1; long long idx; };
+__device__ __forceinline__ bool better(const ArgMax &a, const ArgMax &b) {   // a beats b (Q10)
+    if (a.ml != b.ml) return a.ml > b.ml;
+    if (a.h1 != b.h1) return a.h1 < b.h1;
+    return a.idx < b.idx;
+}
+
+__device__ __forceinline__ bool pathological(const tredsw_grid_problem &P, int h1, int h2) {
+    const int lo = min(h1, h2) / P.period, hi = max(h1, h2) / P.period;
+    if (P.expansion) return P.recessive ? (lo >= P.cutoff_risk) : (hi >= P.cutoff_risk);
+    return P.recessive ? (hi <= P.cutoff_risk) : (lo <= P.cutoff_risk);
+}
+
+// one block per problem
+__global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int nproblems) {
+    __shared__ ArgMax s_best[256];
+    __shared__ double s_sum[256], s_path[256];
+    __shared__ int s_cnt[256];
+    for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x) {
+        const tredsw_grid_problem P = g.prob[pi];
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const double *surf = g.surface + P.off_surface;
+        const long long total = (long long)P.n_h1 * P.n_h2;
+        ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
+        int cnt = 0;
+        for (long long t = threadIdx.x; t < total; t += blockDim.x) {
+            const double ml = surf[t];
+            if (ml == -INFINITY) continue;   // not evaluated (h1 > h2)
+            ++cnt;
+            ArgMax c{ml, h1s[t / P.n_h2], t};
+            if (better(c, best)) best = c;
+        }
+        s_best[threadIdx.x] = best; s_cnt[threadIdx.x] = cnt;
+        __syncthreads();
+        for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+            if (threadIdx.x < d) {
+                if (better(s_best[threadIdx.x + d], s_best[threadIdx.x])) s_best[threadIdx.x] = s_best[threadIdx.x + d];
+                s_cnt[threadIdx.x] += s_cnt[threadIdx.x + d];
+            }
+            __syncthreads();
+        }
+        const ArgMax top = s_best[0];
+        const int npoints = s_cnt[0];
+        __syncthreads();
+        // marginals: P_h1[i1] = sum_i2 w, P_h2[i2] = sum_i1 w, w = exp(ml - max)
+        double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+        double sum_all = 0.0, sum_path = 0.0;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int i1 = warp; i1 < P.n_h1; i1 += nwarps) {
+            const int h1 = h1s[i1];
+            double acc = 0.0, accp = 0.0;
+            for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
+                const double ml = surf[(long long)i1 * P.n_h2 + i2];
+                if (ml == -INFINITY) continue;
+                const double w = exp(ml - top.ml);
+                acc += w;
+                const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+                if (pathological(P, h1, h2)) accp += w;
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                acc += __shfl_down_sync(0xffffffffu, acc, d);
+                accp += __shfl_down_sync(0xffffffffu, accp, d);
+            }
+            if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; }
+        }
+        for (int i2 = threadIdx.x; i2 < P.n_h2; i2 += blockDim.x) {
+            double acc = 0.0;
+            for (int i1 = 0; i1 < P.n_h1; ++i1) {
+                const double ml = surf[(long long)i1 * P.n_h2 + i2];
+                if (ml == -INFINITY) continue;
+                acc += exp(ml - top.ml);
+            }
+            ph2[i2] = acc;
+        }
+        s_sum[threadIdx.x] = sum_all; s_path[threadIdx.x] = sum_path;
+        __syncthreads();
+        for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+            if (threadIdx.x < d) { s_sum[threadIdx.x] += s_sum[threadIdx.x + d]; s_path[threadIdx.x] += s_path[threadIdx.x + d]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            tredsw_grid_result r;
+            r.max_ml = top.ml; r.sum_all = s_sum[0]; r.sum_path = s_path[0];
+            r.arg_i1 = npoints ? (int)(top.idx / P.n_h2) : -1;
+            r.arg_i2 = npoints ? (int)(top.idx % P.n_h2) : -1;
+            r.n_points = npoints; r.pad = 0;
+            g.res[pi] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- KDE of paired-end lengths (models.py:428-435) -------------------------------------------------
+// scipy.stats.gaussian_kde with Scott's factor n^(-1/5): covariance = var(ddof=1) * factor^2,
+// pdf[x] ~ sum_i exp(-((x - x_i) / sd)^2 / 2); the normalisation constant cancels in pdf / pdf.sum().
+// Lengths are integers, so the sum runs over a histogram of distinct values.
+constexpr int KDE_OFF = 1024;                  // histogram covers lengths in [-1024, 1024)
+__global__ void __launch_bounds__(1024) pe_kde_kernel(const int32_t *lens, const int64_t *off, int nproblems,
+                                                      double *pdf_out) {
+    __shared__ int hist[2 * KDE_OFF];
+    __shared__ double red[1024];
+    __shared__ double s_mean, s_sd;
+    for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x) {
+        const int32_t *x = lens + off[pi];
+        const int n = (int)(off[pi + 1] - off[pi]);
+        double *out = pdf_out + (int64_t)pi * SPAN;
+        for (int i = threadIdx.x; i < 2 * KDE_OFF; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int v = x[i];
+            s += (double)v;
+            v = max(-KDE_OFF, min(KDE_OFF - 1, v));
+            atomicAdd(&hist[v + KDE_OFF], 1);
+        }
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
+        if (threadIdx.x == 0) s_mean = n > 0 ? red[0] / (double)n : 0.0;
+        __syncthreads();
+        double ss = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { double d = (double)x[i] - s_mean; ss += d * d; }
+        red[threadIdx.x] = ss;
+        __syncthreads();
+        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
+        if (threadIdx.x == 0) {
+            const double var = n > 1 ? red[0] / (double)(n - 1) : 0.0;
+            const double factor = pow((double)n, -1.0 / 5.0);
+            s_sd = sqrt(var * factor * factor);
+        }
+        __syncthreads();
+        double val = 0.0;
+        if (threadIdx.x < SPAN && n > 0) {
+            const double xs = (double)threadIdx.x / s_sd;
+            for (int b = 0; b < 2 * KDE_OFF; ++b) {
+                const int c = hist[b];
+                if (c == 0) continue;
+                const double r = (double)(b - KDE_OFF) / s_sd - xs;
+                val += (double)c * exp(-(r * r) / 2.0);
+            }
+        }
+        red[threadIdx.x] = threadIdx.x < SPAN ? val : 0.0;
+        __syncthreads();
+        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
+        if (threadIdx.x < SPAN) out[threadIdx.x] = val / red[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem *problems, int32_t nproblems,
+                                      const int32_t *ipool, int64_t n_ipool, const double *dpool,
+                                      int64_t n_dpool, double *surface, int64_t n_surface, double *marg,
+                                      int64_t n_marg, tredsw_grid_result *results, uint32_t flags) {
+    if (!ctx) { tredsw_set_error("null context"); return TREDSW_ERR_ARG; }
+    if (nproblems < 0 || !problems || !results) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    if (nproblems == 0) return TREDSW_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    GridParams g{};
+    int rc;
+    long long max_points = 0;
+    if (!dev_ptrs(flags)) {
+        for (int i = 0; i < nproblems; ++i) {
+            const tredsw_grid_problem &P = problems[i];
+            if (P.n_h1 < 0 || P.n_h2 < 0 || P.period < 1 || P.readlen < 1 ||
+                P.off_surface + (long long)P.n_h1 * P.n_h2 > n_surface || P.off_ph1 + P.n_h1 > n_marg ||
+                P.off_ph2 + P.n_h2 > n_marg) { tredsw_set_error("grid problem %d out of range", i); return TREDSW_ERR_ARG; }
+            long long t = (long long)P.n_h1 * P.n_h2;
+            if (t > max_points) max_points = t;
+        }
+    } else {
+        max_points = n_surface;   // upper bound
+    }
+    if ((rc = stage_in(ctx, ctx->d_prob, problems, (size_t)nproblems, flags, &g.prob))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_ipool, ipool, (size_t)n_ipool, flags, &g.ipool))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_dpool, dpool, (size_t)n_dpool, flags, &g.dpool))) return rc;
+    if (dev_ptrs(flags)) { g.surface = surface; g.marg = marg; g.res = results; }
+    else {
+        if ((rc = ctx->d_surface.ensure((size_t)(n_surface > 0 ? n_surface : 1) * sizeof(double)))) return rc;
+        if ((rc = ctx->d_marg.ensure((size_t)(n_marg > 0 ? n_marg : 1) * sizeof(double)))) return rc;
+        if ((rc = ctx->d_res.ensure((size_t)nproblems * sizeof(tredsw_grid_result)))) return rc;
+        g.surface = ctx->d_surface.as<double>(); g.marg = ctx->d_marg.as<double>();
+        g.res = ctx->d_res.as<tredsw_grid_result>();
+    }
+    g.small_value = exp(-10.0);
+    g.really_small = exp(-100.0);
+    g.log_small = log(g.small_value);
+    long long tiles = (max_points + 255) / 256;
+    if (tiles < 1) tiles = 1;
+    int gx = (int)(tiles > 4096 ? 4096 : tiles);
+    int gy = nproblems > 65535 ? 65535 : nproblems;
+    grid_surface_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, nproblems);
+    CUDA_TRY(cudaGetLastError());
+    int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
+    grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev_ptrs(flags)) {
+        if (surface && n_surface > 0)
+            CUDA_TRY(cudaMemcpyAsync(surface, g.surface, (size_t)n_surface * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (marg && n_marg > 0)
+            CUDA_TRY(cudaMemcpyAsync(marg, g.marg, (size_t)n_marg * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(results, g.res, (size_t)nproblems * sizeof(tredsw_grid_result), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return TREDSW_OK;
+}
+
+extern "C" int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t *off, int32_t nproblems,
+                             double *pdf_out, uint32_t flags) {
+    if (!ctx) { tredsw_set_error("null context"); return TREDSW_ERR_ARG; }
+    if (nproblems < 0 || !off || !pdf_out) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    if (nproblems == 0) return TREDSW_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int32_t *d_lens; const int64_t *d_off; double *d_out;
+    int rc;
+    if (dev_ptrs(flags)) { d_lens = lens; d_off = off; d_out = pdf_out; }
+    else {
+        if ((rc = stage_in(ctx, ctx->d_ipool, lens, (size_t)off[nproblems], flags, &d_lens))) return rc;
+        if ((rc = stage_in(ctx, ctx->d_qoff, off, (size_t)nproblems + 1, flags, &d_off))) return rc;
+        if ((rc = ctx->d_dpool.ensure((size_t)nproblems * SPAN * sizeof(double)))) return rc;
+        d_out = ctx->d_dpool.as<double>();
+    }
+    int gb = nproblems > ctx->sm_count * 2 ? ctx->sm_count * 2 : nproblems;
+    pe_kde_kernel<<<gb, 1024, 0, ctx->stream>>>(d_lens, d_off, nproblems, d_out);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev_ptrs(flags)) {
+        CUDA_TRY(cudaMemcpyAsync(pdf_out, d_out, (size_t)nproblems * SPAN * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return TREDSW_OK;
+}
