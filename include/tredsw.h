@@ -153,8 +153,10 @@ typedef struct {
     int32_t recessive;
     int32_t cutoff_risk;
     double half_depth;          /* D */
-    double stutter_x;           /* w0 + w1*K + w3*gc + w4*score  (models.py:79-84,156) */
-    double stutter_w2;          /* w2, multiplies h // K */
+    double stutter_a;           /* w0 + w1*K            logistic stutter model, models.py:79-84,156:  */
+    double stutter_w2;          /* w2                   z = ((a + w2*(h // K)) + c3) + c4,             */
+    double stutter_c3;          /* w3 * gc              sigma = 1 / (1 + exp(-z))                      */
+    double stutter_c4;          /* w4 * score */
     /* offsets into the shared arrays below */
     int64_t off_span;           /* ipool: n_span keys (bp) followed by n_span counts */
     int64_t off_part;           /* ipool: n_part keys (bp) followed by n_part counts */

@@ -47,7 +47,7 @@ class GridProblem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "period", "readlen", "ploidy", "n_rept", "max_partial", "run_pe", "pe_ref", "pe_minpe",
         "n_span", "n_part", "n_target", "n_h1", "n_h2", "expansion", "recessive", "cutoff_risk")] + \
-        [(n, ctypes.c_double) for n in ("half_depth", "stutter_x", "stutter_w2")] + \
+        [(n, ctypes.c_double) for n in ("half_depth", "stutter_a", "stutter_w2", "stutter_c3", "stutter_c4")] + \
         [(n, ctypes.c_int64) for n in ("off_span", "off_part", "off_target", "off_h1", "off_h2",
                                        "off_pdf", "off_step", "off_surface", "off_ph1", "off_ph2")]
 
@@ -63,7 +63,7 @@ GRID_PROBLEM_DTYPE = np.dtype(
     [(n, "<i4") for n in ("period", "readlen", "ploidy", "n_rept", "max_partial", "run_pe", "pe_ref",
                           "pe_minpe", "n_span", "n_part", "n_target", "n_h1", "n_h2", "expansion",
                           "recessive", "cutoff_risk")] +
-    [(n, "<f8") for n in ("half_depth", "stutter_x", "stutter_w2")] +
+    [(n, "<f8") for n in ("half_depth", "stutter_a", "stutter_w2", "stutter_c3", "stutter_c4")] +
     [(n, "<i8") for n in ("off_span", "off_part", "off_target", "off_h1", "off_h2", "off_pdf",
                           "off_step", "off_surface", "off_ph1", "off_ph2")])
 GRID_RESULT_DTYPE = np.dtype([("max_ml", "<f8"), ("sum_all", "<f8"), ("sum_path", "<f8"),

@@ -31,7 +31,8 @@ struct GridParams {
 };
 
 __device__ __forceinline__ double sigma_h(const tredsw_grid_problem &P, int h) {
-    const double z = P.stutter_x + P.stutter_w2 * (double)(h / P.period);
+    double z = __dadd_rn(P.stutter_a, __dmul_rn(P.stutter_w2, (double)(h / P.period)));
+    z = __dadd_rn(__dadd_rn(z, P.stutter_c3), P.stutter_c4);
     return 1.0 / (1.0 + exp(-1.0 * z));
 }
 

@@ -1,0 +1,467 @@
+"""
+TRED caller entry point: parse the target regions of the input BAMs, classify full / partial / repeat
+reads on the GPU, evaluate the likelihood grids on the GPU and report the most likely repeat sizes.
+
+Keeps the reference's ``tredparse/tred.py`` surface: ``set_argparse`` (:64-103), ``read_csv``
+(:401-440), ``runBam`` (:153-169), ``run`` (:180-278), ``counter_s`` (:149-150), ``to_json``
+(:296-313), ``to_vcf`` (:316-374), ``main`` (:451-539) and the JSON layout.
+
+Differences that are the point of this build:
+  * ``run`` batches *all loci of a sample* into one Smith-Waterman launch and one likelihood-grid launch
+    instead of looping ``runBam`` per locus (``runBam`` is still there and gives identical results);
+  * samples are sharded over GPUs (``--gpus``), one worker process per GPU, instead of over CPU cores
+    with ``multiprocessing.Pool`` (tred.py:528-532).  No collective: workers return their dicts.
+S3 / ``@HLI-id`` inputs are out of scope.
+"""
+import argparse
+import gzip
+import json
+import logging
+import os
+import os.path as op
+import shutil
+import sys
+import time
+from datetime import datetime as dt, timedelta
+
+import numpy as np
+
+from . import __version__, ssw
+from .utils import DefaultHelpParser, InputParams, mkdir
+from .bam_parser import BamDepth, BamReadLen, BamParser, BamParserResults, PEextractor, SPAN, \
+    read_alignment
+from .models import IntegratedCaller, GridBatch, MIN_SPANNING_PAIRS, pe_kde, mean_std, histogram, \
+    calc_label
+from .meta import TREDsRepo
+
+logging.basicConfig()
+logger = logging.getLogger(__name__)
+
+INFO = """##INFO=<ID=RPA,Number=1,Type=String,Description="Repeats per allele">
+##INFO=<ID=END,Number=1,Type=Integer,Description="End position of variant">
+##INFO=<ID=MOTIF,Number=1,Type=String,Description="Canonical repeat motif">
+##INFO=<ID=NS,Number=1,Type=Integer,Description="Number of samples with data">
+##INFO=<ID=REF,Number=1,Type=Integer,Description="Reference copy number">
+##INFO=<ID=CR,Number=1,Type=Integer,Description="Disease copy number cutoff">
+##INFO=<ID=IH,Number=1,Type=String,Description="Inheritance">
+##INFO=<ID=RL,Number=1,Type=Integer,Description="Reference STR track length in bp">
+##INFO=<ID=VT,Number=1,Type=String,Description="Variant type">
+##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">
+##FORMAT=<ID=GA,Number=1,Type=String,Description="Genotype with absolute copy numbers">
+##FORMAT=<ID=FR,Number=1,Type=String,Description="Full spanning reads aligned to locus">
+##FORMAT=<ID=PR,Number=1,Type=String,Description="Partial reads aligned to locus">
+##FORMAT=<ID=RR,Number=1,Type=String,Description="Repeat-only reads aligned to locus">
+##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Mean read depth around locus">
+##FORMAT=<ID=FDP,Number=1,Type=Integer,Description="Full spanning read depth">
+##FORMAT=<ID=PDP,Number=1,Type=Integer,Description="Partial read depth">
+##FORMAT=<ID=RDP,Number=1,Type=Integer,Description="Repeat read depth">
+##FORMAT=<ID=PEDP,Number=1,Type=Integer,Description="Paired-end read depth">
+##FORMAT=<ID=CI,Number=1,Type=String,Description="95% conf interval of estimates">
+##FORMAT=<ID=PP,Number=1,Type=Float,Description="Posterior probability of disease">
+##FORMAT=<ID=LABEL,Number=1,Type=String,Description="Risk assessment">
+"""
+
+
+def set_argparse():
+    TRED_NAMES = TREDsRepo().names
+    p = DefaultHelpParser(description=__doc__, prog=op.basename(__file__),
+                          formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("infile", nargs="?", help="Input path (BAM, list of BAMs, or csv format)")
+    p.add_argument("--ref", help="Reference genome version",
+                   choices=("hg38", "hg38_nochr", "hg19", "hg19_nochr"), default="hg38")
+    p.add_argument("--tred", help="STR disorder, default is to run all", action="append",
+                   choices=sorted(TRED_NAMES), default=None)
+    p.add_argument("--haploid", help="Treat these chromosomes as haploid", action="append")
+    p.add_argument("--useclippedreads", default=False, action="store_true",
+                   help="Include clipped reads in inference")
+    p.add_argument("--noalts", default=False, action="store_true",
+                   help="Do not scan extra sites for mismapped reads, faster but less accurate")
+    p.add_argument("--norepeatpairs", default=False, action="store_true",
+                   help="Exclude pairs of repeat-only reads from evidence")
+    p.add_argument("--log", choices=("INFO", "DEBUG"), default="INFO", help="Print debug logs, DEBUG=verbose")
+    p.add_argument("--version", action="version", version="%(prog)s " + __version__)
+    p.add_argument("--toy", help=argparse.SUPPRESS, action="store_true")
+
+    g = p.add_argument_group("Performance options")
+    g.add_argument("--cpus", help="Accepted for compatibility with the reference CLI (host cores are "
+                   "not the compute resource here)", type=int, default=os.cpu_count())
+    g.add_argument("--gpus", help="Number of GPUs to shard samples over", type=int, default=1)
+    g.add_argument("--maxinsert", default=300, type=int, help="Maximum number of repeats")
+    g.add_argument("--fullsearch", default=False, action="store_true", help="Full grid search")
+
+    g = p.add_argument_group("I/O options")
+    g.add_argument("--workdir", default=os.getcwd(), help="Specify work dir")
+    g.add_argument("--cleanup", default=False, action="store_true", help="Cleanup the workdir after done")
+    g.add_argument("--checkexists", default=False, action="store_true", help="Do not run if JSON output exists")
+    g.add_argument("--no-output", default=False, action="store_true", help="Do not write JSON and VCF output")
+    return p
+
+
+def bam_path(bam):
+    if bam.startswith(("s3://", "http://", "ftp://", "https://")):
+        return bam
+    return op.abspath(bam)
+
+
+def check_bam(bam):
+    logger.debug("Working on `{}`".format(bam))
+    try:
+        read_alignment(bam).close()
+    except (IOError, ValueError) as e:
+        logger.error("Cannot retrieve file `{}` ({})".format(bam, e))
+        return None
+    return bam
+
+
+def counter_s(c):
+    return ";".join("{}|{}".format(k, int(v)) for k, v in sorted(c.items()))
+
+
+def runBam(inputParams):
+    """Parse one BAM at one locus and run the caller on it.  :return: BamParserResults"""
+    maxinsert = inputParams.kwargs["maxinsert"]
+    fullsearch = inputParams.kwargs["fullsearch"]
+    bp = BamParser(inputParams)
+    bp.parse()
+    integratedCaller = IntegratedCaller(bp, maxinsert=maxinsert, fullsearch=fullsearch)
+    integratedCaller.call(**inputParams.kwargs)
+    return BamParserResults(inputParams, bp, integratedCaller)
+
+
+class _Caller:
+    """Result holder with IntegratedCaller's result attributes (batched path)."""
+
+
+def run_batched(ips):
+    """All loci of one sample: one SW launch + one KDE launch + one grid launch.
+    :param ips: list of InputParams (same BAM).  :return: list of BamParserResults (None on failure)."""
+    parsers, all_seqs, all_names, rfam, fams, spans = [], [], [], [], [], []
+    for ip in ips:
+        bp = BamParser(ip)
+        sam = read_alignment(bp.bam)
+        reads = bp.select_reads(sam)
+        sam.close()
+        fams.append(bp._buildDB())
+        spans.append((len(all_seqs), len(all_seqs) + len(reads)))
+        all_seqs += [r.query_sequence for r in reads]
+        all_names += [r.query_name for r in reads]
+        rfam += [len(fams) - 1] * len(reads)
+        parsers.append(bp)
+    if all_seqs:
+        out = ssw.classify_reads(all_seqs, np.array(rfam, dtype=np.int32), np.concatenate(fams))
+    else:
+        out = np.zeros((0, 8), dtype=np.int32)
+    pes, need_kde = [], []
+    for bp, (a, b) in zip(parsers, spans):
+        bp.sw_results = out[a:b]
+        bp.absorb(all_names[a:b], all_seqs[a:b], out[a:b])
+        pe = PEextractor(bp)
+        pes.append(pe)
+        if len(pe.global_lens) >= 100 and len(pe.target_lens) >= MIN_SPANNING_PAIRS:
+            need_kde.append(len(pes) - 1)
+    pdfs = {}
+    if need_kde:
+        k = pe_kde([pes[i].global_lens for i in need_kde])
+        pdfs = {i: k[j] for j, i in enumerate(need_kde)}
+    batch = GridBatch()
+    idx = []
+    for i, (ip, bp, pe) in enumerate(zip(ips, parsers, pes)):
+        period = bp.repeatSize
+        obs_spanning = dict((k * period, v) for k, v in bp.counts["FULL"].items())
+        obs_partial = dict((k * period, v) for k, v in bp.counts["PREF"].items())
+        idx.append(batch.add(bp.tred, period, bp.READLEN, obs_spanning, obs_partial, bp.rept, bp.ploidy,
+                             bp.depth, pdfs.get(i), pe.target_lens, pe.ref, pe.MINPE,
+                             maxinsert=ip.kwargs["maxinsert"], fullsearch=ip.kwargs["fullsearch"]))
+    batch.run()
+    results = []
+    for ip, bp, pe, gi in zip(ips, parsers, pes, idx):
+        c = _Caller()
+        c.PEDP, c.PEG, c.PET = len(pe.target_lens), mean_std(pe.global_lens), mean_std(pe.target_lens)
+        c.P_PEG, c.P_PET = histogram(pe.global_lens), histogram(pe.target_lens)
+        period = bp.repeatSize
+        if gi < 0:
+            alleles, PP, CIs = (-1, -1), -1, None
+            c.P_h1 = c.P_h2 = c.P_h1h2 = ""
+        else:
+            s = batch.summarize(gi)
+            alleles, PP, CIs = s["alleles"], s["PP"], s["CIs"]
+            c.P_h1, c.P_h2, c.P_h1h2 = s["P_h1"], s["P_h2"], s["P_h1h2"]
+        c.alleles = sorted(x // period for x in alleles)
+        c.label = calc_label(bp.tred, c.alleles)
+        c.CI = "{}-{}|{}-{}".format(*CIs) if CIs else ""
+        c.PP = PP
+        results.append(BamParserResults(ip, bp, c))
+    return results
+
+
+def run(arg):
+    """Run the TRED caller on a list of TREDs for one sample.  :return: dict of calls"""
+    samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
+    gender = "Unknown"
+    ydepth = -1
+    tredCalls = {"inferredGender": gender, "depthY": ydepth}
+    if check_bam(bam) is None:
+        return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
+
+    if any(repo[tred].is_xlinked for tred in tredNames):
+        try:
+            bd = BamDepth(bam, repo.ref, logger)
+            ydepth = bd.get_Y_depth()
+            gender = "Male" if ydepth > 1 else "Female"
+        except Exception:
+            pass
+        logger.debug("Inferred gender: {} (depthY={})".format(gender, ydepth))
+        tredCalls["inferredGender"] = gender
+        tredCalls["depthY"] = ydepth
+
+    READLEN = 150
+    try:
+        READLEN = BamReadLen(bam, logger).readlen
+    except Exception:
+        pass
+    logger.debug("Read length: {}bp".format(READLEN))
+    tredCalls["readLen"] = READLEN
+
+    ips, depths = [], {}
+    for tred in tredNames:
+        bd = BamDepth(bam, repo.ref, logger)
+        xtred = repo[tred]
+        WINDOW_START = max(0, xtred.repeat_start - SPAN)
+        WINDOW_END = xtred.repeat_end + SPAN
+        try:
+            depth = bd.region_depth(xtred.chr, WINDOW_START, WINDOW_END)
+        except Exception as e:
+            depth = 30
+            logger.error("Exception on `{}` {} ({}). Set depth={}".format(bam, tred, e, depth))
+        logger.debug("Inferred depth at locus {}: {}".format(tred, depth))
+        depths[tred] = depth
+        ips.append(InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
+                               fullsearch=fullsearch, gender=gender, depth=depth, clip=clip, alts=alts,
+                               repeatpairs=repeatpairs, log=log))
+    try:
+        results = run_batched(ips)
+    except Exception as e:
+        # keep the reference's per-locus isolation (tred.py:245-249): retry one locus at a time
+        logger.error("Batched run failed on `{}` ({}); falling back to per-locus calls".format(bam, e))
+        results = []
+        for ip in ips:
+            try:
+                results.append(runBam(ip))
+            except Exception as e2:
+                logger.error("Exception on `{}` {} ({})".format(bam, ip.tredName, e2))
+                results.append(None)
+
+    for tred, tpResult in zip(tredNames, results):
+        if tpResult is None:
+            continue
+        alleles = tpResult.alleles
+        tredCalls[tred + ".1"] = alleles[0]
+        tredCalls[tred + ".2"] = alleles[1]
+        tredCalls[tred + ".FR"] = counter_s(tpResult.counts["FULL"])
+        tredCalls[tred + ".PR"] = counter_s(tpResult.counts["PREF"])
+        tredCalls[tred + ".RR"] = counter_s(tpResult.counts["REPT"])
+        tredCalls[tred + ".DP"] = depths[tred]
+        tredCalls[tred + ".FDP"] = tpResult.FDP
+        tredCalls[tred + ".PDP"] = tpResult.PDP
+        tredCalls[tred + ".RDP"] = tpResult.RDP
+        tredCalls[tred + ".PEDP"] = tpResult.PEDP
+        tredCalls[tred + ".PEG"] = tpResult.PEG
+        tredCalls[tred + ".PET"] = tpResult.PET
+        tredCalls[tred + ".CI"] = tpResult.CI
+        tredCalls[tred + ".PP"] = tpResult.PP
+        tredCalls[tred + ".label"] = tpResult.label
+        tredCalls[tred + ".details"] = tpResult.details
+        tredCalls[tred + ".P_h1"] = tpResult.P_h1
+        tredCalls[tred + ".P_h2"] = tpResult.P_h2
+        tredCalls[tred + ".P_h1h2"] = tpResult.P_h1h2
+        tredCalls[tred + ".P_PEG"] = tpResult.P_PEG
+        tredCalls[tred + ".P_PET"] = tpResult.P_PET
+    return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
+
+
+def vcfstanza(sampleid, bam, tredCalls, ref):
+    m = "##fileformat=VCFv4.1\n"
+    now = dt.now()
+    m += "##fileDate={}{:02d}{:02d}\n".format(now.year, now.month, now.day)
+    m += "##source={} {}\n".format(__file__, bam)
+    m += "##reference={}\n".format(ref)
+    m += "##inferredGender={} depthY={}\n".format(tredCalls["inferredGender"], tredCalls["depthY"])
+    m += "##readLen={}bp\n".format(tredCalls["readLen"])
+    m += INFO
+    header = "CHROM POS ID REF ALT QUAL FILTER INFO FORMAT\n".split() + [sampleid]
+    m += "#" + "\t".join(header)
+    return m
+
+
+def to_json(results, ref, repo, treds=("HD",), store=None):
+    sampleid = results["samplekey"]
+    calls = results["tredCalls"]
+    if not calls:
+        logger.debug("No calls are found for {} `{}`".format(sampleid, results["bam"]))
+        return
+    jsonfile = ".".join((sampleid, "json"))
+    js = json.dumps(results, sort_keys=True, indent=4, separators=(",", ": "))
+    print(js)
+    with open(jsonfile, "w") as fw:
+        print(js, file=fw)
+
+
+def to_vcf(results, ref, repo, treds=("HD",), store=None):
+    registry = {tred: repo.get_info(tred) for tred in treds}
+    sampleid, bam, calls = results["samplekey"], results["bam"], results["tredCalls"]
+    if not calls:
+        return
+    vcffile = ".".join((sampleid, "tred.vcf.gz"))
+    contents = []
+    for tred in treds:
+        if tred + ".1" not in calls:
+            continue
+        a, b = calls[tred + ".1"], calls[tred + ".2"]
+        chr, start, ref_copy, repeat, info = registry[tred]
+        alleles = set([a, b])
+        rpa = sorted(alleles - set([ref_copy]))
+        alt = ",".join(x * repeat for x in rpa) if (rpa and rpa[0] != -1) else "."
+        if rpa:
+            info += ";RPA={}".format(",".join(str(x) for x in rpa))
+            if ref_copy in alleles:
+                gt = "0/1"
+            elif len(rpa) == 1:
+                gt = "1/1"
+            else:
+                gt = "1/2"
+        else:
+            gt = "0/0"
+        gb = "{}/{}".format(a, b)
+        fields = "{}:{}:{}:{}:{}:{}:{}:{}:{}:{}:{}:{:.4g}:{}".format(
+            gt, gb, calls[tred + ".FR"], calls[tred + ".PR"], calls[tred + ".RR"], calls[tred + ".DP"],
+            calls[tred + ".FDP"], calls[tred + ".PDP"], calls[tred + ".RDP"], calls[tred + ".PEDP"],
+            calls[tred + ".CI"], calls[tred + ".PP"], calls[tred + ".label"])
+        m = "\t".join(str(x) for x in (chr, start, tred, ref_copy * repeat, alt, ".", ".", info,
+                                       "GT:GB:FR:PR:RR:DP:FDP:PDP:RDP:PEDP:CI:PP:LABEL", fields))
+        contents.append((chr, start, m))
+    with gzip.open(vcffile, "wt") as fw:
+        print(vcfstanza(sampleid, bam, calls, ref), file=fw)
+        contents.sort()
+        for chr, start, m in contents:
+            print(m, file=fw)
+    logger.debug("VCF file written to `{}`".format(vcffile))
+
+
+def read_csv(csvfile, args):
+    if csvfile[0] == "@":
+        raise ValueError("@HLI-id inputs are not supported by this build")
+    if csvfile.endswith(".bam") or csvfile.endswith(".cram"):
+        bam = bam_path(csvfile)
+        samplekey = op.basename(bam).rsplit(".", 1)[0]
+        return [(samplekey, bam, None)]
+    with open(csvfile) as fp:
+        rows = [r.strip() for r in fp if r.strip()]
+    header = rows[0]
+    contents = []
+    if header.endswith(".bam") and header.count(",") == 0:
+        for row in rows:
+            bam = bam_path(row)
+            contents.append((op.basename(bam).rsplit(".", 1)[0], bam, None))
+        return contents
+    for row in rows:
+        atoms = row.split(",")
+        samplekey, bam = atoms[:2]
+        tred = atoms[2] if len(atoms) == 3 else None
+        bam = bam_path(bam)
+        if bam.endswith(".bam"):
+            contents.append((samplekey, bam, tred))
+    return contents
+
+
+def write_vcf_json(results, ref, repo, treds, store):
+    try:
+        to_vcf(results, ref, repo, treds=treds, store=store)
+        to_json(results, ref, repo, treds=treds, store=store)
+    except Exception as e:
+        print("Error writing: {} ({})".format(results.get("samplekey"), e), file=sys.stderr)
+
+
+def _worker(rank, ngpus, task_args, queue):
+    os.environ["TREDSW_DEVICE"] = str(rank)
+    for i in range(rank, len(task_args), ngpus):
+        queue.put((i, run(task_args[i])))
+    queue.put((-1, rank))
+
+
+def main(args):
+    p = set_argparse()
+    args = p.parse_args(args)
+    loglevel = getattr(logging, args.log.upper(), "INFO")
+    logger.setLevel(loglevel)
+    logger.debug("Commandline Arguments:{}".format(vars(args)))
+
+    start = time.time()
+    workdir = args.workdir
+    cwd = os.getcwd()
+    if workdir != cwd:
+        mkdir(workdir, logger=logger)
+    infile = args.infile
+    if not infile:
+        sys.exit(not p.print_help())
+    samples = read_csv(infile, args)
+    logger.debug("Total samples: {}".format(len(samples)))
+
+    task_args = []
+    sites = op.join(os.getcwd(), "sites")
+    os.chdir(workdir)
+    ref = args.ref
+    repo = TREDsRepo(ref=ref, toy=args.toy, sites=sites)
+    repo.set_ploidy(args.haploid)
+    treds = args.tred or repo.names
+    if args.toy:
+        treds = ["HD"]
+    for samplekey, bam, tred in samples:
+        jsonfile = ".".join((samplekey, "json"))
+        if args.checkexists and op.exists(jsonfile):
+            logger.debug("File `{}` exists. Skipped computation.".format(jsonfile))
+            continue
+        _treds = [tred] if tred else treds
+        task_args.append((samplekey, bam, repo, _treds, args.maxinsert, args.fullsearch,
+                          args.useclippedreads, (not args.noalts), (not args.norepeatpairs), args.log))
+    if not task_args:
+        logger.debug("All jobs already completed.")
+        os.chdir(cwd)
+        return
+
+    ngpus = max(1, min(args.gpus, len(task_args)))
+    if ngpus == 1:
+        for ta in task_args:
+            results = run(ta)
+            if not args.no_output:
+                write_vcf_json(results, ref, repo, treds, None)
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        queue = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, ngpus, task_args, queue)) for r in range(ngpus)]
+        for pr in procs:
+            pr.start()
+        done, pending, nxt = 0, {}, 0
+        while done < ngpus:
+            i, res = queue.get()
+            if i < 0:
+                done += 1
+                continue
+            pending[i] = res
+            while nxt in pending:                      # emit in input order, like Pool.imap
+                if not args.no_output:
+                    write_vcf_json(pending.pop(nxt), ref, repo, treds, None)
+                else:
+                    pending.pop(nxt)
+                nxt += 1
+        for pr in procs:
+            pr.join()
+
+    print("Elapsed time={}".format(timedelta(seconds=time.time() - start)), file=sys.stderr)
+    os.chdir(cwd)
+    if args.cleanup:
+        shutil.rmtree(workdir)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
