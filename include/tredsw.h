@@ -198,6 +198,76 @@ int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem *problems,
 int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t *off, int32_t nproblems,
                   double *pdf_out, uint32_t flags);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole (sample, locus) problems in one call: reads -> Smith-Waterman + classification -> tallies ->
+ * candidate ranges -> KDE -> likelihood grid -> call / CI / PP / label, everything on the device.
+ * == the body of tred.run's per-locus loop (tredparse/tred.py:225-275) for a whole cohort shard,
+ * minus BAM I/O.  Only the CLI defaults repeatpairs=True, clip=False are supported here.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t family;             /* index into families / loci */
+    int32_t ploidy;             /* 1 or 2 (bam_parser.py:58-61) */
+    int32_t n_global;           /* global pair lengths (KDE input) */
+    int32_t n_target;           /* spanning pair lengths */
+    int64_t off_global;         /* offsets into pe_lens */
+    int64_t off_target;
+    double depth;               /* mean depth of the locus window */
+} tredsw_problem;
+
+typedef struct {                /* model-side constants of a locus (meta.py:103-129, models.py:114-118) */
+    int32_t period;
+    int32_t readlen;
+    int32_t pe_ref;             /* repeat_end - repeat_start + 1 */
+    int32_t pe_minpe;           /* bam_parser.py:361 */
+    int32_t expansion;
+    int32_t recessive;
+    int32_t cutoff_prerisk;
+    int32_t cutoff_risk;
+} tredsw_locus;
+
+typedef struct {
+    const int8_t *rbuf;         /* read codes, flat */
+    const int64_t *roff;        /* nreads + 1 */
+    const int32_t *read_problem;/* nreads: owning problem of each read */
+    const tredsw_problem *problems;
+    const int32_t *pe_lens;     /* pooled pair lengths */
+    int64_t n_pe_lens;
+    int32_t nreads;
+    int32_t nproblems;
+    int32_t max_read_len;       /* upper bound on read length (required) */
+    int32_t nfamilies;
+    /* the following three are always HOST pointers (small, shape decisions are made on the host) */
+    const tredsw_family *families;
+    const tredsw_locus *loci;
+    const double *step_pmf;     /* nfamilies x 37 */
+    double stutter_w[5];        /* logistic weights, models.py:79-84 */
+    double gc, score;           /* models.py:106 */
+    int32_t maxinsert;
+    int32_t fullsearch;
+    int8_t mat25[25];
+    int8_t pad_[3];
+    int32_t gap_open, gap_extend;
+} tredsw_cohort;
+
+typedef struct {
+    int32_t allele1, allele2;   /* units, sorted; -1/-1 when there is no evidence */
+    int32_t ci[4];              /* h1_lo, h1_hi, h2_lo, h2_hi (units); -1 when missing */
+    int32_t label;              /* 0 ok, 1 prerisk, 2 risk, 3 missing */
+    int32_t n_points;
+    int32_t fdp, pdp, rdp;      /* FULL / PREF(+POST) / REPT read counts */
+    int32_t run_pe;
+    double pp;                  /* -1 when missing */
+    double lik;
+} tredsw_call;
+
+/* buffers in `c`, `calls`, `read_out` (optional, nreads x 8 like tredsw_classify_reads) and `hist`
+ * (optional, nproblems x 3 x (hist_units+1) int32: FULL, PREF, REPT histograms by units) are host or
+ * device pointers according to `flags`.  stats (optional, host, 8 x int64): [0..3] as in
+ * tredsw_classify_reads, [4] grid points evaluated, [5] surface arena overflow (0 = ok). */
+int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
+                          int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

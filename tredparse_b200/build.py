@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtredsw.so")
-SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu"]
-HEADERS = ["common.cuh", "sw_sweep.cuh", os.path.join("..", "..", "include", "tredsw.h")]
+SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu"]
+HEADERS = ["common.cuh", "sw_sweep.cuh", "internal.cuh", "kde.cuh", os.path.join("..", "..", "include", "tredsw.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

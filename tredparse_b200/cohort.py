@@ -1,0 +1,197 @@
+"""
+Cohort path: many (sample, locus) problems through ONE device pipeline call
+(``tredsw_genotype_batch``: Smith-Waterman + classification -> tallies -> candidate ranges -> KDE ->
+likelihood grid -> call / CI / PP / label), sharded by (sample, locus) over GPUs with no collective.
+
+This is the batched equivalent of looping ``tred.runBam`` (``tredparse/tred.py:153-169,225-249``) and is
+what ``bench.py`` times.  ``CohortBatch`` packs problems (from ``simulate`` or from BAM-derived read
+sets) into flat buffers; ``run_host`` goes through the C ABI with host buffers (H2D / D2H inside the
+call); ``to_device`` + ``run_device`` keep every buffer resident in HBM (torch tensors used purely as
+device-memory plumbing) and only enqueue kernels.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, ssw
+from .models import NoiseModel, StepModel
+
+LABELS = {0: "ok", 1: "prerisk", 2: "risk", 3: "missing"}
+
+PROBLEM_DTYPE = np.dtype([("family", "<i4"), ("ploidy", "<i4"), ("n_global", "<i4"), ("n_target", "<i4"),
+                          ("off_global", "<i8"), ("off_target", "<i8"), ("depth", "<f8")])
+LOCUS_DTYPE = np.dtype([(n, "<i4") for n in ("period", "readlen", "pe_ref", "pe_minpe", "expansion",
+                                              "recessive", "cutoff_prerisk", "cutoff_risk")])
+CALL_DTYPE = np.dtype([("allele1", "<i4"), ("allele2", "<i4"), ("ci", "<i4", 4), ("label", "<i4"),
+                       ("n_points", "<i4"), ("fdp", "<i4"), ("pdp", "<i4"), ("rdp", "<i4"),
+                       ("run_pe", "<i4"), ("pp", "<f8"), ("lik", "<f8")])
+
+
+class Cohort(ctypes.Structure):
+    """tredsw_cohort (include/tredsw.h)"""
+    _fields_ = [("rbuf", ctypes.c_void_p), ("roff", ctypes.c_void_p), ("read_problem", ctypes.c_void_p),
+                ("problems", ctypes.c_void_p), ("pe_lens", ctypes.c_void_p), ("n_pe_lens", ctypes.c_int64),
+                ("nreads", ctypes.c_int32), ("nproblems", ctypes.c_int32), ("max_read_len", ctypes.c_int32),
+                ("nfamilies", ctypes.c_int32), ("families", ctypes.c_void_p), ("loci", ctypes.c_void_p),
+                ("step_pmf", ctypes.c_void_p), ("stutter_w", ctypes.c_double * 5), ("gc", ctypes.c_double),
+                ("score", ctypes.c_double), ("maxinsert", ctypes.c_int32), ("fullsearch", ctypes.c_int32),
+                ("mat25", ctypes.c_int8 * 25), ("pad_", ctypes.c_int8 * 3), ("gap_open", ctypes.c_int32),
+                ("gap_extend", ctypes.c_int32)]
+
+
+assert PROBLEM_DTYPE.itemsize == 40 and LOCUS_DTYPE.itemsize == 32 and CALL_DTYPE.itemsize == 64
+
+
+def _bind(lib):
+    if not getattr(lib, "_cohort_bound", False):
+        lib.tredsw_genotype_batch.restype = ctypes.c_int
+        lib.tredsw_genotype_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(Cohort), ctypes.c_uint32,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int32, ctypes.c_void_p]
+        lib._cohort_bound = True
+
+
+class CohortBatch:
+    """Flat buffers of a list of problems (objects with tred, readlen, ploidy, depth, reads, roff,
+    global_lens, target_lens — see simulate.Problem)."""
+
+    def __init__(self, problems, maxinsert=300, fullsearch=False, score=1.0, gc=.68, match=1, mismatch=5,
+                 gap_open=7, gap_extend=2):
+        self.maxinsert, self.fullsearch = maxinsert, fullsearch
+        self.score, self.gc = score, gc
+        self.match, self.mismatch, self.gap_open, self.gap_extend = match, mismatch, gap_open, gap_extend
+        fam_index, fams, loci, step_rows = {}, [], [], []
+        step = StepModel()
+        n = len(problems)
+        P = np.zeros(n, dtype=PROBLEM_DTYPE)
+        rbufs, roffs, rprob, pe = [], [np.zeros(1, dtype=np.int64)], [], []
+        rbase, pebase, max_len = 0, 0, 1
+        for i, pr in enumerate(problems):
+            t = pr.tred
+            key = (t.name, pr.readlen)
+            if key not in fam_index:
+                period = len(t.repeat)
+                fam_index[key] = len(fams)
+                fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, -(-pr.readlen // period)))
+                L = np.zeros(1, dtype=LOCUS_DTYPE)
+                ref = t.repeat_end - t.repeat_start + 1
+                L["period"], L["readlen"], L["pe_ref"], L["pe_minpe"] = period, pr.readlen, ref, ref - 1 + 2 * 9 + 2
+                L["expansion"], L["recessive"] = int(t.is_expansion), int(t.is_recessive)
+                L["cutoff_prerisk"], L["cutoff_risk"] = int(t.cutoff_prerisk), int(t.cutoff_risk)
+                loci.append(L)
+                step_rows.append(step.step_size_by_period[period])
+            f = fam_index[key]
+            reads = np.asarray(pr.reads, dtype=np.int8)
+            roff = np.asarray(pr.roff, dtype=np.int64)
+            nr = len(roff) - 1
+            rbufs.append(reads)
+            roffs.append(roff[1:] + rbase)
+            rbase += int(roff[-1])
+            rprob.append(np.full(nr, i, dtype=np.int32))
+            if nr:
+                max_len = max(max_len, int(np.max(np.diff(roff))))
+            g = np.asarray(pr.global_lens, dtype=np.int32)
+            tl = np.asarray(pr.target_lens, dtype=np.int32)
+            P[i] = (f, pr.ploidy, len(g), len(tl), pebase, pebase + len(g), pr.depth)
+            pe += [g, tl]
+            pebase += len(g) + len(tl)
+        self.nproblems = n
+        self.problems = P
+        self.rbuf = np.ascontiguousarray(np.concatenate(rbufs) if rbufs else np.zeros(0, np.int8), dtype=np.int8)
+        self.roff = np.ascontiguousarray(np.concatenate(roffs), dtype=np.int64)
+        self.read_problem = np.ascontiguousarray(np.concatenate(rprob) if rprob else np.zeros(0, np.int32), dtype=np.int32)
+        self.pe_lens = np.ascontiguousarray(np.concatenate(pe) if pe else np.zeros(0, np.int32), dtype=np.int32)
+        self.nreads = len(self.roff) - 1
+        self.max_read_len = max_len
+        self.families = np.ascontiguousarray(np.concatenate(fams))
+        self.loci = np.ascontiguousarray(np.concatenate(loci))
+        self.step_pmf = np.ascontiguousarray(np.stack(step_rows), dtype=np.float64)
+        self.hist_units = int(self.families["max_units"].max())
+        self.objects = problems
+        self._dev = None
+
+    # ---- descriptor -----------------------------------------------------------------------------------
+    def _descriptor(self, rbuf, roff, rprob, problems, pe_lens):
+        c = Cohort()
+        c.rbuf, c.roff, c.read_problem, c.problems, c.pe_lens = rbuf, roff, rprob, problems, pe_lens
+        c.n_pe_lens, c.nreads, c.nproblems = len(self.pe_lens), self.nreads, self.nproblems
+        c.max_read_len, c.nfamilies = self.max_read_len, len(self.families)
+        c.families, c.loci, c.step_pmf = self.families.ctypes.data, self.loci.ctypes.data, self.step_pmf.ctypes.data
+        for i, w in enumerate(NoiseModel().weights):
+            c.stutter_w[i] = w
+        c.gc, c.score = self.gc, self.score
+        c.maxinsert, c.fullsearch = self.maxinsert, int(self.fullsearch)
+        mat = ssw.score_matrix(self.match, self.mismatch).ravel()
+        for i in range(25):
+            c.mat25[i] = int(mat[i])
+        c.gap_open, c.gap_extend = self.gap_open, self.gap_extend
+        return c
+
+    # ---- host buffers through the C ABI (H2D + kernels + D2H inside the call) -------------------------
+    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False):
+        ctx = ctx or _lib.default_context()
+        _bind(ctx.lib)
+        calls = np.zeros(self.nproblems, dtype=CALL_DTYPE)
+        read_out = np.zeros((self.nreads, 8), dtype=np.int32) if want_reads else None
+        hist = np.zeros((self.nproblems, 3, self.hist_units + 1), dtype=np.int32) if want_hist else None
+        stats = np.zeros(8, dtype=np.int64) if want_stats else None
+        c = self._descriptor(self.rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
+                             self.problems.ctypes.data, self.pe_lens.ctypes.data)
+        for attempt in range(2):
+            rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), 0, _lib.ptr(calls), _lib.ptr(read_out),
+                                               _lib.ptr(hist), self.hist_units, _lib.ptr(stats))
+            if rc == 0 or "arena overflow" not in _lib.last_error():
+                break
+        _lib.check(rc, "tredsw_genotype_batch")
+        self.h2d_bytes = (self.rbuf.nbytes + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
+                          self.pe_lens.nbytes + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
+        self.d2h_bytes = calls.nbytes + (read_out.nbytes if want_reads else 0) + (hist.nbytes if want_hist else 0)
+        out = {"calls": calls}
+        if want_reads:
+            out["reads"] = read_out
+        if want_hist:
+            out["hist"] = hist
+        if want_stats:
+            out["stats"] = stats
+        return out
+
+    # ---- device-resident buffers (torch = memory + stream plumbing only) ------------------------------
+    def to_device(self, device):
+        import torch
+        dev = torch.device("cuda", device)
+        t = lambda a, dt: torch.from_numpy(a.view(dt) if a.dtype.fields else a).to(dev)
+        self._dev = {
+            "rbuf": t(self.rbuf, np.int8), "roff": t(self.roff, np.int64), "rprob": t(self.read_problem, np.int32),
+            "problems": torch.from_numpy(self.problems.view(np.uint8)).to(dev),
+            "pe_lens": t(self.pe_lens, np.int32),
+            "calls": torch.zeros(self.nproblems * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev),
+        }
+        return self
+
+    def run_device(self, ctx):
+        """Enqueue the pipeline on ctx's stream; results stay on the device (``calls_from_device``)."""
+        _bind(ctx.lib)
+        d = self._dev
+        c = self._descriptor(d["rbuf"].data_ptr(), d["roff"].data_ptr(), d["rprob"].data_ptr(),
+                             d["problems"].data_ptr(), d["pe_lens"].data_ptr())
+        rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), _lib.DEVICE_PTRS, d["calls"].data_ptr(),
+                                           None, None, 0, None)
+        _lib.check(rc, "tredsw_genotype_batch")
+
+    def calls_from_device(self):
+        return self._dev["calls"].cpu().numpy().view(CALL_DTYPE)
+
+
+def decode_call(call, period=None):
+    """tredsw_call record -> dict with the reference's field names."""
+    missing = call["allele1"] < 0
+    return {"alleles": [int(call["allele1"]), int(call["allele2"])],
+            "CI": "" if missing else "{}-{}|{}-{}".format(*[int(x) for x in call["ci"]]),
+            "PP": -1 if missing else float(call["pp"]), "label": LABELS.get(int(call["label"]), "error"),
+            "FDP": int(call["fdp"]), "PDP": int(call["pdp"]), "RDP": int(call["rdp"]),
+            "lik": float(call["lik"]), "n_points": int(call["n_points"]), "run_pe": bool(call["run_pe"])}
+
+
+def shard(n_items, rank, world):
+    """Static round-robin partition of (sample, locus) problems over GPUs (no collective)."""
+    return list(range(rank, n_items, world))

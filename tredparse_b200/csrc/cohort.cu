@@ -1,0 +1,374 @@
+// cohort.cu — whole (sample, locus) problems on the device: the per-locus loop body of
+// tredparse/tred.py:225-275 for a cohort shard, minus BAM I/O.
+//
+//   reads --sw_family--> (tag, h) per read            bam_parser.py:123-182
+//         --tally-----> FULL / PREF(+POST) / REPT histograms per problem      bam_parser.py:259-268, 256
+//         --plan------> observed keys, run_pe, candidate lists (Q9 duplicates kept)   models.py:224-257, 399-403
+//         --kde-------> normalised pair-length pdf per problem                 models.py:428-435
+//         --grid------> log-likelihood surface + max / arg-max / marginals / PP sums  models.py:260-302
+//         --finalize--> alleles, CI (Q11), PP, label                          models.py:287-290, 319-392, 406-413
+//
+// No host round trip between the stages; one problem = one thread in the bookkeeping kernels.
+#include "internal.cuh"
+#include "kde.cuh"
+
+namespace {
+
+constexpr int FLANKMATCH = 9;
+constexpr int NSTEP = 37;
+
+struct CohortDev {
+    const tredsw_problem *problems;
+    const tredsw_family *families;
+    const tredsw_locus *loci;
+    const int32_t *read_problem;
+    const int32_t *read_out;     // nreads x 8
+    int nreads, nproblems;
+    int HU;                      // histogram units capacity (bins 0..HU)
+    int KC;                      // key capacity per problem
+    int HL;                      // candidate-list capacity per problem
+    int32_t *hist;               // nproblems x 3 x (HU+1)
+    int32_t *ipool;              // [pe_lens copy | per-problem slots]
+    int64_t slot_base;           // offset of the first slot in ipool
+    double *dpool;               // [nproblems x 1000 pdf | nfamilies x 37 step]
+    int64_t step_base;
+    tredsw_grid_problem *gp;
+    int32_t *nbase;              // nproblems x 2: length of the sorted "base" part of h1 / h2 lists
+    double *marg;                // nproblems x 2 x HL
+    unsigned long long *counters;// [0] surface arena cursor, [1] overflow flag, [2] points
+    long long surface_cap;
+    int maxinsert, fullsearch;
+    double w0, w1, w2, w3, w4, gc, score;
+};
+
+__global__ void read_family_kernel(const int32_t *read_problem, const tredsw_problem *problems, int nreads,
+                                   int nproblems, int32_t *read_family) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nreads) {
+        int p = read_problem[r];
+        read_family[r] = (p >= 0 && p < nproblems) ? problems[p].family : -1;
+    }
+}
+
+__global__ void tally_kernel(CohortDev c) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c.nreads) return;
+    const int32_t *o = c.read_out + (int64_t)r * 8;
+    const int tag = o[0], h = o[1];
+    const int p = c.read_problem[r];
+    if (p < 0 || p >= c.nproblems || tag <= 0 || tag == TREDSW_TAG_HANG || h < 0 || h > c.HU) return;
+    // PREF and POST share one histogram (bam_parser.py:77)
+    const int which = tag == TREDSW_TAG_FULL ? 0 : (tag == TREDSW_TAG_REPT ? 2 : 1);
+    atomicAdd(&c.hist[((int64_t)p * 3 + which) * (c.HU + 1) + h], 1);
+}
+
+// one thread per problem
+__global__ void plan_kernel(CohortDev c) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.nproblems) return;
+    const tredsw_problem pr = c.problems[p];
+    const tredsw_locus L = c.loci[pr.family];
+    const int P = L.period;
+    const int t2 = L.readlen - 2 * FLANKMATCH, t3 = L.readlen - 3 * FLANKMATCH;
+    const int32_t *hf = c.hist + ((int64_t)p * 3 + 0) * (c.HU + 1);
+    const int32_t *hp = hf + (c.HU + 1), *hr = hp + (c.HU + 1);
+    int32_t *slot = c.ipool + c.slot_base + (int64_t)p * (4 * c.KC + 2 * c.HL);
+    int32_t *skey = slot, *scnt = slot + c.KC, *pkey = slot + 2 * c.KC, *pcnt = slot + 3 * c.KC;
+    int32_t *h1s = slot + 4 * c.KC, *h2s = h1s + c.HL;
+    int ns = 0, np_ = 0, max_full = 0, max_partial = 0, n_rept = 0;
+    for (int k = 0; k <= c.HU; ++k) {
+        if (hf[k] > 0 && ns < c.KC) { skey[ns] = k * P; scnt[ns] = hf[k]; ++ns; max_full = k * P; }
+        if (hp[k] > 0 && np_ < c.KC) { pkey[np_] = k * P; pcnt[np_] = hp[k]; ++np_; max_partial = k * P; }
+        n_rept += hr[k];
+    }
+    // scnt / pcnt must directly follow the keys for the grid kernel (keys[n] then counts[n])
+    for (int i = 0; i < ns; ++i) skey[ns + i] = scnt[i];
+    for (int i = 0; i < np_; ++i) pkey[np_ + i] = pcnt[i];
+    int above = 0;
+    for (int i = 0; i < np_; ++i) if (pkey[i] > max_full + P) above += pkey[np_ + i];
+    const bool has_pe = pr.n_global >= 100 && pr.n_target >= 5;
+    const bool run_pe = max_partial >= t3 && above > 1 && has_pe;
+    int mp_model = t2;
+    if (np_ > 0 && max_partial > mp_model) mp_model = max_partial;
+    // base = sorted(set(span keys) U {max_partial})
+    int nb = 0;
+    int32_t *base = h1s;    // build in place, copy below
+    bool placed = (np_ == 0);
+    for (int i = 0; i < ns; ++i) {
+        const int k = skey[i];
+        if (!placed && max_partial < k) { base[nb++] = max_partial; placed = true; }
+        if (!placed && max_partial == k) placed = true;
+        base[nb++] = k;
+    }
+    if (!placed) base[nb++] = max_partial;
+    tredsw_grid_problem g;
+    memset(&g, 0, sizeof(g));
+    g.period = P; g.readlen = L.readlen; g.ploidy = pr.ploidy; g.n_rept = n_rept;
+    g.max_partial = mp_model; g.run_pe = run_pe ? 1 : 0; g.pe_ref = L.pe_ref; g.pe_minpe = L.pe_minpe;
+    g.n_span = ns; g.n_part = np_; g.n_target = run_pe ? pr.n_target : 0;
+    g.expansion = L.expansion; g.recessive = L.recessive; g.cutoff_risk = L.cutoff_risk;
+    g.half_depth = pr.depth / 2;
+    g.stutter_a = c.w0 + c.w1 * (double)P; g.stutter_w2 = c.w2; g.stutter_c3 = c.w3 * c.gc; g.stutter_c4 = c.w4 * c.score;
+    g.off_span = skey - c.ipool; g.off_part = pkey - c.ipool; g.off_target = pr.off_target;
+    g.off_h1 = h1s - c.ipool; g.off_h2 = h2s - c.ipool;
+    g.off_pdf = run_pe ? (int64_t)p * KDE_SPAN : -1;
+    g.off_step = c.step_base + (int64_t)pr.family * NSTEP;
+    g.off_ph1 = (int64_t)p * 2 * c.HL; g.off_ph2 = g.off_ph1 + c.HL;
+    int n1 = 0, n2 = 0, nb1 = 0, nb2 = 0;
+    if (nb > 0) {
+        if (c.fullsearch) {
+            for (int h = P; h <= P * c.maxinsert && n1 < c.HL; h += P) { h1s[n1] = h; h2s[n1] = h; ++n1; }
+            n2 = n1; nb1 = n1; nb2 = n2;
+        } else {
+            const bool ext1 = (max_full == 0), ext2 = (n_rept > 0 || run_pe);
+            for (int i = 0; i < nb; ++i) h2s[i] = base[i];       // base was built in h1s
+            n1 = nb; n2 = nb; nb1 = nb; nb2 = nb;
+            for (int h = max_partial + P; h <= P * c.maxinsert; h += P) {
+                if (ext1 && n1 < c.HL) h1s[n1++] = h;
+                if (ext2 && n2 < c.HL) h2s[n2++] = h;
+            }
+        }
+        if (pr.ploidy == 1) { n2 = 1; nb2 = 1; }
+    }
+    g.n_h1 = n1; g.n_h2 = n2;
+    const long long need = (long long)n1 * n2;
+    long long off = 0;
+    if (need > 0) {
+        off = (long long)atomicAdd(&c.counters[0], (unsigned long long)need);
+        if (off + need > c.surface_cap) { atomicExch(&c.counters[1], 1ull); g.n_h1 = 0; g.n_h2 = -1; off = 0; }   // n_h2 = -1 marks the overflow
+    }
+    g.off_surface = off;
+    c.gp[p] = g;
+    c.nbase[2 * p] = nb1; c.nbase[2 * p + 1] = nb2;
+}
+
+__global__ void __launch_bounds__(1024) cohort_kde_kernel(CohortDev c, const int32_t *pe_lens) {
+    for (int p = blockIdx.x; p < c.nproblems; p += gridDim.x) {
+        if (!c.gp[p].run_pe) continue;          // block-uniform
+        const tredsw_problem pr = c.problems[p];
+        kde_block(pe_lens + pr.off_global, pr.n_global, c.dpool + (int64_t)p * KDE_SPAN);
+    }
+}
+
+// 95% interval over the merged, sorted keys of a marginal (models.py:319-340).  The candidate list is a
+// sorted base part [0, nb) followed by an ascending extension [nb, n); equal keys are summed (the
+// reference's defaultdict); entries failing `used` never became keys.
+template <class Used>
+__device__ void ci_of(const int32_t *hs, const double *w, int n, int nb, Used used, int &lo, int &hi) {
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) if (used(hs[i])) total += w[i];
+    int a = 0, b = nb;
+    double cum = 0.0;
+    bool in_range = false, any = false;
+    int k = 0;
+    lo = 0; hi = 0;
+    while (a < nb || b < n) {
+        int key;
+        if (a < nb && (b >= n || hs[a] <= hs[b])) key = hs[a]; else key = hs[b];
+        double v = 0.0;
+        while (a < nb && hs[a] == key) { v += w[a]; ++a; }
+        while (b < n && hs[b] == key) { v += w[b]; ++b; }
+        if (!used(key)) continue;
+        any = true;
+        k = key;
+        cum += v;
+        if (!in_range && cum > .025 * total) { in_range = true; lo = key; }
+        if (cum > .975 * total) break;
+    }
+    hi = any ? k : 0;
+}
+
+__global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tredsw_call *calls) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.nproblems) return;
+    const tredsw_grid_problem g = c.gp[p];
+    const tredsw_locus L = c.loci[c.problems[p].family];
+    const int32_t *hf = c.hist + ((int64_t)p * 3 + 0) * (c.HU + 1);
+    tredsw_call out;
+    memset(&out, 0, sizeof(out));
+    int fdp = 0, pdp = 0;
+    for (int k = 0; k <= c.HU; ++k) { fdp += hf[k]; pdp += hf[(c.HU + 1) + k]; }
+    out.fdp = fdp; out.pdp = pdp; out.rdp = g.n_rept; out.run_pe = g.run_pe;
+    int a1 = -1, a2 = -1;
+    if (g.n_h1 == 0 || res[p].n_points == 0) {
+        out.allele1 = out.allele2 = -1;
+        out.ci[0] = out.ci[1] = out.ci[2] = out.ci[3] = -1;
+        out.pp = -1; out.lik = -1; out.n_points = (g.n_h2 < 0) ? -1 : 0;   // -1: surface arena overflow
+    } else {
+        const tredsw_grid_result r = res[p];
+        const int32_t *h1s = c.ipool + g.off_h1, *h2s = c.ipool + g.off_h2;
+        const int h1 = h1s[r.arg_i1];
+        const int h2 = g.ploidy == 1 ? h1 : h2s[r.arg_i2];
+        a1 = min(h1, h2) / g.period; a2 = max(h1, h2) / g.period;
+        out.allele1 = a1; out.allele2 = a2;
+        out.pp = fmin(1.0, r.sum_path / r.sum_all);
+        out.lik = r.max_ml; out.n_points = r.n_points;
+        const double *ph1 = c.marg + g.off_ph1, *ph2 = c.marg + g.off_ph2;
+        int lo1, hi1, lo2, hi2;
+        if (g.ploidy == 1) {
+            ci_of(h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo1, hi1);
+            lo2 = lo1; hi2 = hi1;
+        } else {
+            int mx2 = h2s[0], mn1 = h1s[0];
+            for (int i = 1; i < g.n_h2; ++i) mx2 = max(mx2, h2s[i]);
+            for (int i = 1; i < g.n_h1; ++i) mn1 = min(mn1, h1s[i]);
+            ci_of(h1s, ph1, g.n_h1, c.nbase[2 * p], [mx2](int h) { return h <= mx2; }, lo1, hi1);
+            ci_of(h2s, ph2, g.n_h2, c.nbase[2 * p + 1], [mn1](int h) { return h >= mn1; }, lo2, hi2);
+        }
+        out.ci[0] = lo1 / g.period; out.ci[1] = hi1 / g.period; out.ci[2] = lo2 / g.period; out.ci[3] = hi2 / g.period;
+        atomicAdd(&c.counters[2], (unsigned long long)r.n_points);
+    }
+    // label (models.py:370-392)
+    int label = (a1 != -1) ? 0 : 3;
+    if (L.expansion) {
+        const int crit = L.recessive ? a1 : a2;
+        if (L.cutoff_prerisk <= crit && crit < L.cutoff_risk) label = 1;
+        else if (crit >= L.cutoff_risk) label = 2;
+    } else {
+        const int crit = L.recessive ? a2 : a1;
+        if (L.cutoff_prerisk <= crit && crit < L.cutoff_risk) label = 1;
+        else if (0 < crit && crit <= L.cutoff_risk) label = 2;
+    }
+    out.label = label;
+    calls[p] = out;
+}
+
+}  // namespace
+
+extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
+                                     int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats) {
+    if (!ctx || !c || !calls) { tredsw_set_error("null argument"); return TREDSW_ERR_ARG; }
+    if (c->nproblems <= 0 || c->nreads < 0 || c->nfamilies <= 0 || !c->families || !c->loci || !c->step_pmf ||
+        c->max_read_len <= 0 || c->maxinsert < 1) { tredsw_set_error("bad cohort descriptor"); return TREDSW_ERR_ARG; }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const bool dev = dev_ptrs(flags);
+    const int nr = c->nreads, np_ = c->nproblems, nf = c->nfamilies;
+    int max_u = 0, min_period = 1 << 30;
+    for (int f = 0; f < nf; ++f) {
+        if (c->families[f].max_units > max_u) max_u = c->families[f].max_units;
+        if (c->loci[f].period < min_period) min_period = c->loci[f].period;
+        if (c->families[f].clip) { tredsw_set_error("clip mode is not supported by tredsw_genotype_batch"); return TREDSW_ERR_UNSUPPORTED; }
+    }
+    const int HU = max_u;
+    if (hist && hist_units != HU) { tredsw_set_error("hist_units must equal the largest max_units (%d)", HU); return TREDSW_ERR_ARG; }
+    const int KC = HU + 2;
+    const int HL = c->maxinsert + KC + 2;
+    int rc;
+    // ---- inputs ------------------------------------------------------------------------------------
+    const int8_t *d_rbuf = c->rbuf; const int64_t *d_roff = c->roff; const int32_t *d_rp = c->read_problem;
+    const tredsw_problem *d_prob = c->problems; const int32_t *d_pe = c->pe_lens;
+    const tredsw_family *d_fam; const tredsw_locus *d_loci;
+    if (!dev) {
+        if (nr > 0) {
+            if ((rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
+            if ((rc = stage_in(ctx, ctx->d_qoff, c->roff, (size_t)nr + 1, 0u, &d_roff))) return rc;
+            if ((rc = stage_in(ctx, ctx->d_qidx, c->read_problem, (size_t)nr, 0u, &d_rp))) return rc;
+        }
+        if ((rc = stage_in(ctx, ctx->d_prob, c->problems, (size_t)np_, 0u, &d_prob))) return rc;
+    }
+    if ((rc = stage_in(ctx, ctx->d_fam, c->families, (size_t)nf, 0u, &d_fam))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_t, c->loci, (size_t)nf, 0u, &d_loci))) return rc;
+    // ---- arenas ------------------------------------------------------------------------------------
+    const int64_t slot_ints = 4 * (int64_t)KC + 2 * (int64_t)HL;
+    const int64_t n_ipool = c->n_pe_lens + (int64_t)np_ * slot_ints;
+    if ((rc = ctx->d_ipool.ensure((size_t)n_ipool * sizeof(int32_t)))) return rc;
+    int32_t *d_ipool = ctx->d_ipool.as<int32_t>();
+    if (c->n_pe_lens > 0)
+        CUDA_TRY(cudaMemcpyAsync(d_ipool, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int32_t),
+                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    (void)d_pe;
+    const int64_t n_dpool = (int64_t)np_ * KDE_SPAN + (int64_t)nf * NSTEP;
+    if ((rc = ctx->d_dpool.ensure((size_t)n_dpool * sizeof(double)))) return rc;
+    double *d_dpool = ctx->d_dpool.as<double>();
+    CUDA_TRY(cudaMemcpyAsync(d_dpool + (int64_t)np_ * KDE_SPAN, c->step_pmf, (size_t)nf * NSTEP * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    // surface arena: default search needs <= (#base) x (#ext) points per problem; start generous, grow on overflow
+    long long per_problem = c->fullsearch ? (long long)c->maxinsert * c->maxinsert : 16LL * HL;
+    long long surface_cap = (long long)np_ * per_problem;
+    if ((size_t)surface_cap * sizeof(double) < ctx->d_surface.cap) surface_cap = (long long)(ctx->d_surface.cap / sizeof(double));
+    if ((rc = ctx->d_surface.ensure((size_t)surface_cap * sizeof(double)))) return rc;
+    if ((rc = ctx->d_marg.ensure((size_t)np_ * 2 * HL * sizeof(double)))) return rc;
+    if ((rc = ctx->d_res.ensure((size_t)np_ * sizeof(tredsw_grid_result)))) return rc;
+    // misc: gp[np] | nbase[2np] | hist | read_family[nr] | read_out[nr*8] | calls[np] | counters
+    const size_t sz_gp = (size_t)np_ * sizeof(tredsw_grid_problem);
+    const size_t sz_hist = (size_t)np_ * 3 * (HU + 1) * sizeof(int32_t);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_gp = carve(sz_gp), o_nb = carve((size_t)np_ * 2 * sizeof(int32_t)), o_hist = carve(sz_hist),
+                 o_rf = carve((size_t)(nr + 1) * sizeof(int32_t)), o_ro = carve((size_t)(nr + 1) * 8 * sizeof(int32_t)),
+                 o_calls = carve((size_t)np_ * sizeof(tredsw_call)), o_cnt = carve(8 * sizeof(unsigned long long)),
+                 o_stats = carve(4 * sizeof(unsigned long long));
+    if ((rc = ctx->d_misc.ensure(off))) return rc;
+    unsigned char *mb = ctx->d_misc.as<unsigned char>();
+    if ((rc = ctx->d_work.ensure(((size_t)4 * nf + 2 + nr + 1) * sizeof(int32_t)))) return rc;
+    CohortDev cd{};
+    cd.problems = d_prob; cd.families = d_fam; cd.loci = d_loci; cd.read_problem = d_rp;
+    cd.nreads = nr; cd.nproblems = np_; cd.HU = HU; cd.KC = KC; cd.HL = HL;
+    cd.hist = (dev && hist) ? hist : reinterpret_cast<int32_t *>(mb + o_hist);
+    cd.ipool = d_ipool; cd.slot_base = c->n_pe_lens;
+    cd.dpool = d_dpool; cd.step_base = (int64_t)np_ * KDE_SPAN;
+    cd.gp = reinterpret_cast<tredsw_grid_problem *>(mb + o_gp);
+    cd.nbase = reinterpret_cast<int32_t *>(mb + o_nb);
+    cd.marg = ctx->d_marg.as<double>();
+    cd.counters = reinterpret_cast<unsigned long long *>(mb + o_cnt);
+    cd.surface_cap = surface_cap;
+    cd.maxinsert = c->maxinsert; cd.fullsearch = c->fullsearch;
+    cd.w0 = c->stutter_w[0]; cd.w1 = c->stutter_w[1]; cd.w2 = c->stutter_w[2]; cd.w3 = c->stutter_w[3]; cd.w4 = c->stutter_w[4];
+    cd.gc = c->gc; cd.score = c->score;
+    int32_t *d_read_family = reinterpret_cast<int32_t *>(mb + o_rf);
+    int32_t *d_read_out = (dev && read_out) ? read_out : reinterpret_cast<int32_t *>(mb + o_ro);
+    cd.read_out = d_read_out;
+    tredsw_call *d_calls = dev ? calls : reinterpret_cast<tredsw_call *>(mb + o_calls);
+    unsigned long long *d_stats = reinterpret_cast<unsigned long long *>(mb + o_stats);
+    CUDA_TRY(cudaMemsetAsync(cd.hist, 0, sz_hist, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(cd.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    // ---- pipeline ----------------------------------------------------------------------------------
+    const int tb = 256;
+    if (nr > 0) {
+        read_family_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(d_rp, d_prob, nr, np_, d_read_family);
+        if ((rc = tredsw_internal_classify(ctx, d_rbuf, d_roff, nr, d_read_family, d_fam, c->families, nf,
+                                           c->max_read_len, c->mat25, c->gap_open, c->gap_extend,
+                                           ctx->d_work.as<int32_t>(), d_read_out, stats ? d_stats : nullptr))) return rc;
+        tally_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
+    }
+    plan_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd);
+    cohort_kde_kernel<<<np_ < ctx->sm_count * 2 ? np_ : ctx->sm_count * 2, 1024, 0, ctx->stream>>>(cd, d_ipool);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = tredsw_internal_grid(ctx, cd.gp, np_, d_ipool, d_dpool, ctx->d_surface.as<double>(), cd.marg,
+                                   ctx->d_res.as<tredsw_grid_result>(), c->fullsearch ? per_problem : 1024))) return rc;
+    finalize_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
+    CUDA_TRY(cudaGetLastError());
+    // ---- outputs -----------------------------------------------------------------------------------
+    if (!dev) {
+        CUDA_TRY(cudaMemcpyAsync(calls, d_calls, (size_t)np_ * sizeof(tredsw_call), cudaMemcpyDeviceToHost, ctx->stream));
+        if (read_out && nr > 0)
+            CUDA_TRY(cudaMemcpyAsync(read_out, d_read_out, (size_t)nr * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (hist) CUDA_TRY(cudaMemcpyAsync(hist, cd.hist, sz_hist, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (stats) {
+        unsigned long long h_cnt[8], h_st[4];
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_st, d_stats, sizeof(h_st), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h_st[i];
+        stats[4] = (int64_t)h_cnt[2]; stats[5] = (int64_t)h_cnt[1]; stats[6] = (int64_t)h_cnt[0]; stats[7] = 0;
+        if (h_cnt[1]) {
+            // the surface arena was too small for this batch: grow it for the next call and report
+            ctx->d_surface.ensure((size_t)(h_cnt[0] + h_cnt[0] / 4) * sizeof(double));
+            tredsw_set_error("likelihood surface arena overflow (%llu points needed); call again", h_cnt[0]);
+            return TREDSW_ERR_UNSUPPORTED;
+        }
+    } else if (!dev) {
+        unsigned long long h_cnt[8];
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_cnt[1]) {
+            ctx->d_surface.ensure((size_t)(h_cnt[0] + h_cnt[0] / 4) * sizeof(double));
+            tredsw_set_error("likelihood surface arena overflow (%llu points needed); call again", h_cnt[0]);
+            return TREDSW_ERR_UNSUPPORTED;
+        }
+    }
+    return TREDSW_OK;
+}

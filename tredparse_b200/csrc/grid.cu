@@ -11,7 +11,8 @@
 //   PS(h)[k]  spanning pdf (models.py:149-168, quirks Q6/Q7)     PT(h)[k] partial pdf (:170-180, Q8)
 //   alpha     mixing weights (:182-190)                           R(h)[x]  rolled PE pdf (:441-458)
 // Arithmetic order follows the reference (sum over keys in the order given, ml1+ml2+ml3+ml4).
-#include "common.cuh"
+#include "internal.cuh"
+#include "kde.cuh"
 #include <math.h>
 
 namespace {
@@ -121,7 +122,8 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const int32_t *tl = g.ipool + P.off_target;
         double acc = 0.0;
         for (int i = 0; i < P.n_target; ++i) {
-            const int x = tl[i];
+            int x = tl[i];
+            if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
             const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
             const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
             double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) grid_surface_kernel(GridParams g, int npr
     for (int pi = blockIdx.y; pi < nproblems; pi += gridDim.y) {
         const tredsw_grid_problem P = g.prob[pi];
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-        const long long total = (long long)P.n_h1 * P.n_h2;
+        const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
         double *surf = g.surface + P.off_surface;
         for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
              t += (long long)gridDim.x * blockDim.x) {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int npro
         const tredsw_grid_problem P = g.prob[pi];
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
         const double *surf = g.surface + P.off_surface;
-        const long long total = (long long)P.n_h1 * P.n_h2;
+        const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
         ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
         int cnt = 0;
         for (long long t = threadIdx.x; t < total; t += blockDim.x) {
@@ -245,64 +247,34 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int npro
     }
 }
 
-// ---- KDE of paired-end lengths (models.py:428-435) -------------------------------------------------
-// scipy.stats.gaussian_kde with Scott's factor n^(-1/5): covariance = var(ddof=1) * factor^2,
-// pdf[x] ~ sum_i exp(-((x - x_i) / sd)^2 / 2); the normalisation constant cancels in pdf / pdf.sum().
-// Lengths are integers, so the sum runs over a histogram of distinct values.
-constexpr int KDE_OFF = 1024;                  // histogram covers lengths in [-1024, 1024)
+// ---- KDE of paired-end lengths (models.py:428-435): see kde.cuh ---------------------------------------
 __global__ void __launch_bounds__(1024) pe_kde_kernel(const int32_t *lens, const int64_t *off, int nproblems,
                                                       double *pdf_out) {
-    __shared__ int hist[2 * KDE_OFF];
-    __shared__ double red[1024];
-    __shared__ double s_mean, s_sd;
-    for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x) {
-        const int32_t *x = lens + off[pi];
-        const int n = (int)(off[pi + 1] - off[pi]);
-        double *out = pdf_out + (int64_t)pi * SPAN;
-        for (int i = threadIdx.x; i < 2 * KDE_OFF; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        double s = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            int v = x[i];
-            s += (double)v;
-            v = max(-KDE_OFF, min(KDE_OFF - 1, v));
-            atomicAdd(&hist[v + KDE_OFF], 1);
-        }
-        red[threadIdx.x] = s;
-        __syncthreads();
-        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
-        if (threadIdx.x == 0) s_mean = n > 0 ? red[0] / (double)n : 0.0;
-        __syncthreads();
-        double ss = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { double d = (double)x[i] - s_mean; ss += d * d; }
-        red[threadIdx.x] = ss;
-        __syncthreads();
-        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
-        if (threadIdx.x == 0) {
-            const double var = n > 1 ? red[0] / (double)(n - 1) : 0.0;
-            const double factor = pow((double)n, -1.0 / 5.0);
-            s_sd = sqrt(var * factor * factor);
-        }
-        __syncthreads();
-        double val = 0.0;
-        if (threadIdx.x < SPAN && n > 0) {
-            const double xs = (double)threadIdx.x / s_sd;
-            for (int b = 0; b < 2 * KDE_OFF; ++b) {
-                const int c = hist[b];
-                if (c == 0) continue;
-                const double r = (double)(b - KDE_OFF) / s_sd - xs;
-                val += (double)c * exp(-(r * r) / 2.0);
-            }
-        }
-        red[threadIdx.x] = threadIdx.x < SPAN ? val : 0.0;
-        __syncthreads();
-        for (int d = 512; d > 0; d >>= 1) { if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d]; __syncthreads(); }
-        if (threadIdx.x < SPAN) out[threadIdx.x] = val / red[0];
-        __syncthreads();
-    }
+    for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x)
+        kde_block(lens + off[pi], (int)(off[pi + 1] - off[pi]), pdf_out + (int64_t)pi * SPAN);
 }
 
 }  // namespace
+
+int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int nproblems,
+                         const int32_t *d_ipool, const double *d_dpool, double *d_surface, double *d_marg,
+                         tredsw_grid_result *d_res, long long points_hint) {
+    GridParams g{};
+    g.prob = d_prob; g.ipool = d_ipool; g.dpool = d_dpool; g.surface = d_surface; g.marg = d_marg; g.res = d_res;
+    g.small_value = exp(-10.0);
+    g.really_small = exp(-100.0);
+    g.log_small = log(g.small_value);
+    long long tiles = (points_hint + 255) / 256;
+    if (tiles < 1) tiles = 1;
+    int gx = (int)(tiles > 4096 ? 4096 : tiles);
+    int gy = nproblems > 65535 ? 65535 : nproblems;
+    grid_surface_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, nproblems);
+    CUDA_TRY(cudaGetLastError());
+    int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
+    grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
+    CUDA_TRY(cudaGetLastError());
+    return TREDSW_OK;
+}
 
 extern "C" int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem *problems, int32_t nproblems,
                                       const int32_t *ipool, int64_t n_ipool, const double *dpool,
@@ -339,18 +311,7 @@ extern "C" int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem
         g.surface = ctx->d_surface.as<double>(); g.marg = ctx->d_marg.as<double>();
         g.res = ctx->d_res.as<tredsw_grid_result>();
     }
-    g.small_value = exp(-10.0);
-    g.really_small = exp(-100.0);
-    g.log_small = log(g.small_value);
-    long long tiles = (max_points + 255) / 256;
-    if (tiles < 1) tiles = 1;
-    int gx = (int)(tiles > 4096 ? 4096 : tiles);
-    int gy = nproblems > 65535 ? 65535 : nproblems;
-    grid_surface_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, nproblems);
-    CUDA_TRY(cudaGetLastError());
-    int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
-    grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
-    CUDA_TRY(cudaGetLastError());
+    if ((rc = tredsw_internal_grid(ctx, g.prob, nproblems, g.ipool, g.dpool, g.surface, g.marg, g.res, max_points))) return rc;
     if (!dev_ptrs(flags)) {
         if (surface && n_surface > 0)
             CUDA_TRY(cudaMemcpyAsync(surface, g.surface, (size_t)n_surface * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

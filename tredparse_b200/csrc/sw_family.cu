@@ -24,7 +24,7 @@
 //   coordinates come from the scalar sweeps of sw_sweep.cuh (forward locate + reverse pass), then the
 //   reference's filter + tag rules; the first candidate that yields a tag is the read's result — the
 //   same result as classifying all 2*max_units alignments and taking max(key=(score, -units)).
-#include "common.cuh"
+#include "internal.cuh"
 #include "sw_sweep.cuh"
 
 namespace {
@@ -325,6 +325,51 @@ int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nitems_bound, 
 
 }  // namespace
 
+int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_t *d_roff, int nreads,
+                             const int32_t *d_read_family, const tredsw_family *d_families,
+                             const tredsw_family *h_families, int nfamilies, int max_m,
+                             const int8_t *mat25, int gap_open, int gap_extend, int32_t *d_work, int32_t *d_out,
+                             unsigned long long *d_stats) {
+    int max_u = 0; unsigned pmask = 0; bool need_generic = false; int max_match = 0;
+    for (int i = 0; i < 25; ++i) if (mat25[i] > max_match) max_match = mat25[i];
+    const bool allow_fast = (long long)max_m * max_match < 256;
+    for (int f = 0; f < nfamilies; ++f) {
+        const tredsw_family &g = h_families[f];
+        if (g.prefix_len < 1 || g.prefix_len > 32 || g.suffix_len < 1 || g.suffix_len > 32 || g.period < 1 ||
+            g.period > 32 || g.max_units < 1 || g.max_units > 4096) { tredsw_set_error("family %d out of range", f); return TREDSW_ERR_ARG; }
+        if (g.max_units > max_u) max_u = g.max_units;
+        bool fast = allow_fast && g.prefix_len == FLANK && g.suffix_len == FLANK && g.period <= 12;
+        if (fast) pmask |= 1u << g.period; else need_generic = true;
+    }
+    const int max_rows = max_m > 0 ? max_m : 1;
+    const size_t smem = (size_t)max_rows * 32 * 4 + (size_t)max_rows * 32 + (size_t)2 * max_u * 32 * 2 + 64;
+    if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
+    ClassifyParams p{};
+    p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
+    int32_t *w = d_work;
+    int32_t *d_count = w, *d_fam_start = w + nfamilies, *d_chunk_start = d_fam_start + nfamilies + 1,
+            *d_cursor = d_chunk_start + nfamilies + 1, *d_order = d_cursor + nfamilies;
+    CUDA_TRY(cudaMemsetAsync(d_count, 0, nfamilies * sizeof(int32_t), ctx->stream));
+    const int tb = 256, nb = (nreads + tb - 1) / tb;
+    fam_count_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_count);
+    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_fam_start, d_chunk_start, d_cursor);
+    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_cursor, d_order, p.out);
+    CUDA_TRY(cudaGetLastError());
+    p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
+    p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
+    p.allow_fast = allow_fast ? 1 : 0;
+    p.stats = d_stats;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
+    const int nitems_bound = nreads / 32 + nfamilies + 1;
+    int rc;
+    if (need_generic) { if ((rc = launch_classify<0>(ctx, p, nitems_bound, smem))) return rc; }
+#define LAUNCH_P(PP) if (pmask & (1u << PP)) { if ((rc = launch_classify<PP>(ctx, p, nitems_bound, smem))) return rc; }
+    LAUNCH_P(1) LAUNCH_P(2) LAUNCH_P(3) LAUNCH_P(4) LAUNCH_P(5) LAUNCH_P(6)
+    LAUNCH_P(7) LAUNCH_P(8) LAUNCH_P(9) LAUNCH_P(10) LAUNCH_P(11) LAUNCH_P(12)
+#undef LAUNCH_P
+    return TREDSW_OK;
+}
+
 extern "C" int tredsw_classify_reads(tredsw_ctx *ctx, const int8_t *rbuf, const int64_t *roff, int32_t nreads,
                                      const int32_t *read_family, const tredsw_family *families,
                                      int32_t nfamilies, const int8_t *mat25, int gap_open, int gap_extend,
@@ -332,61 +377,25 @@ extern "C" int tredsw_classify_reads(tredsw_ctx *ctx, const int8_t *rbuf, const 
     if (!ctx) { tredsw_set_error("null context"); return TREDSW_ERR_ARG; }
     if (nreads < 0 || nfamilies <= 0 || !families || !mat25 || !out) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
     if (nreads == 0) return TREDSW_OK;
-    if (dev_ptrs(flags)) { tredsw_set_error("tredsw_classify_reads: use tredsw_classify_reads_dev for device buffers"); return TREDSW_ERR_UNSUPPORTED; }
+    if (dev_ptrs(flags)) { tredsw_set_error("tredsw_classify_reads takes host buffers; device-resident batches go through tredsw_genotype_batch"); return TREDSW_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     int max_m = 0;
     for (int i = 0; i < nreads; ++i) { int l = (int)(roff[i + 1] - roff[i]); if (l > max_m) max_m = l; }
-    int max_u = 0; unsigned pmask = 0; bool need_generic = false; int max_match = 0;
-    for (int i = 0; i < 25; ++i) if (mat25[i] > max_match) max_match = mat25[i];
-    for (int f = 0; f < nfamilies; ++f) {
-        const tredsw_family &g = families[f];
-        if (g.prefix_len < 1 || g.prefix_len > 32 || g.suffix_len < 1 || g.suffix_len > 32 || g.period < 1 ||
-            g.period > 32 || g.max_units < 1 || g.max_units > 4096) { tredsw_set_error("family %d out of range", f); return TREDSW_ERR_ARG; }
-        if (g.max_units > max_u) max_u = g.max_units;
-        bool fast = g.prefix_len == FLANK && g.suffix_len == FLANK && g.period <= 12 && max_m * max_match < 256;
-        if (fast) pmask |= 1u << g.period; else need_generic = true;
-    }
-    if (max_m * max_match >= 256) { need_generic = true; pmask = 0; }
-    const int max_rows = max_m > 0 ? max_m : 1;
-    const size_t smem = (size_t)max_rows * 32 * 4 + (size_t)max_rows * 32 + (size_t)2 * max_u * 32 * 2 + 64;
-    if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
-
-    ClassifyParams p{};
     int rc;
-    const int32_t *d_rfam;
-    if ((rc = stage_in(ctx, ctx->d_q, rbuf, (size_t)roff[nreads], flags, &p.rbuf))) return rc;
-    if ((rc = stage_in(ctx, ctx->d_qoff, roff, (size_t)nreads + 1, flags, &p.roff))) return rc;
+    const int8_t *d_rbuf; const int64_t *d_roff; const int32_t *d_rfam; const tredsw_family *d_fam;
+    if ((rc = stage_in(ctx, ctx->d_q, rbuf, (size_t)roff[nreads], flags, &d_rbuf))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_qoff, roff, (size_t)nreads + 1, flags, &d_roff))) return rc;
     if ((rc = stage_in(ctx, ctx->d_rfam, read_family, (size_t)nreads, flags, &d_rfam))) return rc;
-    if ((rc = stage_in(ctx, ctx->d_fam, families, (size_t)nfamilies, flags, &p.families))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_fam, families, (size_t)nfamilies, flags, &d_fam))) return rc;
     if ((rc = ctx->d_out.ensure((size_t)nreads * 8 * sizeof(int32_t)))) return rc;
-    // work: count[nfam] | fam_start[nfam+1] | chunk_start[nfam+1] | cursor[nfam] | order[nreads]
-    const size_t nw = (size_t)4 * nfamilies + 2 + nreads;
-    if ((rc = ctx->d_work.ensure(nw * sizeof(int32_t)))) return rc;
+    if ((rc = ctx->d_work.ensure(((size_t)4 * nfamilies + 2 + nreads) * sizeof(int32_t)))) return rc;
     if ((rc = ctx->d_stats.ensure(4 * sizeof(unsigned long long)))) return rc;
-    int32_t *w = ctx->d_work.as<int32_t>();
-    int32_t *d_count = w, *d_fam_start = w + nfamilies, *d_chunk_start = d_fam_start + nfamilies + 1,
-            *d_cursor = d_chunk_start + nfamilies + 1, *d_order = d_cursor + nfamilies;
-    CUDA_TRY(cudaMemsetAsync(d_count, 0, nfamilies * sizeof(int32_t), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    p.out = ctx->d_out.as<int32_t>();
-    const int tb = 256, nb = (nreads + tb - 1) / tb;
-    fam_count_kernel<<<nb, tb, 0, ctx->stream>>>(d_rfam, nreads, nfamilies, d_count);
-    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_fam_start, d_chunk_start, d_cursor);
-    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_rfam, nreads, nfamilies, d_cursor, d_order, p.out);
-    CUDA_TRY(cudaGetLastError());
-    p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
-    p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
-    p.allow_fast = (max_m * max_match < 256) ? 1 : 0;
-    p.stats = stats ? ctx->d_stats.as<unsigned long long>() : nullptr;
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
-    const int nitems_bound = nreads / 32 + nfamilies + 1;
-    if (need_generic) { if ((rc = launch_classify<0>(ctx, p, nitems_bound, smem))) return rc; }
-#define LAUNCH_P(PP) if (pmask & (1u << PP)) { if ((rc = launch_classify<PP>(ctx, p, nitems_bound, smem))) return rc; }
-    LAUNCH_P(1) LAUNCH_P(2) LAUNCH_P(3) LAUNCH_P(4) LAUNCH_P(5) LAUNCH_P(6)
-    LAUNCH_P(7) LAUNCH_P(8) LAUNCH_P(9) LAUNCH_P(10) LAUNCH_P(11) LAUNCH_P(12)
-#undef LAUNCH_P
-    CUDA_TRY(cudaMemcpyAsync(out, p.out, (size_t)nreads * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = tredsw_internal_classify(ctx, d_rbuf, d_roff, nreads, d_rfam, d_fam, families, nfamilies, max_m, mat25,
+                                       gap_open, gap_extend, ctx->d_work.as<int32_t>(), ctx->d_out.as<int32_t>(),
+                                       stats ? ctx->d_stats.as<unsigned long long>() : nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)nreads * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (stats) CUDA_TRY(cudaMemcpyAsync(stats, ctx->d_stats.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return TREDSW_OK;

@@ -1,0 +1,132 @@
+"""
+Synthetic (sample, locus) problems: reads simulated at a TRED locus for a given allele pair, plus the
+paired-end distances the caller uses — the inputs of the hot path without a BAM in between.
+
+Design follows SURVEY.md §8(d) (configs 3-5 of BASELINE.json):
+
+* haplotype = rand(FLANK) + prefix18 + motif x h + suffix18 + rand(FLANK)   (random flanks: no hg38 here)
+* 150 bp (or 250 bp) paired-end reads, fragment length N(350, 75^2) truncated to [200, 999], 15x per
+  haplotype, 0.5 %/base substitution error, read 2 reverse-complemented;
+* the read set of a problem = reads whose leftmost base lies within READLEN of the repeat (the rule of
+  tredparse/bam_parser.py:206-214 in haplotype coordinates) — reads lying wholly inside a long repeat
+  are included, they are the "unmapped with anchored mate" class;
+* target_lens = fragment - (h - ref_copy) * period for pairs whose read 1 starts > 9 bp before and whose
+  read 2 ends > 9 bp after the repeat (bam_parser.py:341-359), kept if < 1000;
+  global_lens = 2,500 draws of the fragment distribution.
+
+Everything is seeded: ``np.random.default_rng(0xB200 + 1000 * locus_idx + pair_idx)`` per problem.
+"""
+import numpy as np
+
+from .ssw import encode
+
+FLANK_BP = 2000
+FRAG_MEAN, FRAG_SD, FRAG_MIN, FRAG_MAX = 350.0, 75.0, 200, 999
+N_GLOBAL = 2500
+_COMP = np.array([3, 2, 1, 0, 4], dtype=np.int8)
+
+
+class Problem:
+    """One (sample, locus) problem ready for the GPU path."""
+    __slots__ = ("tred", "readlen", "ploidy", "depth", "reads", "roff", "global_lens", "target_lens",
+                 "alleles", "names")
+
+    @property
+    def nreads(self):
+        return len(self.roff) - 1
+
+    def read_strings(self):
+        lut = np.array(list("ACGTN"))
+        return ["".join(lut[self.reads[self.roff[i]:self.roff[i + 1]]]) for i in range(self.nreads)]
+
+
+def _fragment_lengths(rng, n):
+    out = np.empty(0, dtype=np.int64)
+    while len(out) < n:
+        x = np.rint(rng.normal(FRAG_MEAN, FRAG_SD, size=int((n - len(out)) * 1.3) + 8)).astype(np.int64)
+        out = np.concatenate([out, x[(x >= FRAG_MIN) & (x <= FRAG_MAX)]])
+    return out[:n]
+
+
+def simulate_problem(tred, alleles, readlen=150, cov_per_hap=15.0, error=0.005, seed=0, depth=None):
+    """alleles: (h1, h2) in repeat units for a diploid problem, (h,) for a haploid one."""
+    rng = np.random.default_rng(seed)
+    prefix, suffix, motif = encode(tred.prefix), encode(tred.suffix), encode(tred.repeat)
+    P = len(motif)
+    ref_copy = tred.ref_copy
+    reads, target = [], []
+    for h in alleles:
+        rep = np.tile(motif, h)
+        nmask = rep == 4                               # 'N' in the motif (GCN loci): any base
+        if nmask.any():
+            rep = rep.copy()
+            rep[nmask] = rng.integers(0, 4, int(nmask.sum()))
+        hap = np.concatenate([rng.integers(0, 4, FLANK_BP).astype(np.int8), prefix, rep.astype(np.int8), suffix,
+                              rng.integers(0, 4, FLANK_BP).astype(np.int8)])
+        rep_start = FLANK_BP + len(prefix)
+        rep_end = rep_start + P * h                   # exclusive
+        L = len(hap)
+        nfrag = int(round(cov_per_hap * L / (2.0 * readlen)))
+        frag = _fragment_lengths(rng, nfrag)
+        start = rng.integers(0, L - frag + 1)
+        end = start + frag                             # exclusive
+        # read 1: forward from the fragment start; read 2: reverse complement of the fragment end
+        s1 = start
+        s2 = end - readlen
+        lo, hi = rep_start - readlen, rep_end + readlen
+        k1 = (s1 >= lo) & (s1 <= hi)
+        k2 = (s2 >= lo) & (s2 <= hi)
+        idx = np.arange(readlen)
+        r1 = hap[s1[k1][:, None] + idx]
+        r2 = _COMP[hap[s2[k2][:, None] + idx]][:, ::-1]
+        for block in (r1, r2):
+            if block.size:
+                err = rng.random(block.shape) < error
+                block = np.where(err, rng.integers(0, 4, block.shape), block).astype(np.int8)
+                reads.append(block)
+        span = (s1 < rep_start - 9) & (end > rep_end + 9)
+        tl = frag[span] - (h - ref_copy) * P
+        target.append(tl[tl < 1000])
+    pr = Problem()
+    pr.tred, pr.readlen, pr.ploidy, pr.alleles = tred, readlen, len(alleles), tuple(alleles)
+    allr = np.concatenate(reads) if reads else np.zeros((0, readlen), dtype=np.int8)
+    order = rng.permutation(len(allr))                # BAM order mixes haplotypes and mates
+    allr = allr[order]
+    pr.reads = np.ascontiguousarray(allr.reshape(-1))
+    pr.roff = np.arange(len(allr) + 1, dtype=np.int64) * readlen
+    pr.global_lens = _fragment_lengths(rng, N_GLOBAL).astype(np.int32)
+    pr.target_lens = (np.concatenate(target) if target else np.zeros(0)).astype(np.int32)
+    pr.depth = float(depth) if depth is not None else cov_per_hap * len(alleles)
+    pr.names = None
+    return pr
+
+
+def draw_allele(rng, tred, risk_fraction=0.01):
+    """One allele (units) from the locus' population histogram (TREDs.meta.csv allele_freq), with a
+    small fraction forced into the risk range."""
+    freq = tred.allele_freq
+    if rng.random() < risk_fraction or not freq:
+        base = int(tred.cutoff_risk)
+        return max(1, base + int(rng.integers(0, 30))) if tred.is_expansion else max(1, base - int(rng.integers(0, 3)))
+    keys = np.array(sorted(freq))
+    p = np.array([freq[k] for k in keys], dtype=float)
+    return int(rng.choice(keys, p=p / p.sum()))
+
+
+def simulate_cohort(repo, names, nsamples, readlen=150, seed=20240000, maxunits=None):
+    """nsamples x len(names) problems, alleles drawn per sample from each locus' allele_freq; gender
+    50/50 (X-linked loci are haploid in males); depth ~ N(35, 5^2)."""
+    problems = []
+    for s in range(nsamples):
+        rng = np.random.default_rng(seed + s)
+        male = rng.random() < 0.5
+        depth = float(np.clip(rng.normal(35, 5), 15, 60))
+        for li, name in enumerate(names):
+            tred = repo[name]
+            ploidy = 1 if (male and tred.is_xlinked) else 2
+            alleles = tuple(sorted(draw_allele(rng, tred) for _ in range(ploidy)))
+            if maxunits:
+                alleles = tuple(min(a, maxunits) for a in alleles)
+            problems.append(simulate_problem(tred, alleles, readlen=readlen, cov_per_hap=depth / 2.0,
+                                             seed=0xB200 + 1000 * li + 7919 * s))
+    return problems
