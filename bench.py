@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""
+bench.py — the genotyping hot path on a synthetic cohort (BASELINE.json configs[3]: samples x 30 TREDs,
+sharded by (sample, locus), one process per GPU, no collective on the data path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--impl reference]
+
+A *step* is one pass of the whole hot path — Smith-Waterman of every read against its locus' template
+family + classification, tallies, candidate ranges, KDE, likelihood grid, call / CI / PP / label — over one
+fixed batch of S samples x 30 loci per GPU (weak scaling: the per-GPU batch is constant as N grows).
+
+Rank 0 prints ONE JSON line:
+  value        loci genotyped / s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H per step
+  roofline     dominant kernel = sw_family classify kernels (integer/DPX-pipe bound);
+               roofline_grid = likelihood grid vs the measured HBM copy bandwidth
+  cpu_baseline the reference's CPU path (ssw.c compiled unmodified + per-call ctypes pattern + numpy/scipy
+               grid) on a bounded sample of the same workload, all host cores
+
+`--impl reference` times only that CPU path (rank 0 alone when launched under torchrun).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "loci genotyped/sec"
+UNIT = "loci/s"
+READLEN = 150
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--samples", type=int, default=192, help="samples per GPU per step (x 30 loci)")
+    p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
+    p.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def distinct_loci(repo):
+    """30 distinct locations among the 32 catalogue names (FXS == FXTAS, SBMA == AR coordinates)."""
+    seen, names = set(), []
+    for n in repo.names:
+        t = repo[n]
+        key = (t.chr, t.repeat_start, t.repeat_end)
+        if key in seen:
+            continue
+        seen.add(key)
+        names.append(n)
+    return names
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fp:
+            d = json.load(fp)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_tables():
+    with open(os.path.join(ROOT, "tredparse_b200", "data", "models.json")) as fp:
+        md = json.load(fp)
+    step = {int(k): np.array(v) for k, v in md["step_size_by_period"].items()}
+    for i in range(6, 18):
+        step[i] = step[6]
+    return step, md["stutter_weights"]
+
+
+def cpu_reference_run(problems, cores=None):
+    """Time the reference-shaped CPU path on `problems`; returns (loci/s, seconds, cores, reads, cells, kind)."""
+    from oracle import ref_percall, sw
+    kind = "reference" if sw.ref_available() else "port"
+    if kind == "port":
+        raise RuntimeError("oracle/_ref/libssw_ref.so missing (build it where /root/reference is mounted)")
+    step, w = model_tables()
+    tasks = [(p.tred, p.readlen, p.ploidy, p.depth, p.read_strings(), p.global_lens, p.target_lens, step, w)
+             for p in problems]
+    t0 = time.perf_counter()
+    res, used = ref_percall.run_pool(tasks, cores)
+    dt = time.perf_counter() - t0
+    reads = sum(r[4] for r in res)
+    cells = sum(r[5] for r in res)
+    return len(problems) / dt, dt, used, reads, cells, kind, res
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path, rank 0 only."""
+    if rank != 0:
+        return
+    from tredparse_b200 import simulate
+    from tredparse_b200.meta import TREDsRepo
+    repo = TREDsRepo()
+    names = distinct_loci(repo)
+    cores = os.cpu_count() or 1
+    # bounded sample: whole samples (30 loci each), about two problems per core, capped
+    nsamp = args.cpu_sample // len(names) if args.cpu_sample else max(1, min(8, (2 * cores) // len(names) + 1))
+    problems = simulate.simulate_cohort(repo, names, nsamp, readlen=READLEN)
+    times = []
+    for it in range(args.warmup + args.steps):
+        v, dt, used, reads, cells, kind, _ = cpu_reference_run(problems, cores)
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(problems) * len(times) / total
+    sample = "{} samples x {} loci = {} problems ({} reads) per step".format(nsamp, len(names), len(problems), reads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/f64",
+        "data": "synthetic",
+        "config": {"workload": "synthetic cohort x 30 TREDs (BASELINE configs[3]), bounded sample: " + sample,
+                   "readlen": READLEN, "maxinsert": 300, "parallelism": "multiprocessing.Pool({})".format(used)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample,
+                         "reads_per_s": reads * len(times) / total,
+                         "sw_gcups": cells * len(times) / total / 1e9},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tredparse_b200 import _lib, cohort, simulate
+    from tredparse_b200.meta import TREDsRepo
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (tredparse_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    repo = TREDsRepo()
+    names = distinct_loci(repo)
+    # this rank's shard of the (sample, locus) list: samples [rank*S, (rank+1)*S) x all loci
+    t_gen = time.perf_counter()
+    problems = simulate.simulate_cohort(repo, names, args.samples, readlen=READLEN,
+                                        seed=20240000 + rank * args.samples)
+    batch = cohort.CohortBatch(problems, maxinsert=300, fullsearch=False)
+    t_gen = time.perf_counter() - t_gen
+
+    stream = torch.cuda.Stream(device=local_rank)
+    ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
+    int_peak = ctx.int_pipe_peak()
+    batch.to_device(local_rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            batch.run_device(ctx)
+    stream.synchronize()
+    # stage timing of one extra (untimed) step, used for the rooflines
+    ctx.enable_timing(True)
+    with torch.cuda.stream(stream):
+        batch.run_device(ctx)
+    stage = ctx.timing()
+    ctx.enable_timing(False)
+    st = batch.run_host(ctx=ctx, want_stats=True)["stats"]      # cell / point counts of this batch
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            batch.run_device(ctx)
+        e1.record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    ms = e0.elapsed_time(e1)
+    calls_dev = batch.calls_from_device()
+
+    # ---- end to end through the C ABI with pinned host buffers -------------------------------------
+    def pin(a):
+        t = torch.from_numpy(a.view(np.uint8) if a.dtype.fields else a).pin_memory()
+        return t.numpy().view(a.dtype) if a.dtype.fields else t.numpy()
+    for name in ("rbuf", "roff", "read_problem", "problems", "pe_lens"):
+        setattr(batch, name, pin(getattr(batch, name)))
+    for _ in range(2):
+        host = batch.run_host(ctx=ctx)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host = batch.run_host(ctx=ctx)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    assert host["calls"].tobytes() == calls_dev.tobytes(), "device-resident and host paths disagree"
+
+    # ---- reduce over ranks --------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+        cnt = torch.tensor([batch.nproblems, batch.nreads, int(st[0]), int(st[1]), int(st[2]), int(st[4]), launches],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        nprob, nreads, alg_cells, ex1, ex2, points, launches = [float(x) for x in cnt]
+    else:
+        nprob, nreads, alg_cells, ex1, ex2, points = batch.nproblems, batch.nreads, int(st[0]), int(st[1]), int(st[2]), int(st[4])
+
+    if rank == 0:
+        sec = ms / 1e3
+        value = nprob * args.steps / sec
+        # roofline of the dominant kernel (this rank's launch): integer / DPX pipe.
+        # executed lane-instructions: phase 1 = 7 packed DPX/PRMT instructions per cell pair (two cells),
+        # phase 2 = 8 scalar instructions per cell (DESIGN.md "SW kernel: instruction budget").
+        sw_s = stage["sw"] / 1e3
+        lane_instr = (int(st[1]) / 2.0) * 7.0 + int(st[2]) * 8.0
+        achieved = lane_instr / sw_s / 1e9
+        hbm, hbm_src = peaks()
+        grid_bytes = 8.0 * int(st[4]) * 2            # surface written once, read once by the reduction
+        grid_s = max(stage["grid"], 1e-6) / 1e3
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16 (SW, DPX s16x2) / f64 (likelihood)",
+            "data": "synthetic",
+            "config": {"workload": "synthetic cohort x 30 TREDs (BASELINE configs[3]): {} samples x {} loci = {} "
+                                   "problems, {} reads per GPU per step".format(args.samples, len(names), batch.nproblems, batch.nreads),
+                       "readlen": READLEN, "maxinsert": 300, "fullsearch": False,
+                       "parallelism": "(sample, locus) shards over {} GPU(s), no collective".format(world),
+                       "l2": "inputs + scratch per step ({:.0f} MB) exceed the 126 MB L2".format(
+                           (batch.rbuf.nbytes + batch.pe_lens.nbytes + 8 * batch.nproblems * 1000) / 1e6)},
+            "reads_per_s": nreads * args.steps / sec,
+            "sw_gcups_algorithmic": alg_cells * args.steps / sec / 1e9,
+            "sw_gcups_executed": (ex1 + ex2) * args.steps / sec / 1e9,
+            "e2e": {"value": nprob * args.steps / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes),
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "classify_kernel<P> (sw_family.cu), all period instantiations of one step",
+                         "bound": "int", "achieved": achieved, "peak": int_peak, "unit": "G lane-instr/s",
+                         "frac": achieved / int_peak, "traffic": None,
+                         "peak_source": "tredsw_int_pipe_peak (VIADDMNMX.S16x2 register loop) measured in this run",
+                         "kernel_ms": stage["sw"], "share_of_step": stage["sw"] / max(stage["total"], 1e-9),
+                         "executed_gcups": (int(st[1]) + int(st[2])) / sw_s / 1e9,
+                         "algorithmic_gcups": int(st[0]) / sw_s / 1e9},
+            "roofline_grid": {"kernel": "grid_surface_kernel + grid_reduce_kernel", "bound": "hbm",
+                              "achieved": grid_bytes / grid_s / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": grid_bytes / grid_s / 1e9 / hbm, "peak_source": hbm_src + " copy bandwidth",
+                              "kernel_ms": stage["grid"], "points": int(st[4]),
+                              "note": "FP64-log bound, not HBM bound: ~30-150 logs per 8-byte point (SURVEY 8d)"},
+            "stage_ms": stage, "setup_s": {"simulate": t_gen},
+        }
+        if not args.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                nsamp = args.cpu_sample // len(names) if args.cpu_sample else max(1, min(8, (2 * cores) // len(names) + 1))
+                sample_problems = problems[:nsamp * len(names)]
+                v, dt, used, reads, cells, kind, res = cpu_reference_run(sample_problems, cores)
+                # the sample doubles as a parity check of the GPU calls
+                agree = sum(1 for r, c in zip(res, calls_dev[:len(res)])
+                            if r[0] == [int(c["allele1"]), int(c["allele2"])])
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": kind,
+                                        "sample": "{} samples x {} loci = {} problems, {} reads, {:.1f} s wall".format(
+                                            nsamp, len(names), len(sample_problems), reads, dt),
+                                        "reads_per_s": reads / dt, "sw_gcups": cells / dt / 1e9,
+                                        "calls_identical_to_gpu": "{}/{}".format(agree, len(res))}
+            except Exception as e:  # the GPU line must still be printed
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

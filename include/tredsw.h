@@ -90,6 +90,17 @@ tredsw_ctx *tredsw_create(int device, void *stream);
 void tredsw_destroy(tredsw_ctx *ctx);
 int tredsw_synchronize(tredsw_ctx *ctx);
 int tredsw_sm_count(tredsw_ctx *ctx);
+/* Kernels launched through this context so far (bench.py's gpu_launches claim). */
+int64_t tredsw_launch_count(tredsw_ctx *ctx);
+/* Stage timing with CUDA events on the context's stream: enable, run calls, then read the device time
+ * of the LAST call's stages in ms: [0] Smith-Waterman classify kernels, [1] likelihood grid (surface +
+ * reduce), [2] KDE, [3] whole call.  Reading synchronises the stream. */
+int tredsw_enable_timing(tredsw_ctx *ctx, int on);
+int tredsw_get_timing(tredsw_ctx *ctx, float *ms4);
+/* Measured integer-pipe peak of this GPU: a register-resident VIADDMNMX.S16x2 loop with 8 independent
+ * chains per thread on every SM; returns giga lane-instructions per second (one 32-bit lane executing
+ * one packed DPX instruction = 1).  The roofline denominator of the Smith-Waterman kernel. */
+int tredsw_int_pipe_peak(tredsw_ctx *ctx, double *giga_lane_instr_per_s);
 
 /* Tags of a classified read (tredparse/bam_parser.py:157-168). */
 enum { TREDSW_TAG_NONE = 0, TREDSW_TAG_FULL = 1, TREDSW_TAG_PREF = 2, TREDSW_TAG_POST = 3,

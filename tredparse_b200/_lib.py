@@ -24,8 +24,9 @@ EXPORTS = [
     "ssw_init", "init_destroy", "ssw_align", "align_destroy", "cigar_int_to_op", "cigar_int_to_len",
     # batched API
     "tredsw_version", "tredsw_device_count", "tredsw_last_error", "tredsw_create", "tredsw_destroy",
-    "tredsw_synchronize", "tredsw_sm_count", "tredsw_align_pairs", "tredsw_classify_reads",
-    "tredsw_likelihood_grid", "tredsw_pe_kde",
+    "tredsw_synchronize", "tredsw_sm_count", "tredsw_launch_count", "tredsw_enable_timing",
+    "tredsw_get_timing", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
+    "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch",
 ]
 
 
@@ -101,6 +102,11 @@ def load():
         lib.tredsw_destroy.argtypes = [_vp]
         lib.tredsw_synchronize.argtypes = [_vp]
         lib.tredsw_sm_count.argtypes = [_vp]
+        lib.tredsw_launch_count.restype = ctypes.c_int64
+        lib.tredsw_launch_count.argtypes = [_vp]
+        lib.tredsw_enable_timing.argtypes = [_vp, ctypes.c_int]
+        lib.tredsw_get_timing.argtypes = [_vp, _vp]
+        lib.tredsw_int_pipe_peak.argtypes = [_vp, _vp]
         lib.tredsw_align_pairs.restype = ctypes.c_int
         lib.tredsw_align_pairs.argtypes = [_vp, _vp, _vp, ctypes.c_int32, _vp, _vp, ctypes.c_int32, _vp,
                                            _vp, ctypes.c_int64, _vp, ctypes.c_int, ctypes.c_int,
@@ -169,6 +175,25 @@ class Context:
 
     def synchronize(self):
         check(self.lib.tredsw_synchronize(self.handle), "tredsw_synchronize")
+
+    @property
+    def launches(self):
+        return int(self.lib.tredsw_launch_count(self.handle))
+
+    def enable_timing(self, on=True):
+        check(self.lib.tredsw_enable_timing(self.handle, int(on)), "tredsw_enable_timing")
+
+    def timing(self):
+        """Device ms of the last call's stages: dict(sw, grid, kde, total)."""
+        ms = (ctypes.c_float * 4)()
+        check(self.lib.tredsw_get_timing(self.handle, ms), "tredsw_get_timing")
+        return {"sw": ms[0], "grid": ms[1], "kde": ms[2], "total": ms[3]}
+
+    def int_pipe_peak(self):
+        """Measured packed-DPX instruction throughput, giga lane-instructions / s."""
+        v = ctypes.c_double(0)
+        check(self.lib.tredsw_int_pipe_peak(self.handle, ctypes.byref(v)), "tredsw_int_pipe_peak")
+        return v.value
 
 
 _default = {}

@@ -326,7 +326,9 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     // ---- pipeline ----------------------------------------------------------------------------------
     const int tb = 256;
+    ctx->mark(6);
     if (nr > 0) {
+        ctx->launches += 2;
         read_family_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(d_rp, d_prob, nr, np_, d_read_family);
         if ((rc = tredsw_internal_classify(ctx, d_rbuf, d_roff, nr, d_read_family, d_fam, c->families, nf,
                                            c->max_read_len, c->mat25, c->gap_open, c->gap_extend,
@@ -334,12 +336,16 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
         tally_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
     }
     plan_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd);
+    ctx->mark(4);
     cohort_kde_kernel<<<np_ < ctx->sm_count * 2 ? np_ : ctx->sm_count * 2, 1024, 0, ctx->stream>>>(cd, d_ipool);
+    ctx->mark(5);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
     if ((rc = tredsw_internal_grid(ctx, cd.gp, np_, d_ipool, d_dpool, ctx->d_surface.as<double>(), cd.marg,
                                    ctx->d_res.as<tredsw_grid_result>(), c->fullsearch ? per_problem : 1024))) return rc;
     finalize_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
     CUDA_TRY(cudaGetLastError());
+    ctx->mark(7);
     // ---- outputs -----------------------------------------------------------------------------------
     if (!dev) {
         CUDA_TRY(cudaMemcpyAsync(calls, d_calls, (size_t)np_ * sizeof(tredsw_call), cudaMemcpyDeviceToHost, ctx->stream));

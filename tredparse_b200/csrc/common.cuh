@@ -51,6 +51,16 @@ struct tredsw_ctx {
     DevBuf d_q, d_qoff, d_t, d_toff, d_qidx, d_tidx, d_out, d_cigar, d_scratch, d_misc, d_fam,
         d_rfam, d_stats, d_work, d_prob, d_ipool, d_dpool, d_surface, d_marg, d_res, d_counter;
     std::mutex mu;
+    long long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid[8] = {false, false, false, false, false, false, false, false};
+    void mark(int i) {            // record event i on the stream when timing is enabled
+        if (!timing) return;
+        if (!ev[i]) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[i], stream);
+        ev_valid[i] = true;
+    }
     ~tredsw_ctx();
 };
 

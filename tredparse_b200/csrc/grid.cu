@@ -268,11 +268,14 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     if (tiles < 1) tiles = 1;
     int gx = (int)(tiles > 4096 ? 4096 : tiles);
     int gy = nproblems > 65535 ? 65535 : nproblems;
+    ctx->mark(2);
     grid_surface_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, nproblems);
     CUDA_TRY(cudaGetLastError());
     int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
     grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
     CUDA_TRY(cudaGetLastError());
+    ctx->mark(3);
+    ctx->launches += 2;
     return TREDSW_OK;
 }
 
@@ -342,6 +345,7 @@ extern "C" int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t
     int gb = nproblems > ctx->sm_count * 2 ? ctx->sm_count * 2 : nproblems;
     pe_kde_kernel<<<gb, 1024, 0, ctx->stream>>>(d_lens, d_off, nproblems, d_out);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
     if (!dev_ptrs(flags)) {
         CUDA_TRY(cudaMemcpyAsync(pdf_out, d_out, (size_t)nproblems * SPAN * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -320,6 +320,7 @@ int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nitems_bound, 
         CUDA_TRY(cudaFuncSetAttribute(classify_kernel<FAST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     classify_kernel<FAST_P><<<nitems_bound, 32, smem, ctx->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
     return TREDSW_OK;
 }
 
@@ -355,6 +356,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_fam_start, d_chunk_start, d_cursor);
     fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_cursor, d_order, p.out);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
     p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
     p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
     p.allow_fast = allow_fast ? 1 : 0;
@@ -362,11 +364,13 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     const int nitems_bound = nreads / 32 + nfamilies + 1;
     int rc;
+    ctx->mark(0);
     if (need_generic) { if ((rc = launch_classify<0>(ctx, p, nitems_bound, smem))) return rc; }
 #define LAUNCH_P(PP) if (pmask & (1u << PP)) { if ((rc = launch_classify<PP>(ctx, p, nitems_bound, smem))) return rc; }
     LAUNCH_P(1) LAUNCH_P(2) LAUNCH_P(3) LAUNCH_P(4) LAUNCH_P(5) LAUNCH_P(6)
     LAUNCH_P(7) LAUNCH_P(8) LAUNCH_P(9) LAUNCH_P(10) LAUNCH_P(11) LAUNCH_P(12)
 #undef LAUNCH_P
+    ctx->mark(1);
     return TREDSW_OK;
 }
 

@@ -276,6 +276,7 @@ extern "C" int tredsw_align_pairs(tredsw_ctx *ctx, const int8_t *qbuf, const int
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_mat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     sw_pairs_kernel<<<blocks, PAIRS_THREADS, 0, ctx->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(out, p.out, (size_t)npairs * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (flags & TREDSW_CIGAR)
         CUDA_TRY(cudaMemcpyAsync(cigar_out, p.cigar_out, (size_t)npairs * cigar_cap * sizeof(uint32_t),
