@@ -26,6 +26,7 @@
 //   same result as classifying all 2*max_units alignments and taking max(key=(score, -units)).
 #include "internal.cuh"
 #include "sw_sweep.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -90,91 +91,108 @@ __device__ __forceinline__ uint32_t sel2(int tf, int tr) {   // PRMT selector: s
     return (uint32_t)tf | ((uint32_t)(8 | tf) << 4) | ((uint32_t)tr << 8) | ((uint32_t)(8 | tr) << 12);
 }
 
-// columns [C0, C1) of a strip whose previous-row H and running F live in registers
-template <int NC, int C0, int C1>
-__device__ __forceinline__ void packed_row(const uint32_t (&sel)[NC], uint32_t (&Hrow)[NC], uint32_t (&Fv)[NC],
-                                           uint32_t w0, uint32_t w1, uint32_t &hd, uint32_t &e, uint32_t &mx,
-                                           uint32_t mgo2, uint32_t mge2) {
-    constexpr uint32_t NEG = 0x80008000u;    // (-32768, -32768): max with it is the identity
+// One DP cell for both strands (packed s16x2), all operands in registers.
+#define PACKED_CELL(HD, E, W0, W1, C, MX)                                                   \
+    {                                                                                         \
+        const uint32_t s_ = sw_prmt(W0, W1, sel[C]);               /* substitution scores */  \
+        const uint32_t t_ = __vmaxs2(E, Fv[C]);                                               \
+        const uint32_t h_ = __viaddmax_s16x2_relu(HD, s_, t_);     /* max(diag+s, E, F, 0) */ \
+        HD = Hrow[C];                                                                         \
+        Hrow[C] = h_;                                                                         \
+        const uint32_t hgo_ = __viaddmax_s16x2(h_, mgo2, 0x80008000u); /* h - go */           \
+        E = __viaddmax_s16x2_relu(E, mge2, hgo_);                  /* max(E-ge, h-go, 0) */   \
+        Fv[C] = __viaddmax_s16x2_relu(Fv[C], mge2, hgo_);                                     \
+        MX = __vmaxs2(MX, h_);                                                                \
+    }
+
+// One pass over all query rows of a strip of NC template columns (previous-row H and running F of every
+// strip column in registers).  Two rows are in flight per iteration, skewed by one column (row j at
+// column s, row j+1 at column s-1): two independent dependency chains for the scheduler.  The H/E values
+// leaving column PMAIN-1 are written to the boundary column (they feed the next strip); columns
+// [PMAIN, NC) are the forked suffix of this strip's template and only contribute to m_suf.
+template <int NC, int PMAIN, bool HAS_IN>
+__device__ __forceinline__ void strip_pass(const uint32_t (&sel)[NC], const SwLut *lut, const uint8_t *codes,
+                                           int lane, int m, int rows2, uint32_t *bnd, uint32_t &m_main,
+                                           uint32_t &m_suf, uint32_t mgo2, uint32_t mge2) {
+    uint32_t Hrow[NC], Fv[NC];
 #pragma unroll
-    for (int c = C0; c < C1; ++c) {
-        const uint32_t s = sw_prmt(w0, w1, sel[c]);             // s16x2 substitution scores
-        const uint32_t t = __vmaxs2(e, Fv[c]);
-        const uint32_t h = __viaddmax_s16x2_relu(hd, s, t);         // max(diag + s, E, F, 0)
-        hd = Hrow[c];
-        Hrow[c] = h;
-        const uint32_t hgo = __viaddmax_s16x2(h, mgo2, NEG);        // h - go per half
-        e = __viaddmax_s16x2_relu(e, mge2, hgo);                    // max(E - ge, h - go, 0)
-        Fv[c] = __viaddmax_s16x2_relu(Fv[c], mge2, hgo);
-        mx = __vmaxs2(mx, h);
+    for (int c = 0; c < NC; ++c) { Hrow[c] = 0; Fv[c] = 0; }
+    uint32_t hin_prev = 0;
+    for (int j = 0; j < rows2; j += 2) {
+        uint32_t hinA = 0, eA = 0, hinB = 0, eB = 0;
+        if (HAS_IN) {
+            const uint32_t bA = bnd[j * 32 + lane], bB = bnd[(j + 1) * 32 + lane];
+            hinA = sw_prmt(bA, 0, 0x4140); eA = sw_prmt(bA, 0, 0x4342);     // bytes -> s16x2 halves
+            hinB = sw_prmt(bB, 0, 0x4140); eB = sw_prmt(bB, 0, 0x4342);
+        }
+        const int codeA = j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST;
+        const int codeB = (j + 1) < m ? (int)codes[(j + 1) * 32 + lane] : SW_CODE_GHOST;
+        const uint32_t wA0 = lut->w0[codeA], wA1 = lut->w1[codeA];
+        const uint32_t wB0 = lut->w0[codeB], wB1 = lut->w1[codeB];
+        uint32_t hdA = hin_prev, hdB = hinA;
+        hin_prev = hinB;
+#pragma unroll
+        for (int s = 0; s <= NC; ++s) {
+            if (s < NC) {
+                if (s < PMAIN) PACKED_CELL(hdA, eA, wA0, wA1, s, m_main)
+                else PACKED_CELL(hdA, eA, wA0, wA1, s, m_suf)
+                if (s == PMAIN - 1) bnd[j * 32 + lane] = sw_prmt(Hrow[PMAIN - 1], eA, 0x6420);
+            }
+            if (s >= 1) {
+                if (s - 1 < PMAIN) PACKED_CELL(hdB, eB, wB0, wB1, s - 1, m_main)
+                else PACKED_CELL(hdB, eB, wB0, wB1, s - 1, m_suf)
+                if (s - 1 == PMAIN - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(Hrow[PMAIN - 1], eB, 0x6420);
+            }
+        }
     }
 }
 
 template <int P>
-__device__ void phase1_packed(const FamilySmem &F, const SwLut *lut, const uint8_t *codes, int lane, int m,
-                              int m_warp, uint32_t *bnd, uint16_t *scores, int go, int ge,
-                              unsigned long long &cells) {
+__device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, const uint8_t *codes, int lane,
+                                           int m, int m_warp, uint32_t *bnd, uint8_t *scores, int go, int ge,
+                                           unsigned long long &cells) {
     constexpr int NC = P + FLANK;
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
     const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
+    const int rows2 = (m_warp + 1) & ~1;
     // rc family: prefix' = rc(suffix), repeat' = rc(repeat), suffix' = rc(prefix)
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
-    uint32_t sel[NC];
-    uint32_t Hrow[NC], Fv[NC];
     uint32_t m_main = 0;          // running maximum over the shared (main) columns, per strand
     // ---- strip 0: the FLANK prefix columns (no fork) -------------------------------------------------
     {
-        uint32_t selp[FLANK], Hp[FLANK], Fp[FLANK];
+        uint32_t sel[FLANK];
 #pragma unroll
-        for (int c = 0; c < FLANK; ++c) {
-            selp[c] = sel2(F.prefix[c], comp(F.suffix[FLANK - 1 - c]));
-            Hp[c] = 0; Fp[c] = 0;
-        }
-        for (int j = 0; j < m_warp; ++j) {
-            const int code = j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST;
-            const uint32_t w0 = lut->w0[code], w1 = lut->w1[code];
-            uint32_t hd = 0, e = 0;
-            packed_row<FLANK, 0, FLANK>(selp, Hp, Fp, w0, w1, hd, e, m_main, mgo2, mge2);
-            // H (bytes 0,2 of the packed halves) and E -> 8-bit boundary word
-            bnd[j * 32 + lane] = sw_prmt(Hp[FLANK - 1], e, 0x6420);
-        }
+        for (int c = 0; c < FLANK; ++c) sel[c] = sel2(F.prefix[c], comp(F.suffix[FLANK - 1 - c]));
+        uint32_t unused = 0;
+        strip_pass<FLANK, FLANK, false>(sel, lut, codes, lane, m, rows2, bnd, m_main, unused, mgo2, mge2);
     }
     // selectors of one strip: P repeat columns then FLANK suffix columns
+    uint32_t sel[NC];
 #pragma unroll
     for (int c = 0; c < P; ++c) sel[c] = sel2(F.repeat[c], comp(F.repeat[P - 1 - c]));
 #pragma unroll
     for (int c = 0; c < FLANK; ++c) sel[P + c] = sel2(F.suffix[c], comp(F.prefix[FLANK - 1 - c]));
     // ---- strips 1..U -----------------------------------------------------------------------------------
     for (int u = 1; u <= F.U; ++u) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { Hrow[c] = 0; Fv[c] = 0; }
         uint32_t m_suf = 0;
-        uint32_t hin_prev = 0;
-        for (int j = 0; j < m_warp; ++j) {
-            const uint32_t b = bnd[j * 32 + lane];
-            const uint32_t hin = sw_prmt(b, 0, 0x4140);      // bytes 0,1 -> halves
-            uint32_t e = sw_prmt(b, 0, 0x4342);              // bytes 2,3 -> halves
-            const int code = j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST;
-            const uint32_t w0 = lut->w0[code], w1 = lut->w1[code];
-            uint32_t hd = hin_prev;
-            hin_prev = hin;
-            packed_row<NC, 0, P>(sel, Hrow, Fv, w0, w1, hd, e, m_main, mgo2, mge2);
-            bnd[j * 32 + lane] = sw_prmt(Hrow[P - 1], e, 0x6420);
-            packed_row<NC, P, NC>(sel, Hrow, Fv, w0, w1, hd, e, m_suf, mgo2, mge2);
-        }
+        strip_pass<NC, P, true>(sel, lut, codes, lane, m, rows2, bnd, m_main, m_suf, mgo2, mge2);
         const uint32_t best = __vmaxs2(m_main, m_suf);
-        scores[(2 * (u - 1) + 0) * 32 + lane] = (uint16_t)(best & 0xffffu);
-        scores[(2 * (u - 1) + 1) * 32 + lane] = (uint16_t)(best >> 16);
+        scores[(2 * (u - 1) + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
+        scores[(2 * (u - 1) + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
     }
     cells += (unsigned long long)m * 2ull * (unsigned long long)(FLANK + F.U * NC);
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int FAST_P>     // 0 = generic phase 1
+// FAST = true : every family with 18-bp flanks, period <= 12 and scores < 256 (packed phase 1, u8 scores)
+// FAST = false: everything else (scalar phase 1, u16 scores)
+// Both are launched over the same item list and skip the items of the other class.
+template <bool FAST>
 __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SwLut lut;
     __shared__ FamilySmem F;
+    typedef typename std::conditional<FAST, uint8_t, uint16_t>::type score_t;
     const int lane = threadIdx.x;
     const int item = blockIdx.x;
     // item -> family (binary search over chunk_start)
@@ -187,20 +205,18 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     const int f = lo;
     {
         const tredsw_family &g = p.families[f];
-        if (lane < 32) { F.prefix[lane] = g.prefix[lane]; F.suffix[lane] = g.suffix[lane]; F.repeat[lane] = g.repeat[lane]; }
+        F.prefix[lane] = g.prefix[lane]; F.suffix[lane] = g.suffix[lane]; F.repeat[lane] = g.repeat[lane];
         if (lane == 0) { F.Lp = g.prefix_len; F.Ls = g.suffix_len; F.P = g.period; F.U = g.max_units; F.clip = g.clip; }
     }
     sw_build_lut(&lut, c_fmat25, lane, 32);
     __syncwarp();
-    // Only families matching this instantiation are processed here (the host launches one
-    // instantiation per shape class over the same item list).
     const bool fast_shape = p.allow_fast && (F.Lp == FLANK && F.Ls == FLANK && F.P >= 1 && F.P <= 12);
-    if (FAST_P == 0) { if (fast_shape) return; }
-    else { if (!(fast_shape && F.P == FAST_P)) return; }
+    if (fast_shape != FAST) return;
 
-    uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                       // [max_rows][32]
-    uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)p.max_rows * 32);  // [max_rows][32]
-    uint16_t *scores = reinterpret_cast<uint16_t *>(codes + (size_t)p.max_rows * 32);  // [2U][32]
+    const int R = p.max_rows + 2;                                                  // + ghost row of the 2-row loop
+    uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                        // [R][32]
+    uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
+    score_t *scores = reinterpret_cast<score_t *>(codes + (size_t)R * 32);         // [2U][32]
 
     const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[f]) + lane;
     const bool valid = idx < p.fam_start[f + 1];
@@ -215,8 +231,16 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     __syncwarp();
 
     unsigned long long cells1 = 0, cells2 = 0;
-    if (FAST_P == 0) phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
-    else phase1_packed<(FAST_P == 0 ? 1 : FAST_P)>(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
+    if constexpr (!FAST) {
+        phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
+    } else {
+        switch (F.P) {
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1); break;
+            PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
+#undef PCASE
+        }
+    }
+    __syncwarp();
 
     // ---- Phase 2: walk candidates in arg-max order until one yields a tag ------------------------------
     int tag = TREDSW_TAG_NONE, best_u = 0, best_score = -1, rb = -1, re = -1, qb = -1, qe = -1, best_rank = -1;
@@ -314,11 +338,11 @@ __global__ void fam_scatter_kernel(const int32_t *read_family, int nreads, int n
     }
 }
 
-template <int FAST_P>
+template <bool FAST>
 int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nitems_bound, size_t smem) {
     if (smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(classify_kernel<FAST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    classify_kernel<FAST_P><<<nitems_bound, 32, smem, ctx->stream>>>(p);
+        CUDA_TRY(cudaFuncSetAttribute(classify_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    classify_kernel<FAST><<<nitems_bound, 32, smem, ctx->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return TREDSW_OK;
@@ -331,7 +355,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                              const tredsw_family *h_families, int nfamilies, int max_m,
                              const int8_t *mat25, int gap_open, int gap_extend, int32_t *d_work, int32_t *d_out,
                              unsigned long long *d_stats) {
-    int max_u = 0; unsigned pmask = 0; bool need_generic = false; int max_match = 0;
+    int max_u = 0; bool need_fast = false, need_generic = false; int max_match = 0;
     for (int i = 0; i < 25; ++i) if (mat25[i] > max_match) max_match = mat25[i];
     const bool allow_fast = (long long)max_m * max_match < 256;
     for (int f = 0; f < nfamilies; ++f) {
@@ -340,10 +364,12 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
             g.period > 32 || g.max_units < 1 || g.max_units > 4096) { tredsw_set_error("family %d out of range", f); return TREDSW_ERR_ARG; }
         if (g.max_units > max_u) max_u = g.max_units;
         bool fast = allow_fast && g.prefix_len == FLANK && g.suffix_len == FLANK && g.period <= 12;
-        if (fast) pmask |= 1u << g.period; else need_generic = true;
+        if (fast) need_fast = true; else need_generic = true;
     }
     const int max_rows = max_m > 0 ? max_m : 1;
-    const size_t smem = (size_t)max_rows * 32 * 4 + (size_t)max_rows * 32 + (size_t)2 * max_u * 32 * 2 + 64;
+    const size_t rows_alloc = (size_t)max_rows + 2;
+    const size_t smem_fast = rows_alloc * 32 * 4 + rows_alloc * 32 + (size_t)2 * max_u * 32 * 1 + 64;
+    const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + (size_t)2 * max_u * 32 * 2 + 64;
     if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
     ClassifyParams p{};
     p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
@@ -365,11 +391,8 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     const int nitems_bound = nreads / 32 + nfamilies + 1;
     int rc;
     ctx->mark(0);
-    if (need_generic) { if ((rc = launch_classify<0>(ctx, p, nitems_bound, smem))) return rc; }
-#define LAUNCH_P(PP) if (pmask & (1u << PP)) { if ((rc = launch_classify<PP>(ctx, p, nitems_bound, smem))) return rc; }
-    LAUNCH_P(1) LAUNCH_P(2) LAUNCH_P(3) LAUNCH_P(4) LAUNCH_P(5) LAUNCH_P(6)
-    LAUNCH_P(7) LAUNCH_P(8) LAUNCH_P(9) LAUNCH_P(10) LAUNCH_P(11) LAUNCH_P(12)
-#undef LAUNCH_P
+    if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nitems_bound, smem))) return rc; }
+    if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nitems_bound, smem_fast))) return rc; }
     ctx->mark(1);
     return TREDSW_OK;
 }
