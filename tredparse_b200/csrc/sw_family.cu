@@ -48,6 +48,9 @@ struct ClassifyParams {
     int go, ge;
     int max_rows;
     int allow_fast;                // scores fit the 8-bit boundary column (max_read_len * match < 256)
+    int match;                     // largest entry of the substitution matrix (band bounds)
+    int max_u;                     // largest max_units of the batch (stride of score_buf)
+    uint16_t *score_buf;           // [items][2*max_u][32] per-template scores (u8 in the fast kernel)
     int32_t *out;
     unsigned long long *stats;     // 4 counters
 };
@@ -91,67 +94,114 @@ __device__ __forceinline__ uint32_t sel2(int tf, int tr) {   // PRMT selector: s
     return (uint32_t)tf | ((uint32_t)(8 | tf) << 4) | ((uint32_t)tr << 8) | ((uint32_t)(8 | tr) << 12);
 }
 
-// One DP cell for both strands (packed s16x2), all operands in registers.
-#define PACKED_CELL(HD, E, W0, W1, C, MX)                                                   \
+// One DP cell for both strands (packed s16x2), all operands in registers; S = substitution scores.
+#define PACKED_CELL(HD, E, S, C, HOUT)                                                        \
     {                                                                                         \
-        const uint32_t s_ = sw_prmt(W0, W1, sel[C]);               /* substitution scores */  \
         const uint32_t t_ = __vmaxs2(E, Fv[C]);                                               \
-        const uint32_t h_ = __viaddmax_s16x2_relu(HD, s_, t_);     /* max(diag+s, E, F, 0) */ \
+        HOUT = __viaddmax_s16x2_relu(HD, S, t_);                   /* max(diag+s, E, F, 0) */ \
         HD = Hrow[C];                                                                         \
-        Hrow[C] = h_;                                                                         \
-        const uint32_t hgo_ = __viaddmax_s16x2(h_, mgo2, 0x80008000u); /* h - go */           \
+        Hrow[C] = HOUT;                                                                       \
+        const uint32_t hgo_ = __viaddmax_s16x2(HOUT, mgo2, 0x80008000u); /* h - go */         \
         E = __viaddmax_s16x2_relu(E, mge2, hgo_);                  /* max(E-ge, h-go, 0) */   \
         Fv[C] = __viaddmax_s16x2_relu(Fv[C], mge2, hgo_);                                     \
-        MX = __vmaxs2(MX, h_);                                                                \
     }
+
+constexpr int STAB_PAD = 36;       // words per query-code row of the score table: >= 12 + FLANK, a multiple of 4
+                                   // (16-byte rows for LDS.128) and == 4 mod 32 so that the rows of different bases
+                                   // start in different bank groups (conflict-free vector loads)
 
 // One pass over all query rows of a strip of NC template columns (previous-row H and running F of every
 // strip column in registers).  Two rows are in flight per iteration, skewed by one column (row j at
 // column s, row j+1 at column s-1): two independent dependency chains for the scheduler.  The H/E values
 // leaving column PMAIN-1 are written to the boundary column (they feed the next strip); columns
 // [PMAIN, NC) are the forked suffix of this strip's template and only contribute to m_suf.
+// Substitution scores of both strands come from a per-family table in shared memory indexed by the
+// query base (row, per lane) and the strip column (uniform): vector LDS on the otherwise idle LSU pipe
+// instead of one PRMT per cell on the saturated integer pipe.
 template <int NC, int PMAIN, bool HAS_IN>
-__device__ __forceinline__ void strip_pass(const uint32_t (&sel)[NC], const SwLut *lut, const uint8_t *codes,
-                                           int lane, int m, int rows2, uint32_t *bnd, uint32_t &m_main,
-                                           uint32_t &m_suf, uint32_t mgo2, uint32_t mge2) {
+__device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
+                                           uint32_t *bnd, uint32_t &m_main, uint32_t &m_suf, uint32_t mgo2,
+                                           uint32_t mge2) {
+    constexpr int NG = (NC + 3) / 4;
     uint32_t Hrow[NC], Fv[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { Hrow[c] = 0; Fv[c] = 0; }
     uint32_t hin_prev = 0;
+    auto code_at = [&](int j) { return j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
+    auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
+    // software pipeline: everything row j needs from shared memory is requested one iteration ahead
+    const uint4 *rowA = row_of(code_at(0)), *rowB = row_of(code_at(1));
+    uint4 gA = rowA[0], gB = rowB[0];
+    uint32_t bA = 0, bB = 0;
+    if (HAS_IN) { bA = bnd[lane]; bB = bnd[32 + lane]; }
+    int codeA2 = code_at(2), codeB2 = code_at(3);
     for (int j = 0; j < rows2; j += 2) {
         uint32_t hinA = 0, eA = 0, hinB = 0, eB = 0;
         if (HAS_IN) {
-            const uint32_t bA = bnd[j * 32 + lane], bB = bnd[(j + 1) * 32 + lane];
             hinA = sw_prmt(bA, 0, 0x4140); eA = sw_prmt(bA, 0, 0x4342);     // bytes -> s16x2 halves
             hinB = sw_prmt(bB, 0, 0x4140); eB = sw_prmt(bB, 0, 0x4342);
         }
-        const int codeA = j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST;
-        const int codeB = (j + 1) < m ? (int)codes[(j + 1) * 32 + lane] : SW_CODE_GHOST;
-        const uint32_t wA0 = lut->w0[codeA], wA1 = lut->w1[codeA];
-        const uint32_t wB0 = lut->w0[codeB], wB1 = lut->w1[codeB];
+        // requests for the next pair of rows (indices clamped; unused past the end)
+        const int jn = min(j + 2, rows2 - 2);
+        const uint4 *rowA2 = row_of(codeA2), *rowB2 = row_of(codeB2);
+        uint32_t bA2 = 0, bB2 = 0;
+        if (HAS_IN) { bA2 = bnd[jn * 32 + lane]; bB2 = bnd[(jn + 1) * 32 + lane]; }
+        const int codeA3 = code_at(j + 4), codeB3 = code_at(j + 5);
+        uint32_t sA[NG * 4], sB[NG * 4];
+        sA[0] = gA.x; sA[1] = gA.y; sA[2] = gA.z; sA[3] = gA.w;
+        sB[0] = gB.x; sB[1] = gB.y; sB[2] = gB.z; sB[3] = gB.w;
         uint32_t hdA = hin_prev, hdB = hinA;
         hin_prev = hinB;
+        uint32_t hA = 0, hB = 0;
 #pragma unroll
         for (int s = 0; s <= NC; ++s) {
+            // table groups are requested one group (4 columns) ahead of their use
+            if ((s & 3) == 0 && s / 4 + 1 < NG) {
+                const uint4 a = rowA[s / 4 + 1];
+                sA[s + 4] = a.x; sA[s + 5] = a.y; sA[s + 6] = a.z; sA[s + 7] = a.w;
+            }
+            if (s >= 1 && ((s - 1) & 3) == 0 && (s - 1) / 4 + 1 < NG) {
+                const uint4 b = rowB[(s - 1) / 4 + 1];
+                sB[s + 3] = b.x; sB[s + 4] = b.y; sB[s + 5] = b.z; sB[s + 6] = b.w;
+            }
+            if (s == NC - 4 || (NC < 4 && s == 0)) { gA = rowA2[0]; gB = rowB2[0]; }   // first group of the next rows
             if (s < NC) {
-                if (s < PMAIN) PACKED_CELL(hdA, eA, wA0, wA1, s, m_main)
-                else PACKED_CELL(hdA, eA, wA0, wA1, s, m_suf)
-                if (s == PMAIN - 1) bnd[j * 32 + lane] = sw_prmt(Hrow[PMAIN - 1], eA, 0x6420);
+                PACKED_CELL(hdA, eA, sA[s], s, hA)
+                if (s == PMAIN - 1) bnd[j * 32 + lane] = sw_prmt(hA, eA, 0x6420);
             }
             if (s >= 1) {
-                if (s - 1 < PMAIN) PACKED_CELL(hdB, eB, wB0, wB1, s - 1, m_main)
-                else PACKED_CELL(hdB, eB, wB0, wB1, s - 1, m_suf)
-                if (s - 1 == PMAIN - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(Hrow[PMAIN - 1], eB, 0x6420);
+                PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
+                if (s - 1 == PMAIN - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
+            }
+            // running maxima: one 3-input max covers both rows whenever their cells are in the same class
+            const bool a_on = s < NC, b_on = s >= 1;
+            const bool a_main = s < PMAIN, b_main = (s - 1) < PMAIN;
+            if (a_on && b_on && a_main == b_main) {
+                if (a_main) m_main = __vimax3_s16x2(m_main, hA, hB); else m_suf = __vimax3_s16x2(m_suf, hA, hB);
+            } else {
+                if (a_on) { if (a_main) m_main = __vmaxs2(m_main, hA); else m_suf = __vmaxs2(m_suf, hA); }
+                if (b_on) { if (b_main) m_main = __vmaxs2(m_main, hB); else m_suf = __vmaxs2(m_suf, hB); }
             }
         }
+        rowA = rowA2; rowB = rowB2; bA = bA2; bB = bB2; codeA2 = codeA3; codeB2 = codeB3;
+    }
+}
+
+// score table of one strip: stab[q][c] = s16x2( score(q, fwd column c), score(q, rc column c) ), q = 0..5
+__device__ __forceinline__ void build_stab(uint32_t *stab, const SwLut *lut, int lane, int ncols,
+                                           const uint32_t *colsel /* smem, per column PRMT selector */) {
+    for (int i = lane; i < 6 * STAB_PAD; i += 32) {
+        const int q = i / STAB_PAD, c = i % STAB_PAD;
+        stab[i] = (c < ncols) ? sw_prmt(lut->w0[q], lut->w1[q], colsel[c]) : 0u;
     }
 }
 
 template <int P>
-__device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, const uint8_t *codes, int lane,
-                                           int m, int m_warp, uint32_t *bnd, uint8_t *scores, int go, int ge,
-                                           unsigned long long &cells) {
+__device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
+                                           const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
+                                           uint8_t *scores, int go, int ge, unsigned long long &cells) {
     constexpr int NC = P + FLANK;
+    static_assert(NC <= STAB_PAD, "strip wider than the score table");
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
     const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
     const int rows2 = (m_warp + 1) & ~1;
@@ -159,23 +209,24 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
     uint32_t m_main = 0;          // running maximum over the shared (main) columns, per strand
     // ---- strip 0: the FLANK prefix columns (no fork) -------------------------------------------------
+    if (lane < FLANK) colsel[lane] = sel2(F.prefix[lane], comp(F.suffix[FLANK - 1 - lane]));
+    __syncwarp();
+    build_stab(stab, lut, lane, FLANK, colsel);
+    __syncwarp();
     {
-        uint32_t sel[FLANK];
-#pragma unroll
-        for (int c = 0; c < FLANK; ++c) sel[c] = sel2(F.prefix[c], comp(F.suffix[FLANK - 1 - c]));
         uint32_t unused = 0;
-        strip_pass<FLANK, FLANK, false>(sel, lut, codes, lane, m, rows2, bnd, m_main, unused, mgo2, mge2);
+        strip_pass<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd, m_main, unused, mgo2, mge2);
     }
-    // selectors of one strip: P repeat columns then FLANK suffix columns
-    uint32_t sel[NC];
-#pragma unroll
-    for (int c = 0; c < P; ++c) sel[c] = sel2(F.repeat[c], comp(F.repeat[P - 1 - c]));
-#pragma unroll
-    for (int c = 0; c < FLANK; ++c) sel[P + c] = sel2(F.suffix[c], comp(F.prefix[FLANK - 1 - c]));
-    // ---- strips 1..U -----------------------------------------------------------------------------------
+    __syncwarp();
+    // ---- strips 1..U: P repeat columns then FLANK suffix columns -------------------------------------
+    if (lane < P) colsel[lane] = sel2(F.repeat[lane], comp(F.repeat[P - 1 - lane]));
+    else if (lane < NC) colsel[lane] = sel2(F.suffix[lane - P], comp(F.prefix[FLANK - 1 - (lane - P)]));
+    __syncwarp();
+    build_stab(stab, lut, lane, NC, colsel);
+    __syncwarp();
     for (int u = 1; u <= F.U; ++u) {
         uint32_t m_suf = 0;
-        strip_pass<NC, P, true>(sel, lut, codes, lane, m, rows2, bnd, m_main, m_suf, mgo2, mge2);
+        strip_pass<NC, P, true>(stab, codes, lane, m, rows2, bnd, m_main, m_suf, mgo2, mge2);
         const uint32_t best = __vmaxs2(m_main, m_suf);
         scores[(2 * (u - 1) + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
         scores[(2 * (u - 1) + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
@@ -192,6 +243,9 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SwLut lut;
     __shared__ FamilySmem F;
+    __shared__ __align__(16) uint32_t stab[6 * STAB_PAD];
+    __shared__ uint32_t colsel[STAB_PAD];
+    // (bnd: the boundary column, codes: the reads, both [rows][32]; per-template scores go to global scratch)
     typedef typename std::conditional<FAST, uint8_t, uint16_t>::type score_t;
     const int lane = threadIdx.x;
     const int item = blockIdx.x;
@@ -216,7 +270,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     const int R = p.max_rows + 2;                                                  // + ghost row of the 2-row loop
     uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                        // [R][32]
     uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
-    score_t *scores = reinterpret_cast<score_t *>(codes + (size_t)R * 32);         // [2U][32]
+    score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)item * (2 * p.max_u) * 32;   // [2U][32], global
 
     const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[f]) + lane;
     const bool valid = idx < p.fam_start[f + 1];
@@ -235,7 +289,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
     } else {
         switch (F.P) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1); break;
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1); break;
             PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
 #undef PCASE
         }
@@ -263,16 +317,22 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             const int u = cr / 2 + 1, s = cr & 1;
             const int n = F.Lp + F.Ls + F.P * u;
             auto cc_f = [&](int i) { return fam_code(F, u, s, n, i); };
+            // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
+            // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
+            // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
+            const int drift = sw_max_drift(cs, m, n, p.match, p.go, p.ge);
+            const int need = (cs + p.match - 1) / p.match;
             int end_ref, end_read;
-            sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read, nullptr);
-            cells2 += (unsigned long long)m * min(n, (end_ref / FAM_W2 + 1) * FAM_W2);
+            sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read, nullptr,
+                                       -(m - need) - drift, (n - need) + drift, &cells2);
             if (end_ref < 0) continue;   // cannot happen: the score was produced by this very template
             auto rc_r = [&](int j) { return (int)codes[(end_read - j) * 32 + lane]; };
             auto cc_r = [&](int i) { return fam_code(F, u, s, n, end_ref - i); };
             int ci, rj;
+            // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A), so it
+            // stays within `drift` of the main diagonal of the reversed sub-matrix.
             sw_sweep<FAM_W2, 1, false>(end_read + 1, end_read + 1, end_ref + 1, rc_r, cc_r, &lut, bnd + lane, 32, p.go,
-                                       p.ge, cs, &ci, &rj, nullptr);
-            cells2 += (unsigned long long)(end_read + 1) * min(end_ref + 1, (ci / FAM_W2 + 1) * FAM_W2);
+                                       p.ge, cs, &ci, &rj, nullptr, -drift, drift, &cells2);
             const int c_rb = end_ref - ci, c_qb = end_read - rj;
             const int t = sw_classify(cs, c_rb, end_ref, c_qb, end_read, m, n, u, F.P, max_units_eff);
             if (t != TREDSW_TAG_NONE) {
@@ -368,8 +428,8 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     }
     const int max_rows = max_m > 0 ? max_m : 1;
     const size_t rows_alloc = (size_t)max_rows + 2;
-    const size_t smem_fast = rows_alloc * 32 * 4 + rows_alloc * 32 + (size_t)2 * max_u * 32 * 1 + 64;
-    const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + (size_t)2 * max_u * 32 * 2 + 64;
+    const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + 64;
+    const size_t smem_fast = smem;
     if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
     ClassifyParams p{};
     p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
@@ -386,10 +446,14 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
     p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
     p.allow_fast = allow_fast ? 1 : 0;
+    p.match = max_match > 0 ? max_match : 1;
     p.stats = d_stats;
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     const int nitems_bound = nreads / 32 + nfamilies + 1;
     int rc;
+    if ((rc = ctx->d_scratch.ensure((size_t)nitems_bound * 2 * max_u * 32 * sizeof(uint16_t)))) return rc;
+    p.score_buf = ctx->d_scratch.as<uint16_t>();
+    p.max_u = max_u;
     ctx->mark(0);
     if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nitems_bound, smem))) return rc; }
     if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nitems_bound, smem_fast))) return rc; }

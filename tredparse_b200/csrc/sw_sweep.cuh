@@ -53,13 +53,25 @@ __device__ __forceinline__ uint32_t sw_sel32(int t) { return 0x8880u + 0x1111u *
 // MODE 1: locate `target`: the first strip that holds a cell equal to target ends the sweep; among such
 //         cells the smallest column, then the smallest row (< m_real) is returned (out_col/out_row);
 //         out_col < 0 when the value never occurs.
+//
+// Band [dlo, dhi] on the diagonal offset d = column - row (pass SW_NO_BAND for none): rows whose cells in
+// a strip all lie outside the band are skipped and read as zero.  This is exact for MODE 1 whenever every
+// path that can end with score == target is known to stay inside the band (a skipped cell only removes
+// paths, so no cell can exceed its true value and a cell equal to target is still reached by a real
+// path): see sw_band_* below for the bounds used.
+#define SW_NO_BAND_LO (-0x3fffffff)
+#define SW_NO_BAND_HI (0x3fffffff)
+
 template <int W, int MODE, bool COLMAX, class RowCode, class ColCode>
 __device__ __forceinline__ int sw_sweep(int m_real, int m_rows, int n, RowCode rowcode, ColCode colcode,
                                         const SwLut *lut, uint32_t *bnd, int stride, int go, int ge,
-                                        int target, int *out_col, int *out_row, int32_t *colmax_out) {
+                                        int target, int *out_col, int *out_row, int32_t *colmax_out,
+                                        int dlo = SW_NO_BAND_LO, int dhi = SW_NO_BAND_HI,
+                                        unsigned long long *visited = nullptr) {
     int mx = 0;
     int best_col = 0x7fffffff, best_row = 0;
     const int mge = -ge;
+    int jlo_prev = 0, jhi_prev = 0;            // rows the previous strip wrote to the boundary column
     for (int c0 = 0; c0 < n; c0 += W) {
         uint32_t sel[W];
         int Hrow[W], F[W], cm[W];
@@ -71,10 +83,15 @@ __device__ __forceinline__ int sw_sweep(int m_real, int m_rows, int n, RowCode r
         }
         const bool first = (c0 == 0);
         const bool last = (c0 + W >= n);
+        // rows of this strip that intersect the band: d = c - j in [dlo, dhi] for some c in [c0, c0+W)
+        const int jlo = max(0, c0 - dhi);
+        const int jhi = min(m_rows, c0 + W - dlo);         // exclusive; c0 + W - 1 - dlo inclusive
         int hin_prev = 0;
-        for (int j = 0; j < m_rows; ++j) {
+        if (!first && jlo > 0 && jlo - 1 >= jlo_prev && jlo - 1 < jhi_prev)
+            hin_prev = (int)(bnd[(size_t)(jlo - 1) * stride] & 0xffffu);
+        for (int j = jlo; j < jhi; ++j) {
             int hin = 0, e = 0;
-            if (!first) {
+            if (!first && j >= jlo_prev && j < jhi_prev) {
                 uint32_t b = bnd[(size_t)j * stride];
                 hin = (int)(b & 0xffffu);
                 e = (int)(b >> 16);
@@ -107,6 +124,8 @@ __device__ __forceinline__ int sw_sweep(int m_real, int m_rows, int n, RowCode r
                 }
             }
         }
+        jlo_prev = jlo; jhi_prev = jhi;
+        if (visited && jhi > jlo) *visited += (unsigned long long)(jhi - jlo) * W;
         if (MODE == 0 && COLMAX) {
 #pragma unroll
             for (int c = 0; c < W; ++c) {
@@ -120,6 +139,15 @@ __device__ __forceinline__ int sw_sweep(int m_real, int m_rows, int n, RowCode r
         *out_row = best_row;
     }
     return mx;
+}
+
+// Largest diagonal deviation a path can afford and still END with score `target`: every aligned pair
+// scores at most `match`, a path uses at most min(m, n) pairs, and drifting d diagonals costs at least
+// go + (d - 1) * ge.  (d < 0: no drift possible beyond 0.)
+__device__ __forceinline__ int sw_max_drift(int target, int m, int n, int match, int go, int ge) {
+    const int slack = min(m, n) * match - target - go;     // budget left for gap extension after one opening
+    if (slack < 0) return 0;
+    return ge > 0 ? 1 + slack / ge : 0x3ffffff;
 }
 
 // Post-filter (src/ssw_wrap.py:213-220) + classification (tredparse/bam_parser.py:133-168).
