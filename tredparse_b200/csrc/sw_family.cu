@@ -50,7 +50,9 @@ struct ClassifyParams {
     int allow_fast;                // scores fit the 8-bit boundary column (max_read_len * match < 256)
     int match;                     // largest entry of the substitution matrix (band bounds)
     int max_u;                     // largest max_units of the batch (stride of score_buf)
-    uint16_t *score_buf;           // [items][2*max_u][32] per-template scores (u8 in the fast kernel)
+    uint16_t *score_buf;           // [CTAs][2*max_u][32] per-template scores (u8 in the fast kernel)
+    uint32_t *pot_buf;             // [CTAs][max_rows+2][32] suffix potentials of the CTA's current item
+    int32_t *counter;              // [2] work counters (generic, fast), zeroed before the launches
     int32_t *out;
     unsigned long long *stats;     // 4 counters
 };
@@ -106,34 +108,48 @@ __device__ __forceinline__ uint32_t sel2(int tf, int tr) {   // PRMT selector: s
         Fv[C] = __viaddmax_s16x2_relu(Fv[C], mge2, hgo_);                                     \
     }
 
-constexpr int STAB_PAD = 36;       // words per query-code row of the score table: >= 12 + FLANK, a multiple of 4
+constexpr int STAB_PAD = 36;       // words per query-code row of the score table: >= the widest strip, a multiple of 4
                                    // (16-byte rows for LDS.128) and == 4 mod 32 so that the rows of different bases
                                    // start in different bank groups (conflict-free vector loads)
 
-// One pass over all query rows of a strip of NC template columns (previous-row H and running F of every
-// strip column in registers).  Two rows are in flight per iteration, skewed by one column (row j at
-// column s, row j+1 at column s-1): two independent dependency chains for the scheduler.  The H/E values
-// leaving column PMAIN-1 are written to the boundary column (they feed the next strip); columns
-// [PMAIN, NC) are the forked suffix of this strip's template and only contribute to m_suf.
-// Substitution scores of both strands come from a per-family table in shared memory indexed by the
-// query base (row, per lane) and the strip column (uniform): vector LDS on the otherwise idle LSU pipe
-// instead of one PRMT per cell on the saturated integer pipe.
-template <int NC, int PMAIN, bool HAS_IN>
+// Columns per main strip: K whole repeat units, about 24 columns.
+__host__ __device__ constexpr int strip_units(int P) { return P >= 24 ? 1 : 24 / P; }
+
+// One pass over all query rows of a strip of NC template columns made of K = NC / PER units of PER
+// columns (previous-row H and running F of every strip column in registers).  Two rows are in flight per
+// iteration, skewed by one column (row j at column s, row j+1 at column s-1): two independent dependency
+// chains for the scheduler.  Substitution scores of both strands come from a per-strip table in shared
+// memory indexed by the query base (row, per lane) and the strip column (uniform): vector LDS on the
+// otherwise idle LSU pipe instead of one PRMT per cell on the saturated integer pipe.
+//
+//   seg[u]  running maximum of H over the columns of unit u (all rows)
+//   mu[u]   (HOOK) best score of any path that leaves unit u's last column into the template's SUFFIX
+//           block, by the suffix potentials of this read (see suffix_pass): for every row j
+//               mu[u] = max(mu[u], H(j-1, last) + A[j], E(j, last -> next) + B[j])
+//           — 2 add-max per row and unit instead of a forked DP over the suffix columns.
+//   bnd     boundary column in shared memory: H/E entering (HAS_IN) and leaving (HAS_OUT) the strip
+//   pot     suffix potentials of this warp's reads in global scratch, one word per row and lane
+template <int NC, int PER, bool HAS_IN, bool HAS_OUT, bool HOOK>
 __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
-                                           uint32_t *bnd, uint32_t &m_main, uint32_t &m_suf, uint32_t mgo2,
-                                           uint32_t mge2) {
+                                           uint32_t *bnd, const uint32_t *pot, uint32_t (&seg)[NC / PER],
+                                           uint32_t (&mu)[NC / PER], uint32_t mgo2, uint32_t mge2) {
+    constexpr int K = NC / PER;
+    static_assert(K * PER == NC, "strip = whole units");
     constexpr int NG = (NC + 3) / 4;
-    uint32_t Hrow[NC], Fv[NC];
+    uint32_t Hrow[NC], Fv[NC], pend[K];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { Hrow[c] = 0; Fv[c] = 0; }
+#pragma unroll
+    for (int u = 0; u < K; ++u) pend[u] = 0;
     uint32_t hin_prev = 0;
     auto code_at = [&](int j) { return j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
     auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
-    // software pipeline: everything row j needs from shared memory is requested one iteration ahead
+    // software pipeline: everything row j needs from memory is requested one iteration ahead
     const uint4 *rowA = row_of(code_at(0)), *rowB = row_of(code_at(1));
     uint4 gA = rowA[0], gB = rowB[0];
-    uint32_t bA = 0, bB = 0;
+    uint32_t bA = 0, bB = 0, pA = 0, pB = 0;
     if (HAS_IN) { bA = bnd[lane]; bB = bnd[32 + lane]; }
+    if (HOOK) { pA = pot[lane]; pB = pot[32 + lane]; }
     int codeA2 = code_at(2), codeB2 = code_at(3);
     for (int j = 0; j < rows2; j += 2) {
         uint32_t hinA = 0, eA = 0, hinB = 0, eB = 0;
@@ -141,11 +157,17 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
             hinA = sw_prmt(bA, 0, 0x4140); eA = sw_prmt(bA, 0, 0x4342);     // bytes -> s16x2 halves
             hinB = sw_prmt(bB, 0, 0x4140); eB = sw_prmt(bB, 0, 0x4342);
         }
+        uint32_t potHA = 0, potEA = 0, potHB = 0, potEB = 0;
+        if (HOOK) {                                                          // signed bytes -> s16x2 halves
+            potHA = sw_prmt(pA, 0, 0x9180); potEA = sw_prmt(pA, 0, 0xb3a2);
+            potHB = sw_prmt(pB, 0, 0x9180); potEB = sw_prmt(pB, 0, 0xb3a2);
+        }
         // requests for the next pair of rows (indices clamped; unused past the end)
         const int jn = min(j + 2, rows2 - 2);
         const uint4 *rowA2 = row_of(codeA2), *rowB2 = row_of(codeB2);
         uint32_t bA2 = 0, bB2 = 0;
         if (HAS_IN) { bA2 = bnd[jn * 32 + lane]; bB2 = bnd[(jn + 1) * 32 + lane]; }
+        if (HOOK) { pA = pot[jn * 32 + lane]; pB = pot[(jn + 1) * 32 + lane]; }
         const int codeA3 = code_at(j + 4), codeB3 = code_at(j + 5);
         uint32_t sA[NG * 4], sB[NG * 4];
         sA[0] = gA.x; sA[1] = gA.y; sA[2] = gA.z; sA[3] = gA.w;
@@ -167,24 +189,84 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
             if (s == NC - 4 || (NC < 4 && s == 0)) { gA = rowA2[0]; gB = rowB2[0]; }   // first group of the next rows
             if (s < NC) {
                 PACKED_CELL(hdA, eA, sA[s], s, hA)
-                if (s == PMAIN - 1) bnd[j * 32 + lane] = sw_prmt(hA, eA, 0x6420);
+                const int u = s / PER, i = s % PER;
+                // running maxima: the 2*PER cells a unit sees per iteration are folded pairwise (VIMNMX3)
+                if (i == 0) pend[u] = hA; else seg[u] = __vimax3_s16x2(seg[u], pend[u], hA);
+                if (HOOK && i == PER - 1) {          // hdA = H(j-1, s) now, eA = E entering column s+1
+                    mu[u] = __viaddmax_s16x2(hdA, potHA, mu[u]);
+                    mu[u] = __viaddmax_s16x2(eA, potEA, mu[u]);
+                }
+                if (HAS_OUT && s == NC - 1) bnd[j * 32 + lane] = sw_prmt(hA, eA, 0x6420);
             }
             if (s >= 1) {
                 PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
-                if (s - 1 == PMAIN - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
-            }
-            // running maxima: one 3-input max covers both rows whenever their cells are in the same class
-            const bool a_on = s < NC, b_on = s >= 1;
-            const bool a_main = s < PMAIN, b_main = (s - 1) < PMAIN;
-            if (a_on && b_on && a_main == b_main) {
-                if (a_main) m_main = __vimax3_s16x2(m_main, hA, hB); else m_suf = __vimax3_s16x2(m_suf, hA, hB);
-            } else {
-                if (a_on) { if (a_main) m_main = __vmaxs2(m_main, hA); else m_suf = __vmaxs2(m_suf, hA); }
-                if (b_on) { if (b_main) m_main = __vmaxs2(m_main, hB); else m_suf = __vmaxs2(m_suf, hB); }
+                const int u = (s - 1) / PER, i = (s - 1) % PER;
+                if (i == PER - 1) seg[u] = __vimax3_s16x2(seg[u], pend[u], hB); else pend[u] = hB;
+                if (HOOK && i == PER - 1) {
+                    mu[u] = __viaddmax_s16x2(hdB, potHB, mu[u]);
+                    mu[u] = __viaddmax_s16x2(eB, potEB, mu[u]);
+                }
+                if (HAS_OUT && s - 1 == NC - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
             }
         }
         rowA = rowA2; rowB = rowB2; bA = bA2; bB = bB2; codeA2 = codeA3; codeB2 = codeB3;
     }
+}
+
+// Suffix potentials: the DP of the read against the template's SUFFIX block, run backwards (rows from the
+// last query base up, columns from the last suffix base to the first), both strands packed.
+//   G(j,c)  = best score of a path that STARTS with the aligned pair (j, c) and ends anywhere
+//   GH(j,c) = best score still to gain after the pair (j, c) (>= 0: the path may stop there)
+//   GE(j,c) = best score still to gain for a path that is in a template-axis gap at (j, c)
+//     GH(j,c) = max(0, G(j+1,c+1), max(GE(j,c+1), GF(j+1,c)) - go)      G(j,c) = s(j,c) + GH(j,c)
+//     GE(j,c) = max(GH(j,c), GE(j,c+1) - ge)                             GF(j,c) = max(GH(j,c), GF(j+1,c) - ge)
+// Every cell of the forward DP over the suffix block of template u is, in the (max,+) sense, a linear
+// function of the H/E column entering the block plus the paths that start inside the block, so
+//     max H over the suffix block of template u = max(fresh, max_j H_u(j-1,last)+A[j], max_j E_u(j)+B[j])
+// with A[j] = G(j,0), B[j] = GE(j,0) and fresh = max G — none of which depends on u.
+// pot[j] = A_fwd | A_rc << 8 | B_fwd << 16 | B_rc << 24 (signed bytes; 0x80 = -128 on ghost rows).
+template <int NC>
+__device__ __forceinline__ void suffix_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
+                                            uint32_t *pot, uint32_t &fresh, uint32_t mgo2, uint32_t mge2) {
+    constexpr int NG = (NC + 3) / 4;
+    uint32_t Grow[NC], Fv[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { Grow[c] = 0; Fv[c] = 0; }
+    // r = reversed row index; table columns are stored reversed as well (column 0 = last suffix base)
+    auto code_at = [&](int r) { const int j = rows2 - 1 - r; return (j >= 0 && j < m) ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
+    auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
+    uint32_t f0 = 0, f1 = 0;
+#define SUFFIX_CELL(GD, E, S, C, GOUT)                                                        \
+    {                                                                                         \
+        const uint32_t t_ = __vmaxs2(E, Fv[C]);                                               \
+        const uint32_t gh_ = __viaddmax_s16x2_relu(t_, mgo2, GD);  /* max(t-go, G diag, 0) */ \
+        GD = Grow[C];                                                                         \
+        GOUT = __vadd2(gh_, S);                                                               \
+        Grow[C] = GOUT;                                                                       \
+        E = __viaddmax_s16x2(E, mge2, gh_);                                                   \
+        Fv[C] = __viaddmax_s16x2(Fv[C], mge2, gh_);                                           \
+    }
+    for (int r = 0; r < rows2; r += 2) {
+        const uint4 *rowA = row_of(code_at(r)), *rowB = row_of(code_at(r + 1));
+        uint32_t sA[NG * 4], sB[NG * 4];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint4 a = rowA[g], b = rowB[g];
+            sA[4 * g] = a.x; sA[4 * g + 1] = a.y; sA[4 * g + 2] = a.z; sA[4 * g + 3] = a.w;
+            sB[4 * g] = b.x; sB[4 * g + 1] = b.y; sB[4 * g + 2] = b.z; sB[4 * g + 3] = b.w;
+        }
+        uint32_t gdA = 0, gdB = 0, eA = 0, eB = 0, gA = 0, gB = 0;
+#pragma unroll
+        for (int s = 0; s <= NC; ++s) {
+            if (s < NC) { SUFFIX_CELL(gdA, eA, sA[s], s, gA) f0 = __vmaxs2(f0, gA); }
+            if (s >= 1) { SUFFIX_CELL(gdB, eB, sB[s - 1], s - 1, gB) f1 = __vmaxs2(f1, gB); }
+        }
+        const int jA = rows2 - 1 - r, jB = jA - 1;
+        pot[jA * 32 + lane] = jA < m ? sw_prmt(gA, eA, 0x6420) : 0x80808080u;
+        pot[jB * 32 + lane] = jB < m ? sw_prmt(gB, eB, 0x6420) : 0x80808080u;
+    }
+#undef SUFFIX_CELL
+    fresh = __vimax3_s16x2(f0, f1, 0u);
 }
 
 // score table of one strip: stab[q][c] = s16x2( score(q, fwd column c), score(q, rc column c) ), q = 0..5
@@ -199,45 +281,65 @@ __device__ __forceinline__ void build_stab(uint32_t *stab, const SwLut *lut, int
 template <int P>
 __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           uint8_t *scores, int go, int ge, unsigned long long &cells) {
-    constexpr int NC = P + FLANK;
-    static_assert(NC <= STAB_PAD, "strip wider than the score table");
+                                           uint32_t *pot, uint8_t *scores, int go, int ge,
+                                           unsigned long long &cells) {
+    constexpr int K = strip_units(P);
+    constexpr int NC = P * K;
+    static_assert(NC <= STAB_PAD && FLANK <= STAB_PAD, "strip wider than the score table");
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
     const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
     const int rows2 = (m_warp + 1) & ~1;
     // rc family: prefix' = rc(suffix), repeat' = rc(repeat), suffix' = rc(prefix)
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
-    uint32_t m_main = 0;          // running maximum over the shared (main) columns, per strand
-    // ---- strip 0: the FLANK prefix columns (no fork) -------------------------------------------------
+    // ---- suffix potentials (table columns reversed: column c' = suffix base FLANK-1-c') ---------------
+    if (lane < FLANK) colsel[lane] = sel2(F.suffix[FLANK - 1 - lane], comp(F.prefix[lane]));
+    __syncwarp();
+    build_stab(stab, lut, lane, FLANK, colsel);
+    __syncwarp();
+    uint32_t fresh = 0;
+    suffix_pass<FLANK>(stab, codes, lane, m, rows2, pot, fresh, mgo2, mge2);
+    __syncwarp();
+    // ---- strip 0: the FLANK prefix columns -----------------------------------------------------------
     if (lane < FLANK) colsel[lane] = sel2(F.prefix[lane], comp(F.suffix[FLANK - 1 - lane]));
     __syncwarp();
     build_stab(stab, lut, lane, FLANK, colsel);
     __syncwarp();
+    uint32_t run;                   // running maximum over the main columns so far, per strand
     {
-        uint32_t unused = 0;
-        strip_pass<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd, m_main, unused, mgo2, mge2);
+        uint32_t seg0[1] = {0u}, mu0[1] = {0u};
+        strip_pass<FLANK, FLANK, false, true, false>(stab, codes, lane, m, rows2, bnd, pot, seg0, mu0, mgo2, mge2);
+        run = seg0[0];
     }
     __syncwarp();
-    // ---- strips 1..U: P repeat columns then FLANK suffix columns -------------------------------------
-    if (lane < P) colsel[lane] = sel2(F.repeat[lane], comp(F.repeat[P - 1 - lane]));
-    else if (lane < NC) colsel[lane] = sel2(F.suffix[lane - P], comp(F.prefix[FLANK - 1 - (lane - P)]));
+    // ---- main strips: K repeat units each; the suffix of every template is folded in by the potentials --
+    for (int c = lane; c < NC; c += 32) colsel[c] = sel2(F.repeat[c % P], comp(F.repeat[P - 1 - c % P]));
     __syncwarp();
     build_stab(stab, lut, lane, NC, colsel);
     __syncwarp();
-    for (int u = 1; u <= F.U; ++u) {
-        uint32_t m_suf = 0;
-        strip_pass<NC, P, true>(stab, codes, lane, m, rows2, bnd, m_main, m_suf, mgo2, mge2);
-        const uint32_t best = __vmaxs2(m_main, m_suf);
-        scores[(2 * (u - 1) + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
-        scores[(2 * (u - 1) + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
+    int nstrips = 0;
+    for (int u0 = 0; u0 < F.U; u0 += K, ++nstrips) {
+        uint32_t seg[K], mu[K];
+#pragma unroll
+        for (int u = 0; u < K; ++u) { seg[u] = 0; mu[u] = 0; }
+        strip_pass<NC, P, true, true, true>(stab, codes, lane, m, rows2, bnd, pot, seg, mu, mgo2, mge2);
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            run = __vmaxs2(run, seg[u]);
+            if (u0 + u < F.U) {
+                const uint32_t best = __vimax3_s16x2(run, mu[u], fresh);
+                scores[(2 * (u0 + u) + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
+                scores[(2 * (u0 + u) + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
+            }
+        }
     }
-    cells += (unsigned long long)m * 2ull * (unsigned long long)(FLANK + F.U * NC);
+    cells += (unsigned long long)m * 2ull * (unsigned long long)(2 * FLANK + nstrips * NC);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // FAST = true : every family with 18-bp flanks, period <= 12 and scores < 256 (packed phase 1, u8 scores)
 // FAST = false: everything else (scalar phase 1, u16 scores)
-// Both are launched over the same item list and skip the items of the other class.
+// Persistent: one warp per CTA, CTAs pull items (32 reads of one family) from a counter; both kernels
+// walk the same item list and skip the items of the other class.
 template <bool FAST>
 __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,125 +347,134 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     __shared__ FamilySmem F;
     __shared__ __align__(16) uint32_t stab[6 * STAB_PAD];
     __shared__ uint32_t colsel[STAB_PAD];
-    // (bnd: the boundary column, codes: the reads, both [rows][32]; per-template scores go to global scratch)
+    // (bnd: the boundary column, codes: the reads, both [rows][32]; per-template scores and the suffix
+    //  potentials go to this CTA's slot of the global scratch)
     typedef typename std::conditional<FAST, uint8_t, uint16_t>::type score_t;
     const int lane = threadIdx.x;
-    const int item = blockIdx.x;
-    // item -> family (binary search over chunk_start)
-    int lo = 0, hi = p.nfamilies;
-    if (item >= p.chunk_start[p.nfamilies]) return;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (p.chunk_start[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int f = lo;
-    {
-        const tredsw_family &g = p.families[f];
-        F.prefix[lane] = g.prefix[lane]; F.suffix[lane] = g.suffix[lane]; F.repeat[lane] = g.repeat[lane];
-        if (lane == 0) { F.Lp = g.prefix_len; F.Ls = g.suffix_len; F.P = g.period; F.U = g.max_units; F.clip = g.clip; }
-    }
-    sw_build_lut(&lut, c_fmat25, lane, 32);
-    __syncwarp();
-    const bool fast_shape = p.allow_fast && (F.Lp == FLANK && F.Ls == FLANK && F.P >= 1 && F.P <= 12);
-    if (fast_shape != FAST) return;
-
     const int R = p.max_rows + 2;                                                  // + ghost row of the 2-row loop
     uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                        // [R][32]
     uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
-    score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)item * (2 * p.max_u) * 32;   // [2U][32], global
+    score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32;   // [2U][32]
+    uint32_t *pot = p.pot_buf + (size_t)blockIdx.x * R * 32;                       // [R][32]
+    sw_build_lut(&lut, c_fmat25, lane, 32);
+    const int nitems = p.chunk_start[p.nfamilies];
+    unsigned long long alg = 0, cells1 = 0, cells2 = 0;
+    unsigned nal = 0;
 
-    const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[f]) + lane;
-    const bool valid = idx < p.fam_start[f + 1];
-    const int r = valid ? p.order[idx] : -1;
-    int m = 0;
-    const int8_t *q = nullptr;
-    if (valid) { q = p.rbuf + p.roff[r]; m = (int)(p.roff[r + 1] - p.roff[r]); }
-    bool too_long = m > p.max_rows;
-    if (too_long) m = 0;
-    for (int j = 0; j < m; ++j) { int c = q[j]; codes[j * 32 + lane] = (uint8_t)((c < 0 || c > 4) ? 4 : c); }
-    const int m_warp = __reduce_max_sync(0xffffffffu, m);
-    __syncwarp();
+    for (;;) {
+        __syncwarp();
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.counter + (FAST ? 1 : 0), 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        // item -> family (binary search over chunk_start)
+        int lo = 0, hi = p.nfamilies;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (p.chunk_start[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int f = lo;
+        {
+            const tredsw_family &g = p.families[f];
+            F.prefix[lane] = g.prefix[lane]; F.suffix[lane] = g.suffix[lane]; F.repeat[lane] = g.repeat[lane];
+            if (lane == 0) { F.Lp = g.prefix_len; F.Ls = g.suffix_len; F.P = g.period; F.U = g.max_units; F.clip = g.clip; }
+        }
+        __syncwarp();
+        const bool fast_shape = p.allow_fast && (F.Lp == FLANK && F.Ls == FLANK && F.P >= 1 && F.P <= 12);
+        if (fast_shape != FAST) continue;
 
-    unsigned long long cells1 = 0, cells2 = 0;
-    if constexpr (!FAST) {
-        phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
-    } else {
-        switch (F.P) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1); break;
-            PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
+        const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[f]) + lane;
+        const bool valid = idx < p.fam_start[f + 1];
+        const int r = valid ? p.order[idx] : -1;
+        int m = 0;
+        const int8_t *q = nullptr;
+        if (valid) { q = p.rbuf + p.roff[r]; m = (int)(p.roff[r + 1] - p.roff[r]); }
+        bool too_long = m > p.max_rows;
+        if (too_long) m = 0;
+        for (int j = 0; j < m; ++j) { int c = q[j]; codes[j * 32 + lane] = (uint8_t)((c < 0 || c > 4) ? 4 : c); }
+        const int m_warp = __reduce_max_sync(0xffffffffu, m);
+        __syncwarp();
+
+        if constexpr (!FAST) {
+            phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
+        } else {
+            switch (F.P) {
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, pot, scores, p.go, p.ge, cells1); break;
+                PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
 #undef PCASE
+            }
         }
-    }
-    __syncwarp();
+        __syncwarp();
 
-    // ---- Phase 2: walk candidates in arg-max order until one yields a tag ------------------------------
-    int tag = TREDSW_TAG_NONE, best_u = 0, best_score = -1, rb = -1, re = -1, qb = -1, qe = -1, best_rank = -1;
-    if (valid && m > 0) {
-        const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
-        int last_score = 0x7fffffff, last_rank = -1;
-        auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
-        for (;;) {
-            int cs = -1, cr = -1;
-            for (int rank = 0; rank < 2 * F.U; ++rank) {
-                const int sc = scores[rank * 32 + lane];
-                const int n = F.Lp + F.Ls + F.P * (rank / 2 + 1);
-                const int min_len = min(m, n) / 2;
-                if (sc < max(min_len, 30)) continue;
-                if (sc > last_score || (sc == last_score && rank <= last_rank)) continue;   // already tried
-                if (sc > cs) { cs = sc; cr = rank; }
-            }
-            if (cr < 0) break;
-            last_score = cs; last_rank = cr;
-            const int u = cr / 2 + 1, s = cr & 1;
-            const int n = F.Lp + F.Ls + F.P * u;
-            auto cc_f = [&](int i) { return fam_code(F, u, s, n, i); };
-            // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
-            // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
-            // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
-            const int drift = sw_max_drift(cs, m, n, p.match, p.go, p.ge);
-            const int need = (cs + p.match - 1) / p.match;
-            int end_ref, end_read;
-            sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read, nullptr,
-                                       -(m - need) - drift, (n - need) + drift, &cells2);
-            if (end_ref < 0) continue;   // cannot happen: the score was produced by this very template
-            auto rc_r = [&](int j) { return (int)codes[(end_read - j) * 32 + lane]; };
-            auto cc_r = [&](int i) { return fam_code(F, u, s, n, end_ref - i); };
-            int ci, rj;
-            // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A), so it
-            // stays within `drift` of the main diagonal of the reversed sub-matrix.
-            sw_sweep<FAM_W2, 1, false>(end_read + 1, end_read + 1, end_ref + 1, rc_r, cc_r, &lut, bnd + lane, 32, p.go,
-                                       p.ge, cs, &ci, &rj, nullptr, -drift, drift, &cells2);
-            const int c_rb = end_ref - ci, c_qb = end_read - rj;
-            const int t = sw_classify(cs, c_rb, end_ref, c_qb, end_read, m, n, u, F.P, max_units_eff);
-            if (t != TREDSW_TAG_NONE) {
-                tag = t; best_u = u; best_score = cs; rb = c_rb; re = end_ref; qb = c_qb; qe = end_read;
-                best_rank = cr;
-                break;
+        // ---- Phase 2: walk candidates in arg-max order until one yields a tag --------------------------
+        int tag = TREDSW_TAG_NONE, best_u = 0, best_score = -1, rb = -1, re = -1, qb = -1, qe = -1, best_rank = -1;
+        if (valid && m > 0) {
+            const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
+            int last_score = 0x7fffffff, last_rank = -1;
+            auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
+            for (;;) {
+                int cs = -1, cr = -1;
+                for (int rank = 0; rank < 2 * F.U; ++rank) {
+                    const int sc = scores[rank * 32 + lane];
+                    const int n = F.Lp + F.Ls + F.P * (rank / 2 + 1);
+                    const int min_len = min(m, n) / 2;
+                    if (sc < max(min_len, 30)) continue;
+                    if (sc > last_score || (sc == last_score && rank <= last_rank)) continue;   // already tried
+                    if (sc > cs) { cs = sc; cr = rank; }
+                }
+                if (cr < 0) break;
+                last_score = cs; last_rank = cr;
+                const int u = cr / 2 + 1, s = cr & 1;
+                const int n = F.Lp + F.Ls + F.P * u;
+                auto cc_f = [&](int i) { return fam_code(F, u, s, n, i); };
+                // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
+                // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
+                // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
+                const int drift = sw_max_drift(cs, m, n, p.match, p.go, p.ge);
+                const int need = (cs + p.match - 1) / p.match;
+                int end_ref, end_read;
+                sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read, nullptr,
+                                           -(m - need) - drift, (n - need) + drift, &cells2);
+                if (end_ref < 0) continue;   // cannot happen: the score was produced by this very template
+                auto rc_r = [&](int j) { return (int)codes[(end_read - j) * 32 + lane]; };
+                auto cc_r = [&](int i) { return fam_code(F, u, s, n, end_ref - i); };
+                int ci, rj;
+                // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A), so it
+                // stays within `drift` of the main diagonal of the reversed sub-matrix.
+                sw_sweep<FAM_W2, 1, false>(end_read + 1, end_read + 1, end_ref + 1, rc_r, cc_r, &lut, bnd + lane, 32, p.go,
+                                           p.ge, cs, &ci, &rj, nullptr, -drift, drift, &cells2);
+                const int c_rb = end_ref - ci, c_qb = end_read - rj;
+                const int t = sw_classify(cs, c_rb, end_ref, c_qb, end_read, m, n, u, F.P, max_units_eff);
+                if (t != TREDSW_TAG_NONE) {
+                    tag = t; best_u = u; best_score = cs; rb = c_rb; re = end_ref; qb = c_qb; qe = end_read;
+                    best_rank = cr;
+                    break;
+                }
             }
         }
-    }
-    if (valid) {
-        int32_t *o = p.out + (int64_t)r * 8;
-        o[0] = too_long ? -1 : tag; o[1] = best_u; o[2] = best_score; o[3] = rb; o[4] = re; o[5] = qb; o[6] = qe;
-        o[7] = best_rank;
-    }
-    if (p.stats) {
-        unsigned long long alg = 0;
-        if (valid && m > 0) {
+        if (valid) {
+            int32_t *o = p.out + (int64_t)r * 8;
+            o[0] = too_long ? -1 : tag; o[1] = best_u; o[2] = best_score; o[3] = rb; o[4] = re; o[5] = qb; o[6] = qe;
+            o[7] = best_rank;
+        }
+        if (p.stats && valid && m > 0) {
             unsigned long long sum_n = 0;
             for (int u = 1; u <= F.U; ++u) sum_n += 2ull * (unsigned long long)(F.Lp + F.Ls + F.P * u);
-            alg = (unsigned long long)m * sum_n;
+            alg += (unsigned long long)m * sum_n;
+            nal += (unsigned)(2 * F.U);
         }
-        unsigned long long c1 = cells1, c2 = cells2;
+    }
+    if (p.stats) {
+        unsigned long long c1 = cells1, c2 = cells2, na = nal;
         for (int d = 16; d > 0; d >>= 1) {
             alg += __shfl_down_sync(0xffffffffu, alg, d);
             c1 += __shfl_down_sync(0xffffffffu, c1, d);
             c2 += __shfl_down_sync(0xffffffffu, c2, d);
+            na += __shfl_down_sync(0xffffffffu, na, d);
         }
-        unsigned nal = __reduce_add_sync(0xffffffffu, (valid && m > 0) ? (unsigned)(2 * F.U) : 0u);
         if (lane == 0) {
             atomicAdd(&p.stats[0], alg); atomicAdd(&p.stats[1], c1); atomicAdd(&p.stats[2], c2);
-            atomicAdd(&p.stats[3], (unsigned long long)nal);
+            atomicAdd(&p.stats[3], na);
         }
     }
 }
@@ -399,12 +510,25 @@ __global__ void fam_scatter_kernel(const int32_t *read_family, int nreads, int n
 }
 
 template <bool FAST>
-int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nitems_bound, size_t smem) {
-    if (smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(classify_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    classify_kernel<FAST><<<nitems_bound, 32, smem, ctx->stream>>>(p);
+int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nctas, size_t smem) {
+    classify_kernel<FAST><<<nctas, 32, smem, ctx->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
+    return TREDSW_OK;
+}
+
+// resident CTAs per SM of the persistent kernels (registers / shared memory), times the SM count
+int persistent_ctas(tredsw_ctx *ctx, size_t smem, int *out) {
+    int a = 0, b = 0;
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, classify_kernel<true>, 32, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, classify_kernel<false>, 32, smem));
+    int per_sm = a > b ? a : b;
+    if (per_sm < 1) per_sm = 1;
+    *out = per_sm * ctx->sm_count;
     return TREDSW_OK;
 }
 
@@ -429,7 +553,6 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     const int max_rows = max_m > 0 ? max_m : 1;
     const size_t rows_alloc = (size_t)max_rows + 2;
     const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + 64;
-    const size_t smem_fast = smem;
     if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
     ClassifyParams p{};
     p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
@@ -450,13 +573,21 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.stats = d_stats;
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     const int nitems_bound = nreads / 32 + nfamilies + 1;
-    int rc;
-    if ((rc = ctx->d_scratch.ensure((size_t)nitems_bound * 2 * max_u * 32 * sizeof(uint16_t)))) return rc;
+    int rc, nctas = 0;
+    if ((rc = persistent_ctas(ctx, smem, &nctas))) return rc;
+    if (nctas > nitems_bound) nctas = nitems_bound;
+    // per-CTA scratch: scores [2*max_u][32] u16, potentials [rows][32] u32, then the two work counters
+    const size_t score_bytes = (size_t)nctas * 2 * max_u * 32 * sizeof(uint16_t);
+    const size_t pot_bytes = (size_t)nctas * rows_alloc * 32 * sizeof(uint32_t);
+    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + 16))) return rc;
     p.score_buf = ctx->d_scratch.as<uint16_t>();
+    p.pot_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes);
+    p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes);
     p.max_u = max_u;
+    CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
     ctx->mark(0);
-    if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nitems_bound, smem))) return rc; }
-    if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nitems_bound, smem_fast))) return rc; }
+    if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nctas, smem))) return rc; }
+    if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nctas, smem))) return rc; }
     ctx->mark(1);
     return TREDSW_OK;
 }
