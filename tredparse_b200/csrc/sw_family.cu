@@ -52,6 +52,8 @@ struct ClassifyParams {
     int max_u;                     // largest max_units of the batch (stride of score_buf)
     uint16_t *score_buf;           // [CTAs][2*max_u][32] per-template scores (u8 in the fast kernel)
     uint32_t *pot_buf;             // [CTAs][max_rows+2][32] suffix potentials of the CTA's current item
+    uint32_t *gbnd_buf;            // [CTAs][nslots][max_rows+2][32] boundary column entering every main strip
+    int nslots;
     int32_t *counter;              // [2] work counters (generic, fast), zeroed before the launches
     int32_t *out;
     unsigned long long *stats;     // 4 counters
@@ -128,11 +130,13 @@ __host__ __device__ constexpr int strip_units(int P) { return P >= 24 ? 1 : 24 /
 //               mu[u] = max(mu[u], H(j-1, last) + A[j], E(j, last -> next) + B[j])
 //           — 2 add-max per row and unit instead of a forked DP over the suffix columns.
 //   bnd     boundary column in shared memory: H/E entering (HAS_IN) and leaving (HAS_OUT) the strip
+//   gout    (HAS_OUT) copy of the leaving boundary column in global scratch: phase 2 restarts from it
 //   pot     suffix potentials of this warp's reads in global scratch, one word per row and lane
 template <int NC, int PER, bool HAS_IN, bool HAS_OUT, bool HOOK>
 __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
-                                           uint32_t *bnd, const uint32_t *pot, uint32_t (&seg)[NC / PER],
-                                           uint32_t (&mu)[NC / PER], uint32_t mgo2, uint32_t mge2) {
+                                           uint32_t *bnd, uint32_t *gout, const uint32_t *pot,
+                                           uint32_t (&seg)[NC / PER], uint32_t (&mu)[NC / PER], uint32_t mgo2,
+                                           uint32_t mge2) {
     constexpr int K = NC / PER;
     static_assert(K * PER == NC, "strip = whole units");
     constexpr int NG = (NC + 3) / 4;
@@ -196,7 +200,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
                     mu[u] = __viaddmax_s16x2(hdA, potHA, mu[u]);
                     mu[u] = __viaddmax_s16x2(eA, potEA, mu[u]);
                 }
-                if (HAS_OUT && s == NC - 1) bnd[j * 32 + lane] = sw_prmt(hA, eA, 0x6420);
+                if (HAS_OUT && s == NC - 1) { const uint32_t w = sw_prmt(hA, eA, 0x6420); bnd[j * 32 + lane] = w; gout[j * 32 + lane] = w; }
             }
             if (s >= 1) {
                 PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
@@ -206,7 +210,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
                     mu[u] = __viaddmax_s16x2(hdB, potHB, mu[u]);
                     mu[u] = __viaddmax_s16x2(eB, potEB, mu[u]);
                 }
-                if (HAS_OUT && s - 1 == NC - 1) bnd[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
+                if (HAS_OUT && s - 1 == NC - 1) { const uint32_t w = sw_prmt(hB, eB, 0x6420); bnd[(j + 1) * 32 + lane] = w; gout[(j + 1) * 32 + lane] = w; }
             }
         }
         rowA = rowA2; rowB = rowB2; bA = bA2; bB = bB2; codeA2 = codeA3; codeB2 = codeB3;
@@ -278,10 +282,118 @@ __device__ __forceinline__ void build_stab(uint32_t *stab, const SwLut *lut, int
     }
 }
 
+// Phase-2 strip: the same packed DP over one strip, but recording WHERE the maxima are.
+//   colkey[c] = max over rows of (H << 8 | 255 - row), per strand half (unsigned compare): the column
+//               maximum and the smallest row attaining it — what ssw.c's end_ref / end_read need.
+//   bin       this lane's boundary column entering the strip (lane offset folded in, 32-word row stride)
+//   bout      (CAPTURE) the H/E column leaving unit `kstar` of the strip = the column entering the
+//             suffix block of this lane's winning template
+// Control flow is uniform across the warp; only addresses and the captured unit differ per lane.
+template <int NC, int PER, bool CAPTURE>
+__device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
+                                             const uint32_t *bin, uint32_t *bout, int kstar,
+                                             uint32_t (&colkey)[NC], uint32_t mgo2, uint32_t mge2) {
+    constexpr int NG = (NC + 3) / 4;
+    uint32_t Hrow[NC], Fv[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { Hrow[c] = 0; Fv[c] = 0; colkey[c] = 0; }
+    uint32_t hin_prev = 0;
+    auto code_at = [&](int j) { return j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
+    auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
+    uint32_t bA = bin[0], bB = bin[32];
+    for (int j = 0; j < rows2; j += 2) {
+        const uint32_t hinA = sw_prmt(bA, 0, 0x4140), hinB = sw_prmt(bB, 0, 0x4140);
+        uint32_t eA = sw_prmt(bA, 0, 0x4342), eB = sw_prmt(bB, 0, 0x4342);
+        const int jn = min(j + 2, rows2 - 2);
+        bA = bin[jn * 32]; bB = bin[(jn + 1) * 32];
+        const uint4 *rowA = row_of(code_at(j)), *rowB = row_of(code_at(j + 1));
+        uint32_t sA[NG * 4], sB[NG * 4];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint4 a = rowA[g], b = rowB[g];
+            sA[4 * g] = a.x; sA[4 * g + 1] = a.y; sA[4 * g + 2] = a.z; sA[4 * g + 3] = a.w;
+            sB[4 * g] = b.x; sB[4 * g + 1] = b.y; sB[4 * g + 2] = b.z; sB[4 * g + 3] = b.w;
+        }
+        const uint32_t rcA = 0x00010001u * (uint32_t)(255 - j), rcB = rcA - 0x00010001u;
+        uint32_t hdA = hin_prev, hdB = hinA;
+        hin_prev = hinB;
+        uint32_t hA = 0, hB = 0, keyA_prev = 0;
+#pragma unroll
+        for (int s = 0; s <= NC; ++s) {
+            uint32_t keyA = 0;
+            if (s < NC) {
+                PACKED_CELL(hdA, eA, sA[s], s, hA)
+                keyA = hA * 256u + rcA;                          // IMAD on the FMA pipe: H < 256 per half
+                if (CAPTURE && s % PER == PER - 1) { if (kstar == s / PER) bout[j * 32] = sw_prmt(hA, eA, 0x6420); }
+            }
+            if (s >= 1) {
+                PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
+                const uint32_t keyB = hB * 256u + rcB;
+                colkey[s - 1] = __vimax3_u16x2(colkey[s - 1], keyA_prev, keyB);
+                if (CAPTURE && (s - 1) % PER == PER - 1) { if (kstar == (s - 1) / PER) bout[(j + 1) * 32] = sw_prmt(hB, eB, 0x6420); }
+            }
+            keyA_prev = keyA;
+        }
+    }
+}
+
+// Exact end coordinates (ssw.c's end_ref, end_read) of every lane's winning template, warp-uniform.
+// The winner (units u, strand s, score cs) is the first template in arg-max order, so no shorter template
+// of the same strand reaches cs: the first column whose maximum equals cs lies in unit u's own columns
+// or in the suffix block (never in the first FLANK columns: cs >= 30 > FLANK * match).  Recompute the
+// main strip that holds unit u from its stored entering boundary (keys for its columns, the boundary
+// leaving unit u captured), then the suffix block, and read the answer off the column keys.
+template <int P>
+__device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
+                                           const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
+                                           const uint32_t *gbnd, int R, int go, int ge, int cs, int u, int strand,
+                                           int *end_ref, int *end_read, unsigned long long &cells) {
+    constexpr int K = strip_units(P);
+    constexpr int NC = P * K;
+    const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
+    const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
+    const int rows2 = (m_warp + 1) & ~1;
+    auto comp = [](int c) { return c < 4 ? 3 - c : c; };
+    const int tstar = (u - 1) / K, kstar = (u - 1) % K;      // lanes without a candidate pass u = 1
+    const int sh = strand ? 16 : 0;
+    int found_col = -1, found_row = 0;
+    {
+        // main strip tstar (the repeat table of phase 1 is still in shared memory)
+        uint32_t colkey[NC];
+        strip_locate<NC, P, true>(stab, codes, lane, m, rows2, gbnd + (size_t)tstar * R * 32 + lane, bnd + lane, kstar,
+                                  colkey, mgo2, mge2);
+#pragma unroll
+        for (int c = NC - 1; c >= 0; --c) {
+            const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
+            if (c / P == kstar && (int)(k16 >> 8) == cs) { found_col = FLANK + (tstar * K) * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+        }
+    }
+    __syncwarp();
+    // suffix block of every lane's own template, entered through the captured boundary
+    if (lane < FLANK) colsel[lane] = sel2(F.suffix[lane], comp(F.prefix[FLANK - 1 - lane]));
+    __syncwarp();
+    build_stab(stab, lut, lane, FLANK, colsel);
+    __syncwarp();
+    {
+        uint32_t colkey[FLANK];
+        strip_locate<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd + lane, nullptr, 0, colkey, mgo2, mge2);
+        if (found_col < 0) {
+#pragma unroll
+            for (int c = FLANK - 1; c >= 0; --c) {
+                const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
+                if ((int)(k16 >> 8) == cs) { found_col = FLANK + u * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+            }
+        }
+    }
+    __syncwarp();
+    *end_ref = found_col; *end_read = found_row;
+    cells += (unsigned long long)m * 2ull * (unsigned long long)(NC + FLANK);
+}
+
 template <int P>
 __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           uint32_t *pot, uint8_t *scores, int go, int ge,
+                                           uint32_t *pot, uint32_t *gbnd, int R, uint8_t *scores, int go, int ge,
                                            unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
@@ -307,7 +419,7 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
     uint32_t run;                   // running maximum over the main columns so far, per strand
     {
         uint32_t seg0[1] = {0u}, mu0[1] = {0u};
-        strip_pass<FLANK, FLANK, false, true, false>(stab, codes, lane, m, rows2, bnd, pot, seg0, mu0, mgo2, mge2);
+        strip_pass<FLANK, FLANK, false, true, false>(stab, codes, lane, m, rows2, bnd, gbnd, pot, seg0, mu0, mgo2, mge2);
         run = seg0[0];
     }
     __syncwarp();
@@ -321,7 +433,9 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
         uint32_t seg[K], mu[K];
 #pragma unroll
         for (int u = 0; u < K; ++u) { seg[u] = 0; mu[u] = 0; }
-        strip_pass<NC, P, true, true, true>(stab, codes, lane, m, rows2, bnd, pot, seg, mu, mgo2, mge2);
+        // (the boundary leaving strip t enters strip t+1: slot t+1 of the global copy)
+        strip_pass<NC, P, true, true, true>(stab, codes, lane, m, rows2, bnd, gbnd + (size_t)(nstrips + 1) * R * 32, pot,
+                                            seg, mu, mgo2, mge2);
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             run = __vmaxs2(run, seg[u]);
@@ -356,6 +470,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
     score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32;   // [2U][32]
     uint32_t *pot = p.pot_buf + (size_t)blockIdx.x * R * 32;                       // [R][32]
+    uint32_t *gbnd = p.gbnd_buf + (size_t)blockIdx.x * p.nslots * R * 32;          // [nslots][R][32]
     sw_build_lut(&lut, c_fmat25, lane, 32);
     const int nitems = p.chunk_start[p.nfamilies];
     unsigned long long alg = 0, cells1 = 0, cells2 = 0;
@@ -399,7 +514,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
         } else {
             switch (F.P) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, pot, scores, p.go, p.ge, cells1); break;
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, pot, gbnd, R, scores, p.go, p.ge, cells1); break;
                 PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
 #undef PCASE
             }
@@ -408,48 +523,87 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
 
         // ---- Phase 2: walk candidates in arg-max order until one yields a tag --------------------------
         int tag = TREDSW_TAG_NONE, best_u = 0, best_score = -1, rb = -1, re = -1, qb = -1, qe = -1, best_rank = -1;
-        if (valid && m > 0) {
-            const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
-            int last_score = 0x7fffffff, last_rank = -1;
-            auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
-            for (;;) {
-                int cs = -1, cr = -1;
-                for (int rank = 0; rank < 2 * F.U; ++rank) {
-                    const int sc = scores[rank * 32 + lane];
-                    const int n = F.Lp + F.Ls + F.P * (rank / 2 + 1);
-                    const int min_len = min(m, n) / 2;
-                    if (sc < max(min_len, 30)) continue;
-                    if (sc > last_score || (sc == last_score && rank <= last_rank)) continue;   // already tried
-                    if (sc > cs) { cs = sc; cr = rank; }
+        const bool active = valid && m > 0;
+        // next candidate after (last_score, last_rank) in the reference's arg-max order
+        auto pick = [&](int last_score, int last_rank, int &cs, int &cr) {
+            cs = -1; cr = -1;
+            if (!active) return;
+            for (int rank = 0; rank < 2 * F.U; ++rank) {
+                const int sc = scores[rank * 32 + lane];
+                const int n = F.Lp + F.Ls + F.P * (rank / 2 + 1);
+                const int min_len = min(m, n) / 2;
+                if (sc < max(min_len, 30)) continue;
+                if (sc > last_score || (sc == last_score && rank <= last_rank)) continue;   // already tried
+                if (sc > cs) { cs = sc; cr = rank; }
+            }
+        };
+        int cs, cr;
+        pick(0x7fffffff, -1, cs, cr);
+        // end coordinates of every lane's first candidate in one warp-uniform packed pass
+        int fast_end_ref = -1, fast_end_read = 0;
+        if constexpr (FAST) {
+            if (FLANK * p.match < 30 && __any_sync(0xffffffffu, cr >= 0)) {
+                const int lu = cr >= 0 ? cr / 2 + 1 : 1, ls = cr >= 0 ? (cr & 1) : 0, lcs = cr >= 0 ? cs : 0x7fff;
+                switch (F.P) {
+#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
+                    PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
+#undef PCASE
                 }
-                if (cr < 0) break;
-                last_score = cs; last_rank = cr;
+                if (cr < 0) fast_end_ref = -1;
+            }
+        }
+        if (active) {
+            const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
+            auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
+            for (bool first = true; cr >= 0; first = false) {
                 const int u = cr / 2 + 1, s = cr & 1;
                 const int n = F.Lp + F.Ls + F.P * u;
                 auto cc_f = [&](int i) { return fam_code(F, u, s, n, i); };
-                // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
-                // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
-                // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
-                const int drift = sw_max_drift(cs, m, n, p.match, p.go, p.ge);
-                const int need = (cs + p.match - 1) / p.match;
                 int end_ref, end_read;
-                sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read, nullptr,
-                                           -(m - need) - drift, (n - need) + drift, &cells2);
-                if (end_ref < 0) continue;   // cannot happen: the score was produced by this very template
-                auto rc_r = [&](int j) { return (int)codes[(end_read - j) * 32 + lane]; };
-                auto cc_r = [&](int i) { return fam_code(F, u, s, n, end_ref - i); };
-                int ci, rj;
-                // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A), so it
-                // stays within `drift` of the main diagonal of the reversed sub-matrix.
-                sw_sweep<FAM_W2, 1, false>(end_read + 1, end_read + 1, end_ref + 1, rc_r, cc_r, &lut, bnd + lane, 32, p.go,
-                                           p.ge, cs, &ci, &rj, nullptr, -drift, drift, &cells2);
-                const int c_rb = end_ref - ci, c_qb = end_read - rj;
-                const int t = sw_classify(cs, c_rb, end_ref, c_qb, end_read, m, n, u, F.P, max_units_eff);
-                if (t != TREDSW_TAG_NONE) {
-                    tag = t; best_u = u; best_score = cs; rb = c_rb; re = end_ref; qb = c_qb; qe = end_read;
-                    best_rank = cr;
-                    break;
+                if (first && fast_end_ref >= 0) {
+                    end_ref = fast_end_ref; end_read = fast_end_read;
+                } else {
+                    // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
+                    // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
+                    // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
+                    const int drift = sw_max_drift(cs, m, n, p.match, p.go, p.ge);
+                    const int need = (cs + p.match - 1) / p.match;
+                    sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read,
+                                               nullptr, -(m - need) - drift, (n - need) + drift, &cells2);
                 }
+                if (end_ref >= 0) {      // (always: the score was produced by this very template)
+                    // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A); it
+                    // lives in the (end_read+1) x (end_ref+1) rectangle, which bounds its aligned pairs and
+                    // therefore how far it can drift from the corner's diagonal.
+                    const int rdrift = sw_max_drift(cs, end_read + 1, end_ref + 1, p.match, p.go, p.ge);
+                    int ci = -1, rj = 0;
+                    if (rdrift == 0) {   // no gap affordable: walk the diagonal
+                        const int lim = min(end_read, end_ref) + 1;
+                        int h = 0;
+                        for (int k = 0; k < lim; ++k) {
+                            const int qc = codes[(end_read - k) * 32 + lane];
+                            const int sc = (int)sw_prmt(lut.w0[qc], lut.w1[qc], sw_sel32(fam_code(F, u, s, n, end_ref - k)));
+                            h = max(0, h + sc);
+                            if (h == cs) { ci = rj = k; break; }
+                        }
+                        cells2 += (unsigned long long)lim;
+                    }
+                    if (ci < 0) {
+                        auto rc_r = [&](int j) { return (int)codes[(end_read - j) * 32 + lane]; };
+                        auto cc_r = [&](int i) { return fam_code(F, u, s, n, end_ref - i); };
+                        sw_sweep<FAM_W2, 1, false>(end_read + 1, end_read + 1, end_ref + 1, rc_r, cc_r, &lut, bnd + lane, 32,
+                                                   p.go, p.ge, cs, &ci, &rj, nullptr, -rdrift, rdrift, &cells2);
+                    }
+                    const int c_rb = end_ref - ci, c_qb = end_read - rj;
+                    const int t = sw_classify(cs, c_rb, end_ref, c_qb, end_read, m, n, u, F.P, max_units_eff);
+                    if (t != TREDSW_TAG_NONE) {
+                        tag = t; best_u = u; best_score = cs; rb = c_rb; re = end_ref; qb = c_qb; qe = end_read;
+                        best_rank = cr;
+                        break;
+                    }
+                }
+                const int ls = cs, lr = cr;
+                pick(ls, lr, cs, cr);
             }
         }
         if (valid) {
@@ -539,7 +693,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                              const tredsw_family *h_families, int nfamilies, int max_m,
                              const int8_t *mat25, int gap_open, int gap_extend, int32_t *d_work, int32_t *d_out,
                              unsigned long long *d_stats) {
-    int max_u = 0; bool need_fast = false, need_generic = false; int max_match = 0;
+    int max_u = 0, nslots = 1; bool need_fast = false, need_generic = false; int max_match = 0;
     for (int i = 0; i < 25; ++i) if (mat25[i] > max_match) max_match = mat25[i];
     const bool allow_fast = (long long)max_m * max_match < 256;
     for (int f = 0; f < nfamilies; ++f) {
@@ -548,7 +702,11 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
             g.period > 32 || g.max_units < 1 || g.max_units > 4096) { tredsw_set_error("family %d out of range", f); return TREDSW_ERR_ARG; }
         if (g.max_units > max_u) max_u = g.max_units;
         bool fast = allow_fast && g.prefix_len == FLANK && g.suffix_len == FLANK && g.period <= 12;
-        if (fast) need_fast = true; else need_generic = true;
+        if (fast) {
+            need_fast = true;
+            const int k = strip_units(g.period), slots = (g.max_units + k - 1) / k + 1;
+            if (slots > nslots) nslots = slots;
+        } else need_generic = true;
     }
     const int max_rows = max_m > 0 ? max_m : 1;
     const size_t rows_alloc = (size_t)max_rows + 2;
@@ -579,10 +737,13 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     // per-CTA scratch: scores [2*max_u][32] u16, potentials [rows][32] u32, then the two work counters
     const size_t score_bytes = (size_t)nctas * 2 * max_u * 32 * sizeof(uint16_t);
     const size_t pot_bytes = (size_t)nctas * rows_alloc * 32 * sizeof(uint32_t);
-    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + 16))) return rc;
+    const size_t gbnd_bytes = pot_bytes * nslots;
+    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + gbnd_bytes + 16))) return rc;
     p.score_buf = ctx->d_scratch.as<uint16_t>();
     p.pot_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes);
-    p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes);
+    p.gbnd_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes);
+    p.nslots = nslots;
+    p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes + gbnd_bytes);
     p.max_u = max_u;
     CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
     ctx->mark(0);
