@@ -27,6 +27,7 @@
 #include "internal.cuh"
 #include "sw_sweep.cuh"
 #include <type_traits>
+#include <algorithm>
 
 namespace {
 
@@ -42,7 +43,9 @@ struct ClassifyParams {
     const int8_t *rbuf; const int64_t *roff;
     const int32_t *order;          // read indices grouped by family
     const int32_t *fam_start;      // [nfam+1] offsets into order
-    const int32_t *chunk_start;    // [nfam+1] offsets into the item (warp-chunk) list
+    const int32_t *chunk_start;    // [nfam+1] offsets into the item (warp-chunk) list, families in fam_perm order
+    const int32_t *fam_perm;       // [nfam] families sorted by period: CTAs that run at the same time mostly
+                                   // share one instantiation of the strip loops (instruction cache)
     const tredsw_family *families;
     int nfamilies;
     int go, ge;
@@ -54,6 +57,7 @@ struct ClassifyParams {
     uint32_t *pot_buf;             // [CTAs][max_rows+2][32] suffix potentials of the CTA's current item
     uint32_t *gbnd_buf;            // [CTAs][nslots][max_rows+2][32] boundary column entering every main strip
     int nslots;
+    uint32_t one;                  // == 1, opaque to the compiler: keeps x = Hdiag * one + S an IMAD (FMA pipe)
     int32_t *counter;              // [2] work counters (generic, fast), zeroed before the launches
     int32_t *out;
     unsigned long long *stats;     // 4 counters
@@ -98,16 +102,23 @@ __device__ __forceinline__ uint32_t sel2(int tf, int tr) {   // PRMT selector: s
     return (uint32_t)tf | ((uint32_t)(8 | tf) << 4) | ((uint32_t)tr << 8) | ((uint32_t)(8 | tr) << 12);
 }
 
-// One DP cell for both strands (packed s16x2), all operands in registers; S = substitution scores.
+// One DP cell for both strands (packed s16x2), all operands in registers.  Four integer-pipe instructions:
+//     E~ = E + go, F~ = F + go (gap states stored biased by the opening cost, never clamped: E~ >= H >= 0)
+//     S  = substitution score + go (table), so that x = Hdiag + S >= 0 in both halves and the add cannot
+//          borrow across them: it is issued as an IMAD (x = Hdiag * one + S) on the otherwise idle FMA pipe
+//     y  = max(x, E~, F~)                       VIMNMX3
+//     H  = max(y - go, 0)                       VIADDMNMX.RELU
+//     E~ = max(E~ - ge, H), F~ likewise         VIADDMNMX x 2
+// which is H = max(0, Hdiag + s, E, F), E' = max(E - ge, H - go), F' = max(F - ge, H - go).
 #define PACKED_CELL(HD, E, S, C, HOUT)                                                        \
     {                                                                                         \
-        const uint32_t t_ = __vmaxs2(E, Fv[C]);                                               \
-        HOUT = __viaddmax_s16x2_relu(HD, S, t_);                   /* max(diag+s, E, F, 0) */ \
+        const uint32_t x_ = HD * one + S;                                                     \
+        const uint32_t y_ = __vimax3_s16x2(x_, E, Fv[C]);                                     \
+        HOUT = __viaddmax_s16x2_relu(y_, mgo2, mgo2);   /* (third operand: any value <= 0) */ \
         HD = Hrow[C];                                                                         \
         Hrow[C] = HOUT;                                                                       \
-        const uint32_t hgo_ = __viaddmax_s16x2(HOUT, mgo2, 0x80008000u); /* h - go */         \
-        E = __viaddmax_s16x2_relu(E, mge2, hgo_);                  /* max(E-ge, h-go, 0) */   \
-        Fv[C] = __viaddmax_s16x2_relu(Fv[C], mge2, hgo_);                                     \
+        E = __viaddmax_s16x2(E, mge2, HOUT);                                                  \
+        Fv[C] = __viaddmax_s16x2(Fv[C], mge2, HOUT);                                          \
     }
 
 constexpr int STAB_PAD = 36;       // words per query-code row of the score table: >= the widest strip, a multiple of 4
@@ -129,14 +140,15 @@ __host__ __device__ constexpr int strip_units(int P) { return P >= 24 ? 1 : 24 /
 //           block, by the suffix potentials of this read (see suffix_pass): for every row j
 //               mu[u] = max(mu[u], H(j-1, last) + A[j], E(j, last -> next) + B[j])
 //           — 2 add-max per row and unit instead of a forked DP over the suffix columns.
-//   bnd     boundary column in shared memory: H/E entering (HAS_IN) and leaving (HAS_OUT) the strip
-//   gout    (HAS_OUT) copy of the leaving boundary column in global scratch: phase 2 restarts from it
+//   bin     (HAS_IN) boundary column entering the strip, bout (HAS_OUT) the one leaving it: H | E~ << 16 as
+//           bytes per strand, one word per row and lane in this CTA's global scratch (L1/L2 resident,
+//           requested one iteration ahead); every strip keeps its own slot, phase 2 restarts from them
 //   pot     suffix potentials of this warp's reads in global scratch, one word per row and lane
 template <int NC, int PER, bool HAS_IN, bool HAS_OUT, bool HOOK>
 __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
-                                           uint32_t *bnd, uint32_t *gout, const uint32_t *pot,
+                                           const uint32_t *bin, uint32_t *bout, const uint32_t *pot,
                                            uint32_t (&seg)[NC / PER], uint32_t (&mu)[NC / PER], uint32_t mgo2,
-                                           uint32_t mge2) {
+                                           uint32_t mge2, uint32_t one) {
     constexpr int K = NC / PER;
     static_assert(K * PER == NC, "strip = whole units");
     constexpr int NG = (NC + 3) / 4;
@@ -152,7 +164,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
     const uint4 *rowA = row_of(code_at(0)), *rowB = row_of(code_at(1));
     uint4 gA = rowA[0], gB = rowB[0];
     uint32_t bA = 0, bB = 0, pA = 0, pB = 0;
-    if (HAS_IN) { bA = bnd[lane]; bB = bnd[32 + lane]; }
+    if (HAS_IN) { bA = bin[lane]; bB = bin[32 + lane]; }
     if (HOOK) { pA = pot[lane]; pB = pot[32 + lane]; }
     int codeA2 = code_at(2), codeB2 = code_at(3);
     for (int j = 0; j < rows2; j += 2) {
@@ -170,7 +182,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
         const int jn = min(j + 2, rows2 - 2);
         const uint4 *rowA2 = row_of(codeA2), *rowB2 = row_of(codeB2);
         uint32_t bA2 = 0, bB2 = 0;
-        if (HAS_IN) { bA2 = bnd[jn * 32 + lane]; bB2 = bnd[(jn + 1) * 32 + lane]; }
+        if (HAS_IN) { bA2 = bin[jn * 32 + lane]; bB2 = bin[(jn + 1) * 32 + lane]; }
         if (HOOK) { pA = pot[jn * 32 + lane]; pB = pot[(jn + 1) * 32 + lane]; }
         const int codeA3 = code_at(j + 4), codeB3 = code_at(j + 5);
         uint32_t sA[NG * 4], sB[NG * 4];
@@ -200,7 +212,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
                     mu[u] = __viaddmax_s16x2(hdA, potHA, mu[u]);
                     mu[u] = __viaddmax_s16x2(eA, potEA, mu[u]);
                 }
-                if (HAS_OUT && s == NC - 1) { const uint32_t w = sw_prmt(hA, eA, 0x6420); bnd[j * 32 + lane] = w; gout[j * 32 + lane] = w; }
+                if (HAS_OUT && s == NC - 1) bout[j * 32 + lane] = sw_prmt(hA, eA, 0x6420);
             }
             if (s >= 1) {
                 PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
@@ -210,7 +222,7 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
                     mu[u] = __viaddmax_s16x2(hdB, potHB, mu[u]);
                     mu[u] = __viaddmax_s16x2(eB, potEB, mu[u]);
                 }
-                if (HAS_OUT && s - 1 == NC - 1) { const uint32_t w = sw_prmt(hB, eB, 0x6420); bnd[(j + 1) * 32 + lane] = w; gout[(j + 1) * 32 + lane] = w; }
+                if (HAS_OUT && s - 1 == NC - 1) bout[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
             }
         }
         rowA = rowA2; rowB = rowB2; bA = bA2; bB = bB2; codeA2 = codeA3; codeB2 = codeB3;
@@ -228,10 +240,11 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
 // function of the H/E column entering the block plus the paths that start inside the block, so
 //     max H over the suffix block of template u = max(fresh, max_j H_u(j-1,last)+A[j], max_j E_u(j)+B[j])
 // with A[j] = G(j,0), B[j] = GE(j,0) and fresh = max G — none of which depends on u.
-// pot[j] = A_fwd | A_rc << 8 | B_fwd << 16 | B_rc << 24 (signed bytes; 0x80 = -128 on ghost rows).
+// pot[j] = A_fwd | A_rc << 8 | (B_fwd - go) << 16 | (B_rc - go) << 24 (signed bytes; 0x80 = -128 on ghost rows).
 template <int NC>
 __device__ __forceinline__ void suffix_pass(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
                                             uint32_t *pot, uint32_t &fresh, uint32_t mgo2, uint32_t mge2) {
+    // (the forward cells keep E biased by +go, so the stored E potential is B - go)
     constexpr int NG = (NC + 3) / 4;
     uint32_t Grow[NC], Fv[NC];
 #pragma unroll
@@ -266,8 +279,8 @@ __device__ __forceinline__ void suffix_pass(const uint32_t *stab, const uint8_t 
             if (s >= 1) { SUFFIX_CELL(gdB, eB, sB[s - 1], s - 1, gB) f1 = __vmaxs2(f1, gB); }
         }
         const int jA = rows2 - 1 - r, jB = jA - 1;
-        pot[jA * 32 + lane] = jA < m ? sw_prmt(gA, eA, 0x6420) : 0x80808080u;
-        pot[jB * 32 + lane] = jB < m ? sw_prmt(gB, eB, 0x6420) : 0x80808080u;
+        pot[jA * 32 + lane] = jA < m ? sw_prmt(gA, __vadd2(eA, mgo2), 0x6420) : 0x80808080u;
+        pot[jB * 32 + lane] = jB < m ? sw_prmt(gB, __vadd2(eB, mgo2), 0x6420) : 0x80808080u;
     }
 #undef SUFFIX_CELL
     fresh = __vimax3_s16x2(f0, f1, 0u);
@@ -275,10 +288,11 @@ __device__ __forceinline__ void suffix_pass(const uint32_t *stab, const uint8_t 
 
 // score table of one strip: stab[q][c] = s16x2( score(q, fwd column c), score(q, rc column c) ), q = 0..5
 __device__ __forceinline__ void build_stab(uint32_t *stab, const SwLut *lut, int lane, int ncols,
-                                           const uint32_t *colsel /* smem, per column PRMT selector */) {
+                                           const uint32_t *colsel /* smem, per column PRMT selector */,
+                                           uint32_t bias2 = 0u /* added to both halves (PACKED_CELL: go) */) {
     for (int i = lane; i < 6 * STAB_PAD; i += 32) {
         const int q = i / STAB_PAD, c = i % STAB_PAD;
-        stab[i] = (c < ncols) ? sw_prmt(lut->w0[q], lut->w1[q], colsel[c]) : 0u;
+        stab[i] = (c < ncols) ? __vadd2(sw_prmt(lut->w0[q], lut->w1[q], colsel[c]), bias2) : 0u;
     }
 }
 
@@ -292,7 +306,7 @@ __device__ __forceinline__ void build_stab(uint32_t *stab, const SwLut *lut, int
 template <int NC, int PER, bool CAPTURE>
 __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t *codes, int lane, int m, int rows2,
                                              const uint32_t *bin, uint32_t *bout, int kstar,
-                                             uint32_t (&colkey)[NC], uint32_t mgo2, uint32_t mge2) {
+                                             uint32_t (&colkey)[NC], uint32_t mgo2, uint32_t mge2, uint32_t one) {
     constexpr int NG = (NC + 3) / 4;
     uint32_t Hrow[NC], Fv[NC];
 #pragma unroll
@@ -346,12 +360,13 @@ __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t
 template <int P>
 __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           const uint32_t *gbnd, int R, int go, int ge, int cs, int u, int strand,
-                                           int *end_ref, int *end_read, unsigned long long &cells) {
+                                           const uint32_t *gbnd, int R, int go, int ge, uint32_t one, int cs, int u,
+                                           int strand, int *end_ref, int *end_read, unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
     const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
+    const uint32_t go2 = (uint32_t)go * 0x00010001u;
     const int rows2 = (m_warp + 1) & ~1;
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
     const int tstar = (u - 1) / K, kstar = (u - 1) % K;      // lanes without a candidate pass u = 1
@@ -361,7 +376,7 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
         // main strip tstar (the repeat table of phase 1 is still in shared memory)
         uint32_t colkey[NC];
         strip_locate<NC, P, true>(stab, codes, lane, m, rows2, gbnd + (size_t)tstar * R * 32 + lane, bnd + lane, kstar,
-                                  colkey, mgo2, mge2);
+                                  colkey, mgo2, mge2, one);
 #pragma unroll
         for (int c = NC - 1; c >= 0; --c) {
             const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
@@ -372,11 +387,11 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
     // suffix block of every lane's own template, entered through the captured boundary
     if (lane < FLANK) colsel[lane] = sel2(F.suffix[lane], comp(F.prefix[FLANK - 1 - lane]));
     __syncwarp();
-    build_stab(stab, lut, lane, FLANK, colsel);
+    build_stab(stab, lut, lane, FLANK, colsel, go2);
     __syncwarp();
     {
         uint32_t colkey[FLANK];
-        strip_locate<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd + lane, nullptr, 0, colkey, mgo2, mge2);
+        strip_locate<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd + lane, nullptr, 0, colkey, mgo2, mge2, one);
         if (found_col < 0) {
 #pragma unroll
             for (int c = FLANK - 1; c >= 0; --c) {
@@ -392,14 +407,15 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
 
 template <int P>
 __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
-                                           const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           uint32_t *pot, uint32_t *gbnd, int R, uint8_t *scores, int go, int ge,
+                                           const uint8_t *codes, int lane, int m, int m_warp, uint32_t *pot,
+                                           uint32_t *gbnd, int R, uint8_t *scores, int go, int ge, uint32_t one,
                                            unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
     static_assert(NC <= STAB_PAD && FLANK <= STAB_PAD, "strip wider than the score table");
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
     const uint32_t mge2 = (uint32_t)((-ge) & 0xffff) | ((uint32_t)((-ge) & 0xffff) << 16);
+    const uint32_t go2 = (uint32_t)go * 0x00010001u;
     const int rows2 = (m_warp + 1) & ~1;
     // rc family: prefix' = rc(suffix), repeat' = rc(repeat), suffix' = rc(prefix)
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
@@ -414,28 +430,28 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
     // ---- strip 0: the FLANK prefix columns -----------------------------------------------------------
     if (lane < FLANK) colsel[lane] = sel2(F.prefix[lane], comp(F.suffix[FLANK - 1 - lane]));
     __syncwarp();
-    build_stab(stab, lut, lane, FLANK, colsel);
+    build_stab(stab, lut, lane, FLANK, colsel, go2);
     __syncwarp();
     uint32_t run;                   // running maximum over the main columns so far, per strand
     {
         uint32_t seg0[1] = {0u}, mu0[1] = {0u};
-        strip_pass<FLANK, FLANK, false, true, false>(stab, codes, lane, m, rows2, bnd, gbnd, pot, seg0, mu0, mgo2, mge2);
+        strip_pass<FLANK, FLANK, false, true, false>(stab, codes, lane, m, rows2, nullptr, gbnd, pot, seg0, mu0, mgo2, mge2, one);
         run = seg0[0];
     }
     __syncwarp();
     // ---- main strips: K repeat units each; the suffix of every template is folded in by the potentials --
     for (int c = lane; c < NC; c += 32) colsel[c] = sel2(F.repeat[c % P], comp(F.repeat[P - 1 - c % P]));
     __syncwarp();
-    build_stab(stab, lut, lane, NC, colsel);
+    build_stab(stab, lut, lane, NC, colsel, go2);
     __syncwarp();
     int nstrips = 0;
     for (int u0 = 0; u0 < F.U; u0 += K, ++nstrips) {
         uint32_t seg[K], mu[K];
 #pragma unroll
         for (int u = 0; u < K; ++u) { seg[u] = 0; mu[u] = 0; }
-        // (the boundary leaving strip t enters strip t+1: slot t+1 of the global copy)
-        strip_pass<NC, P, true, true, true>(stab, codes, lane, m, rows2, bnd, gbnd + (size_t)(nstrips + 1) * R * 32, pot,
-                                            seg, mu, mgo2, mge2);
+        // (slot t of the scratch = boundary entering main strip t; the strip writes slot t+1)
+        strip_pass<NC, P, true, true, true>(stab, codes, lane, m, rows2, gbnd + (size_t)nstrips * R * 32,
+                                            gbnd + (size_t)(nstrips + 1) * R * 32, pot, seg, mu, mgo2, mge2, one);
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             run = __vmaxs2(run, seg[u]);
@@ -461,16 +477,18 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     __shared__ FamilySmem F;
     __shared__ __align__(16) uint32_t stab[6 * STAB_PAD];
     __shared__ uint32_t colsel[STAB_PAD];
-    // (bnd: the boundary column, codes: the reads, both [rows][32]; per-template scores and the suffix
-    //  potentials go to this CTA's slot of the global scratch)
+    // (shared memory holds the reads as codes [rows][32] and the score table; per-template scores, suffix
+    //  potentials and all boundary columns live in this CTA's slot of the global scratch, which stays in
+    //  L1/L2 and is streamed with one-iteration-ahead requests — so occupancy is bounded by registers only)
     typedef typename std::conditional<FAST, uint8_t, uint16_t>::type score_t;
     const int lane = threadIdx.x;
     const int R = p.max_rows + 2;                                                  // + ghost row of the 2-row loop
-    uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                        // [R][32]
-    uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
+    uint8_t *codes = reinterpret_cast<uint8_t *>(smem_raw);                        // [R][32]
     score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32;   // [2U][32]
     uint32_t *pot = p.pot_buf + (size_t)blockIdx.x * R * 32;                       // [R][32]
-    uint32_t *gbnd = p.gbnd_buf + (size_t)blockIdx.x * p.nslots * R * 32;          // [nslots][R][32]
+    uint32_t *gbnd = p.gbnd_buf + (size_t)blockIdx.x * (p.nslots + 1) * R * 32;    // [nslots + 1][R][32]
+    uint32_t *bnd = gbnd + (size_t)p.nslots * R * 32;                              // last slot: phase-2 scratch column
+    const uint32_t one = p.one;
     sw_build_lut(&lut, c_fmat25, lane, 32);
     const int nitems = p.chunk_start[p.nfamilies];
     unsigned long long alg = 0, cells1 = 0, cells2 = 0;
@@ -488,7 +506,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             int mid = (lo + hi) >> 1;
             if (p.chunk_start[mid] <= item) lo = mid; else hi = mid;
         }
-        const int f = lo;
+        const int f = p.fam_perm[lo];
         {
             const tredsw_family &g = p.families[f];
             F.prefix[lane] = g.prefix[lane]; F.suffix[lane] = g.suffix[lane]; F.repeat[lane] = g.repeat[lane];
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         const bool fast_shape = p.allow_fast && (F.Lp == FLANK && F.Ls == FLANK && F.P >= 1 && F.P <= 12);
         if (fast_shape != FAST) continue;
 
-        const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[f]) + lane;
+        const int idx = p.fam_start[f] + 32 * (item - p.chunk_start[lo]) + lane;
         const bool valid = idx < p.fam_start[f + 1];
         const int r = valid ? p.order[idx] : -1;
         int m = 0;
@@ -514,7 +532,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
         } else {
             switch (F.P) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, pot, gbnd, R, scores, p.go, p.ge, cells1); break;
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, pot, gbnd, R, scores, p.go, p.ge, one, cells1); break;
                 PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
 #undef PCASE
             }
@@ -545,7 +563,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             if (FLANK * p.match < 30 && __any_sync(0xffffffffu, cr >= 0)) {
                 const int lu = cr >= 0 ? cr / 2 + 1 : 1, ls = cr >= 0 ? (cr & 1) : 0, lcs = cr >= 0 ? cs : 0x7fff;
                 switch (F.P) {
-#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
+#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, one, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
                     PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
 #undef PCASE
                 }
@@ -642,15 +660,14 @@ __global__ void fam_count_kernel(const int32_t *read_family, int nreads, int nfa
     }
 }
 // single block: exclusive scans -> fam_start, chunk_start; cursor := fam_start
-__global__ void fam_scan_kernel(const int32_t *count, int nfam, int32_t *fam_start, int32_t *chunk_start,
-                                int32_t *cursor) {
+__global__ void fam_scan_kernel(const int32_t *count, int nfam, const int32_t *perm, int32_t *fam_start,
+                                int32_t *chunk_start, int32_t *cursor) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int a = 0, b = 0;
-        for (int f = 0; f < nfam; ++f) {
-            fam_start[f] = a; chunk_start[f] = b; cursor[f] = a;
-            a += count[f]; b += (count[f] + 31) / 32;
-        }
-        fam_start[nfam] = a; chunk_start[nfam] = b;
+        for (int f = 0; f < nfam; ++f) { fam_start[f] = a; cursor[f] = a; a += count[f]; }
+        fam_start[nfam] = a;
+        for (int i = 0; i < nfam; ++i) { chunk_start[i] = b; b += (count[perm[i]] + 31) / 32; }
+        chunk_start[nfam] = b;
     }
 }
 __global__ void fam_scatter_kernel(const int32_t *read_family, int nreads, int nfam, int32_t *cursor,
@@ -672,15 +689,20 @@ int launch_classify(tredsw_ctx *ctx, const ClassifyParams &p, int nctas, size_t 
 }
 
 // resident CTAs per SM of the persistent kernels (registers / shared memory), times the SM count
-int persistent_ctas(tredsw_ctx *ctx, size_t smem, int *out) {
+int persistent_ctas(tredsw_ctx *ctx, size_t smem, bool need_fast, bool need_generic, int *out) {
     int a = 0, b = 0;
     if (smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, classify_kernel<true>, 32, smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, classify_kernel<false>, 32, smem));
-    int per_sm = a > b ? a : b;
+    if (need_fast) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, classify_kernel<true>, 32, smem));
+    if (need_generic) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, classify_kernel<false>, 32, smem));
+    int per_sm = need_fast ? a : b;          // the packed kernel is the one that matters when both run
+    static const int env_cap = [] { const char *e = getenv("TREDSW_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    // measured on B200 (profiles/): beyond 8 resident warps per SM the strip loops of the concurrently running
+    // phases no longer fit the instruction caches (L0 6 KB / L1.5 32 KB) and throughput drops
+    const int cap = env_cap > 0 ? env_cap : 8;
+    if (per_sm > cap) per_sm = cap;
     if (per_sm < 1) per_sm = 1;
     *out = per_sm * ctx->sm_count;
     return TREDSW_OK;
@@ -695,7 +717,11 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                              unsigned long long *d_stats) {
     int max_u = 0, nslots = 1; bool need_fast = false, need_generic = false; int max_match = 0;
     for (int i = 0; i < 25; ++i) if (mat25[i] > max_match) max_match = mat25[i];
-    const bool allow_fast = (long long)max_m * max_match < 256;
+    int min_mat = 0;
+    for (int i = 0; i < 25; ++i) if (mat25[i] < min_mat) min_mat = mat25[i];
+    // packed kernel: scores fit a byte, suffix potentials fit a signed byte, biased scores stay >= 0
+    const bool allow_fast = (long long)max_m * max_match < 256 && FLANK * max_match <= 120 && gap_open + min_mat >= 0 &&
+                            gap_open >= 0 && gap_open <= 100 && gap_extend >= 0;
     for (int f = 0; f < nfamilies; ++f) {
         const tredsw_family &g = h_families[f];
         if (g.prefix_len < 1 || g.prefix_len > 32 || g.suffix_len < 1 || g.suffix_len > 32 || g.period < 1 ||
@@ -710,8 +736,8 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     }
     const int max_rows = max_m > 0 ? max_m : 1;
     const size_t rows_alloc = (size_t)max_rows + 2;
-    const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + 64;
-    if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for the shared-memory boundary column (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
+    const size_t smem = rows_alloc * 32 + 64;
+    if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for shared memory (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
     ClassifyParams p{};
     p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
     int32_t *w = d_work;
@@ -720,10 +746,6 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     CUDA_TRY(cudaMemsetAsync(d_count, 0, nfamilies * sizeof(int32_t), ctx->stream));
     const int tb = 256, nb = (nreads + tb - 1) / tb;
     fam_count_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_count);
-    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_fam_start, d_chunk_start, d_cursor);
-    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_cursor, d_order, p.out);
-    CUDA_TRY(cudaGetLastError());
-    ctx->launches += 3;
     p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
     p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
     p.allow_fast = allow_fast ? 1 : 0;
@@ -732,19 +754,32 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     const int nitems_bound = nreads / 32 + nfamilies + 1;
     int rc, nctas = 0;
-    if ((rc = persistent_ctas(ctx, smem, &nctas))) return rc;
+    if ((rc = persistent_ctas(ctx, smem, need_fast, need_generic, &nctas))) return rc;
     if (nctas > nitems_bound) nctas = nitems_bound;
     // per-CTA scratch: scores [2*max_u][32] u16, potentials [rows][32] u32, then the two work counters
     const size_t score_bytes = (size_t)nctas * 2 * max_u * 32 * sizeof(uint16_t);
     const size_t pot_bytes = (size_t)nctas * rows_alloc * 32 * sizeof(uint32_t);
-    const size_t gbnd_bytes = pot_bytes * nslots;
-    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + gbnd_bytes + 16))) return rc;
+    const size_t gbnd_bytes = pot_bytes * (nslots + 1);
+    const size_t perm_bytes = (((size_t)nfamilies * sizeof(int32_t)) + 15) & ~(size_t)15;
+    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + gbnd_bytes + 16 + perm_bytes))) return rc;
     p.score_buf = ctx->d_scratch.as<uint16_t>();
     p.pot_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes);
     p.gbnd_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes);
-    p.nslots = nslots;
+    p.nslots = nslots; p.one = 1u;
     p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes + gbnd_bytes);
     p.max_u = max_u;
+    int32_t *d_perm = p.counter + 4;
+    {   // families by period (stable), so that concurrently running CTAs share strip-loop instantiations
+        std::vector<int32_t> perm(nfamilies);
+        for (int f = 0; f < nfamilies; ++f) perm[f] = f;
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return h_families[a].period < h_families[b].period; });
+        CUDA_TRY(cudaMemcpyAsync(d_perm, perm.data(), nfamilies * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    p.fam_perm = d_perm;
+    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_perm, d_fam_start, d_chunk_start, d_cursor);
+    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_cursor, d_order, p.out);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
     CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
     ctx->mark(0);
     if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nctas, smem))) return rc; }
