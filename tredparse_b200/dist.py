@@ -1,0 +1,106 @@
+"""
+Multi-GPU plumbing: (sample, locus) problems are independent (tredparse/tred.py:225-249 reads nothing but
+its own BAM window), so the path shards with NO data-path collective — the only exchanges are the final
+host gather of per-problem results (the reference's analogue: ``Pool.imap`` returning dicts,
+tred.py:528-532) and the max / sum of timings and counters that ``bench.py`` reports.
+
+One process per GPU under ``torch.distributed`` (backend ``nccl`` on the GPU box, ``gloo`` in the CPU
+tests); every helper degrades to the single-process case when the process group is not initialised.
+"""
+import os
+
+import numpy as np
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment (defaults: single process)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init(backend, device_id=None):
+    """Initialise the default process group from the environment (MASTER_ADDR defaults to 127.0.0.1)."""
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if not dist.is_initialized():
+        kw = {"device_id": device_id} if device_id is not None else {}
+        dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _active():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def shard_indices(n_items, rank, world, costs=None):
+    """Indices of the problems rank `rank` owns.
+
+    Without costs: round-robin (problem i -> rank i % world), which keeps every sample's loci spread over
+    all GPUs.  With per-problem costs (e.g. reads x template cells): longest-processing-time greedy, ties
+    broken by index so that every rank computes the same partition without communicating."""
+    if costs is None:
+        return list(range(rank, n_items, world))
+    order = sorted(range(n_items), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += float(costs[i])
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def gather_records(local, indices, n_total, dst=0):
+    """Host gather of per-problem result records (a numpy structured/plain array, one row per owned
+    problem) into problem order on rank `dst`; other ranks get None.  `indices` = shard_indices(...)."""
+    local = np.ascontiguousarray(local)
+    if not _active():
+        out = np.zeros((n_total,) + local.shape[1:], dtype=local.dtype)
+        out[np.asarray(indices, dtype=np.int64)] = local
+        return out
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    payload = (np.asarray(indices, dtype=np.int64), local.view(np.uint8).reshape(len(local), -1) if len(local) else
+               np.zeros((0, local.dtype.itemsize), np.uint8))
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object(payload, bucket, dst=dst)
+    if rank != dst:
+        return None
+    out = np.zeros((n_total,) + local.shape[1:], dtype=local.dtype)
+    flat = out.view(np.uint8).reshape(n_total, -1)
+    seen = np.zeros(n_total, dtype=bool)
+    for idx, rows in bucket:
+        if len(idx):
+            assert not seen[idx].any(), "a problem was computed by two ranks"
+            flat[idx] = rows
+            seen[idx] = True
+    assert seen.all(), "some problems were computed by no rank"
+    return out
+
+
+def reduce_max_sum(maxima, sums, device="cpu"):
+    """(max over ranks of each entry of `maxima`, sum over ranks of each entry of `sums`) as float lists —
+    the timing (max) and unit counters (sum) of bench.py.  Identity without a process group."""
+    if not _active():
+        return [float(x) for x in maxima], [float(x) for x in sums]
+    import torch
+    import torch.distributed as dist
+    a = torch.tensor([float(x) for x in maxima], dtype=torch.float64, device=device)
+    b = torch.tensor([float(x) for x in sums], dtype=torch.float64, device=device)
+    if len(maxima):
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+    if len(sums):
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    return [float(x) for x in a.cpu()], [float(x) for x in b.cpu()]
+
+
+def barrier():
+    if _active():
+        import torch.distributed as dist
+        dist.barrier()
