@@ -40,9 +40,10 @@ READLEN = 150
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--samples", type=int, default=192, help="samples per GPU per step (x 30 loci)")
+    p.add_argument("--samples", type=int, default=384, help="samples per GPU per step (x 30 loci)")
+    p.add_argument("--depth", type=int, default=2, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
     p.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -83,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -127,6 +128,14 @@ def model_tables():
     return step, md["stutter_weights"]
 
 
+def cpu_sample_size(args, cores, nloci):
+    """Bounded CPU sample: whole samples (30 loci each) worth about 12 s of wall time at the ~1.5 loci/s/core
+    the reference path reaches (unmodified ssw.c behind the per-call ctypes pattern + numpy/scipy grid)."""
+    if args.cpu_sample:
+        return max(1, args.cpu_sample // nloci)
+    return max(1, min(16, int(round(12.0 * 1.5 * cores / nloci))))
+
+
 def cpu_reference_run(problems, cores=None):
     """Time the reference-shaped CPU path on `problems`; returns (loci/s, seconds, cores, reads, cells, kind)."""
     from oracle import ref_percall, sw
@@ -153,8 +162,7 @@ def run_reference(args, rank):
     repo = TREDsRepo()
     names = distinct_loci(repo)
     cores = os.cpu_count() or 1
-    # bounded sample: whole samples (30 loci each), about two problems per core, capped
-    nsamp = args.cpu_sample // len(names) if args.cpu_sample else max(1, min(8, (2 * cores) // len(names) + 1))
+    nsamp = cpu_sample_size(args, cores, len(names))
     problems = simulate.simulate_cohort(repo, names, nsamp, readlen=READLEN)
     times = []
     for it in range(args.warmup + args.steps):
@@ -191,15 +199,14 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from tredparse_b200 import _lib, cohort, simulate
+    from tredparse_b200 import _lib, cohort, simulate, dist as tdist
     from tredparse_b200.meta import TREDsRepo
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (tredparse_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tdist.init("nccl", device_id=torch.device("cuda", local_rank))
 
     repo = TREDsRepo()
     names = distinct_loci(repo)
@@ -246,48 +253,53 @@ def main():
         e1.record(stream)
     stream.synchronize()
     barrier()
-    clocks = sampler.stop()
     launches = ctx.launches - launches0
     ms = e0.elapsed_time(e1)
     calls_dev = batch.calls_from_device()
 
     # ---- end to end through the C ABI with pinned host buffers -------------------------------------
+    # Every step copies its inputs H2D from pinned memory and its calls D2H inside the timed region;
+    # `depth` calls are kept in flight (cohort streaming: the copy of batch k+1 overlaps the kernels of k).
     def pin(a):
         t = torch.from_numpy(a.view(np.uint8) if a.dtype.fields else a).pin_memory()
         return t.numpy().view(a.dtype) if a.dtype.fields else t.numpy()
     for name in ("rbuf", "roff", "read_problem", "problems", "pe_lens"):
         setattr(batch, name, pin(getattr(batch, name)))
-    for _ in range(2):
-        host = batch.run_host(ctx=ctx)
+    pipe = cohort.HostPipeline(local_rank, depth=max(1, args.depth))
+    for host in pipe.map([batch] * (2 * max(1, args.depth))):
+        pass
     barrier()
+    e2e_launch0 = pipe.launches
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        host = batch.run_host(ctx=ctx)
+    for host in pipe.map([batch] * args.steps):
+        pass
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()
+    e2e_launches = pipe.launches - e2e_launch0
+    pipe.close()
     assert host["calls"].tobytes() == calls_dev.tobytes(), "device-resident and host paths disagree"
 
-    # ---- reduce over ranks --------------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
-        cnt = torch.tensor([batch.nproblems, batch.nreads, int(st[0]), int(st[1]), int(st[2]), int(st[4]), launches],
-                           dtype=torch.float64, device="cuda")
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        nprob, nreads, alg_cells, ex1, ex2, points, launches = [float(x) for x in cnt]
-    else:
-        nprob, nreads, alg_cells, ex1, ex2, points = batch.nproblems, batch.nreads, int(st[0]), int(st[1]), int(st[2]), int(st[4])
+    # ---- reduce over ranks: timings MAX, unit counters SUM (no data-path collective anywhere) --------
+    (ms, t_e2e_ms), cnt = tdist.reduce_max_sum(
+        [ms, t_e2e * 1e3],
+        [batch.nproblems, batch.nreads, int(st[0]), int(st[1]), int(st[2]), int(st[4]), launches],
+        device="cuda" if world > 1 else "cpu")
+    t_e2e = t_e2e_ms / 1e3
+    nprob, nreads, alg_cells, ex1, ex2, points, launches = cnt
 
     if rank == 0:
         sec = ms / 1e3
         value = nprob * args.steps / sec
-        # roofline of the dominant kernel (this rank's launch): integer / DPX pipe.
-        # executed lane-instructions: phase 1 = 7 packed DPX/PRMT instructions per cell pair (two cells),
-        # phase 2 = 8 scalar instructions per cell (DESIGN.md "SW kernel: instruction budget").
+        # roofline of the dominant kernel (this rank's launch): integer (ALU) pipe.
+        # executed ALU lane-instructions = executed DP cells x ALU_PER_CELL.  ALU_PER_CELL is calibrated on the
+        # committed ncu capture of this kernel (profiles/: sm__inst_executed_pipe_alu x 32 lanes / executed
+        # cells): 5.8 ALU instructions per packed cell pair (4 for the cell, 0.5 running max, 0.67 suffix
+        # hooks, byte (un)packing) -> 2.9 per cell; the few scalar phase-2 cells cost ~9 each.
+        ALU_PER_CELL, ALU_PER_SCALAR_CELL = 2.9, 9.0
         sw_s = stage["sw"] / 1e3
-        lane_instr = (int(st[1]) / 2.0) * 7.0 + int(st[2]) * 8.0
+        lane_instr = int(st[1]) * ALU_PER_CELL + int(st[2]) * ALU_PER_SCALAR_CELL
         achieved = lane_instr / sw_s / 1e9
         hbm, hbm_src = peaks()
         grid_bytes = 8.0 * int(st[4]) * 2            # surface written once, read once by the reduction
@@ -308,13 +320,15 @@ def main():
             "sw_gcups_executed": (ex1 + ex2) * args.steps / sec / 1e9,
             "e2e": {"value": nprob * args.steps / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes),
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches),
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "calls_in_flight": max(1, args.depth)},
+            "gpu_launches": int(launches) + int(e2e_launches),
             "clocks": clocks,
             "roofline": {"kernel": "classify_kernel<P> (sw_family.cu), all period instantiations of one step",
                          "bound": "int", "achieved": achieved, "peak": int_peak, "unit": "G lane-instr/s",
                          "frac": achieved / int_peak, "traffic": None,
-                         "peak_source": "tredsw_int_pipe_peak (VIADDMNMX.S16x2 register loop) measured in this run",
+                         "peak_source": "tredsw_int_pipe_peak (VIADDMNMX.S16x2 register loop, 64 lanes/clk/SM) measured in this run; "
+                                        "achieved = executed DP cells x 2.9 ALU instr/cell (calibrated on the ncu capture in profiles/)",
+                         "algorithmic_int_ops_per_s": 10.0 * int(st[0]) / sw_s,
                          "kernel_ms": stage["sw"], "share_of_step": stage["sw"] / max(stage["total"], 1e-9),
                          "executed_gcups": (int(st[1]) + int(st[2])) / sw_s / 1e9,
                          "algorithmic_gcups": int(st[0]) / sw_s / 1e9},
@@ -328,7 +342,7 @@ def main():
         if not args.no_cpu_baseline:
             try:
                 cores = os.cpu_count() or 1
-                nsamp = args.cpu_sample // len(names) if args.cpu_sample else max(1, min(8, (2 * cores) // len(names) + 1))
+                nsamp = min(cpu_sample_size(args, cores, len(names)), args.samples)
                 sample_problems = problems[:nsamp * len(names)]
                 v, dt, used, reads, cells, kind, res = cpu_reference_run(sample_problems, cores)
                 # the sample doubles as a parity check of the GPU calls

@@ -182,6 +182,57 @@ class CohortBatch:
         return self._dev["calls"].cpu().numpy().view(CALL_DTYPE)
 
 
+class HostPipeline:
+    """Keeps `depth` host-buffer calls in flight on one GPU: every slot owns a context (its own stream and
+    staging buffers) and a host thread, so the H2D copy of one batch overlaps the kernels of the previous
+    one and the tail of one step is filled by the head of the next.  This is the cohort-streaming pattern
+    (read BAM windows of batch k+1 while batch k is on the GPU); ctypes releases the GIL during the call.
+
+        with HostPipeline(device=0, depth=2) as pipe:
+            for out in pipe.map(batches):        # results in submission order
+                ...
+    """
+
+    def __init__(self, device=0, depth=2):
+        from concurrent.futures import ThreadPoolExecutor
+        import queue
+        self.contexts = [_lib.Context(device) for _ in range(depth)]
+        self._free = queue.Queue()
+        for c in self.contexts:
+            self._free.put(c)
+        self._pool = ThreadPoolExecutor(max_workers=depth)
+
+    def _run(self, batch, kwargs):
+        ctx = self._free.get()
+        try:
+            return batch.run_host(ctx=ctx, **kwargs)
+        finally:
+            self._free.put(ctx)
+
+    def submit(self, batch, **kwargs):
+        return self._pool.submit(self._run, batch, kwargs)
+
+    def map(self, batches, **kwargs):
+        futures = [self.submit(b, **kwargs) for b in batches]
+        for f in futures:
+            yield f.result()
+
+    @property
+    def launches(self):
+        return sum(c.launches for c in self.contexts)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for c in self.contexts:
+            c.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def decode_call(call, period=None):
     """tredsw_call record -> dict with the reference's field names."""
     missing = call["allele1"] < 0
@@ -193,5 +244,6 @@ def decode_call(call, period=None):
 
 
 def shard(n_items, rank, world):
-    """Static round-robin partition of (sample, locus) problems over GPUs (no collective)."""
-    return list(range(rank, n_items, world))
+    """Static round-robin partition of (sample, locus) problems over GPUs (no collective); see dist.py."""
+    from .dist import shard_indices
+    return shard_indices(n_items, rank, world)

@@ -337,7 +337,9 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     }
     plan_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd);
     ctx->mark(4);
-    cohort_kde_kernel<<<np_ < ctx->sm_count * 2 ? np_ : ctx->sm_count * 2, 1024, 0, ctx->stream>>>(cd, d_ipool);
+    // one block per problem (most exit at once: only problems with run_pe need the KDE); the hardware block
+    // scheduler balances the sparse, uneven survivors better than a strided loop would
+    cohort_kde_kernel<<<np_, 1024, 0, ctx->stream>>>(cd, d_ipool);
     ctx->mark(5);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 3;

@@ -136,21 +136,63 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
     return ml;
 }
 
-// grid: x = tiles of points, y = problem
-__global__ void __launch_bounds__(256) grid_surface_kernel(GridParams g, int nproblems) {
-    for (int pi = blockIdx.y; pi < nproblems; pi += gridDim.y) {
-        const tredsw_grid_problem P = g.prob[pi];
-        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-        const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
-        double *surf = g.surface + P.off_surface;
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-             t += (long long)gridDim.x * blockDim.x) {
+// The surfaces of a batch differ in size by orders of magnitude (a handful of points for a locus with
+// spanning reads only, 10^4-10^6 when the h2 range is extended or with --fullsearch), so the points of all
+// problems are flattened into tiles of GRID_TILE points: tile_start = exclusive prefix sum of the tiles per
+// problem (device scan), then a persistent kernel strides over the tiles.
+constexpr int GRID_TILE = 256;
+
+__global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_problem *prob, int nproblems,
+                                                          long long *tile_start) {
+    __shared__ long long part[1024];
+    const int tid = threadIdx.x;
+    const int chunk = (nproblems + 1023) / 1024;
+    const int lo = min(nproblems, tid * chunk), hi = min(nproblems, lo + chunk);
+    auto tiles_of = [&](int i) {
+        const long long t = prob[i].n_h2 > 0 ? (long long)prob[i].n_h1 * prob[i].n_h2 : 0;
+        return (t + GRID_TILE - 1) / GRID_TILE;
+    };
+    long long s = 0;
+    for (int i = lo; i < hi; ++i) s += tiles_of(i);
+    part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {               // inclusive Hillis-Steele scan of the partial sums
+        const long long v = tid >= d ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    long long run = part[tid] - s;
+    for (int i = lo; i < hi; ++i) { tile_start[i] = run; run += tiles_of(i); }
+    if (tid == 1023) tile_start[nproblems] = part[1023];
+}
+
+__global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, int nproblems, const long long *tile_start) {
+    const long long ntiles = tile_start[nproblems];
+    __shared__ int s_pi;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) {                        // tile -> problem: last p with tile_start[p] <= tile
+            int lo = 0, hi = nproblems;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (tile_start[mid] <= tile) lo = mid; else hi = mid;
+            }
+            s_pi = lo;
+        }
+        __syncthreads();
+        const int pi = s_pi;
+        __syncthreads();
+        const tredsw_grid_problem &P = g.prob[pi];
+        const long long total = (long long)P.n_h1 * P.n_h2;
+        const long long t = (tile - tile_start[pi]) * GRID_TILE + threadIdx.x;
+        if (t < total) {
+            const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
             const int i1 = (int)(t / P.n_h2), i2 = (int)(t % P.n_h2);
             const int h1 = h1s[i1];
             const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
             double ml = -INFINITY;
             if (h1 <= h2) ml = point_ml(P, g, h1, h2);
-            surf[t] = ml;
+            g.surface[P.off_surface + t] = ml;
         }
     }
 }
@@ -264,13 +306,15 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     g.small_value = exp(-10.0);
     g.really_small = exp(-100.0);
     g.log_small = log(g.small_value);
-    long long tiles = (points_hint + 255) / 256;
-    if (tiles < 1) tiles = 1;
-    int gx = (int)(tiles > 4096 ? 4096 : tiles);
-    int gy = nproblems > 65535 ? 65535 : nproblems;
+    (void)points_hint;
+    int rc;
+    if ((rc = ctx->d_tiles.ensure(((size_t)nproblems + 1) * sizeof(long long)))) return rc;
+    long long *d_tiles = ctx->d_tiles.as<long long>();
     ctx->mark(2);
-    grid_surface_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, nproblems);
+    grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_tiles);
+    grid_surface_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tiles);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
     int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
     grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
     CUDA_TRY(cudaGetLastError());
