@@ -28,6 +28,7 @@
 #include "sw_sweep.cuh"
 #include <type_traits>
 #include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -652,12 +653,70 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
 }
 
 // ---- grouping of reads by family on the device (counting sort) ------------------------------------
-__global__ void fam_count_kernel(const int32_t *read_family, int nreads, int nfam, int32_t *count) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- exact q-gram pre-filter --------------------------------------------------------------------------
+// About half of the reads fetched around a locus (bam_parser.py:206-214 takes everything in the window)
+// cannot pass min_score = max(min_len, 30) (bam_parser.py:134) against any template: they lie in the
+// flanking genome.  q-gram lemma for this scoring: an alignment with score S >= 30 has M matches, X
+// mismatches and g gap runs with M - b X - go g >= 30; its matches form at most X + g + Z + 1 exact runs
+// (Z = aligned N bases, which score 0), and a run of length r shares r - q + 1 q-grams with the template:
+//     shared q-grams >= 30 + X (b - (q-1)) + g (go - (q-1)) - (q-1)(Z + 1) >= 30 - (q-1)(Z + 1)
+// for q - 1 <= min(b, go).  So a read with fewer than 30 - (q-1)(#N + 1) positions whose q-gram occurs in
+// ANY template of the family (per strand) has no candidate at all: it is given the "no tag" record here
+// and never reaches the Smith-Waterman kernel.  Exact — no alignment is lost (parity tests cover it).
+struct QgramInfo { int q; int min_score; };       // q == 0: filter off for this family (N in the templates)
+constexpr int QTAB_WORDS = 256;                   // 4096 six-mers x 2 bits (forward / reverse-complement templates)
+
+__global__ void prefilter_kernel(const int8_t *rbuf, const int64_t *roff, int nreads, const int32_t *read_family,
+                                 int nfam, const tredsw_family *families, const uint32_t *qtab, const QgramInfo *qinfo,
+                                 int b_minus, int32_t *eff_family, unsigned long long *stats) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long alg = 0; unsigned nal = 0;
     if (r < nreads) {
         int f = read_family[r];
-        if (f >= 0 && f < nfam) atomicAdd(&count[f], 1);
+        if (f < 0 || f >= nfam) f = -1;
+        if (f >= 0 && qinfo[f].q > 0) {
+            const int q = qinfo[f].q;
+            const uint32_t mask = (1u << (2 * q)) - 1u;
+            const uint32_t *tab = qtab + (size_t)f * QTAB_WORDS;
+            const int8_t *s = rbuf + roff[r];
+            const int m = (int)(roff[r + 1] - roff[r]);
+            uint32_t code = 0; int run = 0, nN = 0, hf = 0, hr = 0;
+            for (int j = 0; j < m; ++j) {
+                const int c = s[j];
+                if (c < 0 || c > 3) { ++nN; run = 0; continue; }
+                code = ((code << 2) | (uint32_t)c) & mask;
+                if (++run >= q) {
+                    const uint32_t e = (tab[code >> 4] >> ((code & 15u) * 2u)) & 3u;
+                    hf += e & 1u; hr += e >> 1;
+                }
+            }
+            const int thr = qinfo[f].min_score - (q - 1) * (nN + 1);
+            if (hf < thr && hr < thr) {
+                if (stats) {
+                    const tredsw_family &g = families[f];
+                    unsigned long long sum_n = 0;
+                    for (int u = 1; u <= g.max_units; ++u) sum_n += 2ull * (unsigned long long)(g.prefix_len + g.suffix_len + g.period * u);
+                    alg = (unsigned long long)m * sum_n; nal = 2u * (unsigned)g.max_units;
+                }
+                f = -2;
+            }
+        }
+        eff_family[r] = f;
     }
+    if (stats) {
+        for (int d = 16; d > 0; d >>= 1) { alg += __shfl_down_sync(0xffffffffu, alg, d); nal += __shfl_down_sync(0xffffffffu, nal, d); }
+        if ((threadIdx.x & 31) == 0 && alg) { atomicAdd(&stats[0], alg); atomicAdd(&stats[3], (unsigned long long)nal); }
+    }
+}
+
+// (reads arrive grouped by problem, so the lanes of a warp mostly share one family: the atomics are
+//  aggregated per warp and distinct family — one atomic instead of up to 32 on the same counter)
+__global__ void fam_count_kernel(const int32_t *read_family, int nreads, int nfam, int32_t *count) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = r < nreads ? read_family[r] : -1;
+    if (f >= nfam) f = -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, f);
+    if (f >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[f], __popc(peers));
 }
 // single block: exclusive scans -> fam_start, chunk_start; cursor := fam_start
 __global__ void fam_scan_kernel(const int32_t *count, int nfam, const int32_t *perm, int32_t *fam_start,
@@ -672,11 +731,20 @@ __global__ void fam_scan_kernel(const int32_t *count, int nfam, const int32_t *p
 }
 __global__ void fam_scatter_kernel(const int32_t *read_family, int nreads, int nfam, int32_t *cursor,
                                    int32_t *order, int32_t *out) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int f = r < nreads ? read_family[r] : -1;
+    if (f >= nfam) f = -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, f);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (f >= 0 && lane == leader) base = atomicAdd(&cursor[f], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
     if (r < nreads) {
-        int f = read_family[r];
-        if (f >= 0 && f < nfam) order[atomicAdd(&cursor[f], 1)] = r;
-        else { int32_t *o = out + (int64_t)r * 8; o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = -1; }
+        if (f >= 0) order[base + __popc(peers & ((1u << lane) - 1u))] = r;
+        else if (f == -2) {      // pre-filtered: the record of a read without candidates
+            int32_t *o = out + (int64_t)r * 8; o[0] = TREDSW_TAG_NONE; o[1] = 0; o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = -1;
+        } else { int32_t *o = out + (int64_t)r * 8; o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = -1; }
     }
 }
 
@@ -745,7 +813,6 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
             *d_cursor = d_chunk_start + nfamilies + 1, *d_order = d_cursor + nfamilies;
     CUDA_TRY(cudaMemsetAsync(d_count, 0, nfamilies * sizeof(int32_t), ctx->stream));
     const int tb = 256, nb = (nreads + tb - 1) / tb;
-    fam_count_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_count);
     p.order = d_order; p.fam_start = d_fam_start; p.chunk_start = d_chunk_start;
     p.nfamilies = nfamilies; p.go = gap_open; p.ge = gap_extend; p.max_rows = max_rows;
     p.allow_fast = allow_fast ? 1 : 0;
@@ -761,7 +828,10 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     const size_t pot_bytes = (size_t)nctas * rows_alloc * 32 * sizeof(uint32_t);
     const size_t gbnd_bytes = pot_bytes * (nslots + 1);
     const size_t perm_bytes = (((size_t)nfamilies * sizeof(int32_t)) + 15) & ~(size_t)15;
-    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + gbnd_bytes + 16 + perm_bytes))) return rc;
+    const size_t qtab_bytes = (size_t)nfamilies * QTAB_WORDS * sizeof(uint32_t);
+    const size_t qinfo_bytes = (((size_t)nfamilies * sizeof(QgramInfo)) + 15) & ~(size_t)15;
+    const size_t eff_bytes = (((size_t)nreads * sizeof(int32_t)) + 15) & ~(size_t)15;
+    if ((rc = ctx->d_scratch.ensure(score_bytes + pot_bytes + gbnd_bytes + 16 + perm_bytes + qtab_bytes + qinfo_bytes + eff_bytes))) return rc;
     p.score_buf = ctx->d_scratch.as<uint16_t>();
     p.pot_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes);
     p.gbnd_buf = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes);
@@ -776,12 +846,71 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
         CUDA_TRY(cudaMemcpyAsync(d_perm, perm.data(), nfamilies * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     p.fam_perm = d_perm;
-    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_perm, d_fam_start, d_chunk_start, d_cursor);
-    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_read_family, nreads, nfamilies, d_cursor, d_order, p.out);
-    CUDA_TRY(cudaGetLastError());
-    ctx->launches += 3;
-    CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
+    // q-gram pre-filter tables: per family 4096 x 2 bits (q-grams of all forward / all reverse-complement templates)
+    uint32_t *d_qtab = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(d_perm) + perm_bytes);
+    QgramInfo *d_qinfo = reinterpret_cast<QgramInfo *>(reinterpret_cast<unsigned char *>(d_qtab) + qtab_bytes);
+    int32_t *d_eff = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(d_qinfo) + qinfo_bytes);
+    int b_minus = 0;
+    {
+        // q - 1 <= min(mismatch penalty, gap open); only for match == 1 and N scoring <= 0 everywhere
+        int max_off = -128; bool n_ok = true, diag_ok = true;
+        for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) {
+            const int v = mat25[i * 5 + j];
+            if (i == 4 || j == 4) { if (v > 0) n_ok = false; }
+            else if (i == j) { if (v != 1) diag_ok = false; }
+            else if (v > max_off) max_off = v;
+        }
+        b_minus = -max_off;
+        int q = 6;
+        if (q > b_minus + 1) q = b_minus + 1;
+        if (q > gap_open + 1) q = gap_open + 1;
+        static const bool env_off = getenv("TREDSW_NO_PREFILTER") != nullptr;
+        const bool usable = n_ok && diag_ok && q >= 4 && !env_off;
+        std::vector<uint32_t> tab((size_t)nfamilies * QTAB_WORDS, 0u);
+        std::vector<QgramInfo> info(nfamilies);
+        std::vector<int8_t> t;
+        for (int f = 0; f < nfamilies; ++f) {
+            const tredsw_family &g = h_families[f];
+            bool hasN = false;
+            for (int i = 0; i < g.prefix_len; ++i) if (g.prefix[i] < 0 || g.prefix[i] > 3) hasN = true;
+            for (int i = 0; i < g.suffix_len; ++i) if (g.suffix[i] < 0 || g.suffix[i] > 3) hasN = true;
+            for (int i = 0; i < g.period; ++i) if (g.repeat[i] < 0 || g.repeat[i] > 3) hasN = true;
+            info[f].q = (usable && !hasN) ? q : 0;
+            info[f].min_score = 30;                         // bam_parser.py:134: min_score = max(min_len, 30)
+            if (!info[f].q) continue;
+            // every q-gram of a template with u >= u0 units already occurs in the template with u0 units
+            const int u0 = (q - 1 + g.period - 1) / g.period + 1;
+            const uint32_t mask = (1u << (2 * q)) - 1u;
+            uint32_t *tf = tab.data() + (size_t)f * QTAB_WORDS;
+            for (int u = 1; u <= std::min(g.max_units, u0 + 1); ++u) {
+                t.clear();
+                for (int i = 0; i < g.prefix_len; ++i) t.push_back(g.prefix[i]);
+                for (int k = 0; k < u; ++k) for (int i = 0; i < g.period; ++i) t.push_back(g.repeat[i]);
+                for (int i = 0; i < g.suffix_len; ++i) t.push_back(g.suffix[i]);
+                const int n = (int)t.size();
+                uint32_t cf = 0, cr = 0;
+                for (int i = 0; i < n; ++i) {
+                    cf = ((cf << 2) | (uint32_t)t[i]) & mask;                       // forward template, left to right
+                    cr = ((cr << 2) | (uint32_t)(3 - t[n - 1 - i])) & mask;         // its reverse complement, left to right
+                    if (i >= q - 1) {
+                        tf[cf >> 4] |= 1u << ((cf & 15u) * 2u);
+                        tf[cr >> 4] |= 2u << ((cr & 15u) * 2u);
+                    }
+                }
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_qtab, tab.data(), qtab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_qinfo, info.data(), nfamilies * sizeof(QgramInfo), cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->mark(0);
+    prefilter_kernel<<<nb, tb, 0, ctx->stream>>>(d_rbuf, d_roff, nreads, d_read_family, nfamilies, d_families, d_qtab,
+                                                 d_qinfo, b_minus, d_eff, d_stats);
+    fam_count_kernel<<<nb, tb, 0, ctx->stream>>>(d_eff, nreads, nfamilies, d_count);
+    fam_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_count, nfamilies, d_perm, d_fam_start, d_chunk_start, d_cursor);
+    fam_scatter_kernel<<<nb, tb, 0, ctx->stream>>>(d_eff, nreads, nfamilies, d_cursor, d_order, p.out);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 4;
+    CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
     if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nctas, smem))) return rc; }
     if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nctas, smem))) return rc; }
     ctx->mark(1);
