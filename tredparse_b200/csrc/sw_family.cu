@@ -128,6 +128,11 @@ constexpr int STAB_PAD = 36;       // words per query-code row of the score tabl
 
 // Columns per main strip: K whole repeat units, about 24 columns.
 __host__ __device__ constexpr int strip_units(int P) { return P >= 24 ? 1 : 24 / P; }
+// The strip loops are instantiated per period PI; a family whose period is G * PI (G = 2, 4) runs through the
+// PI instantiation with "sub-units" of PI columns — the hooks of every G-th sub-unit are its real units.
+// Fewer distinct loop bodies run at the same time (25 of the 30 catalogue loci have period 3, three more 6
+// or 12): they compete for the instruction cache, see DESIGN.md.
+__host__ __device__ constexpr int instance_period(int P) { return (P == 6 || P == 12) ? 3 : P; }
 
 // One pass over all query rows of a strip of NC template columns made of K = NC / PER units of PER
 // columns (previous-row H and running F of every strip column in registers).  Two rows are in flight per
@@ -316,7 +321,13 @@ __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t
     auto code_at = [&](int j) { return j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
     auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
     uint32_t bA = bin[0], bB = bin[32];
+    // capture without branches: unit k's leaving H / E~ are ANDed with an all-ones mask only for k == kstar
+    constexpr int KU = CAPTURE ? NC / PER : 1;
+    uint32_t kmask[KU];
+#pragma unroll
+    for (int k = 0; k < KU; ++k) kmask[k] = (CAPTURE && k == kstar) ? 0xffffffffu : 0u;
     for (int j = 0; j < rows2; j += 2) {
+        uint32_t capHA = 0, capEA = 0, capHB = 0, capEB = 0;
         const uint32_t hinA = sw_prmt(bA, 0, 0x4140), hinB = sw_prmt(bB, 0, 0x4140);
         uint32_t eA = sw_prmt(bA, 0, 0x4342), eB = sw_prmt(bB, 0, 0x4342);
         const int jn = min(j + 2, rows2 - 2);
@@ -339,16 +350,17 @@ __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t
             if (s < NC) {
                 PACKED_CELL(hdA, eA, sA[s], s, hA)
                 keyA = hA * 256u + rcA;                          // IMAD on the FMA pipe: H < 256 per half
-                if (CAPTURE && s % PER == PER - 1) { if (kstar == s / PER) bout[j * 32] = sw_prmt(hA, eA, 0x6420); }
+                if (CAPTURE && s % PER == PER - 1) { capHA |= hA & kmask[s / PER]; capEA |= eA & kmask[s / PER]; }
             }
             if (s >= 1) {
                 PACKED_CELL(hdB, eB, sB[s - 1], s - 1, hB)
                 const uint32_t keyB = hB * 256u + rcB;
                 colkey[s - 1] = __vimax3_u16x2(colkey[s - 1], keyA_prev, keyB);
-                if (CAPTURE && (s - 1) % PER == PER - 1) { if (kstar == (s - 1) / PER) bout[(j + 1) * 32] = sw_prmt(hB, eB, 0x6420); }
+                if (CAPTURE && (s - 1) % PER == PER - 1) { capHB |= hB & kmask[(s - 1) / PER]; capEB |= eB & kmask[(s - 1) / PER]; }
             }
             keyA_prev = keyA;
         }
+        if (CAPTURE) { bout[j * 32] = sw_prmt(capHA, capEA, 0x6420); bout[(j + 1) * 32] = sw_prmt(capHB, capEB, 0x6420); }
     }
 }
 
@@ -361,8 +373,8 @@ __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t
 template <int P>
 __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           const uint32_t *gbnd, int R, int go, int ge, uint32_t one, int cs, int u,
-                                           int strand, int *end_ref, int *end_read, unsigned long long &cells) {
+                                           const uint32_t *gbnd, int R, int go, int ge, uint32_t one, int G, int cs,
+                                           int u, int strand, int *end_ref, int *end_read, unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
@@ -370,7 +382,8 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
     const uint32_t go2 = (uint32_t)go * 0x00010001u;
     const int rows2 = (m_warp + 1) & ~1;
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
-    const int tstar = (u - 1) / K, kstar = (u - 1) % K;      // lanes without a candidate pass u = 1
+    const int su = G * u - 1;                                // last sub-unit of unit u (lanes without a candidate: u = 1)
+    const int tstar = su / K, kstar = su % K;                // (K is a multiple of G: units do not straddle strips)
     const int sh = strand ? 16 : 0;
     int found_col = -1, found_row = 0;
     {
@@ -381,7 +394,7 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
 #pragma unroll
         for (int c = NC - 1; c >= 0; --c) {
             const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
-            if (c / P == kstar && (int)(k16 >> 8) == cs) { found_col = FLANK + (tstar * K) * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+            if (c / P <= kstar && c / P > kstar - G && (int)(k16 >> 8) == cs) { found_col = FLANK + (tstar * K) * P + c; found_row = 255 - (int)(k16 & 0xffu); }
         }
     }
     __syncwarp();
@@ -397,7 +410,7 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
 #pragma unroll
             for (int c = FLANK - 1; c >= 0; --c) {
                 const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
-                if ((int)(k16 >> 8) == cs) { found_col = FLANK + u * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+                if ((int)(k16 >> 8) == cs) { found_col = FLANK + u * F.P + c; found_row = 255 - (int)(k16 & 0xffu); }
             }
         }
     }
@@ -409,7 +422,7 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
 template <int P>
 __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *pot,
-                                           uint32_t *gbnd, int R, uint8_t *scores, int go, int ge, uint32_t one,
+                                           uint32_t *gbnd, int R, uint8_t *scores, int go, int ge, uint32_t one, int G,
                                            unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
@@ -441,12 +454,12 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
     }
     __syncwarp();
     // ---- main strips: K repeat units each; the suffix of every template is folded in by the potentials --
-    for (int c = lane; c < NC; c += 32) colsel[c] = sel2(F.repeat[c % P], comp(F.repeat[P - 1 - c % P]));
+    for (int c = lane; c < NC; c += 32) colsel[c] = sel2(F.repeat[c % F.P], comp(F.repeat[F.P - 1 - c % F.P]));
     __syncwarp();
     build_stab(stab, lut, lane, NC, colsel, go2);
     __syncwarp();
     int nstrips = 0;
-    for (int u0 = 0; u0 < F.U; u0 += K, ++nstrips) {
+    for (int u0 = 0; u0 < F.U * G; u0 += K, ++nstrips) {        // u0, u: sub-units of P columns
         uint32_t seg[K], mu[K];
 #pragma unroll
         for (int u = 0; u < K; ++u) { seg[u] = 0; mu[u] = 0; }
@@ -456,10 +469,12 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             run = __vmaxs2(run, seg[u]);
-            if (u0 + u < F.U) {
+            const int su = u0 + u + 1;                              // sub-units completed
+            if (su % G == 0 && su <= F.U * G) {
+                const int ur = su / G - 1;                          // 0-based real unit
                 const uint32_t best = __vimax3_s16x2(run, mu[u], fresh);
-                scores[(2 * (u0 + u) + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
-                scores[(2 * (u0 + u) + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
+                scores[(2 * ur + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
+                scores[(2 * ur + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
             }
         }
     }
@@ -532,9 +547,9 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         if constexpr (!FAST) {
             phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
         } else {
-            switch (F.P) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, pot, gbnd, R, scores, p.go, p.ge, one, cells1); break;
-                PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
+            switch (instance_period(F.P)) {
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, pot, gbnd, R, scores, p.go, p.ge, one, F.P / PP, cells1); break;
+                PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
 #undef PCASE
             }
         }
@@ -563,9 +578,9 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         if constexpr (FAST) {
             if (FLANK * p.match < 30 && __any_sync(0xffffffffu, cr >= 0)) {
                 const int lu = cr >= 0 ? cr / 2 + 1 : 1, ls = cr >= 0 ? (cr & 1) : 0, lcs = cr >= 0 ? cs : 0x7fff;
-                switch (F.P) {
-#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, one, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
-                    PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11) PCASE(12)
+                switch (instance_period(F.P)) {
+#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, one, F.P / PP, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
+                    PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
 #undef PCASE
                 }
                 if (cr < 0) fast_end_ref = -1;
@@ -798,7 +813,8 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
         bool fast = allow_fast && g.prefix_len == FLANK && g.suffix_len == FLANK && g.period <= 12;
         if (fast) {
             need_fast = true;
-            const int k = strip_units(g.period), slots = (g.max_units + k - 1) / k + 1;
+            const int pi = instance_period(g.period), sub = g.period / pi;      // sub-units per unit
+            const int k = strip_units(pi), slots = (g.max_units * sub + k - 1) / k + 1;
             if (slots > nslots) nslots = slots;
         } else need_generic = true;
     }
@@ -839,10 +855,12 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes + gbnd_bytes);
     p.max_u = max_u;
     int32_t *d_perm = p.counter + 4;
-    {   // families by period (stable), so that concurrently running CTAs share strip-loop instantiations
+    {   // families by loop instantiation (stable), so that concurrently running CTAs share strip-loop code:
+        // measured, mixing instantiations on an SM costs far more than the order could ever gain
         std::vector<int32_t> perm(nfamilies);
         for (int f = 0; f < nfamilies; ++f) perm[f] = f;
-        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return h_families[a].period < h_families[b].period; });
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+            return instance_period(h_families[a].period) < instance_period(h_families[b].period); });
         CUDA_TRY(cudaMemcpyAsync(d_perm, perm.data(), nfamilies * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     p.fam_perm = d_perm;
