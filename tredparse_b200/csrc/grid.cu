@@ -14,6 +14,7 @@
 #include "internal.cuh"
 #include "kde.cuh"
 #include <math.h>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -141,6 +142,7 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
 // problems are flattened into tiles of GRID_TILE points: tile_start = exclusive prefix sum of the tiles per
 // problem (device scan), then a persistent kernel strides over the tiles.
 constexpr int GRID_TILE = 256;
+constexpr int GRID_CLUSTER = 8;       // CTAs per problem in the cluster variant of the reduction
 
 __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_problem *prob, int nproblems,
                                                           long long *tile_start) {
@@ -210,82 +212,122 @@ __device__ __forceinline__ bool pathological(const tredsw_grid_problem &P, int h
     return P.recessive ? (hi <= P.cutoff_risk) : (lo <= P.cutoff_risk);
 }
 
-// one block per problem
-__global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int nproblems) {
+// Reductions of one problem's surface (models.py:277-302, 342-368): max / arg-max with key (ml, -h1, order)
+// (Q10), the exp-normalised marginals P_h1 / P_h2 and the PP sums.  CS = 1: one CTA per problem (the usual
+// handful-to-thousands of points).  CS = 8: a thread-block CLUSTER of 8 CTAs per problem for the large
+// surfaces (extended ranges, --fullsearch: 10^4 - 10^6 points): rows / columns are dealt to the CTAs of the
+// cluster, the per-CTA partial results meet in distributed shared memory in rank order, so the result is
+// deterministic.  Both variants are launched over all problems; each skips the problems of the other class.
+template <int CS>
+__global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int nproblems, long long small_limit) {
+    namespace cg = cooperative_groups;
     __shared__ ArgMax s_best[256];
     __shared__ double s_sum[256], s_path[256];
     __shared__ int s_cnt[256];
-    for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x) {
-        const tredsw_grid_problem P = g.prob[pi];
-        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-        const double *surf = g.surface + P.off_surface;
-        const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
-        ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
-        int cnt = 0;
-        for (long long t = threadIdx.x; t < total; t += blockDim.x) {
-            const double ml = surf[t];
+    __shared__ ArgMax c_best;          // this CTA's partial results, read by the other CTAs of the cluster
+    __shared__ int c_cnt;
+    __shared__ double c_sum, c_path;
+    const int pi = blockIdx.x / CS;
+    unsigned crank = 0;
+    if (CS > 1) crank = cg::this_cluster().block_rank();
+    if (pi >= nproblems) return;
+    const tredsw_grid_problem P = g.prob[pi];
+    const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
+    if (CS == 1 ? total > small_limit : total <= small_limit) return;     // uniform over the cluster
+    const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+    const double *surf = g.surface + P.off_surface;
+    const int tid = threadIdx.x;
+    // ---- max / arg-max / number of evaluated points: rows crank, crank + CS, ... ----------------------
+    ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
+    int cnt = 0;
+    for (int i1 = (int)crank; i1 < P.n_h1; i1 += CS) {
+        const int h1 = h1s[i1];
+        const long long row = (long long)i1 * P.n_h2;
+        for (int i2 = tid; i2 < P.n_h2; i2 += 256) {
+            const double ml = surf[row + i2];
             if (ml == -INFINITY) continue;   // not evaluated (h1 > h2)
             ++cnt;
-            ArgMax c{ml, h1s[t / P.n_h2], t};
+            ArgMax c{ml, h1, row + i2};
             if (better(c, best)) best = c;
         }
-        s_best[threadIdx.x] = best; s_cnt[threadIdx.x] = cnt;
-        __syncthreads();
-        for (int d = blockDim.x / 2; d > 0; d >>= 1) {
-            if (threadIdx.x < d) {
-                if (better(s_best[threadIdx.x + d], s_best[threadIdx.x])) s_best[threadIdx.x] = s_best[threadIdx.x + d];
-                s_cnt[threadIdx.x] += s_cnt[threadIdx.x + d];
-            }
-            __syncthreads();
-        }
-        const ArgMax top = s_best[0];
-        const int npoints = s_cnt[0];
-        __syncthreads();
-        // marginals: P_h1[i1] = sum_i2 w, P_h2[i2] = sum_i1 w, w = exp(ml - max)
-        double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
-        double sum_all = 0.0, sum_path = 0.0;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        for (int i1 = warp; i1 < P.n_h1; i1 += nwarps) {
-            const int h1 = h1s[i1];
-            double acc = 0.0, accp = 0.0;
-            for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
-                const double ml = surf[(long long)i1 * P.n_h2 + i2];
-                if (ml == -INFINITY) continue;
-                const double w = exp(ml - top.ml);
-                acc += w;
-                const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
-                if (pathological(P, h1, h2)) accp += w;
-            }
-            for (int d = 16; d > 0; d >>= 1) {
-                acc += __shfl_down_sync(0xffffffffu, acc, d);
-                accp += __shfl_down_sync(0xffffffffu, accp, d);
-            }
-            if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; }
-        }
-        for (int i2 = threadIdx.x; i2 < P.n_h2; i2 += blockDim.x) {
-            double acc = 0.0;
-            for (int i1 = 0; i1 < P.n_h1; ++i1) {
-                const double ml = surf[(long long)i1 * P.n_h2 + i2];
-                if (ml == -INFINITY) continue;
-                acc += exp(ml - top.ml);
-            }
-            ph2[i2] = acc;
-        }
-        s_sum[threadIdx.x] = sum_all; s_path[threadIdx.x] = sum_path;
-        __syncthreads();
-        for (int d = blockDim.x / 2; d > 0; d >>= 1) {
-            if (threadIdx.x < d) { s_sum[threadIdx.x] += s_sum[threadIdx.x + d]; s_path[threadIdx.x] += s_path[threadIdx.x + d]; }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            tredsw_grid_result r;
-            r.max_ml = top.ml; r.sum_all = s_sum[0]; r.sum_path = s_path[0];
-            r.arg_i1 = npoints ? (int)(top.idx / P.n_h2) : -1;
-            r.arg_i2 = npoints ? (int)(top.idx % P.n_h2) : -1;
-            r.n_points = npoints; r.pad = 0;
-            g.res[pi] = r;
+    }
+    s_best[tid] = best; s_cnt[tid] = cnt;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (tid < d) {
+            if (better(s_best[tid + d], s_best[tid])) s_best[tid] = s_best[tid + d];
+            s_cnt[tid] += s_cnt[tid + d];
         }
         __syncthreads();
+    }
+    ArgMax top = s_best[0];
+    int npoints = s_cnt[0];
+    if (CS > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        if (tid == 0) { c_best = top; c_cnt = npoints; }
+        cluster.sync();
+        top = ArgMax{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL}; npoints = 0;
+        for (int r = 0; r < CS; ++r) {
+            const ArgMax o = *cluster.map_shared_rank(&c_best, r);
+            if (better(o, top)) top = o;
+            npoints += *cluster.map_shared_rank(&c_cnt, r);
+        }
+        cluster.sync();
+    }
+    __syncthreads();
+    // ---- marginals: P_h1[i1] = sum_i2 w, P_h2[i2] = sum_i1 w, w = exp(ml - max) ------------------------
+    double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+    double sum_all = 0.0, sum_path = 0.0;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = 8;
+    for (int i1 = (int)crank * nwarps + warp; i1 < P.n_h1; i1 += nwarps * CS) {
+        const int h1 = h1s[i1];
+        double acc = 0.0, accp = 0.0;
+        for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
+            const double ml = surf[(long long)i1 * P.n_h2 + i2];
+            if (ml == -INFINITY) continue;
+            const double w = exp(ml - top.ml);
+            acc += w;
+            const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+            if (pathological(P, h1, h2)) accp += w;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            acc += __shfl_down_sync(0xffffffffu, acc, d);
+            accp += __shfl_down_sync(0xffffffffu, accp, d);
+        }
+        if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; }
+    }
+    for (int i2 = (int)crank * 256 + tid; i2 < P.n_h2; i2 += 256 * CS) {
+        double acc = 0.0;
+        for (int i1 = 0; i1 < P.n_h1; ++i1) {
+            const double ml = surf[(long long)i1 * P.n_h2 + i2];
+            if (ml == -INFINITY) continue;
+            acc += exp(ml - top.ml);
+        }
+        ph2[i2] = acc;
+    }
+    s_sum[tid] = sum_all; s_path[tid] = sum_path;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (tid < d) { s_sum[tid] += s_sum[tid + d]; s_path[tid] += s_path[tid + d]; }
+        __syncthreads();
+    }
+    double tot_all = s_sum[0], tot_path = s_path[0];
+    if (CS > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        if (tid == 0) { c_sum = tot_all; c_path = tot_path; }
+        cluster.sync();
+        tot_all = 0.0; tot_path = 0.0;
+        if (crank == 0 && tid == 0)
+            for (int r = 0; r < CS; ++r) { tot_all += *cluster.map_shared_rank(&c_sum, r); tot_path += *cluster.map_shared_rank(&c_path, r); }
+        cluster.sync();
+    }
+    if (crank == 0 && tid == 0) {
+        tredsw_grid_result r;
+        r.max_ml = top.ml; r.sum_all = tot_all; r.sum_path = tot_path;
+        r.arg_i1 = npoints ? (int)(top.idx / P.n_h2) : -1;
+        r.arg_i2 = npoints ? (int)(top.idx % P.n_h2) : -1;
+        r.n_points = npoints; r.pad = 0;
+        g.res[pi] = r;
     }
 }
 
@@ -315,11 +357,20 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     grid_surface_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tiles);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-    int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
-    grid_reduce_kernel<<<gb, 256, 0, ctx->stream>>>(g, nproblems);
+    const long long small_limit = 16384;
+    grid_reduce_kernel<1><<<nproblems, 256, 0, ctx->stream>>>(g, nproblems, small_limit);
     CUDA_TRY(cudaGetLastError());
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)nproblems * GRID_CLUSTER); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = GRID_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_reduce_kernel<GRID_CLUSTER>, g, nproblems, small_limit));
+    }
     ctx->mark(3);
-    ctx->launches += 2;
+    ctx->launches += 3;
     return TREDSW_OK;
 }
 
