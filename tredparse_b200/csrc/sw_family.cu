@@ -364,17 +364,19 @@ __device__ __forceinline__ void strip_locate(const uint32_t *stab, const uint8_t
     }
 }
 
-// Exact end coordinates (ssw.c's end_ref, end_read) of every lane's winning template, warp-uniform.
-// The winner (units u, strand s, score cs) is the first template in arg-max order, so no shorter template
-// of the same strand reaches cs: the first column whose maximum equals cs lies in unit u's own columns
-// or in the suffix block (never in the first FLANK columns: cs >= 30 > FLANK * match).  Recompute the
-// main strip that holds unit u from its stored entering boundary (keys for its columns, the boundary
-// leaving unit u captured), then the suffix block, and read the answer off the column keys.
+// Exact end coordinates (ssw.c's end_ref, end_read) of every lane's current candidate (units u, strand,
+// score cs), warp-uniform.  end_ref is the first template column whose maximum equals cs.  Phase 1 kept the
+// running maximum of the main columns after every unit (runs[]): if some unit u_main <= u is the first whose
+// running maximum equals cs, the column lies in that unit's own columns (never in the first FLANK columns:
+// cs >= 30 > FLANK * match) — recompute the main strip holding it from its stored entering boundary and read
+// the answer off per-column keys.  Otherwise it lies in the suffix block of template u: recompute the strip
+// holding unit u, capture the boundary column leaving unit u, then run the suffix block from it.
 template <int P>
-__device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
-                                           const uint8_t *codes, int lane, int m, int m_warp, uint32_t *bnd,
-                                           const uint32_t *gbnd, int R, int go, int ge, uint32_t one, int G, int cs,
-                                           int u, int strand, int *end_ref, int *end_read, unsigned long long &cells) {
+__device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *stab2,
+                                           uint32_t *colsel, bool &suffix_table_ready, const uint8_t *codes, int lane,
+                                           int m, int m_warp, uint32_t *bnd, const uint32_t *gbnd, int R, int go, int ge,
+                                           uint32_t one, int G, int cs, int u, int u_main, int strand, int *end_ref,
+                                           int *end_read, unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
     const uint32_t mgo2 = (uint32_t)((-go) & 0xffff) | ((uint32_t)((-go) & 0xffff) << 16);
@@ -382,48 +384,54 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
     const uint32_t go2 = (uint32_t)go * 0x00010001u;
     const int rows2 = (m_warp + 1) & ~1;
     auto comp = [](int c) { return c < 4 ? 3 - c : c; };
-    const int su = G * u - 1;                                // last sub-unit of unit u (lanes without a candidate: u = 1)
+    const int su = G * (u_main > 0 ? u_main : u) - 1;        // last sub-unit of the unit of interest (idle lanes: u = 1)
     const int tstar = su / K, kstar = su % K;                // (K is a multiple of G: units do not straddle strips)
     const int sh = strand ? 16 : 0;
     int found_col = -1, found_row = 0;
     {
-        // main strip tstar (the repeat table of phase 1 is still in shared memory)
+        // main strip tstar (the repeat table of phase 1 stays in shared memory)
         uint32_t colkey[NC];
-        strip_locate<NC, P, true>(stab, codes, lane, m, rows2, gbnd + (size_t)tstar * R * 32 + lane, bnd + lane, kstar,
-                                  colkey, mgo2, mge2, one);
+        strip_locate<NC, P, true>(stab, codes, lane, m, rows2, gbnd + (size_t)tstar * R * 32 + lane, bnd + lane,
+                                  u_main > 0 ? -1 : kstar, colkey, mgo2, mge2, one);
+        if (u_main > 0) {
 #pragma unroll
-        for (int c = NC - 1; c >= 0; --c) {
-            const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
-            if (c / P <= kstar && c / P > kstar - G && (int)(k16 >> 8) == cs) { found_col = FLANK + (tstar * K) * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+            for (int c = NC - 1; c >= 0; --c) {
+                const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
+                if (c / P <= kstar && c / P > kstar - G && (int)(k16 >> 8) == cs) { found_col = FLANK + (tstar * K) * P + c; found_row = 255 - (int)(k16 & 0xffu); }
+            }
         }
     }
     __syncwarp();
-    // suffix block of every lane's own template, entered through the captured boundary
-    if (lane < FLANK) colsel[lane] = sel2(F.suffix[lane], comp(F.prefix[FLANK - 1 - lane]));
-    __syncwarp();
-    build_stab(stab, lut, lane, FLANK, colsel, go2);
-    __syncwarp();
-    {
+    cells += (unsigned long long)m * 2ull * (unsigned long long)NC;
+    if (__any_sync(0xffffffffu, u_main <= 0 && cs < 0x7fff)) {
+        // suffix block of every lane's own template, entered through the captured boundary
+        if (!suffix_table_ready) {
+            if (lane < FLANK) colsel[lane] = sel2(F.suffix[lane], comp(F.prefix[FLANK - 1 - lane]));
+            __syncwarp();
+            build_stab(stab2, lut, lane, FLANK, colsel, go2);
+            __syncwarp();
+            suffix_table_ready = true;
+        }
         uint32_t colkey[FLANK];
-        strip_locate<FLANK, FLANK, false>(stab, codes, lane, m, rows2, bnd + lane, nullptr, 0, colkey, mgo2, mge2, one);
-        if (found_col < 0) {
+        strip_locate<FLANK, FLANK, false>(stab2, codes, lane, m, rows2, bnd + lane, nullptr, 0, colkey, mgo2, mge2, one);
+        if (u_main <= 0) {
 #pragma unroll
             for (int c = FLANK - 1; c >= 0; --c) {
                 const uint32_t k16 = (colkey[c] >> sh) & 0xffffu;
                 if ((int)(k16 >> 8) == cs) { found_col = FLANK + u * F.P + c; found_row = 255 - (int)(k16 & 0xffu); }
             }
         }
+        __syncwarp();
+        cells += (unsigned long long)m * 2ull * (unsigned long long)FLANK;
     }
-    __syncwarp();
     *end_ref = found_col; *end_read = found_row;
-    cells += (unsigned long long)m * 2ull * (unsigned long long)(NC + FLANK);
 }
 
 template <int P>
 __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut, uint32_t *stab, uint32_t *colsel,
                                            const uint8_t *codes, int lane, int m, int m_warp, uint32_t *pot,
-                                           uint32_t *gbnd, int R, uint8_t *scores, int go, int ge, uint32_t one, int G,
-                                           unsigned long long &cells) {
+                                           uint32_t *gbnd, int R, uint8_t *scores, uint8_t *runs, int go, int ge,
+                                           uint32_t one, int G, unsigned long long &cells) {
     constexpr int K = strip_units(P);
     constexpr int NC = P * K;
     static_assert(NC <= STAB_PAD && FLANK <= STAB_PAD, "strip wider than the score table");
@@ -475,6 +483,8 @@ __device__ __noinline__ void phase1_packed(const FamilySmem &F, const SwLut *lut
                 const uint32_t best = __vimax3_s16x2(run, mu[u], fresh);
                 scores[(2 * ur + 0) * 32 + lane] = (uint8_t)(best & 0xffu);
                 scores[(2 * ur + 1) * 32 + lane] = (uint8_t)((best >> 16) & 0xffu);
+                runs[(2 * ur + 0) * 32 + lane] = (uint8_t)(run & 0xffu);      // running maximum of the main columns
+                runs[(2 * ur + 1) * 32 + lane] = (uint8_t)((run >> 16) & 0xffu);
             }
         }
     }
@@ -491,19 +501,24 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SwLut lut;
     __shared__ FamilySmem F;
-    __shared__ __align__(16) uint32_t stab[6 * STAB_PAD];
+    __shared__ __align__(16) uint32_t stab[6 * STAB_PAD], stab2[6 * STAB_PAD];
     __shared__ uint32_t colsel[STAB_PAD];
-    // (shared memory holds the reads as codes [rows][32] and the score table; per-template scores, suffix
-    //  potentials and all boundary columns live in this CTA's slot of the global scratch, which stays in
-    //  L1/L2 and is streamed with one-iteration-ahead requests — so occupancy is bounded by registers only)
+    // (shared memory: the reads as codes [rows][32], the score table and ONE boundary column [rows][32] for
+    //  phase 2, whose scalar sweeps walk it with dependent load -> compute -> store chains that must not pay
+    //  L2 latency per row; per-template scores, suffix potentials and the per-strip boundary columns of
+    //  phase 1 live in this CTA's slot of the global scratch, streamed with one-iteration-ahead requests)
     typedef typename std::conditional<FAST, uint8_t, uint16_t>::type score_t;
     const int lane = threadIdx.x;
     const int R = p.max_rows + 2;                                                  // + ghost row of the 2-row loop
-    uint8_t *codes = reinterpret_cast<uint8_t *>(smem_raw);                        // [R][32]
-    score_t *scores = reinterpret_cast<score_t *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32;   // [2U][32]
+    uint32_t *bnd = reinterpret_cast<uint32_t *>(smem_raw);                        // [R][32] phase-2 boundary column
+    uint8_t *codes = reinterpret_cast<uint8_t *>(bnd + (size_t)R * 32);            // [R][32]
+    // per-CTA slot of 2*max_u*32 u16-sized elements: generic kernel = u16 scores; packed kernel = u8 scores in
+    // the first half, u8 running main maxima (runs) in the second
+    unsigned char *slot = reinterpret_cast<unsigned char *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32 * sizeof(uint16_t);
+    score_t *scores = reinterpret_cast<score_t *>(slot);                           // [2U][32]
+    uint8_t *runs = slot + (size_t)(2 * p.max_u) * 32;                             // [2U][32] (packed kernel only)
     uint32_t *pot = p.pot_buf + (size_t)blockIdx.x * R * 32;                       // [R][32]
     uint32_t *gbnd = p.gbnd_buf + (size_t)blockIdx.x * (p.nslots + 1) * R * 32;    // [nslots + 1][R][32]
-    uint32_t *bnd = gbnd + (size_t)p.nslots * R * 32;                              // last slot: phase-2 scratch column
     const uint32_t one = p.one;
     sw_build_lut(&lut, c_fmat25, lane, 32);
     const int nitems = p.chunk_start[p.nfamilies];
@@ -548,7 +563,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
             phase1_generic(F, &lut, codes, lane, m, m_warp, bnd, scores, p.go, p.ge, cells1);
         } else {
             switch (instance_period(F.P)) {
-#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, pot, gbnd, R, scores, p.go, p.ge, one, F.P / PP, cells1); break;
+#define PCASE(PP) case PP: phase1_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, pot, gbnd, R, scores, runs, p.go, p.ge, one, F.P / PP, cells1); break;
                 PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
 #undef PCASE
             }
@@ -573,30 +588,34 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         };
         int cs, cr;
         pick(0x7fffffff, -1, cs, cr);
-        // end coordinates of every lane's first candidate in one warp-uniform packed pass
-        int fast_end_ref = -1, fast_end_read = 0;
-        if constexpr (FAST) {
-            if (FLANK * p.match < 30 && __any_sync(0xffffffffu, cr >= 0)) {
-                const int lu = cr >= 0 ? cr / 2 + 1 : 1, ls = cr >= 0 ? (cr & 1) : 0, lcs = cr >= 0 ? cs : 0x7fff;
-                switch (instance_period(F.P)) {
-#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, colsel, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, one, F.P / PP, lcs, lu, ls, &fast_end_ref, &fast_end_read, cells1); break;
-                    PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
+        // Rounds: every lane that still has a candidate evaluates it — end coordinates from one warp-uniform
+        // packed pass (locate_packed), begin coordinates and the tag per lane — until all lanes are settled.
+        // Almost every read settles in the first round.
+        const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
+        auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
+        bool suffix_table_ready = false;
+        while (__any_sync(0xffffffffu, cr >= 0)) {
+            const bool pending = cr >= 0;
+            const int u = pending ? cr / 2 + 1 : 1, s = pending ? (cr & 1) : 0;
+            int fast_end_ref = -1, fast_end_read = 0;
+            if constexpr (FAST) {
+                if (FLANK * p.match < 30) {
+                    int u_main = 0;                      // first unit whose running main maximum equals cs
+                    if (pending) for (int k = 1; k <= u; ++k) if ((int)runs[(2 * (k - 1) + s) * 32 + lane] == cs) { u_main = k; break; }
+                    switch (instance_period(F.P)) {
+#define PCASE(PP) case PP: locate_packed<PP>(F, &lut, stab, stab2, colsel, suffix_table_ready, codes, lane, m, m_warp, bnd, gbnd, R, p.go, p.ge, one, F.P / PP, pending ? cs : 0x7fff, u, u_main, s, &fast_end_ref, &fast_end_read, cells1); break;
+                        PCASE(1) PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(7) PCASE(8) PCASE(9) PCASE(10) PCASE(11)
 #undef PCASE
+                    }
+                    if (!pending) fast_end_ref = -1;
                 }
-                if (cr < 0) fast_end_ref = -1;
             }
-        }
-        if (active) {
-            const int max_units_eff = F.clip ? (m + F.P - 1) / F.P : F.U;
-            auto rc_f = [&](int j) { return (int)codes[j * 32 + lane]; };
-            for (bool first = true; cr >= 0; first = false) {
-                const int u = cr / 2 + 1, s = cr & 1;
+            if (pending) {
                 const int n = F.Lp + F.Ls + F.P * u;
                 auto cc_f = [&](int i) { return fam_code(F, u, s, n, i); };
-                int end_ref, end_read;
-                if (first && fast_end_ref >= 0) {
-                    end_ref = fast_end_ref; end_read = fast_end_read;
-                } else {
+                int end_ref = fast_end_ref, end_read = fast_end_read;
+                if (end_ref < 0) {
+                    // (generic kernel, or a scoring scheme outside the packed pass's preconditions)
                     // Exact banding (sw_sweep.cuh): a path ending with score cs drifts at most `drift` diagonals
                     // from the diagonal it starts on.  Forward: it starts at some (i0, j0) with i0 <= n - need,
                     // j0 <= m - need, where need = ceil(cs / match) aligned pairs are indispensable.
@@ -605,6 +624,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
                     sw_sweep<FAM_W2, 1, false>(m, m, n, rc_f, cc_f, &lut, bnd + lane, 32, p.go, p.ge, cs, &end_ref, &end_read,
                                                nullptr, -(m - need) - drift, (n - need) + drift, &cells2);
                 }
+                bool settled = false;
                 if (end_ref >= 0) {      // (always: the score was produced by this very template)
                     // Reverse: only a path leaving the corner (end_ref, end_read) can reach cs (Appendix A); it
                     // lives in the (end_read+1) x (end_ref+1) rectangle, which bounds its aligned pairs and
@@ -633,12 +653,13 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
                     if (t != TREDSW_TAG_NONE) {
                         tag = t; best_u = u; best_score = cs; rb = c_rb; re = end_ref; qb = c_qb; qe = end_read;
                         best_rank = cr;
-                        break;
+                        settled = true;
                     }
                 }
-                const int ls = cs, lr = cr;
-                pick(ls, lr, cs, cr);
+                if (settled) cr = -1;
+                else { const int ls = cs, lr = cr; pick(ls, lr, cs, cr); }
             }
+            __syncwarp();
         }
         if (valid) {
             int32_t *o = p.out + (int64_t)r * 8;
@@ -820,7 +841,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     }
     const int max_rows = max_m > 0 ? max_m : 1;
     const size_t rows_alloc = (size_t)max_rows + 2;
-    const size_t smem = rows_alloc * 32 + 64;
+    const size_t smem = rows_alloc * 32 * 4 + rows_alloc * 32 + 64;
     if (smem > ctx->smem_optin) { tredsw_set_error("reads too long for shared memory (%zu B)", smem); return TREDSW_ERR_UNSUPPORTED; }
     ClassifyParams p{};
     p.rbuf = d_rbuf; p.roff = d_roff; p.families = d_families; p.out = d_out;
@@ -855,12 +876,17 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes + gbnd_bytes);
     p.max_u = max_u;
     int32_t *d_perm = p.counter + 4;
-    {   // families by loop instantiation (stable), so that concurrently running CTAs share strip-loop code:
-        // measured, mixing instantiations on an SM costs far more than the order could ever gain
+    {   // Item order: families grouped by loop instantiation (measured: mixing instantiations on an SM costs far
+        // more than any order could gain — they compete for the instruction cache), the groups with the fewest
+        // families first: their items run cold code and are the slowest, so they must not form the tail of the
+        // launch; the big uniform group (period 3 for the catalogue) finishes it with short, even items.
         std::vector<int32_t> perm(nfamilies);
-        for (int f = 0; f < nfamilies; ++f) perm[f] = f;
+        int group_size[33] = {0};
+        for (int f = 0; f < nfamilies; ++f) { perm[f] = f; ++group_size[instance_period(h_families[f].period)]; }
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
-            return instance_period(h_families[a].period) < instance_period(h_families[b].period); });
+            const int pa = instance_period(h_families[a].period), pb = instance_period(h_families[b].period);
+            if (group_size[pa] != group_size[pb]) return group_size[pa] < group_size[pb];
+            return pa < pb; });
         CUDA_TRY(cudaMemcpyAsync(d_perm, perm.data(), nfamilies * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     p.fam_perm = d_perm;
