@@ -64,7 +64,19 @@ __device__ __forceinline__ double pe_roll(const double *pdf, int h, int ref, int
     return pdf[y];
 }
 
-__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2) {
+// log(max(v, eps)) with a one-entry memo: consecutive keys very often give bit-identical mixtures (every
+// partial key far below both alleles sees the same alpha*c1 + (1-alpha)*c2; every pair length shifted off
+// the KDE support sees eps), and log of the same double is the same double — so the surface is unchanged
+// while most of the FP64 log evaluations of a large (h1, h2) grid disappear.
+struct LogMemo {
+    double v, l;
+    __device__ __forceinline__ double operator()(double x, double eps, double log_small) {
+        if (x != v) { v = x; l = (x < eps) ? log_small : log(x); }
+        return l;
+    }
+};
+
+__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, double lgamma_k1) {
     const int32_t *skey = g.ipool + P.off_span, *scnt = skey + P.n_span;
     const int32_t *pkey = g.ipool + P.off_part, *pcnt = pkey + P.n_part;
     const double *step = g.dpool + P.off_step;
@@ -77,11 +89,12 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
         const double sg1 = sigma_h(P, h1), sg2 = sigma_h(P, h2);
         double acc = 0.0;
+        LogMemo lg{-1.0, 0.0};
         for (int i = 0; i < P.n_span; ++i) {
             const int k = skey[i];
             const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
             double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
-            double l = (v < eps) ? g.log_small : log(v);
+            double l = lg(v, eps, g.log_small);
             acc = __dadd_rn(acc, __dmul_rn(l, (double)scnt[i]));
         }
         ml = acc;
@@ -95,11 +108,12 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
         const double sg1 = sigma_h(P, hc1), sg2 = sigma_h(P, hc2);
         double acc = 0.0;
+        LogMemo lg{-1.0, 0.0};
         for (int i = 0; i < P.n_part; ++i) {
             const int k = pkey[i];
             const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
             double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
-            double l = (v < eps) ? g.log_small : log(v);
+            double l = lg(v, eps, g.log_small);
             acc = __dadd_rn(acc, __dmul_rn(l, (double)pcnt[i]));
         }
         ml2 = acc;
@@ -111,7 +125,7 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double mu = (double)(d1 + d2) * P.half_depth / (double)P.readlen;
         const double kk = (double)P.n_rept;
         const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
-        const double pk = xl - lgamma(kk + 1.0) - mu;
+        const double pk = xl - lgamma_k1 - mu;          // lgamma(n_rept + 1): once per tile
         double prob = exp(pk);
         if (!(prob > g.really_small)) prob = g.really_small;
         ml = __dadd_rn(ml, log(prob));
@@ -122,13 +136,14 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double *pdf = g.dpool + P.off_pdf;
         const int32_t *tl = g.ipool + P.off_target;
         double acc = 0.0;
+        LogMemo lg{-1.0, 0.0};
         for (int i = 0; i < P.n_target; ++i) {
             int x = tl[i];
             if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
             const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
             const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
             double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
-            double l = (v < eps) ? g.log_small : log(v);
+            double l = lg(v, eps, g.log_small);
             acc = __dadd_rn(acc, l);
         }
         ml4 = acc;
@@ -172,6 +187,7 @@ __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_prob
 __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, int nproblems, const long long *tile_start) {
     const long long ntiles = tile_start[nproblems];
     __shared__ int s_pi;
+    __shared__ double s_lgamma;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (threadIdx.x == 0) {                        // tile -> problem: last p with tile_start[p] <= tile
             int lo = 0, hi = nproblems;
@@ -180,20 +196,24 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, i
                 if (tile_start[mid] <= tile) lo = mid; else hi = mid;
             }
             s_pi = lo;
+            s_lgamma = lgamma((double)g.prob[lo].n_rept + 1.0);
         }
         __syncthreads();
         const int pi = s_pi;
+        const double lgamma_k1 = s_lgamma;
         __syncthreads();
         const tredsw_grid_problem &P = g.prob[pi];
         const long long total = (long long)P.n_h1 * P.n_h2;
         const long long t = (tile - tile_start[pi]) * GRID_TILE + threadIdx.x;
         if (t < total) {
             const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-            const int i1 = (int)(t / P.n_h2), i2 = (int)(t % P.n_h2);
+            int i1, i2;
+            if (total < 0x7fffffffLL) { i1 = (int)((unsigned)t / (unsigned)P.n_h2); i2 = (int)((unsigned)t - (unsigned)i1 * (unsigned)P.n_h2); }
+            else { i1 = (int)(t / P.n_h2); i2 = (int)(t % P.n_h2); }
             const int h1 = h1s[i1];
             const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
             double ml = -INFINITY;
-            if (h1 <= h2) ml = point_ml(P, g, h1, h2);
+            if (h1 <= h2) ml = point_ml(P, g, h1, h2, lgamma_k1);
             g.surface[P.off_surface + t] = ml;
         }
     }
