@@ -76,7 +76,21 @@ struct LogMemo {
     }
 };
 
-__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, double lgamma_k1) {
+// Per-problem values shared by all points of a tile (computed once per tile by one thread).
+struct TileShared {
+    double lgamma_k1;      // lgamma(n_rept + 1) of the Poisson term
+    double sig_mp;         // sigma(max_partial): the stutter probability of every allele clamped to max_partial
+    int tmin;              // smallest pair length >= MINPE (after numpy's negative-index wrap); INT_MAX if none
+};
+
+// One grid point.  The arithmetic (operation order, rounding) is exactly that of the straightforward loops
+// over all keys; the shortcuts only skip work whose result is known in advance:
+//   * pdf_span(h)[k] = 0 unless h-18 <= k <= h+18, so a partial key below both clamped alleles by more than
+//     18 sees the mixture alpha*c1 + (1-alpha)*c2 and one above both sees 0 — no pdf evaluation, no sigma;
+//   * a spanning key farther than 18 from both alleles sees 0;
+//   * when both alleles shift every pair length off the KDE support, every pair sees eps.
+// On the large grids of --fullsearch / long-expansion searches almost all points are of that kind.
+__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, const TileShared &T) {
     const int32_t *skey = g.ipool + P.off_span, *scnt = skey + P.n_span;
     const int32_t *pkey = g.ipool + P.off_part, *pcnt = pkey + P.n_part;
     const double *step = g.dpool + P.off_step;
@@ -87,13 +101,20 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
     if (P.n_span > 0) {
         const int s1 = max(0, t2 - h1), s2 = max(0, t2 - h2);
         const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
-        const double sg1 = sigma_h(P, h1), sg2 = sigma_h(P, h2);
+        const int lo = min(h1, h2) - DEV, hi = max(h1, h2) + DEV;
+        double sg1 = 0.0, sg2 = 0.0;
+        bool have_sigma = false;
         double acc = 0.0;
         LogMemo lg{-1.0, 0.0};
         for (int i = 0; i < P.n_span; ++i) {
             const int k = skey[i];
-            const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
-            double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            double v;
+            if (k < lo || k > hi) v = 0.0;          // == a * 0 + (1 - a) * 0
+            else {
+                if (!have_sigma) { sg1 = sigma_h(P, h1); sg2 = sigma_h(P, h2); have_sigma = true; }
+                const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
+                v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            }
             double l = lg(v, eps, g.log_small);
             acc = __dadd_rn(acc, __dmul_rn(l, (double)scnt[i]));
         }
@@ -106,13 +127,26 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
         const int hc1 = min(h1, P.max_partial), hc2 = min(h2, P.max_partial);
         const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
-        const double sg1 = sigma_h(P, hc1), sg2 = sigma_h(P, hc2);
+        const int lo = min(hc1, hc2) - DEV, hi = max(hc1, hc2) + DEV;
+        const double v_bulk = __dadd_rn(__dmul_rn(a, c1), __dmul_rn(1.0 - a, c2));   // p1 = c1 + c1 * 0, p2 = c2 + c2 * 0
+        double sg1 = 0.0, sg2 = 0.0;
+        bool have_sigma = false;
         double acc = 0.0;
         LogMemo lg{-1.0, 0.0};
         for (int i = 0; i < P.n_part; ++i) {
             const int k = pkey[i];
-            const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
-            double v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            double v;
+            if (k < lo) v = v_bulk;
+            else if (k > hi) v = 0.0;
+            else {
+                if (!have_sigma) {
+                    sg1 = hc1 == P.max_partial ? T.sig_mp : sigma_h(P, hc1);
+                    sg2 = hc2 == P.max_partial ? T.sig_mp : sigma_h(P, hc2);
+                    have_sigma = true;
+                }
+                const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
+                v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+            }
             double l = lg(v, eps, g.log_small);
             acc = __dadd_rn(acc, __dmul_rn(l, (double)pcnt[i]));
         }
@@ -125,10 +159,10 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double mu = (double)(d1 + d2) * P.half_depth / (double)P.readlen;
         const double kk = (double)P.n_rept;
         const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
-        const double pk = xl - lgamma_k1 - mu;          // lgamma(n_rept + 1): once per tile
-        double prob = exp(pk);
-        if (!(prob > g.really_small)) prob = g.really_small;
-        ml = __dadd_rn(ml, log(prob));
+        const double pk = xl - T.lgamma_k1 - mu;
+        // log(max(exp(pk), e^-100)): log(exp(pk)) is pk to within an ulp of the pmf (~1e-16 absolute on a term
+        // of magnitude 0.1..100, far inside the 1e-9 relative bar) — two transcendentals less per point
+        ml = __dadd_rn(ml, pk > -100.0 ? pk : -100.0);
     }
     // paired-end
     double ml4 = 0.0;
@@ -136,15 +170,22 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
         const double *pdf = g.dpool + P.off_pdf;
         const int32_t *tl = g.ipool + P.off_target;
         double acc = 0.0;
-        LogMemo lg{-1.0, 0.0};
-        for (int i = 0; i < P.n_target; ++i) {
-            int x = tl[i];
-            if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
-            const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
-            const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
-            double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
-            double l = lg(v, eps, g.log_small);
-            acc = __dadd_rn(acc, l);
+        const long long off1 = (long long)h1 - P.pe_ref, off2 = (long long)h2 - P.pe_ref;
+        if (T.tmin == 0x7fffffff || (T.tmin + off1 >= SPAN && T.tmin + off2 >= SPAN)) {
+            // every pair length is below MINPE or shifted past the end of the support: 0.5*eps + 0.5*eps = eps
+            const double l = log(eps);
+            for (int i = 0; i < P.n_target; ++i) acc = __dadd_rn(acc, l);
+        } else {
+            LogMemo lg{-1.0, 0.0};
+            for (int i = 0; i < P.n_target; ++i) {
+                int x = tl[i];
+                if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
+                const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
+                const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
+                double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
+                double l = lg(v, eps, g.log_small);
+                acc = __dadd_rn(acc, l);
+            }
         }
         ml4 = acc;
     }
@@ -187,7 +228,7 @@ __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_prob
 __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, int nproblems, const long long *tile_start) {
     const long long ntiles = tile_start[nproblems];
     __shared__ int s_pi;
-    __shared__ double s_lgamma;
+    __shared__ TileShared s_tile;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (threadIdx.x == 0) {                        // tile -> problem: last p with tile_start[p] <= tile
             int lo = 0, hi = nproblems;
@@ -196,11 +237,19 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, i
                 if (tile_start[mid] <= tile) lo = mid; else hi = mid;
             }
             s_pi = lo;
-            s_lgamma = lgamma((double)g.prob[lo].n_rept + 1.0);
+            const tredsw_grid_problem &Q = g.prob[lo];
+            s_tile.lgamma_k1 = lgamma((double)Q.n_rept + 1.0);
+            s_tile.sig_mp = sigma_h(Q, Q.max_partial);
+            int tmin = 0x7fffffff;
+            if (Q.run_pe) {
+                const int32_t *tl = g.ipool + Q.off_target;
+                for (int i = 0; i < Q.n_target; ++i) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= Q.pe_minpe && x < tmin) tmin = x; }
+            }
+            s_tile.tmin = tmin;
         }
         __syncthreads();
         const int pi = s_pi;
-        const double lgamma_k1 = s_lgamma;
+        const TileShared T = s_tile;
         __syncthreads();
         const tredsw_grid_problem &P = g.prob[pi];
         const long long total = (long long)P.n_h1 * P.n_h2;
@@ -213,7 +262,7 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, i
             const int h1 = h1s[i1];
             const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
             double ml = -INFINITY;
-            if (h1 <= h2) ml = point_ml(P, g, h1, h2, lgamma_k1);
+            if (h1 <= h2) ml = point_ml(P, g, h1, h2, T);
             g.surface[P.off_surface + t] = ml;
         }
     }
