@@ -915,13 +915,14 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
         std::vector<int8_t> t;
         for (int f = 0; f < nfamilies; ++f) {
             const tredsw_family &g = h_families[f];
-            bool hasN = false;
-            for (int i = 0; i < g.prefix_len; ++i) if (g.prefix[i] < 0 || g.prefix[i] > 3) hasN = true;
-            for (int i = 0; i < g.suffix_len; ++i) if (g.suffix[i] < 0 || g.suffix[i] > 3) hasN = true;
-            for (int i = 0; i < g.period; ++i) if (g.repeat[i] < 0 || g.repeat[i] > 3) hasN = true;
-            info[f].q = (usable && !hasN) ? q : 0;
+            // N in a template (GCN / NGC motifs) scores 0 against every base: such a pair neither breaks the
+            // score nor earns it.  Count it as "compatible": runs of compatible pairs are broken by mismatches
+            // and gaps only, so the same bound holds for q-grams compared with N as a wildcard — every template
+            // q-gram with N's is expanded to the concrete q-grams it is compatible with.
+            info[f].q = usable ? q : 0;
             info[f].min_score = 30;                         // bam_parser.py:134: min_score = max(min_len, 30)
             if (!info[f].q) continue;
+            bool too_many_n = false;
             // every q-gram of a template with u >= u0 units already occurs in the template with u0 units
             const int u0 = (q - 1 + g.period - 1) / g.period + 1;
             const uint32_t mask = (1u << (2 * q)) - 1u;
@@ -932,16 +933,34 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                 for (int k = 0; k < u; ++k) for (int i = 0; i < g.period; ++i) t.push_back(g.repeat[i]);
                 for (int i = 0; i < g.suffix_len; ++i) t.push_back(g.suffix[i]);
                 const int n = (int)t.size();
-                uint32_t cf = 0, cr = 0;
-                for (int i = 0; i < n; ++i) {
-                    cf = ((cf << 2) | (uint32_t)t[i]) & mask;                       // forward template, left to right
-                    cr = ((cr << 2) | (uint32_t)(3 - t[n - 1 - i])) & mask;         // its reverse complement, left to right
-                    if (i >= q - 1) {
-                        tf[cf >> 4] |= 1u << ((cf & 15u) * 2u);
-                        tf[cr >> 4] |= 2u << ((cr & 15u) * 2u);
+                for (int i = 0; i + q <= n; ++i) {
+                    // forward q-gram t[i..i+q) and the reverse complement's q-gram that covers the same bases
+                    int npos[8], nn = 0;
+                    uint32_t cf = 0, cr = 0;
+                    for (int k = 0; k < q; ++k) {
+                        const int c = t[i + k];
+                        const bool isn = c < 0 || c > 3;
+                        if (isn && nn < 8) npos[nn] = k;
+                        if (isn) ++nn;
+                        cf |= (uint32_t)(isn ? 0 : c) << (2 * (q - 1 - k));
+                        cr |= (uint32_t)(isn ? 0 : 3 - c) << (2 * k);       // position k of the forward gram = q-1-k from the right
+                    }
+                    if (nn > 4) { too_many_n = true; break; }
+                    for (uint32_t e = 0; e < (1u << (2 * nn)); ++e) {       // all fillings of the N positions
+                        uint32_t xf = cf, xr = cr;
+                        for (int z = 0; z < nn; ++z) {
+                            const uint32_t b = (e >> (2 * z)) & 3u;
+                            xf |= b << (2 * (q - 1 - npos[z]));
+                            xr |= (3u - b) << (2 * npos[z]);
+                        }
+                        xf &= mask; xr &= mask;
+                        tf[xf >> 4] |= 1u << ((xf & 15u) * 2u);
+                        tf[xr >> 4] |= 2u << ((xr & 15u) * 2u);
                     }
                 }
+                if (too_many_n) break;
             }
+            if (too_many_n) info[f].q = 0;
         }
         CUDA_TRY(cudaMemcpyAsync(d_qtab, tab.data(), qtab_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d_qinfo, info.data(), nfamilies * sizeof(QgramInfo), cudaMemcpyHostToDevice, ctx->stream));
