@@ -168,12 +168,14 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
     uint32_t hin_prev = 0;
     auto code_at = [&](int j) { return j < m ? (int)codes[j * 32 + lane] : SW_CODE_GHOST; };
     auto row_of = [&](int code) { return reinterpret_cast<const uint4 *>(stab + code * STAB_PAD); };
-    // software pipeline: everything row j needs from memory is requested one iteration ahead
+    // software pipeline: shared-memory operands of row j are requested one iteration ahead, the global ones
+    // (boundary column, potentials: L2 latency) two iterations ahead
     const uint4 *rowA = row_of(code_at(0)), *rowB = row_of(code_at(1));
     uint4 gA = rowA[0], gB = rowB[0];
-    uint32_t bA = 0, bB = 0, pA = 0, pB = 0;
-    if (HAS_IN) { bA = bin[lane]; bB = bin[32 + lane]; }
-    if (HOOK) { pA = pot[lane]; pB = pot[32 + lane]; }
+    uint32_t bA = 0, bB = 0, pA = 0, pB = 0, bA2 = 0, bB2 = 0, pA2 = 0, pB2 = 0;
+    const int j1 = min(2, rows2 - 2);
+    if (HAS_IN) { bA = bin[lane]; bB = bin[32 + lane]; bA2 = bin[j1 * 32 + lane]; bB2 = bin[(j1 + 1) * 32 + lane]; }
+    if (HOOK) { pA = pot[lane]; pB = pot[32 + lane]; pA2 = pot[j1 * 32 + lane]; pB2 = pot[(j1 + 1) * 32 + lane]; }
     int codeA2 = code_at(2), codeB2 = code_at(3);
     for (int j = 0; j < rows2; j += 2) {
         uint32_t hinA = 0, eA = 0, hinB = 0, eB = 0;
@@ -186,12 +188,12 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
             potHA = sw_prmt(pA, 0, 0x9180); potEA = sw_prmt(pA, 0, 0xb3a2);
             potHB = sw_prmt(pB, 0, 0x9180); potEB = sw_prmt(pB, 0, 0xb3a2);
         }
-        // requests for the next pair of rows (indices clamped; unused past the end)
-        const int jn = min(j + 2, rows2 - 2);
+        // requests for the rows after next (indices clamped; unused past the end)
+        const int jn = min(j + 4, rows2 - 2);
         const uint4 *rowA2 = row_of(codeA2), *rowB2 = row_of(codeB2);
-        uint32_t bA2 = 0, bB2 = 0;
-        if (HAS_IN) { bA2 = bin[jn * 32 + lane]; bB2 = bin[(jn + 1) * 32 + lane]; }
-        if (HOOK) { pA = pot[jn * 32 + lane]; pB = pot[(jn + 1) * 32 + lane]; }
+        uint32_t bA3 = 0, bB3 = 0, pA3 = 0, pB3 = 0;
+        if (HAS_IN) { bA3 = bin[jn * 32 + lane]; bB3 = bin[(jn + 1) * 32 + lane]; }
+        if (HOOK) { pA3 = pot[jn * 32 + lane]; pB3 = pot[(jn + 1) * 32 + lane]; }
         const int codeA3 = code_at(j + 4), codeB3 = code_at(j + 5);
         uint32_t sA[NG * 4], sB[NG * 4];
         sA[0] = gA.x; sA[1] = gA.y; sA[2] = gA.z; sA[3] = gA.w;
@@ -233,7 +235,8 @@ __device__ __forceinline__ void strip_pass(const uint32_t *stab, const uint8_t *
                 if (HAS_OUT && s - 1 == NC - 1) bout[(j + 1) * 32 + lane] = sw_prmt(hB, eB, 0x6420);
             }
         }
-        rowA = rowA2; rowB = rowB2; bA = bA2; bB = bB2; codeA2 = codeA3; codeB2 = codeB3;
+        rowA = rowA2; rowB = rowB2; codeA2 = codeA3; codeB2 = codeB3;
+        bA = bA2; bB = bB2; bA2 = bA3; bB2 = bB3; pA = pA2; pB = pB2; pA2 = pA3; pB2 = pB3;
     }
 }
 
@@ -391,9 +394,15 @@ __device__ __noinline__ void locate_packed(const FamilySmem &F, const SwLut *lut
     const int sh = strand ? 16 : 0;
     int found_col = -1, found_row = 0;
     {
-        // main strip tstar (the repeat table of phase 1 stays in shared memory)
+        // main strip tstar (the repeat table of phase 1 stays in shared memory).  Every lane restarts from its
+        // own strip's stored boundary column: stage it into shared memory first — 2 x rows independent,
+        // sector-sized loads per lane in flight at once instead of an L2 round trip per row pair in the loop.
+        {
+            const uint32_t *src = gbnd + (size_t)tstar * R * 32 + lane;
+            for (int j = 0; j < rows2; ++j) bnd[j * 32 + lane] = src[j * 32];
+        }
         uint32_t colkey[NC];
-        strip_locate<NC, P, true>(stab, codes, lane, m, rows2, gbnd + (size_t)tstar * R * 32 + lane, bnd + lane,
+        strip_locate<NC, P, true>(stab, codes, lane, m, rows2, bnd + lane, bnd + lane,
                                   u_main > 0 ? -1 : kstar, colkey, mgo2, mge2, one);
         if (u_main > 0) {
 #pragma unroll
