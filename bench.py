@@ -43,7 +43,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--samples", type=int, default=384, help="samples per GPU per step (x 30 loci)")
-    p.add_argument("--depth", type=int, default=2, help="host-buffer calls kept in flight by the e2e pipeline")
+    p.add_argument("--depth", type=int, default=3, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
     p.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -73,7 +73,8 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (every 100 ms: faster polling
+    contends for the driver and measurably slows the host-buffer calls of the e2e leg)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -84,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -303,6 +304,14 @@ def _main(args):
     barrier()
     clocks = sampler.stop()
     e2e_launches = pipe.launches - e2e_launch0
+    e2e_kernel_ms = None
+    if os.environ.get("TREDSW_E2E_TIMING"):
+        for c in pipe.contexts:
+            c.enable_timing(True)
+        for host in pipe.map([batch] * (2 * max(1, args.depth))):
+            pass
+        e2e_kernel_ms = [c.timing() for c in pipe.contexts]
+        sys.stderr.write("e2e per-call device stage times: {}\n".format(e2e_kernel_ms))
     pipe.close()
     assert host["calls"].tobytes() == calls_dev.tobytes(), "device-resident and host paths disagree"
 

@@ -142,7 +142,7 @@ __global__ void plan_kernel(CohortDev c) {
     c.nbase[2 * p] = nb1; c.nbase[2 * p + 1] = nb2;
 }
 
-__global__ void __launch_bounds__(1024) cohort_kde_kernel(CohortDev c, const int32_t *pe_lens) {
+__global__ void __launch_bounds__(KDE_THREADS) cohort_kde_kernel(CohortDev c, const int32_t *pe_lens) {
     for (int p = blockIdx.x; p < c.nproblems; p += gridDim.x) {
         if (!c.gp[p].run_pe) continue;          // block-uniform
         const tredsw_problem pr = c.problems[p];
@@ -339,7 +339,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     ctx->mark(4);
     // one block per problem (most exit at once: only problems with run_pe need the KDE); the hardware block
     // scheduler balances the sparse, uneven survivors better than a strided loop would
-    cohort_kde_kernel<<<np_, 1024, 0, ctx->stream>>>(cd, d_ipool);
+    cohort_kde_kernel<<<np_, KDE_THREADS, 0, ctx->stream>>>(cd, d_ipool);
     ctx->mark(5);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 3;

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int npro
 }
 
 // ---- KDE of paired-end lengths (models.py:428-435): see kde.cuh ---------------------------------------
-__global__ void __launch_bounds__(1024) pe_kde_kernel(const int32_t *lens, const int64_t *off, int nproblems,
+__global__ void __launch_bounds__(KDE_THREADS) pe_kde_kernel(const int32_t *lens, const int64_t *off, int nproblems,
                                                       double *pdf_out) {
     for (int pi = blockIdx.x; pi < nproblems; pi += gridDim.x)
         kde_block(lens + off[pi], (int)(off[pi + 1] - off[pi]), pdf_out + (int64_t)pi * SPAN);
@@ -506,8 +506,8 @@ extern "C" int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t
         if ((rc = ctx->d_dpool.ensure((size_t)nproblems * SPAN * sizeof(double)))) return rc;
         d_out = ctx->d_dpool.as<double>();
     }
-    int gb = nproblems > ctx->sm_count * 2 ? ctx->sm_count * 2 : nproblems;
-    pe_kde_kernel<<<gb, 1024, 0, ctx->stream>>>(d_lens, d_off, nproblems, d_out);
+    int gb = nproblems > ctx->sm_count * 8 ? ctx->sm_count * 8 : nproblems;
+    pe_kde_kernel<<<gb, KDE_THREADS, 0, ctx->stream>>>(d_lens, d_off, nproblems, d_out);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     if (!dev_ptrs(flags)) {

@@ -1,4 +1,4 @@
-// kde.cuh — Gaussian KDE of paired-end lengths on the grid 0..999, one 1024-thread block per problem.
+// kde.cuh — Gaussian KDE of paired-end lengths on the grid 0..999, one 256-thread block per problem.
 //
 // Replaces PEMaxLikModel.__init__ (tredparse/models.py:428-435): scipy.stats.gaussian_kde with Scott's
 // factor n^(-1/5) — covariance = var(ddof=1) * factor^2, pdf[x] ~ sum_i exp(-((x - x_i)/sd)^2 / 2) — then
@@ -13,49 +13,91 @@
 constexpr int KDE_SPAN = 1000;
 constexpr int KDE_OFF = 1024;
 
+// Block size: KDE_THREADS threads, KDE_SPAN / KDE_THREADS grid points each.  (256 threads, not one thread
+// per grid point: a 1024-thread block cannot become resident next to the persistent Smith-Waterman CTAs of a
+// concurrently running call — registers — and would stall its whole call behind them.)
+constexpr int KDE_THREADS = 256;
+constexpr int KDE_PER_THREAD = (KDE_SPAN + KDE_THREADS - 1) / KDE_THREADS;
+
+__device__ __forceinline__ double kde_block_sum(double *red, double v) {
+    const int tid = threadIdx.x;
+    red[tid] = v;
+    __syncthreads();
+    for (int d = KDE_THREADS / 2; d > 0; d >>= 1) { if (tid < d) red[tid] += red[tid + d]; __syncthreads(); }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+
 __device__ __forceinline__ void kde_block(const int32_t *x, int n, double *out) {
     __shared__ int hist[2 * KDE_OFF];
-    __shared__ double red[1024];
-    __shared__ double s_mean, s_sd;
+    __shared__ double red[KDE_THREADS];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 2 * KDE_OFF; i += blockDim.x) hist[i] = 0;
+    for (int i = tid; i < 2 * KDE_OFF; i += KDE_THREADS) hist[i] = 0;
     __syncthreads();
     double s = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += KDE_THREADS) {
         int v = x[i];
         s += (double)v;
         v = max(-KDE_OFF, min(KDE_OFF - 1, v));
         atomicAdd(&hist[v + KDE_OFF], 1);
     }
-    red[tid] = s;
-    __syncthreads();
-    for (int d = 512; d > 0; d >>= 1) { if (tid < d) red[tid] += red[tid + d]; __syncthreads(); }
-    if (tid == 0) s_mean = n > 0 ? red[0] / (double)n : 0.0;
-    __syncthreads();
+    const double mean = n > 0 ? kde_block_sum(red, s) / (double)n : (kde_block_sum(red, s), 0.0);
     double ss = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) { double d = (double)x[i] - s_mean; ss += d * d; }
-    red[tid] = ss;
+    for (int i = tid; i < n; i += KDE_THREADS) { double d = (double)x[i] - mean; ss += d * d; }
+    const double tot = kde_block_sum(red, ss);
+    const double var = n > 1 ? tot / (double)(n - 1) : 0.0;
+    const double factor = pow((double)n, -1.0 / 5.0);
+    const double sd = sqrt(var * factor * factor);
+    // compact the occupied histogram bins in ascending order (deterministic: the sums below run in the same
+    // order as a plain scan over all bins); typically a few hundred of the 2048 bins are occupied
+    __shared__ short cbin[2 * KDE_OFF];
+    __shared__ int ccnt[2 * KDE_OFF];
+    __shared__ int scan[KDE_THREADS];
+    constexpr int PER = 2 * KDE_OFF / KDE_THREADS;
+    int mine_n = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) mine_n += hist[tid * PER + k] != 0;
+    scan[tid] = mine_n;
     __syncthreads();
-    for (int d = 512; d > 0; d >>= 1) { if (tid < d) red[tid] += red[tid + d]; __syncthreads(); }
-    if (tid == 0) {
-        const double var = n > 1 ? red[0] / (double)(n - 1) : 0.0;
-        const double factor = pow((double)n, -1.0 / 5.0);
-        s_sd = sqrt(var * factor * factor);
+    for (int d = 1; d < KDE_THREADS; d <<= 1) {
+        const int v = tid >= d ? scan[tid - d] : 0;
+        __syncthreads();
+        scan[tid] += v;
+        __syncthreads();
+    }
+    const int nbins = scan[KDE_THREADS - 1];
+    int w = scan[tid] - mine_n;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = hist[tid * PER + k];
+        if (c != 0) { cbin[w] = (short)(tid * PER + k - KDE_OFF); ccnt[w] = c; ++w; }
     }
     __syncthreads();
-    double val = 0.0;
-    if (tid < KDE_SPAN && n > 0) {
-        const double xs = (double)tid / s_sd;
-        for (int b = 0; b < 2 * KDE_OFF; ++b) {
-            const int c = hist[b];
-            if (c == 0) continue;
-            const double r = (double)(b - KDE_OFF) / s_sd - xs;
-            val += (double)c * exp(-(r * r) / 2.0);
+    double val[KDE_PER_THREAD];
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < KDE_PER_THREAD; ++k) {
+        const int p = tid + k * KDE_THREADS;
+        val[k] = 0.0;
+        if (p < KDE_SPAN && n > 0) {
+            const double xs = (double)p / sd;
+            double acc = 0.0;
+            for (int b = 0; b < nbins; ++b) {
+                const double r = (double)cbin[b] / sd - xs;
+                const double e = -(r * r) / 2.0;
+                if (e < -746.0) continue;               // exp(e) == 0.0 exactly: adding it changes nothing
+                acc += (double)ccnt[b] * exp(e);
+            }
+            val[k] = acc;
         }
+        mine += val[k];
     }
-    red[tid] = tid < KDE_SPAN ? val : 0.0;
-    __syncthreads();
-    for (int d = 512; d > 0; d >>= 1) { if (tid < d) red[tid] += red[tid + d]; __syncthreads(); }
-    if (tid < KDE_SPAN) out[tid] = val / red[0];
+    const double total = kde_block_sum(red, mine);
+#pragma unroll
+    for (int k = 0; k < KDE_PER_THREAD; ++k) {
+        const int p = tid + k * KDE_THREADS;
+        if (p < KDE_SPAN) out[p] = val[k] / total;
+    }
     __syncthreads();
 }
