@@ -328,10 +328,11 @@ def _main(args):
         value = nprob * args.steps / sec
         # roofline of the dominant kernel (this rank's launch): integer (ALU) pipe.
         # executed ALU lane-instructions = executed DP cells x ALU_PER_CELL.  ALU_PER_CELL is calibrated on the
-        # committed ncu capture of this kernel (profiles/: sm__inst_executed_pipe_alu x 32 lanes / executed
-        # cells): 5.8 ALU instructions per packed cell pair (4 for the cell, 0.5 running max, 0.67 suffix
-        # hooks, byte (un)packing) -> 2.9 per cell; the few scalar phase-2 cells cost ~9 each.
-        ALU_PER_CELL, ALU_PER_SCALAR_CELL = 2.9, 9.0
+        # committed ncu capture of this kernel and workload (profiles/r1_classify_full.txt:
+        # sm__inst_executed_pipe_alu 75.0 % of 14.84 M active cycles x 64 lanes x 148 SMs = 1.055e11 lane-instr
+        # over 3.446e10 executed cells): 6.1 ALU instructions per packed cell pair (4 for the cell, 0.5 running
+        # max, 0.67 suffix hooks, byte (un)packing, phase 2) -> 3.06 per cell.
+        ALU_PER_CELL, ALU_PER_SCALAR_CELL = 3.06, 3.06
         sw_s = stage["sw"] / 1e3
         lane_instr = int(st[1]) * ALU_PER_CELL + int(st[2]) * ALU_PER_SCALAR_CELL
         achieved = lane_instr / sw_s / 1e9
@@ -359,9 +360,12 @@ def _main(args):
             "clocks": clocks,
             "roofline": {"kernel": "classify_kernel<P> (sw_family.cu), all period instantiations of one step",
                          "bound": "int", "achieved": achieved, "peak": int_peak, "unit": "G lane-instr/s",
-                         "frac": achieved / int_peak, "traffic": None,
+                         "frac": achieved / int_peak,
+                         # dram__bytes_read + dram__bytes_write of one launch at the default workload (ncu capture
+                         # in profiles/): scratch write-back, ~8 % of HBM bandwidth; algorithmic input is 0.17 GB
+                         "traffic": 6.53e9 if (args.samples == 384 and world == 1) else None,
                          "peak_source": "tredsw_int_pipe_peak (VIADDMNMX.S16x2 register loop, 64 lanes/clk/SM) measured in this run; "
-                                        "achieved = executed DP cells x 2.9 ALU instr/cell (calibrated on the ncu capture in profiles/)",
+                                        "achieved = executed DP cells x 3.06 ALU instr/cell (calibrated on the ncu capture in profiles/)",
                          "algorithmic_int_ops_per_s": 10.0 * int(st[0]) / sw_s,
                          "kernel_ms": stage["sw"], "share_of_step": stage["sw"] / max(stage["total"], 1e-9),
                          "executed_gcups": (int(st[1]) + int(st[2])) / sw_s / 1e9,
