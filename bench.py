@@ -354,7 +354,7 @@ def _main(args):
             "sw_gcups_algorithmic": alg_cells * args.steps / sec / 1e9,
             "sw_gcups_executed": (ex1 + ex2) * args.steps / sec / 1e9,
             "e2e": {"value": nprob * args.steps / t_e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes),
+                    "h2d_bytes_per_step": int(batch.h2d_bytes) * world, "d2h_bytes_per_step": int(batch.d2h_bytes) * world,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "calls_in_flight": max(1, args.depth)},
             "gpu_launches": int(launches) + int(e2e_launches),
             "clocks": clocks,
