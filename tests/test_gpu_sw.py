@@ -173,6 +173,63 @@ def test_family_kernel_fast_and_generic_paths_vs_oracle_across_loci():
         assert ntag > len(reads) // 3
 
 
+def test_prefilter_is_exact_on_borderline_reads():
+    """The q-gram pre-filter may only drop reads that cannot reach min_score = 30 against any template.
+    Adversarial reads sit right at the bound: a 28..40 bp piece of a template (either strand) with 0..3
+    substitutions, a 1..3 bp insertion or deletion, or N bases, embedded in random sequence — scores of
+    24..40, i.e. just below and just above the filter's reach.  Every read must get exactly the oracle's
+    record (tag, units, score), including the N-motif loci where template N is a wildcard."""
+    from tredparse_b200 import ssw
+    from tredparse_b200.meta import TREDsRepo
+    from oracle import evidence_oracle as evo
+    repo = TREDsRepo()
+    rng = np.random.default_rng(99)
+    B = "ACGT"
+    rnd = lambda n: "".join(rng.choice(list(B), n))
+    fams, reads, rfam, dbs = [], [], [], []
+    for name in ("HD", "DM1", "DM2", "SCA10", "SCA36", "ULD", "OPMD", "BPES"):
+        t = repo[name]
+        P = len(t.repeat)
+        mu = -(-150 // P)
+        fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, mu))
+        fi = len(fams) - 1
+        db = evo.template_family(t.prefix, t.repeat, t.suffix, mu)
+        for _ in range(40):
+            u = int(rng.integers(1, mu + 1))
+            tpl = db[2 * (u - 1) + int(rng.integers(0, 2))][1].replace("N", B[rng.integers(0, 4)])
+            L = int(rng.integers(28, 41))
+            st = int(rng.integers(0, max(1, len(tpl) - L + 1)))
+            piece = list(tpl[st:st + L])
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                for _k in range(int(rng.integers(0, 4))):
+                    piece[int(rng.integers(0, len(piece)))] = B[rng.integers(0, 4)]
+            elif kind == 1:
+                pos = int(rng.integers(5, len(piece) - 5))
+                piece[pos:pos] = list(rnd(int(rng.integers(1, 4))))
+            elif kind == 2:
+                pos = int(rng.integers(5, len(piece) - 8))
+                del piece[pos:pos + int(rng.integers(1, 4))]
+            else:
+                for _k in range(int(rng.integers(1, 3))):
+                    piece[int(rng.integers(0, len(piece)))] = "N"
+            left = int(rng.integers(0, 150 - len(piece) + 1))
+            read = rnd(left) + "".join(piece) + rnd(150 - len(piece) - left)
+            reads.append(read)
+            rfam.append(fi)
+            dbs.append((db, P, mu))
+    out = ssw.classify_reads(reads, np.array(rfam, dtype=np.int32), np.concatenate(fams))
+    tagged = 0
+    for r, (db, P, mu) in enumerate(dbs):
+        e = _expected_best(reads[r], db, P, mu)
+        if e is None:
+            assert out[r, 0] == 0, (r, out[r])
+        else:
+            tagged += 1
+            assert (out[r, 2], out[r, 1], out[r, 0]) == (e[0], e[1], TAGC[e[2]]), (r, e, out[r])
+    assert 20 < tagged < len(reads) - 20        # the set really straddles the threshold
+
+
 def test_aligner_api_matches_reference_semantics():
     """ssw.Aligner / PyAlignRes keep the reference's call signature and filter rule."""
     from tredparse_b200.ssw import Aligner
