@@ -259,7 +259,15 @@ typedef struct {
     int8_t mat25[25];
     int8_t pad_[3];
     int32_t gap_open, gap_extend;
+    uint32_t input_flags;       /* TREDSW_IN_* below: compact transfer formats, expanded on the device */
+    int32_t reserved_;
+    int64_t n_bases;            /* total bases in rbuf (= roff[nreads]); required with TREDSW_DEVICE_PTRS + PACKED4 */
 } tredsw_cohort;
+
+/* tredsw_cohort.input_flags — halve the host->device bytes of a call; the buffers are expanded into the
+ * regular layouts by two small kernels right after the copy (everything downstream is unchanged): */
+#define TREDSW_IN_READS_PACKED4 1u   /* rbuf holds two base codes per byte: base i in bits 4*(i&1).. of byte i>>1 */
+#define TREDSW_IN_PE_LENS_I16 2u     /* pe_lens points to int16_t values (pair lengths kept are < 1000) */
 
 typedef struct {
     int32_t allele1, allele2;   /* units, sorted; -1/-1 when there is no evidence */

@@ -173,3 +173,25 @@ def test_device_resident_path_equals_host_path(problems):
     stream.synchronize()
     dev = batch.calls_from_device()
     assert dev.tobytes() == host.tobytes()
+
+
+def test_packed_transfer_formats_equal_plain_inputs(problems):
+    """TREDSW_IN_READS_PACKED4 | TREDSW_IN_PE_LENS_I16: half the host->device bytes, byte-identical results
+    (calls and per-read records), odd total base counts included."""
+    from tredparse_b200 import cohort
+    for ps in (problems, problems[:1], problems[3:8]):
+        batch = cohort.CohortBatch(ps)
+        a = batch.run_host(want_reads=True, want_hist=True)
+        b = batch.run_host(want_reads=True, want_hist=True, packed=True)
+        assert a["calls"].tobytes() == b["calls"].tobytes()
+        assert np.array_equal(a["reads"], b["reads"]) and np.array_equal(a["hist"], b["hist"])
+    # a read set whose base count is odd / not a multiple of 8
+    import copy
+    pr = copy.copy(problems[0])
+    pr.reads = problems[0].reads[:-3].copy()
+    pr.roff = problems[0].roff.copy()
+    pr.roff[-1] -= 3
+    batch = cohort.CohortBatch([pr, problems[1]])
+    a = batch.run_host(want_reads=True)
+    b = batch.run_host(want_reads=True, packed=True)
+    assert a["calls"].tobytes() == b["calls"].tobytes() and np.array_equal(a["reads"], b["reads"])

@@ -131,6 +131,19 @@ def test_cohort_packing_offsets(repo):
     assert L["pe_minpe"] == L["pe_ref"] - 1 + 20                               # bam_parser.py:361
 
 
+def test_packed_transfer_formats_roundtrip(repo):
+    """pack_inputs(): two base codes per byte (base i in bits 4*(i&1) of byte i>>1), int16 pair lengths."""
+    probs = simulate.simulate_cohort(repo, ["HD", "OPMD"], 1, readlen=150)
+    batch = cohort.CohortBatch(probs).pack_inputs()
+    pk, pe = batch._packed["rbuf"], batch._packed["pe_lens"]
+    assert pk.dtype == np.uint8 and len(pk) % 4 == 0 and len(pk) >= (len(batch.rbuf) + 1) // 2
+    un = np.empty(2 * len(pk), dtype=np.int8)
+    un[0::2], un[1::2] = pk & 15, pk >> 4
+    assert np.array_equal(un[:len(batch.rbuf)], batch.rbuf)
+    assert pe.dtype == np.int16 and np.array_equal(pe.astype(np.int32), batch.pe_lens)
+    assert pk.nbytes + pe.nbytes < 0.52 * (batch.rbuf.nbytes + batch.pe_lens.nbytes)
+
+
 # ---- likelihood host logic -----------------------------------------------------------------------------
 def test_candidate_ranges_follow_models_py():
     # models.py:239-257 — base = sorted(spanning keys U {max partial}); extended keeps duplicates (Q9)

@@ -36,7 +36,11 @@ class Cohort(ctypes.Structure):
                 ("step_pmf", ctypes.c_void_p), ("stutter_w", ctypes.c_double * 5), ("gc", ctypes.c_double),
                 ("score", ctypes.c_double), ("maxinsert", ctypes.c_int32), ("fullsearch", ctypes.c_int32),
                 ("mat25", ctypes.c_int8 * 25), ("pad_", ctypes.c_int8 * 3), ("gap_open", ctypes.c_int32),
-                ("gap_extend", ctypes.c_int32)]
+                ("gap_extend", ctypes.c_int32), ("input_flags", ctypes.c_uint32), ("reserved_", ctypes.c_int32),
+                ("n_bases", ctypes.c_int64)]
+
+
+IN_READS_PACKED4, IN_PE_LENS_I16 = 1, 2          # tredsw_cohort.input_flags
 
 
 assert PROBLEM_DTYPE.itemsize == 40 and LOCUS_DTYPE.itemsize == 32 and CALL_DTYPE.itemsize == 64
@@ -109,10 +113,28 @@ class CohortBatch:
         self.hist_units = int(self.families["max_units"].max())
         self.objects = problems
         self._dev = None
+        self._packed = None
+
+    def pack_inputs(self):
+        """Compact transfer formats (TREDSW_IN_READS_PACKED4 | TREDSW_IN_PE_LENS_I16): two base codes per byte
+        and int16 pair lengths — half the host->device bytes; the library expands them on the device.  Done
+        once per batch, like the base encoding itself; run_host(packed=True) then sends these buffers."""
+        codes = self.rbuf.view(np.uint8)
+        n = len(codes)
+        pad = (-n) % 8
+        if pad:
+            codes = np.concatenate([codes, np.zeros(pad, np.uint8)])
+        packed = (codes[0::2] & 15) | ((codes[1::2] & 15) << 4)
+        if len(self.pe_lens) and (self.pe_lens.min() < -32768 or self.pe_lens.max() > 32767):
+            raise ValueError("paired-end lengths do not fit int16")
+        self._packed = {"rbuf": np.ascontiguousarray(packed, dtype=np.uint8),
+                        "pe_lens": np.ascontiguousarray(self.pe_lens.astype(np.int16))}
+        return self
 
     # ---- descriptor -----------------------------------------------------------------------------------
-    def _descriptor(self, rbuf, roff, rprob, problems, pe_lens):
+    def _descriptor(self, rbuf, roff, rprob, problems, pe_lens, input_flags=0):
         c = Cohort()
+        c.input_flags, c.n_bases = input_flags, int(len(self.rbuf))
         c.rbuf, c.roff, c.read_problem, c.problems, c.pe_lens = rbuf, roff, rprob, problems, pe_lens
         c.n_pe_lens, c.nreads, c.nproblems = len(self.pe_lens), self.nreads, self.nproblems
         c.max_read_len, c.nfamilies = self.max_read_len, len(self.families)
@@ -128,23 +150,30 @@ class CohortBatch:
         return c
 
     # ---- host buffers through the C ABI (H2D + kernels + D2H inside the call) -------------------------
-    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False):
+    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False, packed=False):
         ctx = ctx or _lib.default_context()
         _bind(ctx.lib)
         calls = np.zeros(self.nproblems, dtype=CALL_DTYPE)
         read_out = np.zeros((self.nreads, 8), dtype=np.int32) if want_reads else None
         hist = np.zeros((self.nproblems, 3, self.hist_units + 1), dtype=np.int32) if want_hist else None
         stats = np.zeros(8, dtype=np.int64) if want_stats else None
-        c = self._descriptor(self.rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
-                             self.problems.ctypes.data, self.pe_lens.ctypes.data)
+        if packed:
+            if self._packed is None:
+                self.pack_inputs()
+            rbuf, pe = self._packed["rbuf"], self._packed["pe_lens"]
+            flags_in = IN_READS_PACKED4 | IN_PE_LENS_I16
+        else:
+            rbuf, pe, flags_in = self.rbuf, self.pe_lens, 0
+        c = self._descriptor(rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
+                             self.problems.ctypes.data, pe.ctypes.data, flags_in)
         for attempt in range(2):
             rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), 0, _lib.ptr(calls), _lib.ptr(read_out),
                                                _lib.ptr(hist), self.hist_units, _lib.ptr(stats))
             if rc == 0 or "arena overflow" not in _lib.last_error():
                 break
         _lib.check(rc, "tredsw_genotype_batch")
-        self.h2d_bytes = (self.rbuf.nbytes + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
-                          self.pe_lens.nbytes + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
+        self.h2d_bytes = (rbuf.nbytes + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
+                          pe.nbytes + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
         self.d2h_bytes = calls.nbytes + (read_out.nbytes if want_reads else 0) + (hist.nbytes if want_hist else 0)
         out = {"calls": calls}
         if want_reads:

@@ -50,6 +50,19 @@ __global__ void read_family_kernel(const int32_t *read_problem, const tredsw_pro
     }
 }
 
+// compact transfer formats -> regular device layouts (tredsw_cohort.input_flags)
+__global__ void unpack_reads4_kernel(const uint32_t *packed, int64_t nwords, uint32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint32_t w = packed[i];                       // 8 bases
+    out[2 * i] = (w & 0xfu) | ((w >> 4) & 0xfu) << 8 | ((w >> 8) & 0xfu) << 16 | ((w >> 12) & 0xfu) << 24;
+    out[2 * i + 1] = ((w >> 16) & 0xfu) | ((w >> 20) & 0xfu) << 8 | ((w >> 24) & 0xfu) << 16 | ((w >> 28) & 0xfu) << 24;
+}
+__global__ void widen_i16_kernel(const int16_t *in, int64_t n, int32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+
 __global__ void tally_kernel(CohortDev c) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= c.nreads) return;
@@ -259,9 +272,26 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     const int8_t *d_rbuf = c->rbuf; const int64_t *d_roff = c->roff; const int32_t *d_rp = c->read_problem;
     const tredsw_problem *d_prob = c->problems; const int32_t *d_pe = c->pe_lens;
     const tredsw_family *d_fam; const tredsw_locus *d_loci;
+    const bool packed4 = (c->input_flags & TREDSW_IN_READS_PACKED4) != 0, pe16 = (c->input_flags & TREDSW_IN_PE_LENS_I16) != 0;
+    if (dev && packed4 && c->n_bases <= 0 && nr > 0) { tredsw_set_error("n_bases is required for packed reads in device memory"); return TREDSW_ERR_ARG; }
+    const int64_t nbases = nr > 0 ? (dev ? c->n_bases : c->roff[nr]) : 0;
+    if (packed4 && nr > 0) {
+        // rbuf holds nibbles: bring the packed words to the device, expand into the byte-per-base buffer
+        const int64_t nwords = (nbases + 7) / 8;
+        const uint32_t *d_pk = reinterpret_cast<const uint32_t *>(c->rbuf);
+        if (!dev) {
+            if ((rc = ctx->d_pk.ensure((size_t)nwords * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_pk.p, c->rbuf, (size_t)(nbases + 1) / 2, cudaMemcpyHostToDevice, ctx->stream));
+            d_pk = ctx->d_pk.as<uint32_t>();
+        }
+        if ((rc = ctx->d_q.ensure((size_t)nwords * 8))) return rc;
+        unpack_reads4_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(d_pk, nwords, ctx->d_q.as<uint32_t>());
+        ctx->launches += 1;
+        d_rbuf = ctx->d_q.as<int8_t>();
+    }
     if (!dev) {
         if (nr > 0) {
-            if ((rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
+            if (!packed4 && (rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
             if ((rc = stage_in(ctx, ctx->d_qoff, c->roff, (size_t)nr + 1, 0u, &d_roff))) return rc;
             if ((rc = stage_in(ctx, ctx->d_qidx, c->read_problem, (size_t)nr, 0u, &d_rp))) return rc;
         }
@@ -274,7 +304,16 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     const int64_t n_ipool = c->n_pe_lens + (int64_t)np_ * slot_ints;
     if ((rc = ctx->d_ipool.ensure((size_t)n_ipool * sizeof(int32_t)))) return rc;
     int32_t *d_ipool = ctx->d_ipool.as<int32_t>();
-    if (c->n_pe_lens > 0)
+    if (c->n_pe_lens > 0 && pe16) {
+        const int16_t *d16 = reinterpret_cast<const int16_t *>(c->pe_lens);
+        if (!dev) {
+            if ((rc = ctx->d_pe16.ensure((size_t)c->n_pe_lens * sizeof(int16_t)))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_pe16.p, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+            d16 = ctx->d_pe16.as<int16_t>();
+        }
+        widen_i16_kernel<<<(unsigned)((c->n_pe_lens + 255) / 256), 256, 0, ctx->stream>>>(d16, c->n_pe_lens, d_ipool);
+        ctx->launches += 1;
+    } else if (c->n_pe_lens > 0)
         CUDA_TRY(cudaMemcpyAsync(d_ipool, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int32_t),
                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     (void)d_pe;
