@@ -287,6 +287,50 @@ typedef struct {
 int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
                           int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats);
 
+/* ------------------------------------------------------------------------------------------------
+ * (C) native BAM ingest (host code, zlib) — replaces the three pysam passes per locus of the reference:
+ * read selection (tredparse/bam_parser.py:194-243), PEextractor (:316-369) and BamDepth.region_depth
+ * (:404-411) with one indexed pass that writes base codes, pair distances and depth into caller-owned
+ * (e.g. pinned) buffers in the layout tredsw_genotype_batch consumes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tredsw_bam tredsw_bam;
+
+typedef struct {
+    int32_t tid;                /* contig of the locus (tredsw_bam_tid) */
+    int32_t repeat_start, repeat_end;
+    int32_t readlen;            /* READLEN: mapped reads must start within +-READLEN of the repeat */
+    int32_t pad;                /* parse / depth window: +-pad around the repeat (SPAN = 1000) */
+    int32_t pe_window;          /* pair window: +-pe_window (DNAPE_ELONGATE = 10000) */
+    int32_t flankmatch;         /* FLANKMATCH = 9: a pair is "target" if it spans the repeat by more than this */
+    int32_t span;               /* pairs with distance >= span are dropped (SPAN = 1000) */
+    int32_t n_alts;             /* alternative (mis-mapping) regions: reads there whose mate lies in the window */
+    int32_t reserved_;
+    const int32_t *alts;        /* n_alts x (tid, start, end) */
+} tredsw_locus_query;
+
+typedef struct {
+    int32_t nreads;             /* reads selected (also counted when a buffer overflowed) */
+    int32_t n_unmapped;
+    int32_t n_global, n_target; /* pair distances written to global_lens / target_lens */
+    int64_t nbases;             /* roff[nreads] */
+    int64_t name_bytes;         /* NUL-separated read names written to `names` */
+    double depth;               /* mean pileup depth of the +-pad window */
+    int32_t overflow;           /* 1: some buffer was too small; counts above tell the sizes needed */
+    int32_t reserved_;
+} tredsw_locus_summary;
+
+/* bai_path NULL: <bam>.bai, then <bam without extension>.bai.  NULL + tredsw_last_error() on failure. */
+tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path);
+void tredsw_bam_close(tredsw_bam *bam);
+int32_t tredsw_bam_nref(tredsw_bam *bam);
+int32_t tredsw_bam_tid(tredsw_bam *bam, const char *contig);     /* -1 when unknown */
+/* names may be NULL (not wanted).  Reads are written in the reference's order: window reads in file
+ * order, then the alt-region reads. */
+int tredsw_bam_extract_locus(tredsw_bam *bam, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
+                             int64_t *roff, int32_t reads_cap, int32_t *global_lens, int32_t global_cap,
+                             int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
+                             tredsw_locus_summary *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,79 @@
+"""Native BAM ingest (csrc/ingest.cpp, host code) against the Python host path that mirrors the reference —
+BamParser.select_reads (bam_parser.py:194-243), PEextractor (:316-369), BamDepth.region_depth (:404-411) —
+on the committed mini BAMs and, where the reference tree is mounted, on its full test BAMs.  No GPU needed."""
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from tredparse_b200 import bamio, ingest, ssw
+from tredparse_b200.bam_parser import BamParser, PEextractor, BamDepth
+from tredparse_b200.meta import TREDsRepo
+from tredparse_b200.utils import InputParams
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = [("t001", "HD"), ("t002", "DM1")]
+BAMS = [(s, t, os.path.join(GOLDEN, s + ".mini.bam")) for s, t in CASES]
+BAMS += [(s + "_full", t, "/root/reference/tests/{}.bam".format(s)) for s, t in CASES
+         if os.path.exists("/root/reference/tests/{}.bam".format(s))]
+
+
+@pytest.fixture(scope="module")
+def repo():
+    return TREDsRepo()
+
+
+def _python_path(bam, tredname, repo, alts):
+    ip = InputParams(bam=bam, READLEN=150, tredName=tredname, repo=repo, maxinsert=300, fullsearch=False,
+                     gender="Unknown", depth=30, clip=False, alts=alts, repeatpairs=True, log="INFO")
+    bp = BamParser(ip)
+    sam = bamio.AlignmentFile(bam)
+    reads = bp.select_reads(sam)
+    sam.close()
+    pe = PEextractor(bp)
+    t = repo[tredname]
+    depth = BamDepth(bam, "hg38", logging.getLogger()).region_depth(t.chr, max(0, t.repeat_start - 1000), t.repeat_end + 1000)
+    return bp, reads, pe, depth
+
+
+@pytest.mark.parametrize("sample,tredname,bam", BAMS, ids=[b[0] for b in BAMS])
+@pytest.mark.parametrize("alts", [False, True])
+def test_extract_locus_equals_python_host_path(sample, tredname, bam, alts, repo):
+    bp, reads, pe, depth = _python_path(bam, tredname, repo, alts)
+    with ingest.BamIngest(bam) as ing:
+        ev = ing.extract_locus(repo[tredname], 150, alts=bp.alt if alts else (), want_names=True)
+    assert ev.nreads == len(reads) > 50
+    assert ev.names == [r.query_name for r in reads]
+    assert ev.read_strings() == ["".join(c if c in "ACGT" else "N" for c in r.query_sequence.upper()) for r in reads]
+    assert np.array_equal(ev.reads, np.concatenate([ssw.encode(r.query_sequence) for r in reads]))
+    assert list(ev.global_lens) == list(pe.global_lens) and len(pe.global_lens) > 1000
+    assert list(ev.target_lens) == list(pe.target_lens) and len(pe.target_lens) >= 5
+    assert ev.depth == depth
+    if not alts:
+        assert ev.n_unmapped == sum(1 for r in reads if r.is_unmapped)
+
+
+def test_missing_locus_and_errors(repo):
+    with ingest.BamIngest(os.path.join(GOLDEN, "t001.mini.bam")) as ing:
+        ev = ing.extract_locus(repo["DM1"], 150)             # chr19: no reads in the chr4 mini BAM
+        assert ev.nreads == 0 and len(ev.global_lens) == 0 and ev.depth == 0.0
+        assert ing.tid("chr4") >= 0 and ing.tid("nope") == -1
+        tiny = ingest.BamIngest(os.path.join(GOLDEN, "t001.mini.bam"))
+        tiny._caps = dict(reads=1, bases=8, pairs=1, names=4)      # forces the overflow / retry path
+        ev2 = tiny.extract_locus(repo["HD"], 150, want_names=True)
+        ev1 = ing.extract_locus(repo["HD"], 150, want_names=True)
+        assert np.array_equal(ev1.reads, ev2.reads) and ev1.names == ev2.names
+        assert list(ev1.global_lens) == list(ev2.global_lens)
+    with pytest.raises(IOError):
+        ingest.BamIngest("/nonexistent.bam")
+
+
+def test_problem_feeds_the_cohort_packer(repo):
+    from tredparse_b200 import cohort
+    with ingest.BamIngest(os.path.join(GOLDEN, "t001.mini.bam")) as a, \
+            ingest.BamIngest(os.path.join(GOLDEN, "t002.mini.bam")) as b:
+        probs = [a.problem(repo["HD"], 150), b.problem(repo["DM1"], 150)]
+    batch = cohort.CohortBatch(probs)
+    assert batch.nproblems == 2 and batch.nreads == probs[0].nreads + probs[1].nreads
+    assert 25 < probs[0].depth < 35 and 40 < probs[1].depth < 55

@@ -27,6 +27,8 @@ EXPORTS = [
     "tredsw_synchronize", "tredsw_sm_count", "tredsw_launch_count", "tredsw_enable_timing",
     "tredsw_get_timing", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
     "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch",
+    # native BAM ingest
+    "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
 ]
 
 

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtredsw.so")
-SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu"]
+SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu", "ingest.cpp"]
 HEADERS = ["common.cuh", "sw_sweep.cuh", "internal.cuh", "kde.cuh", os.path.join("..", "..", "include", "tredsw.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        o = os.path.join(CSRC, os.path.splitext(s)[0] + ".o")
         cmd = [nvcc_path(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-c",
                os.path.join(CSRC, s), "-o", o]
         if verbose:
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode("utf-8", "replace"))
         if pr.returncode:
             raise RuntimeError("nvcc failed on {}".format(s))
-    subprocess.check_call([nvcc_path(), *ARCH, "-shared", "-o", OUT] + objs)
+    subprocess.check_call([nvcc_path(), *ARCH, "-shared", "-o", OUT] + objs + ["-lz"])
     return OUT
 
 

@@ -1,0 +1,385 @@
+// ingest.cpp — native BAM ingest for the genotyping path (host code, zlib only).
+//
+// Replaces, for one locus, the three pysam passes of the reference:
+//   BamParser.parse selection .......... tredparse/bam_parser.py:194-243  (window fetch, READ window, alts)
+//   PEextractor ......................... tredparse/bam_parser.py:316-369  (+-10 kb pair distances)
+//   BamDepth.region_depth ............... tredparse/bam_parser.py:404-411  (pileup depth of the +-1 kb window)
+// with ONE indexed pass over the BGZF blocks of the +-10 kb window, writing the reads as base codes
+// (A,C,G,T,N -> 0..4, src/ssw_wrap.py:229-244), the pair distances and the depth straight into caller-owned
+// (pinned) buffers — the layout tredsw_genotype_batch consumes.  Record order, pairing rule and depth
+// definition are those of the Python host path (tredparse_b200/bam_parser.py, bamio.py), which the tests use
+// as the oracle of this file.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/tredsw.h"
+
+void tredsw_set_error(const char *fmt, ...);
+
+namespace {
+
+struct Bgzf {
+    FILE *fh = nullptr;
+    std::vector<unsigned char> cbuf, block;
+    int64_t block_coffset = -1, next_coffset = 0;
+    size_t pos = 0;
+    z_stream zs;
+    bool zs_init = false;
+
+    bool load(int64_t coffset) {
+        block.clear(); pos = 0; block_coffset = coffset; next_coffset = coffset;
+        if (fseeko(fh, coffset, SEEK_SET) != 0) return false;
+        unsigned char head[18];
+        if (fread(head, 1, 18, fh) != 18) return false;
+        if (head[0] != 31 || head[1] != 139 || !(head[3] & 4)) return false;
+        const int xlen = head[10] | (head[11] << 8);
+        std::vector<unsigned char> extra(xlen);
+        memcpy(extra.data(), head + 12, std::min(6, xlen));
+        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fh) != (size_t)(xlen - 6)) return false;
+        int bsize = -1;
+        for (int off = 0; off + 4 <= xlen;) {
+            const int slen = extra[off + 2] | (extra[off + 3] << 8);
+            if (extra[off] == 66 && extra[off + 1] == 67 && off + 6 <= xlen) bsize = extra[off + 4] | (extra[off + 5] << 8);
+            off += 4 + slen;
+        }
+        if (bsize < 0) return false;
+        const int clen = bsize - xlen - 19;
+        cbuf.resize(clen > 0 ? clen : 0);
+        if (clen > 0 && fread(cbuf.data(), 1, clen, fh) != (size_t)clen) return false;
+        unsigned char tail[8];
+        if (fread(tail, 1, 8, fh) != 8) return false;
+        const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        block.resize(isize);
+        if (isize > 0) {
+            if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) return false; zs_init = true; }
+            else inflateReset(&zs);
+            zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
+            zs.next_out = block.data(); zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END) return false;
+        }
+        next_coffset = coffset + bsize + 1;
+        return true;
+    }
+    void seek(uint64_t voffset) {
+        const int64_t coffset = (int64_t)(voffset >> 16);
+        if (coffset != block_coffset) load(coffset);
+        pos = (size_t)(voffset & 0xffff);
+    }
+    uint64_t tell() const {
+        if (pos >= block.size() && block_coffset >= 0) return (uint64_t)next_coffset << 16;
+        return ((uint64_t)block_coffset << 16) | pos;
+    }
+    size_t read(void *dst, size_t n) {
+        unsigned char *out = (unsigned char *)dst;
+        size_t got = 0;
+        while (n > 0) {
+            size_t avail = block.size() > pos ? block.size() - pos : 0;
+            if (avail == 0) {
+                const int64_t prev = block_coffset;
+                if (!load(next_coffset)) break;
+                if (block.empty()) { if (next_coffset == block_coffset || block_coffset == prev) break; continue; }
+                avail = block.size();
+            }
+            const size_t take = std::min(avail, n);
+            memcpy(out + got, block.data() + pos, take);
+            pos += take; got += take; n -= take;
+        }
+        return got;
+    }
+    ~Bgzf() { if (zs_init) inflateEnd(&zs); if (fh) fclose(fh); }
+};
+
+struct RefIndex {
+    std::unordered_map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+    std::vector<uint64_t> linear;
+};
+
+struct Record {
+    int32_t tid, pos, next_tid, next_pos, tlen, l_seq;
+    uint16_t flag;
+    int32_t ref_len;          // reference span of the CIGAR
+    int32_t qstart, qend;     // query_alignment_start / _end (soft clips)
+    bool has_cigar;
+    std::string name;
+    const unsigned char *seq; // packed 4-bit, valid until the next record is read
+};
+
+}  // namespace
+
+struct tredsw_bam {
+    Bgzf bgzf;
+    std::vector<std::string> names;
+    std::vector<int64_t> lengths;
+    std::unordered_map<std::string, int32_t> tid_of;
+    std::vector<RefIndex> index;
+    bool has_index = false;
+    std::vector<unsigned char> rec;
+
+    bool read_record(Record &r) {
+        int32_t bs;
+        if (bgzf.read(&bs, 4) != 4 || bs < 32) return false;
+        rec.resize(bs);
+        if (bgzf.read(rec.data(), bs) != (size_t)bs) return false;
+        const unsigned char *d = rec.data();
+        auto i32 = [&](int o) { int32_t v; memcpy(&v, d + o, 4); return v; };
+        auto u16 = [&](int o) { uint16_t v; memcpy(&v, d + o, 2); return v; };
+        r.tid = i32(0); r.pos = i32(4);
+        const int l_name = d[8];
+        const int n_cigar = u16(12);
+        r.flag = u16(14); r.l_seq = i32(16); r.next_tid = i32(20); r.next_pos = i32(24); r.tlen = i32(28);
+        int off = 32;
+        r.name.assign((const char *)d + off, l_name > 0 ? l_name - 1 : 0);
+        off += l_name;
+        r.ref_len = 0; r.has_cigar = n_cigar > 0;
+        int qs = 0, qe = r.l_seq;
+        bool lead = true;
+        for (int k = 0; k < n_cigar; ++k) {
+            uint32_t c; memcpy(&c, d + off + 4 * k, 4);
+            const int op = c & 15, len = (int)(c >> 4);
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) r.ref_len += len;   // M D N = X
+            if (lead) { if (op == 4) qs += len; else if (op != 5) lead = false; }
+        }
+        for (int k = n_cigar - 1; k >= 0; --k) {
+            uint32_t c; memcpy(&c, d + off + 4 * k, 4);
+            const int op = c & 15, len = (int)(c >> 4);
+            if (op == 4) qe -= len; else if (op != 5) break;
+        }
+        r.qstart = qs; r.qend = qe;
+        off += 4 * n_cigar;
+        r.seq = d + off;
+        return true;
+    }
+
+    // merged chunk list of an indexed region query (same rule as bamio.BAIIndex.chunks)
+    std::vector<std::pair<uint64_t, uint64_t>> chunks(int tid, int64_t beg, int64_t end) const {
+        std::vector<std::pair<uint64_t, uint64_t>> out;
+        if (tid < 0 || tid >= (int)index.size()) return out;
+        const RefIndex &ri = index[tid];
+        uint64_t min_off = 0;
+        if (!ri.linear.empty()) { const size_t k = (size_t)(beg >> 14); min_off = k < ri.linear.size() ? ri.linear[k] : ri.linear.back(); }
+        const int64_t e1 = end - 1;
+        auto add_bin = [&](uint32_t b) {
+            if (b == 37450) return;
+            auto it = ri.bins.find(b);
+            if (it == ri.bins.end()) return;
+            for (auto &c : it->second) if (c.second > min_off) out.push_back(c);
+        };
+        add_bin(0);
+        const int shifts[5] = {26, 23, 20, 17, 14}, offs[5] = {1, 9, 73, 585, 4681};
+        for (int l = 0; l < 5; ++l)
+            for (int64_t b = offs[l] + (beg >> shifts[l]); b <= offs[l] + (e1 >> shifts[l]); ++b) add_bin((uint32_t)b);
+        std::sort(out.begin(), out.end());
+        std::vector<std::pair<uint64_t, uint64_t>> merged;
+        for (auto &c : out) {
+            if (!merged.empty() && c.first <= merged.back().second) merged.back().second = std::max(merged.back().second, c.second);
+            else merged.push_back(c);
+        }
+        return merged;
+    }
+
+    // records overlapping [start, end) on tid, in file order (bamio.AlignmentFile._iter_indexed)
+    template <class F>
+    void fetch(int tid, int64_t start, int64_t end, F &&fn) {
+        if (start < 0) start = 0;
+        Record r;
+        for (auto &c : chunks(tid, start, end)) {
+            bgzf.seek(c.first);
+            while (bgzf.tell() < c.second) {
+                if (!read_record(r)) break;
+                if (r.tid != tid) { if (r.tid >= 0 && r.tid < tid) continue; return; }
+                if (r.pos >= end) return;
+                int64_t rend = (int64_t)r.pos + r.ref_len;
+                if ((r.flag & 4) || !r.has_cigar || rend <= r.pos) rend = (int64_t)r.pos + 1;
+                if (r.pos < end && rend > start) fn(r);
+            }
+        }
+    }
+};
+
+extern "C" {
+
+tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
+    if (!bam_path) { tredsw_set_error("null path"); return nullptr; }
+    tredsw_bam *b = new tredsw_bam();
+    b->bgzf.fh = fopen(bam_path, "rb");
+    if (!b->bgzf.fh) { tredsw_set_error("cannot open %s", bam_path); delete b; return nullptr; }
+    char magic[4];
+    int32_t l_text = 0, n_ref = 0;
+    if (b->bgzf.read(magic, 4) != 4 || memcmp(magic, "BAM\1", 4) != 0 || b->bgzf.read(&l_text, 4) != 4 || l_text < 0) {
+        tredsw_set_error("%s is not a BAM file", bam_path); delete b; return nullptr;
+    }
+    std::vector<char> text(l_text);
+    if (l_text && b->bgzf.read(text.data(), l_text) != (size_t)l_text) { tredsw_set_error("truncated BAM header"); delete b; return nullptr; }
+    if (b->bgzf.read(&n_ref, 4) != 4 || n_ref < 0) { tredsw_set_error("truncated BAM header"); delete b; return nullptr; }
+    for (int i = 0; i < n_ref; ++i) {
+        int32_t l_name = 0, l_ref = 0;
+        if (b->bgzf.read(&l_name, 4) != 4 || l_name <= 0 || l_name > 4096) { tredsw_set_error("bad reference name"); delete b; return nullptr; }
+        std::vector<char> nm(l_name);
+        if (b->bgzf.read(nm.data(), l_name) != (size_t)l_name || b->bgzf.read(&l_ref, 4) != 4) { tredsw_set_error("truncated BAM header"); delete b; return nullptr; }
+        b->names.emplace_back(nm.data());
+        b->lengths.push_back(l_ref);
+        b->tid_of[b->names.back()] = i;
+    }
+    // index: <bam>.bai, then <bam without extension>.bai (bamio.AlignmentFile)
+    std::string cands[2];
+    if (bai_path) cands[0] = bai_path;
+    else {
+        cands[0] = std::string(bam_path) + ".bai";
+        std::string p(bam_path);
+        const size_t dot = p.rfind('.');
+        cands[1] = (dot == std::string::npos ? p : p.substr(0, dot)) + ".bai";
+    }
+    for (const std::string &cand : cands) {
+        if (cand.empty()) continue;
+        FILE *fi = fopen(cand.c_str(), "rb");
+        if (!fi) continue;
+        fseeko(fi, 0, SEEK_END);
+        const int64_t sz = ftello(fi);
+        fseeko(fi, 0, SEEK_SET);
+        std::vector<unsigned char> data(sz > 0 ? sz : 0);
+        const bool ok = sz >= 8 && fread(data.data(), 1, sz, fi) == (size_t)sz && memcmp(data.data(), "BAI\1", 4) == 0;
+        fclose(fi);
+        if (!ok) continue;
+        size_t off = 4;
+        auto need = [&](size_t n) { return off + n <= data.size(); };
+        int32_t nr = 0;
+        memcpy(&nr, data.data() + off, 4); off += 4;
+        bool good = true;
+        b->index.assign(nr > 0 ? nr : 0, RefIndex());
+        for (int i = 0; i < nr && good; ++i) {
+            int32_t n_bin = 0;
+            if (!need(4)) { good = false; break; }
+            memcpy(&n_bin, data.data() + off, 4); off += 4;
+            for (int k = 0; k < n_bin; ++k) {
+                uint32_t bin; int32_t n_chunk;
+                if (!need(8)) { good = false; break; }
+                memcpy(&bin, data.data() + off, 4); memcpy(&n_chunk, data.data() + off + 4, 4); off += 8;
+                if (n_chunk < 0 || !need((size_t)16 * n_chunk)) { good = false; break; }
+                auto &v = b->index[i].bins[bin];
+                for (int c = 0; c < n_chunk; ++c) {
+                    uint64_t s, e;
+                    memcpy(&s, data.data() + off, 8); memcpy(&e, data.data() + off + 8, 8); off += 16;
+                    v.emplace_back(s, e);
+                }
+            }
+            int32_t n_intv = 0;
+            if (!good || !need(4)) { good = false; break; }
+            memcpy(&n_intv, data.data() + off, 4); off += 4;
+            if (n_intv < 0 || !need((size_t)8 * n_intv)) { good = false; break; }
+            b->index[i].linear.resize(n_intv);
+            if (n_intv) memcpy(b->index[i].linear.data(), data.data() + off, (size_t)8 * n_intv);
+            off += (size_t)8 * n_intv;
+        }
+        if (good) { b->has_index = true; break; }
+        b->index.clear();
+    }
+    if (!b->has_index) { tredsw_set_error("no usable .bai index next to %s", bam_path); delete b; return nullptr; }
+    return b;
+}
+
+void tredsw_bam_close(tredsw_bam *b) { delete b; }
+
+int32_t tredsw_bam_nref(tredsw_bam *b) { return b ? (int32_t)b->names.size() : 0; }
+
+int32_t tredsw_bam_tid(tredsw_bam *b, const char *name) {
+    if (!b || !name) return -1;
+    auto it = b->tid_of.find(name);
+    return it == b->tid_of.end() ? -1 : it->second;
+}
+
+int tredsw_bam_extract_locus(tredsw_bam *b, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
+                             int64_t *roff, int32_t reads_cap, int32_t *global_lens, int32_t global_cap,
+                             int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
+                             tredsw_locus_summary *out) {
+    if (!b || !q || !out || !roff || reads_cap < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    if (q->tid < 0 || q->tid >= (int)b->names.size()) { tredsw_set_error("contig id %d out of range", q->tid); return TREDSW_ERR_ARG; }
+    static const int8_t NIB[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};   // "=ACMGRSVTWYHKDBN"
+    memset(out, 0, sizeof(*out));
+    const int64_t start = q->repeat_start, end = q->repeat_end;
+    const int64_t WIN_S = std::max<int64_t>(0, start - q->pad), WIN_E = end + q->pad;               // parse window
+    const int64_t READ_S = std::max<int64_t>(0, start - q->readlen), READ_E = end + q->readlen;
+    const int64_t PE_S = std::max<int64_t>(start - q->pe_window, 0), PE_E = end + q->pe_window;     // pair window
+    const int64_t tstart = start - q->flankmatch, tend = end + q->flankmatch;
+    int64_t nbases = 0, name_bytes = 0, depth_sum = 0;
+    int32_t nreads = 0;
+    roff[0] = 0;
+    auto emit_read = [&](const Record &r) {
+        if (nreads < reads_cap && nbases + r.l_seq <= rbuf_cap && rbuf) {
+            int8_t *dst = rbuf + nbases;
+            for (int i = 0; i < r.l_seq; ++i) dst[i] = NIB[(r.seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
+            roff[nreads + 1] = nbases + r.l_seq;
+        } else out->overflow = 1;
+        if (names) {
+            if (name_bytes + (int64_t)r.name.size() + 1 <= names_cap) { memcpy(names + name_bytes, r.name.c_str(), r.name.size() + 1); }
+            else out->overflow = 1;
+        }
+        name_bytes += (int64_t)r.name.size() + 1;
+        nbases += r.l_seq;
+        ++nreads;
+    };
+    // pairs of the +-pe_window region, keyed by name in order of first appearance (PEextractor)
+    struct Mate { int32_t pos, ref_end, qstart, qend, l_seq; bool reverse; };
+    std::unordered_map<std::string, int> slot;
+    std::vector<std::pair<Mate, Mate>> pairs;
+    std::vector<int> npair;
+    const int64_t lo = std::min(WIN_S, PE_S), hi = std::max(WIN_E, PE_E);
+    b->fetch(q->tid, lo, hi, [&](const Record &r) {
+        int64_t rend = (int64_t)r.pos + r.ref_len;
+        const bool unmapped = (r.flag & 4) != 0;
+        if (unmapped || !r.has_cigar || rend <= r.pos) rend = (int64_t)r.pos + 1;
+        // (1) reads handed to Smith-Waterman: overlap the +-pad window; mapped ones must start in the READ window
+        if (r.pos < WIN_E && rend > WIN_S) {
+            if (unmapped) { ++out->n_unmapped; emit_read(r); }
+            else if (r.pos >= READ_S && r.pos <= READ_E) emit_read(r);
+            // (3) pileup depth of the +-pad window: reference span of every counted read that overlaps it
+            if (!(r.flag & (4 | 256 | 512 | 1024)) && r.has_cigar) depth_sum += r.ref_len;
+        }
+        // (2) properly paired, mapped, non-duplicate records of the pair window
+        if (r.pos < PE_E && rend > PE_S && (r.flag & 1) && !unmapped && !(r.flag & 1024)) {
+            auto it = slot.find(r.name);
+            Mate m{r.pos, (int32_t)((r.flag & 4) || !r.has_cigar ? -1 : r.pos + r.ref_len), r.qstart, r.qend, r.l_seq, (r.flag & 16) != 0};
+            if (it == slot.end()) { slot.emplace(r.name, (int)pairs.size()); pairs.emplace_back(m, Mate{}); npair.push_back(1); }
+            else if (npair[it->second] == 1) { pairs[it->second].second = m; npair[it->second] = 2; }
+            else ++npair[it->second];
+        }
+    });
+    // alt regions: reads whose MATE lies in the parse window of this locus (bam_parser.py:215-243)
+    for (int a = 0; a < q->n_alts && q->alts; ++a) {
+        const int32_t atid = q->alts[3 * a], as = q->alts[3 * a + 1], ae = q->alts[3 * a + 2];
+        if (atid < 0 || atid >= (int)b->names.size()) continue;
+        b->fetch(atid, as, ae, [&](const Record &r) {
+            if (r.next_tid != q->tid) return;
+            if (r.next_pos < WIN_S || r.next_pos > WIN_E) return;
+            emit_read(r);
+        });
+    }
+    int32_t ng = 0, nt = 0;
+    for (size_t i = 0; i < pairs.size(); ++i) {
+        if (npair[i] < 2) continue;
+        const Mate &x = pairs[i].first, &y = pairs[i].second;
+        if (!(!x.reverse && y.reverse)) continue;
+        int64_t s = x.pos, e = y.ref_end;
+        if (x.qstart > 0) s -= x.qstart;
+        if (y.qend < y.l_seq) e += y.l_seq - y.qend;
+        const int64_t tlen = e - s;
+        if (tlen >= q->span) continue;
+        if (x.pos < tstart && y.ref_end > tend) { if (nt < target_cap && target_lens) target_lens[nt] = (int32_t)tlen; else out->overflow = 1; ++nt; }
+        else { if (ng < global_cap && global_lens) global_lens[ng] = (int32_t)tlen; else out->overflow = 1; ++ng; }
+    }
+    out->nreads = nreads; out->nbases = nbases; out->name_bytes = name_bytes;
+    out->n_global = ng; out->n_target = nt;
+    out->depth = (double)depth_sum * 1.0 / (double)(WIN_E - WIN_S + 1);
+    return TREDSW_OK;
+}
+
+}  // extern "C"

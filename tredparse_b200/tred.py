@@ -29,7 +29,7 @@ import numpy as np
 from . import __version__, ssw
 from .utils import DefaultHelpParser, InputParams, mkdir
 from .bam_parser import BamDepth, BamReadLen, BamParser, BamParserResults, PEextractor, SPAN, \
-    read_alignment
+    FLANKMATCH, read_alignment
 from .models import IntegratedCaller, GridBatch, MIN_SPANNING_PAIRS, pe_kde, mean_std, histogram, \
     calc_label
 from .meta import TREDsRepo
@@ -132,20 +132,47 @@ class _Caller:
     """Result holder with IntegratedCaller's result attributes (batched path)."""
 
 
-def run_batched(ips):
+class _IngestPE:
+    """PEextractor's attributes filled from a native one-pass extraction (ingest.LocusEvidence)."""
+
+    def __init__(self, bp, ev):
+        self.ref = bp.referenceLen
+        self.global_lens = [int(x) for x in ev.global_lens]
+        self.target_lens = [int(x) for x in ev.target_lens]
+        self.MINPE = bp.endRepeat - bp.startRepeat + 2 * FLANKMATCH + 2
+
+
+def locus_evidence(ing, ip_or_bp, tred, readlen, alts, clip, ref):
+    """One native pass over the BAM for one locus (reads + names + pair distances + depth)."""
+    alt = []
+    if alts and not clip:
+        for (c, s, e) in tred.alt:
+            alt.append((c[3:] if "nochr" in ref else c, s, e))
+    return ing.extract_locus(tred, readlen, alts=alt, want_names=True)
+
+
+def run_batched(ips, evidence=None):
     """All loci of one sample: one SW launch + one KDE launch + one grid launch.
-    :param ips: list of InputParams (same BAM).  :return: list of BamParserResults (None on failure)."""
+    :param ips: list of InputParams (same BAM).  :param evidence: {tredName: ingest.LocusEvidence} from the
+    native one-pass BAM ingest (optional; without it the Python BAM reader makes the reference's passes).
+    :return: list of BamParserResults (None on failure)."""
+    evidence = evidence or {}
     parsers, all_seqs, all_names, rfam, fams, spans = [], [], [], [], [], []
     for ip in ips:
         bp = BamParser(ip)
-        sam = read_alignment(bp.bam)
-        reads = bp.select_reads(sam)
-        sam.close()
+        ev = evidence.get(ip.tredName)
+        if ev is not None:
+            seqs, names = ev.read_strings(), ev.names
+        else:
+            sam = read_alignment(bp.bam)
+            reads = bp.select_reads(sam)
+            sam.close()
+            seqs, names = [r.query_sequence for r in reads], [r.query_name for r in reads]
         fams.append(bp._buildDB())
-        spans.append((len(all_seqs), len(all_seqs) + len(reads)))
-        all_seqs += [r.query_sequence for r in reads]
-        all_names += [r.query_name for r in reads]
-        rfam += [len(fams) - 1] * len(reads)
+        spans.append((len(all_seqs), len(all_seqs) + len(seqs)))
+        all_seqs += seqs
+        all_names += names
+        rfam += [len(fams) - 1] * len(seqs)
         parsers.append(bp)
     if all_seqs:
         out = ssw.classify_reads(all_seqs, np.array(rfam, dtype=np.int32), np.concatenate(fams))
@@ -155,7 +182,8 @@ def run_batched(ips):
     for bp, (a, b) in zip(parsers, spans):
         bp.sw_results = out[a:b]
         bp.absorb(all_names[a:b], all_seqs[a:b], out[a:b])
-        pe = PEextractor(bp)
+        ev = evidence.get(bp.inputParams.tredName)
+        pe = _IngestPE(bp, ev) if ev is not None else PEextractor(bp)
         pes.append(pe)
         if len(pe.global_lens) >= 100 and len(pe.target_lens) >= MIN_SPANNING_PAIRS:
             need_kde.append(len(pes) - 1)
@@ -222,24 +250,39 @@ def run(arg):
     logger.debug("Read length: {}bp".format(READLEN))
     tredCalls["readLen"] = READLEN
 
-    ips, depths = [], {}
+    # native ingest: one indexed pass per locus yields reads, pair distances AND depth (csrc/ingest.cpp); the
+    # Python BAM reader (three passes per locus, like the reference's pysam calls) is the fallback
+    ing = None
+    try:
+        from .ingest import BamIngest
+        ing = BamIngest(bam_path(bam))
+    except Exception as e:
+        logger.debug("native BAM ingest unavailable for `{}` ({}); using the Python reader".format(bam, e))
+    ips, depths, evidence = [], {}, {}
     for tred in tredNames:
         bd = BamDepth(bam, repo.ref, logger)
         xtred = repo[tred]
         WINDOW_START = max(0, xtred.repeat_start - SPAN)
         WINDOW_END = xtred.repeat_end + SPAN
         try:
-            depth = bd.region_depth(xtred.chr, WINDOW_START, WINDOW_END)
+            if ing is not None and ing.tid(xtred.chr) >= 0:
+                evidence[tred] = locus_evidence(ing, None, xtred, READLEN, alts, clip, repo.ref)
+                depth = evidence[tred].depth
+            else:
+                depth = bd.region_depth(xtred.chr, WINDOW_START, WINDOW_END)
         except Exception as e:
             depth = 30
+            evidence.pop(tred, None)
             logger.error("Exception on `{}` {} ({}). Set depth={}".format(bam, tred, e, depth))
         logger.debug("Inferred depth at locus {}: {}".format(tred, depth))
         depths[tred] = depth
         ips.append(InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
                                fullsearch=fullsearch, gender=gender, depth=depth, clip=clip, alts=alts,
                                repeatpairs=repeatpairs, log=log))
+    if ing is not None:
+        ing.close()
     try:
-        results = run_batched(ips)
+        results = run_batched(ips, evidence)
     except Exception as e:
         # keep the reference's per-locus isolation (tred.py:245-249): retry one locus at a time
         logger.error("Batched run failed on `{}` ({}); falling back to per-locus calls".format(bam, e))
