@@ -109,3 +109,26 @@ def test_cli_main_writes_reference_layout_json(tmp_path):
     assert keys == {"1", "2", "FR", "PR", "RR", "DP", "FDP", "PDP", "RDP", "PEDP", "PEG", "PET", "CI", "PP",
                     "label", "details", "P_h1", "P_h2", "P_h1h2", "P_PEG", "P_PET"}
     assert os.path.exists(tmp_path / "work" / "t002.tred.vcf.gz")
+
+
+def test_cohort_pipeline_from_native_ingest_equals_run():
+    """BAM -> native one-pass ingest (csrc/ingest.cpp) -> all-device cohort pipeline == tred.run's calls
+    (which go BamParser / IntegratedCaller API -> per-stage kernels), and the README's 15|41."""
+    from tredparse_b200 import tred as T, cohort, ingest
+    from tredparse_b200.meta import TREDsRepo
+    repo = TREDsRepo()
+    probs, want = [], []
+    for sample, name in CASES:
+        bam = os.path.join(GOLDEN, sample + ".mini.bam")
+        calls = T.run((sample, bam, repo, [name], 300, False, False, True, True, "INFO"))["tredCalls"]
+        want.append((calls[name + ".1"], calls[name + ".2"], calls[name + ".CI"], calls[name + ".PP"],
+                     calls[name + ".label"], calls[name + ".FDP"], calls[name + ".PDP"], calls[name + ".RDP"]))
+        with ingest.BamIngest(bam) as ing:
+            probs.append(ing.problem(repo[name], 150, alts=repo[name].alt))
+    out = cohort.CohortBatch(probs).run_host(packed=True)["calls"]
+    for c, w in zip(out, want):
+        d = cohort.decode_call(c)
+        assert (d["alleles"][0], d["alleles"][1], d["CI"], d["label"], d["FDP"], d["PDP"], d["RDP"]) == \
+               (w[0], w[1], w[2], w[4], w[5], w[6], w[7])
+        assert abs(d["PP"] - w[3]) < 1e-9
+    assert cohort.decode_call(out[0])["alleles"] == [15, 41]
