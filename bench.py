@@ -44,6 +44,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--samples", type=int, default=384, help="samples per GPU per step (x 30 loci)")
     p.add_argument("--depth", type=int, default=3, help="host-buffer calls kept in flight by the e2e pipeline")
+    p.add_argument("--streams", type=int, default=3, help="streams the device-resident steps alternate over "
+                   "(2: the tail of one step's persistent SW kernel overlaps the head of the next step)")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
     p.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -267,19 +269,34 @@ def _main(args):
     ctx.enable_timing(False)
     st = batch.run_host(ctx=ctx, want_stats=True)["stats"]      # cell / point counts of this batch
 
+    # the timed steps alternate over `--streams` contexts (each with its own stream and scratch; inputs are
+    # shared, read-only): consecutive steps are independent batches of a cohort, so nothing orders them
+    lanes = [(ctx, stream)]
+    for _ in range(max(1, args.streams) - 1):
+        s2 = torch.cuda.Stream(device=local_rank)
+        lanes.append((_lib.Context(local_rank, stream=s2.cuda_stream), s2))
+    for c2, s2 in lanes[1:]:
+        for _ in range(2):
+            batch.run_device(c2)
+        s2.synchronize()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    launches0 = ctx.launches
+    launches0 = sum(c.launches for c, _ in lanes)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            batch.run_device(ctx)
-        e1.record(stream)
+    e0.record(stream)
+    for _, s2 in lanes[1:]:
+        s2.wait_event(e0)
+    for i in range(args.steps):
+        batch.run_device(lanes[i % len(lanes)][0])
+    for _, s2 in lanes[1:]:
+        ev = torch.cuda.Event()
+        ev.record(s2)
+        stream.wait_event(ev)
+    e1.record(stream)
     stream.synchronize()
     barrier()
-    launches = ctx.launches - launches0
+    launches = sum(c.launches for c, _ in lanes) - launches0
     ms = e0.elapsed_time(e1)
     calls_dev = batch.calls_from_device()
 
@@ -351,7 +368,7 @@ def _main(args):
             "config": {"workload": "synthetic cohort x 30 TREDs (BASELINE configs[3]): {} samples x {} loci = {} "
                                    "problems, {} reads per GPU per step".format(args.samples, len(names), batch.nproblems, batch.nreads),
                        "readlen": READLEN, "maxinsert": 300, "fullsearch": False,
-                       "parallelism": "(sample, locus) shards over {} GPU(s), no collective".format(world),
+                       "parallelism": "(sample, locus) shards over {} GPU(s), no collective; {} stream(s) per GPU".format(world, len(lanes)),
                        "l2": "inputs + scratch per step ({:.0f} MB) exceed the 126 MB L2".format(
                            (batch.rbuf.nbytes + batch.pe_lens.nbytes + 8 * batch.nproblems * 1000) / 1e6)},
             "reads_per_s": nreads * args.steps / sec,
