@@ -4,6 +4,8 @@
 // factor n^(-1/5) — covariance = var(ddof=1) * factor^2, pdf[x] ~ sum_i exp(-((x - x_i)/sd)^2 / 2) — then
 // pdf / pdf.sum() (the normalisation constant cancels).  Lengths are integers, so the sum runs over a
 // histogram of the distinct values (<= 2048 terms per grid point instead of one per pair).
+// The Gaussian is tabulated per problem over the integer distances (the arguments differ from scipy's
+// (x_i - x) / sd by one rounding, ~1e-16 relative — the parity bar on the likelihood is 1e-9).
 // Lengths outside [-1024, 1024) are clamped into the histogram (the reference keeps only tlen < 1000,
 // bam_parser.py:356-357; large negative lengths do not occur for properly oriented pairs).
 #pragma once
@@ -74,6 +76,14 @@ __device__ __forceinline__ void kde_block(const int32_t *x, int n, double *out) 
         if (c != 0) { cbin[w] = (short)(tid * PER + k - KDE_OFF); ccnt[w] = c; ++w; }
     }
     __syncthreads();
+    // The kernel value depends on the integer distance |bin - x| only: tabulate exp(-(d / sd)^2 / 2) once
+    // (2048 exps per problem), then every grid point is a dot product of the occupied bins with the table.
+    __shared__ double gtab[2 * KDE_OFF];
+    for (int d = tid; d < 2 * KDE_OFF; d += KDE_THREADS) {
+        const double r = (double)d / sd;
+        gtab[d] = exp(-(r * r) / 2.0);
+    }
+    __syncthreads();
     double val[KDE_PER_THREAD];
     double mine = 0.0;
 #pragma unroll
@@ -81,13 +91,10 @@ __device__ __forceinline__ void kde_block(const int32_t *x, int n, double *out) 
         const int p = tid + k * KDE_THREADS;
         val[k] = 0.0;
         if (p < KDE_SPAN && n > 0) {
-            const double xs = (double)p / sd;
             double acc = 0.0;
             for (int b = 0; b < nbins; ++b) {
-                const double r = (double)cbin[b] / sd - xs;
-                const double e = -(r * r) / 2.0;
-                if (e < -746.0) continue;               // exp(e) == 0.0 exactly: adding it changes nothing
-                acc += (double)ccnt[b] * exp(e);
+                const int d = abs((int)cbin[b] - p);            // <= 1024 + 999 < 2 * KDE_OFF
+                acc += (double)ccnt[b] * gtab[d];
             }
             val[k] = acc;
         }
