@@ -200,32 +200,65 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
 constexpr int GRID_TILE = 256;
 constexpr int GRID_CLUSTER = 8;       // CTAs per problem in the cluster variant of the reduction
 
+// Problem classes of the reductions, by number of surface points.
+constexpr long long GRID_WARP_LIMIT = 2048;        // <= : one warp per problem
+constexpr long long GRID_BLOCK_LIMIT = 16384;      // <= : one CTA per problem;  > : a cluster of 8 CTAs
+
+// Single block: pt_start = exclusive prefix sum of the points per problem (pt_start[np] = all points), and the
+// index lists of the "block" and "cluster" class problems in ascending order (lists[0] = #block, lists[1] =
+// #cluster, then the block list at lists + 2, the cluster list at lists + 2 + np).
 __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_problem *prob, int nproblems,
-                                                          long long *tile_start) {
-    __shared__ long long part[1024];
+                                                          long long *pt_start, long long *tile_start, int *lists) {
+    __shared__ long long part[1024], tpart[1024];
+    __shared__ int pb[1024], pc[1024];
     const int tid = threadIdx.x;
     const int chunk = (nproblems + 1023) / 1024;
     const int lo = min(nproblems, tid * chunk), hi = min(nproblems, lo + chunk);
-    auto tiles_of = [&](int i) {
-        const long long t = prob[i].n_h2 > 0 ? (long long)prob[i].n_h1 * prob[i].n_h2 : 0;
-        return (t + GRID_TILE - 1) / GRID_TILE;
-    };
-    long long s = 0;
-    for (int i = lo; i < hi; ++i) s += tiles_of(i);
-    part[tid] = s;
+    auto points_of = [&](int i) { return prob[i].n_h2 > 0 ? (long long)prob[i].n_h1 * prob[i].n_h2 : 0LL; };
+    // small surfaces (<= GRID_WARP_LIMIT points) are concatenated point by point (pt_start), the others are
+    // cut into their own tiles of GRID_TILE points (tile_start)
+    long long s = 0, ts = 0;
+    int nb = 0, nc = 0;
+    for (int i = lo; i < hi; ++i) {
+        const long long t = points_of(i);
+        if (t > GRID_WARP_LIMIT) ts += (t + GRID_TILE - 1) / GRID_TILE; else s += t;
+        if (t > GRID_BLOCK_LIMIT) ++nc; else if (t > GRID_WARP_LIMIT) ++nb;
+    }
+    part[tid] = s; tpart[tid] = ts; pb[tid] = nb; pc[tid] = nc;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {               // inclusive Hillis-Steele scan of the partial sums
-        const long long v = tid >= d ? part[tid - d] : 0;
+    for (int d = 1; d < 1024; d <<= 1) {               // inclusive Hillis-Steele scans of the partial sums
+        const long long v = tid >= d ? part[tid - d] : 0, tv = tid >= d ? tpart[tid - d] : 0;
+        const int vb = tid >= d ? pb[tid - d] : 0, vc = tid >= d ? pc[tid - d] : 0;
         __syncthreads();
-        part[tid] += v;
+        part[tid] += v; tpart[tid] += tv; pb[tid] += vb; pc[tid] += vc;
         __syncthreads();
     }
-    long long run = part[tid] - s;
-    for (int i = lo; i < hi; ++i) { tile_start[i] = run; run += tiles_of(i); }
-    if (tid == 1023) tile_start[nproblems] = part[1023];
+    long long run = part[tid] - s, trun = tpart[tid] - ts;
+    int wb = pb[tid] - nb, wc = pc[tid] - nc;
+    for (int i = lo; i < hi; ++i) {
+        const long long t = points_of(i);
+        pt_start[i] = run; tile_start[i] = trun;
+        if (t > GRID_WARP_LIMIT) trun += (t + GRID_TILE - 1) / GRID_TILE; else run += t;
+        if (t > GRID_BLOCK_LIMIT) lists[2 + nproblems + wc++] = i; else if (t > GRID_WARP_LIMIT) lists[2 + wb++] = i;
+    }
+    if (tid == 1023) { pt_start[nproblems] = part[1023]; tile_start[nproblems] = tpart[1023]; lists[0] = pb[1023]; lists[1] = pc[1023]; }
 }
 
-__global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, int nproblems, const long long *tile_start) {
+__device__ __forceinline__ TileShared tile_shared_of(const GridParams &g, const tredsw_grid_problem &Q) {
+    TileShared T;
+    T.lgamma_k1 = lgamma((double)Q.n_rept + 1.0);
+    T.sig_mp = sigma_h(Q, Q.max_partial);
+    int tmin = 0x7fffffff;
+    if (Q.run_pe) {
+        const int32_t *tl = g.ipool + Q.off_target;
+        for (int i = 0; i < Q.n_target; ++i) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= Q.pe_minpe && x < tmin) tmin = x; }
+    }
+    T.tmin = tmin;
+    return T;
+}
+
+// Large and medium surfaces: persistent over their tiles; the per-problem values are computed once per tile.
+__global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParams g, int nproblems, const long long *tile_start) {
     const long long ntiles = tile_start[nproblems];
     __shared__ int s_pi;
     __shared__ TileShared s_tile;
@@ -237,15 +270,7 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, i
                 if (tile_start[mid] <= tile) lo = mid; else hi = mid;
             }
             s_pi = lo;
-            const tredsw_grid_problem &Q = g.prob[lo];
-            s_tile.lgamma_k1 = lgamma((double)Q.n_rept + 1.0);
-            s_tile.sig_mp = sigma_h(Q, Q.max_partial);
-            int tmin = 0x7fffffff;
-            if (Q.run_pe) {
-                const int32_t *tl = g.ipool + Q.off_target;
-                for (int i = 0; i < Q.n_target; ++i) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= Q.pe_minpe && x < tmin) tmin = x; }
-            }
-            s_tile.tmin = tmin;
+            s_tile = tile_shared_of(g, g.prob[lo]);
         }
         __syncthreads();
         const int pi = s_pi;
@@ -268,6 +293,30 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_kernel(GridParams g, i
     }
 }
 
+// Small surfaces: persistent over tiles of GRID_TILE consecutive points of their CONCATENATION, every thread
+// finds its own problem and computes the per-problem values itself — thousands of 10-point surfaces cost a few
+// tiles, not one tile each.
+__global__ void __launch_bounds__(GRID_TILE) grid_surface_points_kernel(GridParams g, int nproblems, const long long *pt_start) {
+    const long long npoints = pt_start[nproblems];
+    for (long long gidx = (long long)blockIdx.x * GRID_TILE + threadIdx.x; gidx < npoints; gidx += (long long)gridDim.x * GRID_TILE) {
+        int lo = 0, hi = nproblems;        // last p with pt_start[p] <= gidx (problems without points here share
+        while (hi - lo > 1) {              // their start with the next one; the last of equals is the owner)
+            const int mid = (lo + hi) >> 1;
+            if (pt_start[mid] <= gidx) lo = mid; else hi = mid;
+        }
+        const tredsw_grid_problem &P = g.prob[lo];
+        const TileShared T = tile_shared_of(g, P);
+        const int t = (int)(gidx - pt_start[lo]);
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const int i1 = t / P.n_h2, i2 = t - i1 * P.n_h2;
+        const int h1 = h1s[i1];
+        const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+        double ml = -INFINITY;
+        if (h1 <= h2) ml = point_ml(P, g, h1, h2, T);
+        g.surface[P.off_surface + t] = ml;
+    }
+}
+
 struct ArgMax { double ml; int h1; long long idx; };
 __device__ __forceinline__ bool better(const ArgMax &a, const ArgMax &b) {   // a beats b (Q10)
     if (a.ml != b.ml) return a.ml > b.ml;
@@ -282,13 +331,13 @@ __device__ __forceinline__ bool pathological(const tredsw_grid_problem &P, int h
 }
 
 // Reductions of one problem's surface (models.py:277-302, 342-368): max / arg-max with key (ml, -h1, order)
-// (Q10), the exp-normalised marginals P_h1 / P_h2 and the PP sums.  CS = 1: one CTA per problem (the usual
-// handful-to-thousands of points).  CS = 8: a thread-block CLUSTER of 8 CTAs per problem for the large
-// surfaces (extended ranges, --fullsearch: 10^4 - 10^6 points): rows / columns are dealt to the CTAs of the
-// cluster, the per-CTA partial results meet in distributed shared memory in rank order, so the result is
-// deterministic.  Both variants are launched over all problems; each skips the problems of the other class.
+// (Q10), the exp-normalised marginals P_h1 / P_h2 and the PP sums.  CS = 1: one CTA per problem (medium
+// surfaces).  CS = 8: a thread-block CLUSTER of 8 CTAs per problem for the large surfaces (extended ranges,
+// --fullsearch: 10^4 - 10^6 points): rows / columns are dealt to the CTAs of the cluster, the per-CTA partial
+// results meet in distributed shared memory in rank order, so the result is deterministic.  Both walk the
+// index list of their class (grid_tiles_kernel); small surfaces take grid_reduce_warp_kernel.
 template <int CS>
-__global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int nproblems, long long small_limit) {
+__global__ void __launch_bounds__(256, 4) grid_reduce_kernel(GridParams g, const int *list, const int *nlist) {
     namespace cg = cooperative_groups;
     __shared__ ArgMax s_best[256];
     __shared__ double s_sum[256], s_path[256];
@@ -296,13 +345,13 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int npro
     __shared__ ArgMax c_best;          // this CTA's partial results, read by the other CTAs of the cluster
     __shared__ int c_cnt;
     __shared__ double c_sum, c_path;
-    const int pi = blockIdx.x / CS;
     unsigned crank = 0;
     if (CS > 1) crank = cg::this_cluster().block_rank();
-    if (pi >= nproblems) return;
+    const int n = *nlist;
+    // persistent over the problems of this class (CTAs of a cluster walk the list together)
+    for (int k = blockIdx.x / CS; k < n; k += (CS > 1 ? n : (int)gridDim.x)) {       // (cluster variant: one problem per cluster)
+    const int pi = list[k];
     const tredsw_grid_problem P = g.prob[pi];
-    const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
-    if (CS == 1 ? total > small_limit : total <= small_limit) return;     // uniform over the cluster
     const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
     const double *surf = g.surface + P.off_surface;
     const int tid = threadIdx.x;
@@ -398,6 +447,79 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(GridParams g, int npro
         r.n_points = npoints; r.pad = 0;
         g.res[pi] = r;
     }
+    __syncthreads();
+    }
+}
+
+// One warp per small surface (<= GRID_WARP_LIMIT points, including the empty ones of loci without evidence):
+// the same reductions with shuffles only — a cohort step has thousands of surfaces of a few dozen points.
+__global__ void __launch_bounds__(256) grid_reduce_warp_kernel(GridParams g, int nproblems) {
+    const int lane = threadIdx.x & 31;
+    const int pi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pi >= nproblems) return;
+    const tredsw_grid_problem P = g.prob[pi];
+    const long long total = P.n_h2 > 0 ? (long long)P.n_h1 * P.n_h2 : 0;
+    if (total > GRID_WARP_LIMIT) return;
+    const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+    const double *surf = g.surface + P.off_surface;
+    ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
+    int cnt = 0;
+    for (int t = lane; t < (int)total; t += 32) {
+        const double ml = surf[t];
+        if (ml == -INFINITY) continue;
+        ++cnt;
+        ArgMax c{ml, h1s[t / P.n_h2], (long long)t};
+        if (better(c, best)) best = c;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        ArgMax o;
+        o.ml = __shfl_down_sync(0xffffffffu, best.ml, d);
+        o.h1 = __shfl_down_sync(0xffffffffu, best.h1, d);
+        o.idx = __shfl_down_sync(0xffffffffu, best.idx, d);
+        if (better(o, best)) best = o;
+        cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    }
+    ArgMax top;
+    top.ml = __shfl_sync(0xffffffffu, best.ml, 0);
+    top.h1 = __shfl_sync(0xffffffffu, best.h1, 0);
+    top.idx = __shfl_sync(0xffffffffu, best.idx, 0);
+    const int npoints = __shfl_sync(0xffffffffu, cnt, 0);
+    double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+    double sum_all = 0.0, sum_path = 0.0;
+    for (int i1 = 0; i1 < P.n_h1; ++i1) {
+        const int h1 = h1s[i1];
+        double acc = 0.0, accp = 0.0;
+        for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
+            const double ml = surf[i1 * P.n_h2 + i2];
+            if (ml == -INFINITY) continue;
+            const double w = exp(ml - top.ml);
+            acc += w;
+            const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+            if (pathological(P, h1, h2)) accp += w;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            acc += __shfl_down_sync(0xffffffffu, acc, d);
+            accp += __shfl_down_sync(0xffffffffu, accp, d);
+        }
+        if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; }
+    }
+    for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
+        double acc = 0.0;
+        for (int i1 = 0; i1 < P.n_h1; ++i1) {
+            const double ml = surf[i1 * P.n_h2 + i2];
+            if (ml == -INFINITY) continue;
+            acc += exp(ml - top.ml);
+        }
+        ph2[i2] = acc;
+    }
+    if (lane == 0) {
+        tredsw_grid_result r;
+        r.max_ml = top.ml; r.sum_all = sum_all; r.sum_path = sum_path;
+        r.arg_i1 = npoints ? (int)(top.idx / P.n_h2) : -1;
+        r.arg_i2 = npoints ? (int)(top.idx % P.n_h2) : -1;
+        r.n_points = npoints; r.pad = 0;
+        g.res[pi] = r;
+    }
 }
 
 // ---- KDE of paired-end lengths (models.py:428-435): see kde.cuh ---------------------------------------
@@ -419,24 +541,32 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     g.log_small = log(g.small_value);
     (void)points_hint;
     int rc;
-    if ((rc = ctx->d_tiles.ensure(((size_t)nproblems + 1) * sizeof(long long)))) return rc;
-    long long *d_tiles = ctx->d_tiles.as<long long>();
+    const size_t pt_bytes = (((size_t)nproblems + 1) * sizeof(long long) + 15) & ~(size_t)15;
+    if ((rc = ctx->d_tiles.ensure(2 * pt_bytes + (2 + 2 * (size_t)nproblems) * sizeof(int)))) return rc;
+    long long *d_pt = ctx->d_tiles.as<long long>();
+    long long *d_tl = reinterpret_cast<long long *>(ctx->d_tiles.as<unsigned char>() + pt_bytes);
+    int *d_lists = reinterpret_cast<int *>(ctx->d_tiles.as<unsigned char>() + 2 * pt_bytes);
     ctx->mark(2);
-    grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_tiles);
-    grid_surface_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tiles);
+    grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_pt, d_tl, d_lists);
+    grid_surface_points_kernel<<<ctx->sm_count * 4, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_pt);
+    grid_surface_tiles_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tl);
     CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-    const long long small_limit = 16384;
-    grid_reduce_kernel<1><<<nproblems, 256, 0, ctx->stream>>>(g, nproblems, small_limit);
+    ctx->launches += 3;
+    // reductions by class: a warp per small surface, a CTA per medium one, a cluster of 8 CTAs per large one
+    grid_reduce_warp_kernel<<<(nproblems + 7) / 8, 256, 0, ctx->stream>>>(g, nproblems);
+    const int nb_block = nproblems < ctx->sm_count * 4 ? nproblems : ctx->sm_count * 4;
+    grid_reduce_kernel<1><<<nb_block, 256, 0, ctx->stream>>>(g, d_lists + 2, d_lists);
     CUDA_TRY(cudaGetLastError());
     {
+        const int nclusters = nproblems;      // one cluster per problem; clusters beyond the class list exit at once
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)nproblems * GRID_CLUSTER); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
+        cfg.gridDim = dim3((unsigned)nclusters * GRID_CLUSTER); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = GRID_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_reduce_kernel<GRID_CLUSTER>, g, nproblems, small_limit));
+        const int *cl_list = d_lists + 2 + nproblems, *cl_n = d_lists + 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_reduce_kernel<GRID_CLUSTER>, g, cl_list, cl_n));
     }
     ctx->mark(3);
     ctx->launches += 3;
