@@ -15,7 +15,7 @@ tredsw_ctx::~tredsw_ctx() {
     cudaSetDevice(device);
     DevBuf *all[] = {&d_q, &d_qoff, &d_t, &d_toff, &d_qidx, &d_tidx, &d_out, &d_cigar, &d_scratch, &d_misc,
                      &d_fam, &d_rfam, &d_stats, &d_work, &d_prob, &d_ipool, &d_dpool, &d_surface, &d_marg,
-                     &d_res, &d_counter, &d_tiles, &d_pk, &d_pe16};
+                     &d_res, &d_counter, &d_tiles, &d_pk, &d_pe16, &d_ftab};
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < 8; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (own_stream && stream) cudaStreamDestroy(stream);

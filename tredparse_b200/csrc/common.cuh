@@ -49,7 +49,7 @@ struct tredsw_ctx {
     size_t smem_optin = 0;
     // staging buffers (host-pointer mode)
     DevBuf d_q, d_qoff, d_t, d_toff, d_qidx, d_tidx, d_out, d_cigar, d_scratch, d_misc, d_fam,
-        d_rfam, d_stats, d_work, d_prob, d_ipool, d_dpool, d_surface, d_marg, d_res, d_counter, d_tiles, d_pk, d_pe16;
+        d_rfam, d_stats, d_work, d_prob, d_ipool, d_dpool, d_surface, d_marg, d_res, d_counter, d_tiles, d_pk, d_pe16, d_ftab;
     std::mutex mu;
     long long launches = 0;
     bool timing = false;

@@ -30,6 +30,26 @@ struct GridParams {
     double *marg;
     tredsw_grid_result *res;
     double small_value, really_small, log_small;
+    // far-region tables of the large surfaces (grid_far_kernel)
+    struct FarInfo *far;            // [nproblems]
+    double *ftab;                   // arena of per-problem tables
+    long long ftab_cap;
+    unsigned long long *fcursor;    // arena cursor
+};
+
+// In the FAR region of a large surface — both alleles beyond every observed key, the partial clamp and the
+// read length, and the longer allele shifted past the KDE support — the four terms collapse:
+//   spanning + partial = one constant c12;  repeat-only = a function of h1 + h2 only;  paired-end = a function
+//   of h1 only.
+// The candidate lists end in arithmetic progressions of step `period` there, so for list indices i1 >= fa1,
+// i2 >= fa2 the point is   ml = ((c12) + rept[(i1-fa1) + (i2-fa2)]) + pe_row[i1-fa1]   — the same three
+// additions in the same order as the general evaluation, on operands produced by the same code, hence the
+// same bits — two table reads instead of tens of logarithms.  On a --fullsearch / long-expansion grid
+// (10^5 - 10^6 points) ~90 % of the points are of this kind.
+struct FarInfo {
+    long long off;      // ftab: pe_row[n_h1 - fa1] then rept[(n_h1 - fa1) + (n_h2 - fa2) - 1]
+    double c12;
+    int fa1, fa2, ok, pad;
 };
 
 __device__ __forceinline__ double sigma_h(const tredsw_grid_problem &P, int h) {
@@ -81,6 +101,9 @@ struct TileShared {
     double lgamma_k1;      // lgamma(n_rept + 1) of the Poisson term
     double sig_mp;         // sigma(max_partial): the stutter probability of every allele clamped to max_partial
     int tmin;              // smallest pair length >= MINPE (after numpy's negative-index wrap); INT_MAX if none
+    int far_ok, fa1, fa2;  // far region of this problem (FarInfo)
+    double c12;
+    const double *pe_row, *rept;
 };
 
 // One grid point.  The arithmetic (operation order, rounding) is exactly that of the straightforward loops
@@ -90,106 +113,112 @@ struct TileShared {
 //   * a spanning key farther than 18 from both alleles sees 0;
 //   * when both alleles shift every pair length off the KDE support, every pair sees eps.
 // On the large grids of --fullsearch / long-expansion searches almost all points are of that kind.
-__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, const TileShared &T) {
+__device__ __forceinline__ double ml_span_term(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2) {
+    if (P.n_span <= 0) return 0.0;
     const int32_t *skey = g.ipool + P.off_span, *scnt = skey + P.n_span;
+    const double *step = g.dpool + P.off_step;
+    const double eps = g.small_value;
+    const int t2 = P.readlen - 18;
+    const int s1 = max(0, t2 - h1), s2 = max(0, t2 - h2);
+    const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
+    const int lo = min(h1, h2) - DEV, hi = max(h1, h2) + DEV;
+    double sg1 = 0.0, sg2 = 0.0;
+    bool have_sigma = false;
+    double acc = 0.0;
+    LogMemo lg{-1.0, 0.0};
+    for (int i = 0; i < P.n_span; ++i) {
+        const int k = skey[i];
+        double v;
+        if (k < lo || k > hi) v = 0.0;          // == a * 0 + (1 - a) * 0
+        else {
+            if (!have_sigma) { sg1 = sigma_h(P, h1); sg2 = sigma_h(P, h2); have_sigma = true; }
+            const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
+            v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+        }
+        double l = lg(v, eps, g.log_small);
+        acc = __dadd_rn(acc, __dmul_rn(l, (double)scnt[i]));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double ml_part_term(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, double sig_mp) {
+    if (P.n_part <= 0) return 0.0;
     const int32_t *pkey = g.ipool + P.off_part, *pcnt = pkey + P.n_part;
     const double *step = g.dpool + P.off_step;
     const double eps = g.small_value;
-    const int t1 = P.readlen - 9, t2 = P.readlen - 18;
-    double ml = 0.0;
-    // spanning
-    if (P.n_span > 0) {
-        const int s1 = max(0, t2 - h1), s2 = max(0, t2 - h2);
-        const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
-        const int lo = min(h1, h2) - DEV, hi = max(h1, h2) + DEV;
-        double sg1 = 0.0, sg2 = 0.0;
-        bool have_sigma = false;
-        double acc = 0.0;
+    const int t1 = P.readlen - 9;
+    const int s1 = min(h1, t1), s2 = min(h2, t1);
+    const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
+    const int hc1 = min(h1, P.max_partial), hc2 = min(h2, P.max_partial);
+    const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
+    const int lo = min(hc1, hc2) - DEV, hi = max(hc1, hc2) + DEV;
+    const double v_bulk = __dadd_rn(__dmul_rn(a, c1), __dmul_rn(1.0 - a, c2));   // p1 = c1 + c1 * 0, p2 = c2 + c2 * 0
+    double sg1 = 0.0, sg2 = 0.0;
+    bool have_sigma = false;
+    double acc = 0.0;
+    LogMemo lg{-1.0, 0.0};
+    for (int i = 0; i < P.n_part; ++i) {
+        const int k = pkey[i];
+        double v;
+        if (k < lo) v = v_bulk;
+        else if (k > hi) v = 0.0;
+        else {
+            if (!have_sigma) {
+                sg1 = hc1 == P.max_partial ? sig_mp : sigma_h(P, hc1);
+                sg2 = hc2 == P.max_partial ? sig_mp : sigma_h(P, hc2);
+                have_sigma = true;
+            }
+            const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
+            v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
+        }
+        double l = lg(v, eps, g.log_small);
+        acc = __dadd_rn(acc, __dmul_rn(l, (double)pcnt[i]));
+    }
+    return acc;
+}
+
+// repeat-only reads: Poisson (scipy: exp(xlogy(k, mu) - gammaln(k + 1) - mu)); dsum = max(h1-L,1) + max(h2-L,1)
+__device__ __forceinline__ double ml_rept_term(const tredsw_grid_problem &P, int dsum, double lgamma_k1) {
+    const double mu = (double)dsum * P.half_depth / (double)P.readlen;
+    const double kk = (double)P.n_rept;
+    const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
+    const double pk = xl - lgamma_k1 - mu;
+    // log(max(exp(pk), e^-100)): log(exp(pk)) is pk to within an ulp of the pmf (~1e-16 absolute on a term
+    // of magnitude 0.1..100, far inside the 1e-9 relative bar) — two transcendentals less per point
+    return pk > -100.0 ? pk : -100.0;
+}
+
+__device__ __forceinline__ double ml_pe_term(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, int tmin) {
+    if (!P.run_pe) return 0.0;
+    const double eps = g.small_value;
+    const double *pdf = g.dpool + P.off_pdf;
+    const int32_t *tl = g.ipool + P.off_target;
+    double acc = 0.0;
+    const long long off1 = (long long)h1 - P.pe_ref, off2 = (long long)h2 - P.pe_ref;
+    if (tmin == 0x7fffffff || (tmin + off1 >= SPAN && tmin + off2 >= SPAN)) {
+        // every pair length is below MINPE or shifted past the end of the support: 0.5*eps + 0.5*eps = eps
+        const double l = log(eps);
+        for (int i = 0; i < P.n_target; ++i) acc = __dadd_rn(acc, l);
+    } else {
         LogMemo lg{-1.0, 0.0};
-        for (int i = 0; i < P.n_span; ++i) {
-            const int k = skey[i];
-            double v;
-            if (k < lo || k > hi) v = 0.0;          // == a * 0 + (1 - a) * 0
-            else {
-                if (!have_sigma) { sg1 = sigma_h(P, h1); sg2 = sigma_h(P, h2); have_sigma = true; }
-                const double p1 = pdf_span(step, h1, sg1, k), p2 = pdf_span(step, h2, sg2, k);
-                v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
-            }
+        for (int i = 0; i < P.n_target; ++i) {
+            int x = tl[i];
+            if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
+            const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
+            const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
+            double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
             double l = lg(v, eps, g.log_small);
-            acc = __dadd_rn(acc, __dmul_rn(l, (double)scnt[i]));
+            acc = __dadd_rn(acc, l);
         }
-        ml = acc;
     }
-    // partial
-    double ml2 = 0.0;
-    if (P.n_part > 0) {
-        const int s1 = min(h1, t1), s2 = min(h2, t1);
-        const double a = (s1 + s2) ? (double)s1 * 1.0 / (double)(s1 + s2) : 0.5;
-        const int hc1 = min(h1, P.max_partial), hc2 = min(h2, P.max_partial);
-        const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
-        const int lo = min(hc1, hc2) - DEV, hi = max(hc1, hc2) + DEV;
-        const double v_bulk = __dadd_rn(__dmul_rn(a, c1), __dmul_rn(1.0 - a, c2));   // p1 = c1 + c1 * 0, p2 = c2 + c2 * 0
-        double sg1 = 0.0, sg2 = 0.0;
-        bool have_sigma = false;
-        double acc = 0.0;
-        LogMemo lg{-1.0, 0.0};
-        for (int i = 0; i < P.n_part; ++i) {
-            const int k = pkey[i];
-            double v;
-            if (k < lo) v = v_bulk;
-            else if (k > hi) v = 0.0;
-            else {
-                if (!have_sigma) {
-                    sg1 = hc1 == P.max_partial ? T.sig_mp : sigma_h(P, hc1);
-                    sg2 = hc2 == P.max_partial ? T.sig_mp : sigma_h(P, hc2);
-                    have_sigma = true;
-                }
-                const double p1 = pdf_part(step, hc1, sg1, c1, k), p2 = pdf_part(step, hc2, sg2, c2, k);
-                v = __dadd_rn(__dmul_rn(a, p1), __dmul_rn(1.0 - a, p2));
-            }
-            double l = lg(v, eps, g.log_small);
-            acc = __dadd_rn(acc, __dmul_rn(l, (double)pcnt[i]));
-        }
-        ml2 = acc;
-    }
-    ml = __dadd_rn(ml, ml2);
-    // repeat-only reads: Poisson (scipy: exp(xlogy(k, mu) - gammaln(k + 1) - mu))
-    {
-        const int d1 = max(h1 - P.readlen, 1), d2 = max(h2 - P.readlen, 1);
-        const double mu = (double)(d1 + d2) * P.half_depth / (double)P.readlen;
-        const double kk = (double)P.n_rept;
-        const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
-        const double pk = xl - T.lgamma_k1 - mu;
-        // log(max(exp(pk), e^-100)): log(exp(pk)) is pk to within an ulp of the pmf (~1e-16 absolute on a term
-        // of magnitude 0.1..100, far inside the 1e-9 relative bar) — two transcendentals less per point
-        ml = __dadd_rn(ml, pk > -100.0 ? pk : -100.0);
-    }
-    // paired-end
-    double ml4 = 0.0;
-    if (P.run_pe) {
-        const double *pdf = g.dpool + P.off_pdf;
-        const int32_t *tl = g.ipool + P.off_target;
-        double acc = 0.0;
-        const long long off1 = (long long)h1 - P.pe_ref, off2 = (long long)h2 - P.pe_ref;
-        if (T.tmin == 0x7fffffff || (T.tmin + off1 >= SPAN && T.tmin + off2 >= SPAN)) {
-            // every pair length is below MINPE or shifted past the end of the support: 0.5*eps + 0.5*eps = eps
-            const double l = log(eps);
-            for (int i = 0; i < P.n_target; ++i) acc = __dadd_rn(acc, l);
-        } else {
-            LogMemo lg{-1.0, 0.0};
-            for (int i = 0; i < P.n_target; ++i) {
-                int x = tl[i];
-                if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
-                const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
-                const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
-                double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
-                double l = lg(v, eps, g.log_small);
-                acc = __dadd_rn(acc, l);
-            }
-        }
-        ml4 = acc;
-    }
-    ml = __dadd_rn(ml, ml4);
+    return acc;
+}
+
+__device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, const TileShared &T) {
+    double ml = ml_span_term(P, g, h1, h2);
+    ml = __dadd_rn(ml, ml_part_term(P, g, h1, h2, T.sig_mp));
+    ml = __dadd_rn(ml, ml_rept_term(P, max(h1 - P.readlen, 1) + max(h2 - P.readlen, 1), T.lgamma_k1));
+    ml = __dadd_rn(ml, ml_pe_term(P, g, h1, h2, T.tmin));
     return ml;
 }
 
@@ -254,7 +283,68 @@ __device__ __forceinline__ TileShared tile_shared_of(const GridParams &g, const 
         for (int i = 0; i < Q.n_target; ++i) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= Q.pe_minpe && x < tmin) tmin = x; }
     }
     T.tmin = tmin;
+    T.far_ok = 0; T.fa1 = T.fa2 = 0; T.c12 = 0.0; T.pe_row = T.rept = nullptr;
     return T;
+}
+
+// One block per medium / large surface (class lists of grid_tiles_kernel): decide the far region and fill its
+// tables.
+__global__ void __launch_bounds__(256) grid_far_kernel(GridParams g, const int *lists, int nproblems) {
+    __shared__ FarInfo s_f;
+    __shared__ TileShared s_t;
+    const int nb = lists[0], nc = lists[1];
+    for (int k = blockIdx.x; k < nb + nc; k += gridDim.x) {
+        const int pi = k < nb ? lists[2 + k] : lists[2 + nproblems + (k - nb)];
+        const tredsw_grid_problem &P = g.prob[pi];
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        if (threadIdx.x == 0) {
+            FarInfo f; f.off = 0; f.c12 = 0.0; f.fa1 = f.fa2 = 0; f.ok = 0; f.pad = 0;
+            TileShared T = tile_shared_of(g, P);
+            if (P.ploidy != 1 && P.n_h1 > 0 && P.n_h2 > 1) {
+                const int32_t *skey = g.ipool + P.off_span;
+                int ks = -1000000;
+                for (int i = 0; i < P.n_span; ++i) ks = max(ks, skey[i]);
+                const int t1 = P.readlen - 9;
+                // h >= H1: no spanning key within 18, partial clamp and mixing weight saturated, h > readlen
+                const int H1 = max(max(ks + DEV + 1, P.max_partial), max(t1, P.readlen + 1));
+                // h >= H2: every pair length >= MINPE is shifted past the support
+                long long H2 = H1;
+                if (P.run_pe && T.tmin != 0x7fffffff) H2 = max((long long)H1, (long long)P.pe_ref + SPAN - T.tmin);
+                auto tail = [&](const int32_t *hs, int n, long long H) {
+                    int i = n - 1;
+                    if (hs[i] < H) return n;
+                    while (i > 0 && hs[i] - hs[i - 1] == P.period && hs[i - 1] >= H) --i;
+                    return i;
+                };
+                f.fa1 = tail(h1s, P.n_h1, H1);
+                f.fa2 = tail(h2s, P.n_h2, H2);
+                const long long r1 = P.n_h1 - f.fa1, r2 = P.n_h2 - f.fa2;
+                if (r1 > 0 && r2 > 0 && r1 * r2 >= 4096) {
+                    const unsigned long long need = (unsigned long long)(r1 + r1 + r2);
+                    const unsigned long long off = atomicAdd(g.fcursor, need);
+                    if ((long long)(off + need) <= g.ftab_cap) {
+                        f.off = (long long)off; f.ok = 1;
+                        const int h1 = h1s[f.fa1], h2 = h2s[f.fa2];
+                        f.c12 = __dadd_rn(ml_span_term(P, g, h1, h2), ml_part_term(P, g, h1, h2, T.sig_mp));
+                    }
+                }
+            }
+            s_f = f; s_t = T;
+            g.far[pi] = f;
+        }
+        __syncthreads();
+        const FarInfo f = s_f;
+        if (f.ok) {
+            const TileShared T = s_t;
+            const int r1 = P.n_h1 - f.fa1, r2 = P.n_h2 - f.fa2;
+            double *pe_row = g.ftab + f.off, *rept = pe_row + r1;
+            const int hfar = h2s[f.fa2];                       // any allele past the support
+            for (int r = threadIdx.x; r < r1; r += blockDim.x) pe_row[r] = ml_pe_term(P, g, h1s[f.fa1 + r], hfar, T.tmin);
+            const int base = h1s[f.fa1] + h2s[f.fa2] - 2 * P.readlen;   // d1 + d2 at (fa1, fa2); both alleles > readlen
+            for (int r = threadIdx.x; r < r1 + r2 - 1; r += blockDim.x) rept[r] = ml_rept_term(P, base + r * P.period, T.lgamma_k1);
+        }
+        __syncthreads();
+    }
 }
 
 // Large and medium surfaces: persistent over their tiles; the per-problem values are computed once per tile.
@@ -270,7 +360,13 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParam
                 if (tile_start[mid] <= tile) lo = mid; else hi = mid;
             }
             s_pi = lo;
-            s_tile = tile_shared_of(g, g.prob[lo]);
+            TileShared T0 = tile_shared_of(g, g.prob[lo]);
+            const FarInfo f = g.far[lo];
+            if (f.ok) {
+                T0.far_ok = 1; T0.fa1 = f.fa1; T0.fa2 = f.fa2; T0.c12 = f.c12;
+                T0.pe_row = g.ftab + f.off; T0.rept = T0.pe_row + (g.prob[lo].n_h1 - f.fa1);
+            }
+            s_tile = T0;
         }
         __syncthreads();
         const int pi = s_pi;
@@ -287,7 +383,12 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParam
             const int h1 = h1s[i1];
             const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
             double ml = -INFINITY;
-            if (h1 <= h2) ml = point_ml(P, g, h1, h2, T);
+            if (h1 <= h2) {
+                if (T.far_ok && i1 >= T.fa1 && i2 >= T.fa2)
+                    ml = __dadd_rn(__dadd_rn(T.c12, T.rept[(i1 - T.fa1) + (i2 - T.fa2)]), T.pe_row[i1 - T.fa1]);
+                else
+                    ml = point_ml(P, g, h1, h2, T);
+            }
             g.surface[P.off_surface + t] = ml;
         }
     }
@@ -548,6 +649,19 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     int *d_lists = reinterpret_cast<int *>(ctx->d_tiles.as<unsigned char>() + 2 * pt_bytes);
     ctx->mark(2);
     grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_pt, d_tl, d_lists);
+    {   // far-region tables of the medium / large surfaces
+        const size_t far_bytes = (((size_t)nproblems * sizeof(FarInfo)) + 255) & ~(size_t)255;
+        const long long cap = 8LL << 20;                                   // doubles (64 MB): tables of ~2000 large surfaces
+        if ((rc = ctx->d_ftab.ensure(far_bytes + 256 + (size_t)cap * sizeof(double)))) return rc;
+        g.far = ctx->d_ftab.as<FarInfo>();
+        g.fcursor = reinterpret_cast<unsigned long long *>(ctx->d_ftab.as<unsigned char>() + far_bytes);
+        g.ftab = reinterpret_cast<double *>(ctx->d_ftab.as<unsigned char>() + far_bytes + 256);
+        g.ftab_cap = cap;
+        CUDA_TRY(cudaMemsetAsync(g.far, 0, far_bytes + 256, ctx->stream));
+        const int nbf = nproblems < ctx->sm_count * 4 ? nproblems : ctx->sm_count * 4;
+        grid_far_kernel<<<nbf, 256, 0, ctx->stream>>>(g, d_lists, nproblems);
+        ctx->launches += 1;
+    }
     grid_surface_points_kernel<<<ctx->sm_count * 4, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_pt);
     grid_surface_tiles_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tl);
     CUDA_TRY(cudaGetLastError());
