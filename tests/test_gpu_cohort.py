@@ -195,3 +195,16 @@ def test_packed_transfer_formats_equal_plain_inputs(problems):
     a = batch.run_host(want_reads=True)
     b = batch.run_host(want_reads=True, packed=True)
     assert a["calls"].tobytes() == b["calls"].tobytes() and np.array_equal(a["reads"], b["reads"])
+
+
+def test_host_pipeline_keeps_order_and_results(problems):
+    """cohort.HostPipeline: several host-buffer calls in flight on one GPU (one context / stream / thread per
+    slot) return, in submission order, exactly what sequential calls return — plain and packed inputs."""
+    from tredparse_b200 import cohort
+    batches = [cohort.CohortBatch(problems[i::3]) for i in range(3)] * 2
+    want = [b.run_host()["calls"].tobytes() for b in batches]
+    with cohort.HostPipeline(0, depth=3) as pipe:
+        got = [o["calls"].tobytes() for o in pipe.map(batches)]
+        got_packed = [o["calls"].tobytes() for o in pipe.map(batches, packed=True)]
+        assert pipe.launches > 0
+    assert got == want and got_packed == want
