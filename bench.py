@@ -158,6 +158,34 @@ def cpu_reference_run(problems, cores=None):
     return len(problems) / dt, dt, used, reads, cells, kind, res
 
 
+def ssw_c_loop_ceiling(problems, max_pairs=60000):
+    """SURVEY 8(d), CPU baseline (2): the reference's own ssw.c in a plain C loop (ssw_init -> ssw_align(flag=1) ->
+    destroy per pair, oracle/ref_batch.c), one core, no Python in the loop — the ceiling of any CPU path built
+    on ssw.c.  Returns microseconds per alignment and forward-matrix GCUPS per core."""
+    from oracle import sw, evidence_oracle as evo
+    queries, templates, qidx, tidx = [], [], [], []
+    for p in problems:
+        t = p.tred
+        mu = -(-p.readlen // len(t.repeat))
+        db = [x for _, x in evo.template_family(t.prefix, t.repeat, t.suffix, mu)]
+        t0 = len(templates)
+        templates += db
+        for r in p.read_strings()[:8]:
+            q0 = len(queries)
+            queries.append(r)
+            qidx += [q0] * len(db)
+            tidx += list(range(t0, t0 + len(db)))
+        if len(qidx) >= max_pairs:
+            break
+    qidx, tidx = np.array(qidx, dtype=np.int32), np.array(tidx, dtype=np.int32)
+    sw.ref_align_pairs(queries[:1], templates[:1], qidx[:1] * 0, tidx[:1] * 0)       # load / warm
+    t0 = time.perf_counter()
+    sw.ref_align_pairs(queries, templates, qidx, tidx)
+    dt = time.perf_counter() - t0
+    cells = sum(len(queries[a]) * len(templates[b]) for a, b in zip(qidx, tidx))
+    return {"pairs": int(len(qidx)), "us_per_alignment": 1e6 * dt / len(qidx), "gcups_per_core": cells / dt / 1e9}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path, rank 0 only."""
     if rank != 0:
@@ -412,7 +440,8 @@ def _main(args):
                                         "sample": "{} samples x {} loci = {} problems, {} reads, {:.1f} s wall".format(
                                             nsamp, len(names), len(sample_problems), reads, dt),
                                         "reads_per_s": reads / dt, "sw_gcups": cells / dt / 1e9,
-                                        "calls_identical_to_gpu": "{}/{}".format(agree, len(res))}
+                                        "calls_identical_to_gpu": "{}/{}".format(agree, len(res)),
+                                        "ssw_c_loop_one_core": ssw_c_loop_ceiling(sample_problems)}
             except Exception as e:  # the GPU line must still be printed
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         emit(line)
