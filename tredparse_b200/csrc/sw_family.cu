@@ -6,24 +6,30 @@
 //     for read: for (units, target, ssw) in db: ssw.align(...) ; classify ; max(res)
 // of tredparse/bam_parser.py:123-182 over src/ssw_wrap.py:177-227 over src/ssw.c:780-871.
 //
-// Mapping: one warp = 32 reads of the same family, one thread = one read.  Every lane walks the same
-// template columns at the same time, so template bases are warp-uniform; query bases are per lane.
+// Stage 0 (prefilter_kernel): an exact q-gram bound drops the reads that cannot reach min_score against
+//   any template of their family (about half of a locus window) before any DP is done.
 //
-// Phase 1 (scores of all 2*max_units templates):
-//   * the templates of a family are nested — prefix + repeat*u is a prefix of prefix + repeat*(u+1) —
-//     so the DP columns of the shared part are computed once and only the suffix columns are "forked"
-//     per u.  A strip = the P columns of repeat unit u followed by the Ls suffix columns of template u,
-//     all in registers (previous-row H and running F per column); query rows stream through; the H/E
-//     column leaving the repeat unit goes to a per-lane boundary column in shared memory.
-//   * the forward template and its reverse complement have identical shape, so both are computed in one
-//     pass as the two int16 halves of packed registers with DPX instructions
-//     (VIADDMNMX.S16x2.RELU, VIMNMX.S16x2); substitution scores for both halves come from one PRMT.
+// Mapping of the DP (classify_kernel): one warp = 32 surviving reads of the same family, one thread = one
+// read; persistent single-warp CTAs pull such items from a counter.  Every lane walks the same template
+// columns at the same time, so template bases are warp-uniform; query bases are per lane.
+//
+// Phase 1 (scores of all 2*max_units templates), all packed int16x2 = forward template | reverse complement:
+//   * the templates of a family are nested — prefix + repeat*u is a prefix of prefix + repeat*(u+1) — so
+//     the main DP (prefix + repeat*max_units) runs once, in 12-column strips held in registers (previous-
+//     row H and running F per column), two query rows in flight; the H/E column between strips lives in
+//     this CTA's global scratch slot (L2), requested two iterations ahead;
+//   * the suffix of every template is NOT recomputed: a backward DP of the read against the suffix block
+//     (suffix_pass, once per read) yields "potentials" A[j], B[j] with which the best score inside the
+//     suffix block of template u is max_j(H_u(j-1) + A[j], E_u(j) + B[j]) — two add-max per row and unit,
+//     hooked into the main strips where a unit ends.
 //   ssw's outputs only depend on column maxima / first-maximum positions, so this is exact.
-// Phase 2 (positions of the winning template only): candidates are visited in the reference's arg-max
-//   order (score desc, units asc, forward before reverse complement); for each, the exact end / begin
-//   coordinates come from the scalar sweeps of sw_sweep.cuh (forward locate + reverse pass), then the
-//   reference's filter + tag rules; the first candidate that yields a tag is the read's result — the
-//   same result as classifying all 2*max_units alignments and taking max(key=(score, -units)).
+// Phase 2 (positions, rounds over candidates in the reference's arg-max order: score desc, units asc,
+//   forward before reverse complement): the running main maximum after every unit tells which strip (or
+//   the suffix block) holds the end cell; that strip is recomputed warp-uniformly with per-column keys
+//   H << 8 | 255 - row (locate_packed); the begin cell comes from a reverse pass per lane — a diagonal walk
+//   when no gap is affordable, else a scalar sweep banded by the gap budget; then the reference's filter +
+//   tag rules.  The first candidate that yields a tag is the read's result — the same result as classifying
+//   all 2*max_units alignments and taking max(key=(score, -units)).
 #include "internal.cuh"
 #include "sw_sweep.cuh"
 #include <type_traits>
