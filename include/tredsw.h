@@ -331,6 +331,14 @@ int tredsw_bam_extract_locus(tredsw_bam *bam, const tredsw_locus_query *q, int8_
                              int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
                              tredsw_locus_summary *out);
 
+/* BamDepth.region_depth (tredparse/bam_parser.py:404-411): sum of pileup column depths over the reads
+ * overlapping [start, end) / (end - start + 1); feeds half_depth of the repeat-only term and the chrY depth of
+ * the gender inference (bam_parser.py:413-429). */
+int tredsw_bam_region_depth(tredsw_bam *bam, int32_t tid, int64_t start, int64_t end, double *depth);
+/* BamReadLen.readlen (tredparse/bam_parser.py:372-391): longest (and optionally shortest) query among the
+ * first first_n + 1 records of the file. */
+int tredsw_bam_read_length(tredsw_bam *bam, int32_t first_n, int32_t *max_out, int32_t *min_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,3 +77,79 @@ def test_problem_feeds_the_cohort_packer(repo):
     batch = cohort.CohortBatch(probs)
     assert batch.nproblems == 2 and batch.nreads == probs[0].nreads + probs[1].nreads
     assert 25 < probs[0].depth < 35 and 40 < probs[1].depth < 55
+
+
+# ---- pre-steps: depth of arbitrary regions, read length, gender (bam_parser.py:372-429, tred.py:201-223) --------
+@pytest.mark.parametrize("sample,tredname,bam", BAMS[:2], ids=[b[0] for b in BAMS[:2]])
+def test_region_depth_and_read_length_equal_python_reader(sample, tredname, bam, repo):
+    t = repo[tredname]
+    sam = bamio.AlignmentFile(bam)
+    rls = []
+    for r in sam.fetch():                                   # BamReadLen.readlen: first 101 records
+        rls.append(r.query_length)
+        if len(rls) > 100:
+            break
+    with ingest.BamIngest(bam) as ing:
+        for (s, e) in [(t.repeat_start - 1000, t.repeat_end + 1000), (t.repeat_start - 50, t.repeat_start + 50),
+                       (t.repeat_start - 9000, t.repeat_start - 8000), (1, 1000)]:
+            s = max(0, s)
+            assert ing.region_depth(t.chr, s, e) == bamio.region_depth(sam, t.chr, s, e)
+        assert ing.read_length(100) == (max(rls), min(rls))
+        with pytest.raises(ValueError):
+            ing.region_depth("chrNope", 1, 100)
+    sam.close()
+    from tredparse_b200.bam_parser import BamReadLen
+    assert BamReadLen(bam, logging.getLogger()).readlen == max(rls)
+
+
+def _ybam(path, ydepth, rng):
+    """A BAM with uniform `ydepth`x coverage of the chrY regions the gender inference looks at."""
+    from tredparse_b200.utils import datafile
+    regions = []
+    with open(datafile("chrY.tsv")) as fp:
+        next(fp)
+        for line in fp:
+            b, row, c, s, e, _ = line.split()
+            if b == "hg38":
+                regions.append((int(row), int(s), int(e)))
+    recs = []
+    for row, s, e in regions[:12]:
+        d = ydepth if row not in BamDepth.Y_SKIP_ROWS else 40        # the skipped rows are covered in everybody
+        n = int(d * (e - s + 1) / 100)
+        for k, pos in enumerate(sorted(rng.integers(s, e - 100, size=n))):
+            recs.append(bamio.AlignedSegment("y{}_{}".format(row, k), 0, 1, int(pos), 60, [(0, 100)], -1, -1, 0,
+                                             "ACGT" * 25))
+    recs.sort(key=lambda r: r.reference_start)
+    bamio.write_bam(path, [("chr4", 190214555), ("chrY", 57227415)], recs)
+
+
+def test_gender_inference_from_chrY_depth(tmp_path):
+    from tredparse_b200 import tred as tredmod
+    repo = TREDsRepo()
+    rng = np.random.default_rng(7)
+    log = logging.getLogger()
+    male, female = str(tmp_path / "m.bam"), str(tmp_path / "f.bam")
+    _ybam(male, 15, rng)
+    _ybam(female, 0.2, rng)
+    ym, yf = BamDepth(male, "hg38", log).get_Y_depth(), BamDepth(female, "hg38", log).get_Y_depth()
+    assert 12 < ym < 18 and yf < 1                           # tred.py:205-208: Male iff depthY > 1
+    # the native reader and the Python reader agree region by region
+    sam = bamio.AlignmentFile(male)
+    with ingest.BamIngest(male) as ing:
+        assert ing.region_depth("chrY", 2784557, 2791188) == bamio.region_depth(sam, "chrY", 2784557, 2791188) > 10
+    sam.close()
+    # no chrY contig -> the lookup raises and the caller keeps "Unknown" (tred.py:209-210)
+    noy = str(tmp_path / "noy.bam")
+    bamio.write_bam(noy, [("chr4", 190214555)],
+                    [bamio.AlignedSegment("r0", 0, 0, 1000, 60, [(0, 100)], -1, -1, 0, "ACGT" * 25)])
+    with pytest.raises(Exception):
+        BamDepth(noy, "hg38", log).get_Y_depth()
+    assert tredmod.presteps(noy, repo, ["FXS"], log) == {"inferredGender": "Unknown", "depthY": -1, "readLen": 100}
+    # a BAM whose header lists chrY but holds no reads there reads as depth 0 -> Female, like the reference
+    assert BamDepth(os.path.join(GOLDEN, "t001.mini.bam"), "hg38", log).get_Y_depth() == 0.0
+    # through tred.run: gender and depthY are reported, readLen detected (tred.py:195-223)
+    for bam, want in ((male, "Male"), (female, "Female")):
+        pre = tredmod.presteps(bam, repo, ["FXS"], log)
+        assert pre["inferredGender"] == want and pre["readLen"] == 100 and pre["depthY"] == (ym if want == "Male" else yf)
+    pre = tredmod.presteps(male, repo, ["HD"], log)            # no X-linked locus requested: gender not inferred
+    assert pre["inferredGender"] == "Unknown" and pre["depthY"] == -1

@@ -9,6 +9,8 @@ Writes into tredparse_b200/data/:
   loci.tsv     one row per TRED with only the columns the hot path, JSON/VCF writers and the cohort
                simulator consume (source: tredparse/data/TREDs.meta.csv, read by meta.py:36-42)
   alts.tsv     alternative (mis-mapping) regions per TRED, hg38 and hg19 (TREDs.alts.csv, meta.py:80-94)
+  chrY.tsv     the first 20 unique chrY regions per build (chrY.<build>.unique_ccn.gc; gender inference,
+               bam_parser.py:413-429)
   models.json  the 37-bin step-size PMF per period and the 5 logistic stutter weights
                (illumina_v3.pcrfree.stepmodel / .stuttermodel, parsed as models.py:46-77 does)
 """
@@ -48,4 +50,15 @@ with open(os.path.join(dst, "models.json"), "w") as fw:
     json.dump({"model": "illumina_v3.pcrfree", "non_unit_step_by_period": non_unit,
                "prob_increase": prob_increase, "step_size_by_period": step,
                "stutter_weights": weights}, fw, indent=1)
+# unique chrY regions used for the gender inference (bam_parser.py:413-429 reads the first rows of
+# chrY.<build>.unique_ccn.gc, skipping ten listed row numbers, until it has five): the first 20 rows per build
+with open(os.path.join(dst, "chrY.tsv"), "w") as fw:
+    fw.write("build\trow\tchr\tstart\tend\tgc\n")
+    for build in ("hg38", "hg19"):
+        with open(os.path.join(src, "chrY.{}.unique_ccn.gc".format(build))) as fp:
+            for i, row in enumerate(fp):
+                if i >= 20:
+                    break
+                c, start, end, gc = row.split()
+                fw.write("\t".join([build, str(i), c, start, end, gc]) + "\n")
 print("wrote", os.listdir(dst))

@@ -14,6 +14,7 @@ What runs where:
          (or per whole cohort shard through ``classify_problems``).
 """
 import logging
+import os
 import math
 from collections import defaultdict
 
@@ -267,6 +268,15 @@ class BamReadLen:
 
     @property
     def readlen(self, firstN=100):
+        try:                                   # native reader (csrc/ingest.cpp); needs the .bai next to the BAM
+            from .ingest import BamIngest
+            with BamIngest(os.path.abspath(self.bamfile)) as ing:
+                rmax, rmin = ing.read_length(firstN)
+            if rmin != rmax:
+                self.logger.debug("Read length: min={}bp max={}bp".format(rmin, rmax))
+            return rmax
+        except (IOError, OSError, _lib.TredswError):
+            pass
         sam = read_alignment(self.bamfile)
         rls = []
         for read in sam.fetch():
@@ -299,9 +309,35 @@ class BamDepth:
             self.logger.debug("Depth of region {}:{}-{}: {}".format(chr, start, end, depth))
         return depth
 
+    # rows of the chrY table that "still have mapped reads" in females and are skipped (bam_parser.py:417-418)
+    Y_SKIP_ROWS = (1, 4, 6, 7, 10, 11, 13, 16, 18, 19)
+
     def get_Y_depth(self, N=5):
-        """Median depth over the first N unique chrY regions.  The chrY region table of the reference
-        (data/chrY.*.unique_ccn.gc) is not shipped with this build (out of scope),
-        so this raises and the caller keeps gender 'Unknown' exactly like the reference does when the
-        lookup fails (tred.py:203-211)."""
-        raise IOError("chrY unique-region table is not part of this build")
+        """Median depth over the first N usable unique chrY regions (bam_parser.py:413-429).  Raises when the
+        BAM has no such contig — the caller then keeps gender 'Unknown' like the reference (tred.py:203-211)."""
+        build = self.ref.split("_")[0]
+        regions = []
+        with open(datafile("chrY.tsv")) as fp:
+            next(fp)
+            for line in fp:
+                b, row, c, start, end, _gc = line.split()
+                if b != build or int(row) in self.Y_SKIP_ROWS:
+                    continue
+                regions.append((c, int(start), int(end)))
+                if len(regions) >= N:
+                    break
+        depths = []
+        ing = None
+        try:
+            from .ingest import BamIngest
+            ing = BamIngest(os.path.abspath(self.bamfile))
+        except Exception:
+            ing = None
+        try:
+            for c, start, end in regions:
+                depths.append(ing.region_depth(c, start, end) if ing is not None else self.region_depth(c, start, end))
+        finally:
+            if ing is not None:
+                ing.close()
+        self.logger.debug("Y depths (first {} regions): {}".format(N, np.array(depths)))
+        return float(np.median(depths))

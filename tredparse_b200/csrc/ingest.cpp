@@ -123,6 +123,7 @@ struct tredsw_bam {
     std::unordered_map<std::string, int32_t> tid_of;
     std::vector<RefIndex> index;
     bool has_index = false;
+    uint64_t first_record = 0;       // virtual offset of the first alignment record
     std::vector<unsigned char> rec;
 
     bool read_record(Record &r) {
@@ -230,6 +231,7 @@ tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
         b->lengths.push_back(l_ref);
         b->tid_of[b->names.back()] = i;
     }
+    b->first_record = b->bgzf.tell();
     // index: <bam>.bai, then <bam without extension>.bai (bamio.AlignmentFile)
     std::string cands[2];
     if (bai_path) cands[0] = bai_path;
@@ -295,6 +297,40 @@ int32_t tredsw_bam_tid(tredsw_bam *b, const char *name) {
     if (!b || !name) return -1;
     auto it = b->tid_of.find(name);
     return it == b->tid_of.end() ? -1 : it->second;
+}
+
+// BamDepth.region_depth (bam_parser.py:404-411): sum of pileup column depths / (end - start + 1).  pysam's
+// default pileup walks every column of every qualifying read overlapping the window, so the column sum is the
+// total reference span of the overlapping reads that are not UNMAP / SECONDARY / QCFAIL / DUP
+// (same restatement as bamio.region_depth).
+int tredsw_bam_region_depth(tredsw_bam *b, int32_t tid, int64_t start, int64_t end, double *depth) {
+    if (!b || !depth) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    if (tid < 0 || tid >= (int)b->names.size()) { tredsw_set_error("contig id %d out of range", tid); return TREDSW_ERR_ARG; }
+    if (end < start) { tredsw_set_error("empty region"); return TREDSW_ERR_ARG; }
+    int64_t total = 0;
+    b->fetch(tid, start, end, [&](const Record &r) {
+        if ((r.flag & (4 | 256 | 512 | 1024)) || !r.has_cigar) return;
+        total += r.ref_len;
+    });
+    *depth = (double)total * 1.0 / (double)(end - start + 1);
+    return TREDSW_OK;
+}
+
+// BamReadLen.readlen (bam_parser.py:372-391): the longest query among the first `first_n` + 1 records of the
+// file (the reference breaks after len(rls) > firstN); min_out may be NULL.
+int tredsw_bam_read_length(tredsw_bam *b, int32_t first_n, int32_t *max_out, int32_t *min_out) {
+    if (!b || !max_out || first_n < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    b->bgzf.seek(b->first_record);
+    Record r;
+    int32_t n = 0, mx = -1, mn = 0x7fffffff;
+    while (n <= first_n && b->read_record(r)) {
+        mx = std::max(mx, r.l_seq); mn = std::min(mn, r.l_seq);
+        ++n;
+    }
+    if (n == 0) { tredsw_set_error("no records"); return TREDSW_ERR_ARG; }
+    *max_out = mx;
+    if (min_out) *min_out = mn;
+    return TREDSW_OK;
 }
 
 int tredsw_bam_extract_locus(tredsw_bam *b, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,

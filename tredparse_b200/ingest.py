@@ -49,6 +49,12 @@ def _bind(lib):
                                              ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                              ctypes.c_int64, ctypes.POINTER(LocusSummary)]
+    lib.tredsw_bam_region_depth.restype = ctypes.c_int
+    lib.tredsw_bam_region_depth.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.POINTER(ctypes.c_double)]
+    lib.tredsw_bam_read_length.restype = ctypes.c_int
+    lib.tredsw_bam_read_length.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                           ctypes.POINTER(ctypes.c_int32)]
     lib._ingest_bound = True
 
 
@@ -94,6 +100,23 @@ class BamIngest:
 
     def tid(self, contig):
         return int(self.lib.tredsw_bam_tid(self.handle, contig.encode()))
+
+    def region_depth(self, contig, start, end):
+        """``BamDepth.region_depth`` (bam_parser.py:404-411) on the native reader."""
+        tid = self.tid(contig)
+        if tid < 0:
+            raise ValueError("invalid contig `{}`".format(contig))
+        d = ctypes.c_double()
+        _lib.check(self.lib.tredsw_bam_region_depth(self.handle, tid, int(start), int(end), ctypes.byref(d)),
+                   "tredsw_bam_region_depth")
+        return float(d.value)
+
+    def read_length(self, firstN=100):
+        """``BamReadLen.readlen`` (bam_parser.py:372-391) -> (max, min) over the first firstN + 1 records."""
+        mx, mn = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self.lib.tredsw_bam_read_length(self.handle, int(firstN), ctypes.byref(mx), ctypes.byref(mn)),
+                   "tredsw_bam_read_length")
+        return int(mx.value), int(mn.value)
 
     def extract_locus(self, tred, readlen, alts=(), want_names=False, pad=SPAN):
         """alts: iterable of (contig, start, end) mis-mapping regions (``TREDsRepo.get_alts``)."""

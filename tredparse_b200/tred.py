@@ -222,33 +222,35 @@ def run_batched(ips, evidence=None):
     return results
 
 
-def run(arg):
-    """Run the TRED caller on a list of TREDs for one sample.  :return: dict of calls"""
-    samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
-    gender = "Unknown"
-    ydepth = -1
-    tredCalls = {"inferredGender": gender, "depthY": ydepth}
-    if check_bam(bam) is None:
-        return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
-
+def presteps(bam, repo, tredNames, logger):
+    """The per-sample pre-steps of tred.run (tred.py:195-223): gender from the chrY depth — only when an X-linked
+    locus is requested; 'Unknown' / -1 when the lookup fails — and the read length (150 when it cannot be read).
+    They decide ploidy (bam_parser.py:58-61) and the number of templates (:73), so they gate parity on real BAMs."""
+    gender, ydepth = "Unknown", -1
     if any(repo[tred].is_xlinked for tred in tredNames):
         try:
-            bd = BamDepth(bam, repo.ref, logger)
-            ydepth = bd.get_Y_depth()
+            ydepth = BamDepth(bam, repo.ref, logger).get_Y_depth()
             gender = "Male" if ydepth > 1 else "Female"
         except Exception:
             pass
         logger.debug("Inferred gender: {} (depthY={})".format(gender, ydepth))
-        tredCalls["inferredGender"] = gender
-        tredCalls["depthY"] = ydepth
-
     READLEN = 150
     try:
         READLEN = BamReadLen(bam, logger).readlen
     except Exception:
         pass
     logger.debug("Read length: {}bp".format(READLEN))
-    tredCalls["readLen"] = READLEN
+    return {"inferredGender": gender, "depthY": ydepth, "readLen": READLEN}
+
+
+def run(arg):
+    """Run the TRED caller on a list of TREDs for one sample.  :return: dict of calls"""
+    samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
+    tredCalls = {"inferredGender": "Unknown", "depthY": -1}
+    if check_bam(bam) is None:
+        return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
+    tredCalls.update(presteps(bam, repo, tredNames, logger))
+    gender, READLEN = tredCalls["inferredGender"], tredCalls["readLen"]
 
     # native ingest: one indexed pass per locus yields reads, pair distances AND depth (csrc/ingest.cpp); the
     # Python BAM reader (three passes per locus, like the reference's pysam calls) is the fallback
