@@ -104,7 +104,22 @@ def test_fullsearch_surface_properties(evidence, k):
     assert R["max_ml"] == finite.max()
     i1, i2 = np.unravel_index(int(np.argmax(finite)), S.shape)            # first maximum == smallest h1 (Q10)
     assert (R["arg_i1"], R["arg_i2"]) == (i1, i2)
-    assert abs(R["sum_all"] - np.exp(finite - finite.max()).sum()) <= 1e-9 * R["sum_all"]
+    W = np.exp(finite - finite.max())
+    assert abs(R["sum_all"] - W.sum()) <= 1e-9 * R["sum_all"]
+    Pd = gb.problems[0]
+    ph1 = gb.marg[Pd["off_ph1"]:Pd["off_ph1"] + Pd["n_h1"]]
+    ph2 = gb.marg[Pd["off_ph2"]:Pd["off_ph2"] + Pd["n_h2"]]
+    np.testing.assert_allclose(ph1, W.sum(axis=1), rtol=1e-9, atol=1e-300)     # marginals (models.py:277-284)
+    np.testing.assert_allclose(ph2, W.sum(axis=0), rtol=1e-9, atol=1e-300)
+    H1 = np.array(h1r)[:, None]
+    H2 = np.array(h2r)[None, :] if pr.ploidy == 2 else H1
+    lo, hi = np.minimum(H1, H2) // P, np.maximum(H1, H2) // P
+    if t.is_expansion:
+        patho = (lo >= t.cutoff_risk) if t.is_recessive else (hi >= t.cutoff_risk)
+    else:
+        patho = (hi <= t.cutoff_risk) if t.is_recessive else (lo <= t.cutoff_risk)
+    want_path = (W * np.broadcast_to(patho, W.shape)).sum()                     # PP numerator (models.py:342-368)
+    assert abs(R["sum_path"] - want_path) <= 1e-9 * max(want_path, 1e-300)
     # (4) the all-device pipeline made the same call
     s = gb.summarize(0, want_joint=False)
     c = cohort.decode_call(call)

@@ -98,3 +98,39 @@ def test_candidate_list_keeps_duplicates_quirk_Q9():
     h2 = doc["outputs"]["h2range"]
     assert len(h2) >= len(set(h2))
     assert doc["outputs"]["n_points"] == sum(1 for a in doc["outputs"]["h1range"] for b in h2 if a <= b)
+
+
+@pytest.mark.parametrize("name", ["t001_HD", "t002_DM1", "t002_DM1_max1200"])
+def test_separability_the_far_region_tables_rely_on(name):
+    """grid.cu replaces most points of a long-expansion surface by table look-ups.  The identities behind it,
+    checked here on the independent closed form (exact equality — the same expression is evaluated):
+      * h2 >= H1 = max(max spanning key + 19, max_partial, READLEN - 9, READLEN + 1): the spanning and partial
+        terms do not depend on h2;
+      * h2 >= H2 = max(H1, pe_ref + 1000 - min{target length >= MINPE}): nor does the paired-end term;
+      * everywhere: the repeat-only term depends on max(h1-L,1) + max(h2-L,1) only."""
+    doc = json.load(open(os.path.join(GOLDEN, "likelihood_{}.json".format(name))))
+    inp, out = doc["inputs"], doc["outputs"]
+    step, w = _models()
+    ml = _closed_form_surface(inp, step, w)
+    K, L = inp["period"], inp["READLEN"]
+    ks = max([int(k) * K for k in inp["FULL"]] or [-10 ** 6])
+    mp = max([L - 18] + [int(k) * K for k in inp["PREF"]])
+    H1 = max(ks + 19, mp, L - 9, L + 1)
+    tl = [x + 1000 if x < 0 else x for x in inp["target_lens"]]
+    tmin = min([x for x in tl if x >= inp["MINPE"]] or [None]) if out["run_pe"] else None
+    H2 = max(H1, inp["pe_ref"] + 1000 - tmin) if tmin is not None else H1
+    rng = np.random.default_rng(11)
+    far = [H2 + int(x) for x in rng.integers(0, 2000, size=6)]
+    mid = [H1 + int(x) for x in rng.integers(0, max(1, H2 - H1), size=6)]
+    for h1 in [K, 5 * K, ks, max(K, ks - K), mp, H1 - 1, H1, H1 + 7 * K, H2, H2 + 40 * K]:
+        if h1 <= 0:
+            continue
+        a = [ml(h1, h2, out["run_pe"]) for h2 in mid + far if h2 >= h1]
+        assert len({(x[0], x[1]) for x in a}) <= 1, h1                      # span, partial: h1 only
+        b = [ml(h1, h2, out["run_pe"]) for h2 in far if h2 >= h1]
+        assert len({x[3] for x in b}) <= 1, h1                              # paired-end: h1 only
+    for _ in range(50):
+        d = int(rng.integers(2, 3000))
+        pts = [(h1, d - max(h1 - L, 1) + L) for h1 in (L - 30, L + 1, L + d // 2) if 1 <= d - max(h1 - L, 1)]
+        pts = [(h1, h2) for h1, h2 in pts if h1 > 0 and h2 > L and h1 <= h2]
+        assert len({ml(h1, h2, False)[2] for h1, h2 in pts}) <= 1

@@ -30,27 +30,46 @@ struct GridParams {
     double *marg;
     tredsw_grid_result *res;
     double small_value, really_small, log_small;
-    // far-region tables of the large surfaces (grid_far_kernel)
+    // per-problem constants and far-region tables of the medium / large surfaces (grid_setup / grid_fill)
     struct FarInfo *far;            // [nproblems]
     double *ftab;                   // arena of per-problem tables
     long long ftab_cap;
     unsigned long long *fcursor;    // arena cursor
 };
 
-// In the FAR region of a large surface — both alleles beyond every observed key, the partial clamp and the
-// read length, and the longer allele shifted past the KDE support — the four terms collapse:
-//   spanning + partial = one constant c12;  repeat-only = a function of h1 + h2 only;  paired-end = a function
-//   of h1 only.
-// The candidate lists end in arithmetic progressions of step `period` there, so for list indices i1 >= fa1,
-// i2 >= fa2 the point is   ml = ((c12) + rept[(i1-fa1) + (i2-fa2)]) + pe_row[i1-fa1]   — the same three
-// additions in the same order as the general evaluation, on operands produced by the same code, hence the
-// same bits — two table reads instead of tens of logarithms.  On a --fullsearch / long-expansion grid
-// (10^5 - 10^6 points) ~90 % of the points are of this kind.
+// Where the longer allele h2 lies beyond every observed key, the partial clamp and the read length
+// (list index i2 >= fam, the MID region), the spanning and partial terms depend on h1 only; where it is also
+// shifted past the KDE support (i2 >= fa2, the FAR region) so does the paired-end term; and the repeat-only
+// term is a function of dsum = max(h1-L,1) + max(h2-L,1) everywhere.  With the per-row table
+// rows[i1] = {span(h1) + partial(h1), pe(h1)} and rept[dsum - 2], a far point is
+//   ml = ((rows[i1].c12) + rept[dsum-2]) + rows[i1].pe
+// and a mid point the same with the paired-end term evaluated directly — the same additions in the same order
+// as the general evaluation, on operands produced by the same device functions, hence the same bits: two
+// table reads instead of tens of logarithms.  On a --fullsearch / long-expansion grid (10^5 - 10^6 points)
+// > 90 % of the points are far, most of the rest mid.
 struct FarInfo {
-    long long off;      // ftab: pe_row[n_h1 - fa1] then rept[(n_h1 - fa1) + (n_h2 - fa2) - 1]
-    double c12;
-    int fa1, fa2, ok, pad;
+    unsigned long long maxkey;   // ordered key of the surface maximum (atomicMax of the tiles kernel); 0 = no point
+    long long off;               // ftab: rows[2 * n_h1] ({c12, pe} pairs), then rept[nd]
+    double lgamma_k1;            // lgamma(n_rept + 1) of the Poisson term
+    double sig_mp;               // sigma(max_partial)
+    int tmin;                    // smallest pair length >= MINPE (after numpy's negative-index wrap); INT_MAX if none
+    int fam, fa2;                // first h2 index of the mid / far region
+    int ok;                      // tables present
+    int sorted;                  // both candidate lists are non-decreasing (lets the reduction skip h1 > h2 chunks)
+    int nd;                      // entries of rept[]
+    int hrep;                    // a far allele (the largest h2)
+    int pad;
 };
+
+// order-preserving map double -> u64 (for atomicMax); 0 is below every value
+__device__ __forceinline__ unsigned long long ord_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double ord_val(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
 
 __device__ __forceinline__ double sigma_h(const tredsw_grid_problem &P, int h) {
     double z = __dadd_rn(P.stutter_a, __dmul_rn(P.stutter_w2, (double)(h / P.period)));
@@ -101,9 +120,6 @@ struct TileShared {
     double lgamma_k1;      // lgamma(n_rept + 1) of the Poisson term
     double sig_mp;         // sigma(max_partial): the stutter probability of every allele clamped to max_partial
     int tmin;              // smallest pair length >= MINPE (after numpy's negative-index wrap); INT_MAX if none
-    int far_ok, fa1, fa2;  // far region of this problem (FarInfo)
-    double c12;
-    const double *pe_row, *rept;
 };
 
 // One grid point.  The arithmetic (operation order, rounding) is exactly that of the straightforward loops
@@ -181,8 +197,8 @@ __device__ __forceinline__ double ml_part_term(const tredsw_grid_problem &P, con
 __device__ __forceinline__ double ml_rept_term(const tredsw_grid_problem &P, int dsum, double lgamma_k1) {
     const double mu = (double)dsum * P.half_depth / (double)P.readlen;
     const double kk = (double)P.n_rept;
-    const double xl = (P.n_rept == 0) ? 0.0 : kk * log(mu);
-    const double pk = xl - lgamma_k1 - mu;
+    const double xl = (P.n_rept == 0) ? 0.0 : __dmul_rn(kk, log(mu));
+    const double pk = __dsub_rn(__dsub_rn(xl, lgamma_k1), mu);    // no FMA contraction: table and direct path agree
     // log(max(exp(pk), e^-100)): log(exp(pk)) is pk to within an ulp of the pmf (~1e-16 absolute on a term
     // of magnitude 0.1..100, far inside the 1e-9 relative bar) — two transcendentals less per point
     return pk > -100.0 ? pk : -100.0;
@@ -283,75 +299,108 @@ __device__ __forceinline__ TileShared tile_shared_of(const GridParams &g, const 
         for (int i = 0; i < Q.n_target; ++i) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= Q.pe_minpe && x < tmin) tmin = x; }
     }
     T.tmin = tmin;
-    T.far_ok = 0; T.fa1 = T.fa2 = 0; T.c12 = 0.0; T.pe_row = T.rept = nullptr;
     return T;
 }
 
-// One block per medium / large surface (class lists of grid_tiles_kernel): decide the far region and fill its
-// tables.
-__global__ void __launch_bounds__(256) grid_far_kernel(GridParams g, const int *lists, int nproblems) {
-    __shared__ FarInfo s_f;
-    __shared__ TileShared s_t;
+// block-wide max of an int (256 threads); every thread gets the result
+__device__ __forceinline__ int block_max_int(int v, int *s8) {
+    v = __reduce_max_sync(0xffffffffu, v);
+    __syncthreads();                                   // s8 may still be read from the previous call
+    if ((threadIdx.x & 31) == 0) s8[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = s8[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) r = max(r, s8[w]);
+    return r;
+}
+
+// One block per medium / large surface (class lists of grid_tiles_kernel): per-problem constants, the
+// mid / far thresholds and the table allocation (FarInfo).  All scans are block-parallel.
+constexpr long long FAR_MIN_POINTS = 4096;     // tables only pay for at least this many mid + far points
+__global__ void __launch_bounds__(256) grid_setup_kernel(GridParams g, const int *lists, int nproblems) {
+    __shared__ int s8[8];
     const int nb = lists[0], nc = lists[1];
+    const int tid = threadIdx.x;
     for (int k = blockIdx.x; k < nb + nc; k += gridDim.x) {
         const int pi = k < nb ? lists[2 + k] : lists[2 + nproblems + (k - nb)];
         const tredsw_grid_problem &P = g.prob[pi];
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-        if (threadIdx.x == 0) {
-            FarInfo f; f.off = 0; f.c12 = 0.0; f.fa1 = f.fa2 = 0; f.ok = 0; f.pad = 0;
-            TileShared T = tile_shared_of(g, P);
-            if (P.ploidy != 1 && P.n_h1 > 0 && P.n_h2 > 1) {
-                const int32_t *skey = g.ipool + P.off_span;
-                int ks = -1000000;
-                for (int i = 0; i < P.n_span; ++i) ks = max(ks, skey[i]);
-                const int t1 = P.readlen - 9;
-                // h >= H1: no spanning key within 18, partial clamp and mixing weight saturated, h > readlen
-                const int H1 = max(max(ks + DEV + 1, P.max_partial), max(t1, P.readlen + 1));
-                // h >= H2: every pair length >= MINPE is shifted past the support
-                long long H2 = H1;
-                if (P.run_pe && T.tmin != 0x7fffffff) H2 = max((long long)H1, (long long)P.pe_ref + SPAN - T.tmin);
-                auto tail = [&](const int32_t *hs, int n, long long H) {
-                    int i = n - 1;
-                    if (hs[i] < H) return n;
-                    while (i > 0 && hs[i] - hs[i - 1] == P.period && hs[i - 1] >= H) --i;
-                    return i;
-                };
-                f.fa1 = tail(h1s, P.n_h1, H1);
-                f.fa2 = tail(h2s, P.n_h2, H2);
-                const long long r1 = P.n_h1 - f.fa1, r2 = P.n_h2 - f.fa2;
-                if (r1 > 0 && r2 > 0 && r1 * r2 >= 4096) {
-                    const unsigned long long need = (unsigned long long)(r1 + r1 + r2);
-                    const unsigned long long off = atomicAdd(g.fcursor, need);
-                    if ((long long)(off + need) <= g.ftab_cap) {
-                        f.off = (long long)off; f.ok = 1;
-                        const int h1 = h1s[f.fa1], h2 = h2s[f.fa2];
-                        f.c12 = __dadd_rn(ml_span_term(P, g, h1, h2), ml_part_term(P, g, h1, h2, T.sig_mp));
-                    }
-                }
+        const int32_t *skey = g.ipool + P.off_span, *tl = g.ipool + P.off_target;
+        const bool two = P.ploidy != 1 && P.n_h2 > 0;
+        int ks = -1000000, ntmin = -0x7fffffff, mx1 = -0x7fffffff, mx2 = -0x7fffffff, unsorted = 0;
+        for (int i = tid; i < P.n_span; i += 256) ks = max(ks, skey[i]);
+        if (P.run_pe)
+            for (int i = tid; i < P.n_target; i += 256) { int x = tl[i]; if (x < 0) x += SPAN; if (x >= P.pe_minpe) ntmin = max(ntmin, -x); }
+        for (int i = tid; i < P.n_h1; i += 256) { mx1 = max(mx1, h1s[i]); if (i > 0 && h1s[i - 1] > h1s[i]) unsorted = 1; }
+        if (two)
+            for (int i = tid; i < P.n_h2; i += 256) { mx2 = max(mx2, h2s[i]); if (i > 0 && h2s[i - 1] > h2s[i]) unsorted = 1; }
+        ks = block_max_int(ks, s8); ntmin = block_max_int(ntmin, s8);
+        mx1 = block_max_int(mx1, s8); mx2 = block_max_int(mx2, s8); unsorted = block_max_int(unsorted, s8);
+        const int tmin = ntmin == -0x7fffffff ? 0x7fffffff : -ntmin;
+        const int t1 = P.readlen - 9;
+        // h2 >= H1: no spanning key within 18, partial clamp and mixing weights saturated, h2 > readlen
+        const int H1 = max(max(ks + DEV + 1, P.max_partial), max(t1, P.readlen + 1));
+        // h2 >= H2: every pair length >= MINPE is shifted past the support as well
+        long long H2 = H1;
+        if (P.run_pe && tmin != 0x7fffffff) H2 = max((long long)H1, (long long)P.pe_ref + SPAN - tmin);
+        int l1 = -1, l2 = -1;                          // last h2 index below H1 / H2
+        if (two)
+            for (int i = tid; i < P.n_h2; i += 256) { const int h = h2s[i]; if (h < H1) l1 = max(l1, i); if (h < H2) l2 = max(l2, i); }
+        l1 = block_max_int(l1, s8); l2 = block_max_int(l2, s8);
+        if (tid == 0) {
+            FarInfo f;
+            f.maxkey = 0; f.off = 0; f.ok = 0; f.pad = 0;
+            f.lgamma_k1 = lgamma((double)P.n_rept + 1.0);
+            f.sig_mp = sigma_h(P, P.max_partial);
+            f.tmin = tmin;
+            f.fam = two ? l1 + 1 : P.n_h2; f.fa2 = two ? l2 + 1 : P.n_h2;
+            f.sorted = unsorted ? 0 : 1;
+            f.hrep = mx2;
+            f.nd = (two && P.n_h1 > 0) ? max(mx1 - P.readlen, 1) + max(mx2 - P.readlen, 1) - 1 : 0;
+            if (two && P.n_h1 > 0 && (long long)(P.n_h2 - f.fam) * P.n_h1 >= FAR_MIN_POINTS) {
+                const unsigned long long need = ((unsigned long long)(2LL * P.n_h1 + f.nd) + 1ULL) & ~1ULL;   // even: rows stay 16-byte aligned
+                const unsigned long long off = atomicAdd(g.fcursor, need);
+                if ((long long)(off + need) <= g.ftab_cap) { f.off = (long long)off; f.ok = 1; }
             }
-            s_f = f; s_t = T;
             g.far[pi] = f;
         }
-        __syncthreads();
-        const FarInfo f = s_f;
-        if (f.ok) {
-            const TileShared T = s_t;
-            const int r1 = P.n_h1 - f.fa1, r2 = P.n_h2 - f.fa2;
-            double *pe_row = g.ftab + f.off, *rept = pe_row + r1;
-            const int hfar = h2s[f.fa2];                       // any allele past the support
-            for (int r = threadIdx.x; r < r1; r += blockDim.x) pe_row[r] = ml_pe_term(P, g, h1s[f.fa1 + r], hfar, T.tmin);
-            const int base = h1s[f.fa1] + h2s[f.fa2] - 2 * P.readlen;   // d1 + d2 at (fa1, fa2); both alleles > readlen
-            for (int r = threadIdx.x; r < r1 + r2 - 1; r += blockDim.x) rept[r] = ml_rept_term(P, base + r * P.period, T.lgamma_k1);
-        }
-        __syncthreads();
     }
 }
 
-// Large and medium surfaces: persistent over their tiles; the per-problem values are computed once per tile.
+// Fill the tables: FILL_SPLIT blocks per problem over the rows and the dsum entries.
+constexpr int FILL_SPLIT = 8;
+__global__ void __launch_bounds__(256) grid_fill_kernel(GridParams g, const int *lists, int nproblems) {
+    const int nb = lists[0], nc = lists[1];
+    for (int kk = blockIdx.x; kk < (nb + nc) * FILL_SPLIT; kk += gridDim.x) {
+        const int k = kk / FILL_SPLIT, part = kk - k * FILL_SPLIT;
+        const int pi = k < nb ? lists[2 + k] : lists[2 + nproblems + (k - nb)];
+        const FarInfo &F = g.far[pi];
+        if (!F.ok) continue;
+        const tredsw_grid_problem &P = g.prob[pi];
+        const int32_t *h1s = g.ipool + P.off_h1;
+        double *rows = g.ftab + F.off, *rept = rows + 2 * (long long)P.n_h1;
+        const int hrep = F.hrep, tmin = F.tmin;
+        const double sig_mp = F.sig_mp, lgk = F.lgamma_k1;
+        const int n = P.n_h1 + F.nd;
+        for (int e = part * 256 + threadIdx.x; e < n; e += 256 * FILL_SPLIT) {
+            if (e < P.n_h1) {
+                const int h1 = h1s[e];
+                rows[2 * e] = __dadd_rn(ml_span_term(P, g, h1, hrep), ml_part_term(P, g, h1, hrep, sig_mp));
+                rows[2 * e + 1] = ml_pe_term(P, g, h1, hrep, tmin);
+            } else {
+                rept[e - P.n_h1] = ml_rept_term(P, e - P.n_h1 + 2, lgk);
+            }
+        }
+    }
+}
+
+// Large and medium surfaces: persistent over their tiles.  Besides the surface, every tile contributes to the
+// maximum of its problem (ordered-key atomicMax — order independent, hence deterministic), so that the
+// reduction needs a single pass.
 __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParams g, int nproblems, const long long *tile_start) {
     const long long ntiles = tile_start[nproblems];
     __shared__ int s_pi;
-    __shared__ TileShared s_tile;
+    __shared__ unsigned long long s_wmax[GRID_TILE / 32];
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (threadIdx.x == 0) {                        // tile -> problem: last p with tile_start[p] <= tile
             int lo = 0, hi = nproblems;
@@ -360,21 +409,14 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParam
                 if (tile_start[mid] <= tile) lo = mid; else hi = mid;
             }
             s_pi = lo;
-            TileShared T0 = tile_shared_of(g, g.prob[lo]);
-            const FarInfo f = g.far[lo];
-            if (f.ok) {
-                T0.far_ok = 1; T0.fa1 = f.fa1; T0.fa2 = f.fa2; T0.c12 = f.c12;
-                T0.pe_row = g.ftab + f.off; T0.rept = T0.pe_row + (g.prob[lo].n_h1 - f.fa1);
-            }
-            s_tile = T0;
         }
         __syncthreads();
         const int pi = s_pi;
-        const TileShared T = s_tile;
-        __syncthreads();
         const tredsw_grid_problem &P = g.prob[pi];
+        const FarInfo &F = g.far[pi];
         const long long total = (long long)P.n_h1 * P.n_h2;
         const long long t = (tile - tile_start[pi]) * GRID_TILE + threadIdx.x;
+        unsigned long long key = 0;
         if (t < total) {
             const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
             int i1, i2;
@@ -384,12 +426,40 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParam
             const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
             double ml = -INFINITY;
             if (h1 <= h2) {
-                if (T.far_ok && i1 >= T.fa1 && i2 >= T.fa2)
-                    ml = __dadd_rn(__dadd_rn(T.c12, T.rept[(i1 - T.fa1) + (i2 - T.fa2)]), T.pe_row[i1 - T.fa1]);
-                else
+                TileShared T;
+                T.lgamma_k1 = F.lgamma_k1; T.sig_mp = F.sig_mp; T.tmin = F.tmin;
+                if (F.ok) {
+                    const double *rows = g.ftab + F.off;
+                    const double rp = rows[2 * (long long)P.n_h1 + (max(h1 - P.readlen, 1) + max(h2 - P.readlen, 1) - 2)];
+                    if (i2 >= F.fam) {
+                        const double2 row = reinterpret_cast<const double2 *>(rows)[i1];
+                        const double pe = (i2 >= F.fa2) ? row.y : ml_pe_term(P, g, h1, h2, T.tmin);
+                        ml = __dadd_rn(__dadd_rn(row.x, rp), pe);
+                    } else {
+                        ml = __dadd_rn(ml_span_term(P, g, h1, h2), ml_part_term(P, g, h1, h2, T.sig_mp));
+                        ml = __dadd_rn(ml, rp);
+                        ml = __dadd_rn(ml, ml_pe_term(P, g, h1, h2, T.tmin));
+                    }
+                } else {
                     ml = point_ml(P, g, h1, h2, T);
+                }
+                key = ord_key(ml);
             }
             g.surface[P.off_surface + t] = ml;
+        }
+        key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
+        key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
+        key = max(key, __shfl_xor_sync(0xffffffffu, key, 4));
+        key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+        key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+        if ((threadIdx.x & 31) == 0) s_wmax[threadIdx.x >> 5] = key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long m = s_wmax[0];
+#pragma unroll
+            for (int w = 1; w < GRID_TILE / 32; ++w) m = max(m, s_wmax[w]);
+            unsigned long long *dst = &g.far[pi].maxkey;
+            if (m != 0 && m > *(volatile unsigned long long *)dst) atomicMax(dst, m);
         }
     }
 }
@@ -431,118 +501,147 @@ __device__ __forceinline__ bool pathological(const tredsw_grid_problem &P, int h
     return P.recessive ? (hi <= P.cutoff_risk) : (lo <= P.cutoff_risk);
 }
 
-// Reductions of one problem's surface (models.py:277-302, 342-368): max / arg-max with key (ml, -h1, order)
-// (Q10), the exp-normalised marginals P_h1 / P_h2 and the PP sums.  CS = 1: one CTA per problem (medium
+// Reductions of one problem's surface (models.py:277-302, 342-368): arg-max with key (ml, -h1, order) (Q10),
+// number of evaluated points, the exp-normalised marginals P_h1 / P_h2 and the PP sums — in ONE pass over the
+// surface (its maximum is already known from the tiles kernel).  CS = 1: one CTA per problem (medium
 // surfaces).  CS = 8: a thread-block CLUSTER of 8 CTAs per problem for the large surfaces (extended ranges,
-// --fullsearch: 10^4 - 10^6 points): rows / columns are dealt to the CTAs of the cluster, the per-CTA partial
-// results meet in distributed shared memory in rank order, so the result is deterministic.  Both walk the
-// index list of their class (grid_tiles_kernel); small surfaces take grid_reduce_warp_kernel.
+// --fullsearch: 10^4 - 10^6 points).  Rows are dealt to the warps of the CTA / cluster; a warp walks its rows
+// in chunks of 256 columns, 8 columns per lane, keeps the column partial sums in registers and reduces the row
+// sums by shuffles; the column partials of the warps meet in shared memory, those of the CTAs of a cluster in
+// distributed shared memory, always in rank order — deterministic.  Chunks of a row that lie entirely in the
+// h1 > h2 half are skipped when the candidate lists are sorted (FarInfo.sorted), and exp(ml - max) is not
+// evaluated where it is exactly 0 (ml - max < -746), which is almost everywhere on a large surface.
+constexpr int RED_CHUNK = 256;        // columns per chunk (8 per lane)
+constexpr int RED_SUPER = 2048;       // columns per exchange through (distributed) shared memory
 template <int CS>
-__global__ void __launch_bounds__(256, 4) grid_reduce_kernel(GridParams g, const int *list, const int *nlist) {
+__global__ void __launch_bounds__(256, 3) grid_reduce_kernel(GridParams g, const int *list, const int *nlist) {
     namespace cg = cooperative_groups;
-    __shared__ ArgMax s_best[256];
-    __shared__ double s_sum[256], s_path[256];
-    __shared__ int s_cnt[256];
+    __shared__ double s_col[8][RED_CHUNK];
+    __shared__ double c_col[CS > 1 ? RED_SUPER : 1];   // this CTA's column partials, read by the cluster
+    __shared__ ArgMax s_best[8];
+    __shared__ double s_sum[8], s_path[8];
+    __shared__ int s_cnt[8];
     __shared__ ArgMax c_best;          // this CTA's partial results, read by the other CTAs of the cluster
     __shared__ int c_cnt;
     __shared__ double c_sum, c_path;
     unsigned crank = 0;
     if (CS > 1) crank = cg::this_cluster().block_rank();
     const int n = *nlist;
-    // persistent over the problems of this class (CTAs of a cluster walk the list together)
-    for (int k = blockIdx.x / CS; k < n; k += (CS > 1 ? n : (int)gridDim.x)) {       // (cluster variant: one problem per cluster)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // persistent over the problems of this class (the CTAs of a cluster walk the list together)
+    for (int k = blockIdx.x / CS; k < n; k += (int)gridDim.x / CS) {
     const int pi = list[k];
-    const tredsw_grid_problem P = g.prob[pi];
+    const tredsw_grid_problem &P = g.prob[pi];
     const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
     const double *surf = g.surface + P.off_surface;
-    const int tid = threadIdx.x;
-    // ---- max / arg-max / number of evaluated points: rows crank, crank + CS, ... ----------------------
+    double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+    const unsigned long long maxkey = g.far[pi].maxkey;
+    const double top_ml = maxkey ? ord_val(maxkey) : -INFINITY;
+    const bool sorted = g.far[pi].sorted != 0 && P.ploidy != 1;
+    const int row0 = (int)crank * 8 + warp, rstep = 8 * CS;
+    for (int i1 = row0; i1 < P.n_h1; i1 += rstep) if (lane == 0) ph1[i1] = 0.0;
     ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL};
     int cnt = 0;
-    for (int i1 = (int)crank; i1 < P.n_h1; i1 += CS) {
-        const int h1 = h1s[i1];
-        const long long row = (long long)i1 * P.n_h2;
-        for (int i2 = tid; i2 < P.n_h2; i2 += 256) {
-            const double ml = surf[row + i2];
-            if (ml == -INFINITY) continue;   // not evaluated (h1 > h2)
-            ++cnt;
-            ArgMax c{ml, h1, row + i2};
-            if (better(c, best)) best = c;
+    double sum_all = 0.0, sum_path = 0.0;              // lane 0 of every warp
+    for (int sb = 0; sb < P.n_h2; sb += RED_SUPER) {
+        const int sb_end = min(sb + RED_SUPER, P.n_h2);
+        for (int cb = sb; cb < sb_end; cb += RED_CHUNK) {
+            const int h2_last = sorted ? h2s[min(cb + RED_CHUNK, P.n_h2) - 1] : 0x7fffffff;
+            int h2c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int c = cb + lane + 32 * j; h2c[j] = (P.ploidy != 1 && c < P.n_h2) ? h2s[c] : 0; }
+            double col[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) col[j] = 0.0;
+            for (int i1 = row0; i1 < P.n_h1; i1 += rstep) {
+                const int h1 = h1s[i1];
+                if (h2_last < h1) continue;                               // the whole chunk has h1 > h2: not evaluated
+                const long long row = (long long)i1 * P.n_h2;
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int c = cb + lane + 32 * j; v[j] = c < P.n_h2 ? surf[row + c] : -INFINITY; }
+                double racc = 0.0, raccp = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double ml = v[j];
+                    if (ml == -INFINITY) continue;                        // not evaluated (h1 > h2) or past the row
+                    ++cnt;
+                    const double d = ml - top_ml;
+                    if (d < -746.0) continue;                             // exp(d) == 0 exactly
+                    const double w = exp(d);
+                    col[j] += w; racc += w;
+                    if (pathological(P, h1, (P.ploidy == 1) ? h1 : h2c[j])) raccp += w;
+                    if (d == 0.0) {
+                        ArgMax c{ml, h1, row + cb + lane + 32 * j};
+                        if (better(c, best)) best = c;
+                    }
+                }
+                if (__any_sync(0xffffffffu, racc != 0.0)) {
+                    for (int dd = 16; dd > 0; dd >>= 1) {
+                        racc += __shfl_down_sync(0xffffffffu, racc, dd);
+                        raccp += __shfl_down_sync(0xffffffffu, raccp, dd);
+                    }
+                    if (lane == 0) { ph1[i1] += racc; sum_all += racc; sum_path += raccp; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_col[warp][lane + 32 * j] = col[j];
+            __syncthreads();
+            double c = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) c += s_col[w][tid];
+            if (CS > 1) c_col[cb - sb + tid] = c;
+            else if (cb + tid < P.n_h2) ph2[cb + tid] = c;
+            __syncthreads();
+        }
+        if (CS > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            for (int x = (int)crank * 256 + tid; x < sb_end - sb; x += 256 * CS) {
+                double acc = 0.0;
+                for (int r = 0; r < CS; ++r) acc += cluster.map_shared_rank(c_col, r)[x];
+                ph2[sb + x] = acc;
+            }
+            cluster.sync();
         }
     }
-    s_best[tid] = best; s_cnt[tid] = cnt;
+    // ---- arg-max / counts / sums: warp -> CTA -> cluster, in rank order ---------------------------------
+    for (int d = 16; d > 0; d >>= 1) {
+        ArgMax o;
+        o.ml = __shfl_down_sync(0xffffffffu, best.ml, d);
+        o.h1 = __shfl_down_sync(0xffffffffu, best.h1, d);
+        o.idx = __shfl_down_sync(0xffffffffu, best.idx, d);
+        if (better(o, best)) best = o;
+        cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    }
+    if (lane == 0) { s_best[warp] = best; s_cnt[warp] = cnt; s_sum[warp] = sum_all; s_path[warp] = sum_path; }
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if (tid < d) {
-            if (better(s_best[tid + d], s_best[tid])) s_best[tid] = s_best[tid + d];
-            s_cnt[tid] += s_cnt[tid + d];
-        }
-        __syncthreads();
-    }
     ArgMax top = s_best[0];
     int npoints = s_cnt[0];
-    if (CS > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        if (tid == 0) { c_best = top; c_cnt = npoints; }
-        cluster.sync();
-        top = ArgMax{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL}; npoints = 0;
-        for (int r = 0; r < CS; ++r) {
-            const ArgMax o = *cluster.map_shared_rank(&c_best, r);
-            if (better(o, top)) top = o;
-            npoints += *cluster.map_shared_rank(&c_cnt, r);
-        }
-        cluster.sync();
-    }
-    __syncthreads();
-    // ---- marginals: P_h1[i1] = sum_i2 w, P_h2[i2] = sum_i1 w, w = exp(ml - max) ------------------------
-    double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
-    double sum_all = 0.0, sum_path = 0.0;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = 8;
-    for (int i1 = (int)crank * nwarps + warp; i1 < P.n_h1; i1 += nwarps * CS) {
-        const int h1 = h1s[i1];
-        double acc = 0.0, accp = 0.0;
-        for (int i2 = lane; i2 < P.n_h2; i2 += 32) {
-            const double ml = surf[(long long)i1 * P.n_h2 + i2];
-            if (ml == -INFINITY) continue;
-            const double w = exp(ml - top.ml);
-            acc += w;
-            const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
-            if (pathological(P, h1, h2)) accp += w;
-        }
-        for (int d = 16; d > 0; d >>= 1) {
-            acc += __shfl_down_sync(0xffffffffu, acc, d);
-            accp += __shfl_down_sync(0xffffffffu, accp, d);
-        }
-        if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; }
-    }
-    for (int i2 = (int)crank * 256 + tid; i2 < P.n_h2; i2 += 256 * CS) {
-        double acc = 0.0;
-        for (int i1 = 0; i1 < P.n_h1; ++i1) {
-            const double ml = surf[(long long)i1 * P.n_h2 + i2];
-            if (ml == -INFINITY) continue;
-            acc += exp(ml - top.ml);
-        }
-        ph2[i2] = acc;
-    }
-    s_sum[tid] = sum_all; s_path[tid] = sum_path;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if (tid < d) { s_sum[tid] += s_sum[tid + d]; s_path[tid] += s_path[tid + d]; }
-        __syncthreads();
-    }
     double tot_all = s_sum[0], tot_path = s_path[0];
+    for (int w = 1; w < 8; ++w) {
+        if (better(s_best[w], top)) top = s_best[w];
+        npoints += s_cnt[w]; tot_all += s_sum[w]; tot_path += s_path[w];
+    }
     if (CS > 1) {
         cg::cluster_group cluster = cg::this_cluster();
-        if (tid == 0) { c_sum = tot_all; c_path = tot_path; }
+        if (tid == 0) { c_best = top; c_cnt = npoints; c_sum = tot_all; c_path = tot_path; }
         cluster.sync();
-        tot_all = 0.0; tot_path = 0.0;
-        if (crank == 0 && tid == 0)
-            for (int r = 0; r < CS; ++r) { tot_all += *cluster.map_shared_rank(&c_sum, r); tot_path += *cluster.map_shared_rank(&c_path, r); }
+        if (crank == 0 && tid == 0) {
+            top = ArgMax{-INFINITY, 0x7fffffff, 0x7fffffffffffffffLL}; npoints = 0; tot_all = 0.0; tot_path = 0.0;
+            for (int r = 0; r < CS; ++r) {
+                const ArgMax o = *cluster.map_shared_rank(&c_best, r);
+                if (better(o, top)) top = o;
+                npoints += *cluster.map_shared_rank(&c_cnt, r);
+                tot_all += *cluster.map_shared_rank(&c_sum, r);
+                tot_path += *cluster.map_shared_rank(&c_path, r);
+            }
+        }
         cluster.sync();
     }
     if (crank == 0 && tid == 0) {
         tredsw_grid_result r;
-        r.max_ml = top.ml; r.sum_all = tot_all; r.sum_path = tot_path;
+        r.max_ml = top_ml; r.sum_all = tot_all; r.sum_path = tot_path;
         r.arg_i1 = npoints ? (int)(top.idx / P.n_h2) : -1;
         r.arg_i2 = npoints ? (int)(top.idx % P.n_h2) : -1;
         r.n_points = npoints; r.pad = 0;
@@ -649,9 +748,9 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     int *d_lists = reinterpret_cast<int *>(ctx->d_tiles.as<unsigned char>() + 2 * pt_bytes);
     ctx->mark(2);
     grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_pt, d_tl, d_lists);
-    {   // far-region tables of the medium / large surfaces
+    {   // per-problem constants and far-region tables of the medium / large surfaces
         const size_t far_bytes = (((size_t)nproblems * sizeof(FarInfo)) + 255) & ~(size_t)255;
-        const long long cap = 8LL << 20;                                   // doubles (64 MB): tables of ~2000 large surfaces
+        const long long cap = 8LL << 20;                                   // doubles (64 MB): tables of ~1000 large surfaces
         if ((rc = ctx->d_ftab.ensure(far_bytes + 256 + (size_t)cap * sizeof(double)))) return rc;
         g.far = ctx->d_ftab.as<FarInfo>();
         g.fcursor = reinterpret_cast<unsigned long long *>(ctx->d_ftab.as<unsigned char>() + far_bytes);
@@ -659,8 +758,11 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
         g.ftab_cap = cap;
         CUDA_TRY(cudaMemsetAsync(g.far, 0, far_bytes + 256, ctx->stream));
         const int nbf = nproblems < ctx->sm_count * 4 ? nproblems : ctx->sm_count * 4;
-        grid_far_kernel<<<nbf, 256, 0, ctx->stream>>>(g, d_lists, nproblems);
-        ctx->launches += 1;
+        grid_setup_kernel<<<nbf, 256, 0, ctx->stream>>>(g, d_lists, nproblems);
+        const long long want = (long long)nproblems * FILL_SPLIT;
+        const int nfill = want < (long long)ctx->sm_count * 8 ? (int)want : ctx->sm_count * 8;
+        grid_fill_kernel<<<nfill, 256, 0, ctx->stream>>>(g, d_lists, nproblems);
+        ctx->launches += 2;
     }
     grid_surface_points_kernel<<<ctx->sm_count * 4, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_pt);
     grid_surface_tiles_kernel<<<ctx->sm_count * 8, GRID_TILE, 0, ctx->stream>>>(g, nproblems, d_tl);
@@ -672,7 +774,7 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     grid_reduce_kernel<1><<<nb_block, 256, 0, ctx->stream>>>(g, d_lists + 2, d_lists);
     CUDA_TRY(cudaGetLastError());
     {
-        const int nclusters = nproblems;      // one cluster per problem; clusters beyond the class list exit at once
+        const int nclusters = nproblems < ctx->sm_count ? nproblems : ctx->sm_count;   // persistent over the class list
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)nclusters * GRID_CLUSTER); cfg.blockDim = dim3(256); cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
