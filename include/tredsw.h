@@ -97,6 +97,11 @@ int64_t tredsw_launch_count(tredsw_ctx *ctx);
  * reduce), [2] KDE, [3] whole call.  Reading synchronises the stream. */
 int tredsw_enable_timing(tredsw_ctx *ctx, int on);
 int tredsw_get_timing(tredsw_ctx *ctx, float *ms4);
+/* Device timestamps of the last timed call on this context, in ms since a process-wide reference event (the first
+ * call of this function records it): [0/1] SW start/end, [2/3] grid, [4/5] KDE, [6] inputs on the device,
+ * [7] calls final, [8] call start, [9] results copied; -1 where a mark was not recorded.  Lets a caller line up
+ * the calls of several contexts that share one GPU (tools/e2e_probe.py). */
+int tredsw_get_timeline(tredsw_ctx *ctx, float *ms10);
 /* Measured integer-pipe peak of this GPU: a register-resident VIADDMNMX.S16x2 loop with 8 independent
  * chains per thread on every SM; returns giga lane-instructions per second (one 32-bit lane executing
  * one packed DPX instruction = 1).  The roofline denominator of the Smith-Waterman kernel. */

@@ -25,6 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=384)
     ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--only", default="", help="comma-separated variant labels to run (default: all)")
+    ap.add_argument("--timeline", type=int, default=0, help="print the device-side timeline of this many calls in flight")
     a = ap.parse_args()
     import torch
     from tredparse_b200 import _lib, cohort, simulate
@@ -46,7 +48,11 @@ def main():
     batch._packed = {k: pin(v) for k, v in batch._packed.items()}
     out = {}
 
+    only = set(x for x in a.only.split(",") if x)
+
     def timed(label, depth, fn):
+        if only and label not in only:
+            return
         ctxs = [_lib.Context(0) for _ in range(depth)]
         import queue
         free = queue.Queue()
@@ -78,6 +84,41 @@ def main():
     def host_call(c):
         batch.run_host(ctx=c, packed=True)
 
+    if a.timeline:
+        # device-side timeline of `depth` host-buffer calls in flight: one row per call, ms since a common reference
+        import queue
+        depth = a.timeline
+        ctxs = [_lib.Context(0) for _ in range(depth)]
+        for c in ctxs:
+            c.enable_timing(True)
+        free = queue.Queue()
+        for i, c in enumerate(ctxs):
+            free.put((i, c))
+        rows = []
+
+        def run(_):
+            i, c = free.get()
+            try:
+                t0 = time.perf_counter()
+                batch.run_host(ctx=c, packed=True)
+                t1 = time.perf_counter()
+                tl = c.timeline()
+                rows.append(dict(ctx=i, host0=t0, host1=t1, **tl))
+            finally:
+                free.put((i, c))
+        with ThreadPoolExecutor(max_workers=depth) as pool:
+            list(pool.map(run, range(2 * depth)))
+            del rows[:]
+            list(pool.map(run, range(4 * depth)))
+        rows.sort(key=lambda r: r["start"])
+        base, hbase = rows[0]["start"], min(r["host0"] for r in rows)
+        keys = ("start", "inputs", "sw0", "sw1", "kde0", "kde1", "grid0", "grid1", "final", "copied")
+        sys.stderr.write("ctx  host_call_ms(begin,end)   " + " ".join("{:>8}".format(k) for k in keys) + "\n")
+        for r in rows:
+            sys.stderr.write("{:3d}  {:8.2f} {:8.2f}     ".format(r["ctx"], 1e3 * (r["host0"] - hbase), 1e3 * (r["host1"] - hbase)) +
+                             " ".join("{:8.2f}".format(r[k] - base) for k in keys) + "\n")
+        print(json.dumps({"timeline_depth": depth, "rows": [{k: (r[k] - base) for k in keys} | {"ctx": r["ctx"]} for r in rows]}))
+        return
     for d in (1, 2, 4, 8):
         timed("dev/{}".format(d), d, dev_call)
     for d in (1, 2, 4, 8):

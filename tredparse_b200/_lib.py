@@ -25,7 +25,7 @@ EXPORTS = [
     # batched API
     "tredsw_version", "tredsw_device_count", "tredsw_last_error", "tredsw_create", "tredsw_destroy",
     "tredsw_synchronize", "tredsw_sm_count", "tredsw_launch_count", "tredsw_enable_timing",
-    "tredsw_get_timing", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
+    "tredsw_get_timing", "tredsw_get_timeline", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
     "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch",
     # native BAM ingest
     "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
@@ -109,6 +109,7 @@ def load():
         lib.tredsw_launch_count.argtypes = [_vp]
         lib.tredsw_enable_timing.argtypes = [_vp, ctypes.c_int]
         lib.tredsw_get_timing.argtypes = [_vp, _vp]
+        lib.tredsw_get_timeline.argtypes = [_vp, _vp]
         lib.tredsw_int_pipe_peak.argtypes = [_vp, _vp]
         lib.tredsw_align_pairs.restype = ctypes.c_int
         lib.tredsw_align_pairs.argtypes = [_vp, _vp, _vp, ctypes.c_int32, _vp, _vp, ctypes.c_int32, _vp,
@@ -191,6 +192,13 @@ class Context:
         ms = (ctypes.c_float * 4)()
         check(self.lib.tredsw_get_timing(self.handle, ms), "tredsw_get_timing")
         return {"sw": ms[0], "grid": ms[1], "kde": ms[2], "total": ms[3]}
+
+    def timeline(self):
+        """Device timestamps (ms since a process-wide reference) of the last timed call: dict of marks."""
+        ms = (ctypes.c_float * 10)()
+        check(self.lib.tredsw_get_timeline(self.handle, ms), "tredsw_get_timeline")
+        names = ("sw0", "sw1", "grid0", "grid1", "kde0", "kde1", "inputs", "final", "start", "copied")
+        return {n: ms[i] for i, n in enumerate(names)}
 
     def int_pipe_peak(self):
         """Measured packed-DPX instruction throughput, giga lane-instructions / s."""

@@ -11,13 +11,26 @@ void tredsw_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+DeviceToken &tredsw_device_token(int device) {
+    static DeviceToken tok[64];
+    return tok[(device >= 0 && device < 64) ? device : 0];
+}
+
 tredsw_ctx::~tredsw_ctx() {
     cudaSetDevice(device);
+    if (done_ev) {
+        DeviceToken &t = tredsw_device_token(device);
+        std::lock_guard<std::mutex> lock(t.mu);
+        if (t.ev == done_ev) { t.ev = nullptr; t.sw_end = nullptr; }
+        cudaEventDestroy(done_ev);
+        if (sw_end_ev) cudaEventDestroy(sw_end_ev);
+    }
     DevBuf *all[] = {&d_q, &d_qoff, &d_t, &d_toff, &d_qidx, &d_tidx, &d_out, &d_cigar, &d_scratch, &d_misc,
                      &d_fam, &d_rfam, &d_stats, &d_work, &d_prob, &d_ipool, &d_dpool, &d_surface, &d_marg,
                      &d_res, &d_counter, &d_tiles, &d_pk, &d_pe16, &d_ftab};
     for (DevBuf *b : all) b->release();
-    for (int i = 0; i < 8; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    h_in.release(); h_out.release(); h_tab.release();
+    for (int i = 0; i < 10; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -92,7 +105,7 @@ int64_t tredsw_launch_count(tredsw_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int tredsw_enable_timing(tredsw_ctx *ctx, int on) {
     if (!ctx) return TREDSW_ERR_ARG;
     ctx->timing = on != 0;
-    for (int i = 0; i < 8; ++i) ctx->ev_valid[i] = false;
+    for (int i = 0; i < 10; ++i) ctx->ev_valid[i] = false;
     return TREDSW_OK;
 }
 
@@ -105,6 +118,29 @@ int tredsw_get_timing(tredsw_ctx *ctx, float *ms4) {
         ms4[k] = 0.f;
         if (ctx->ev_valid[pairs[k][0]] && ctx->ev_valid[pairs[k][1]])
             CUDA_TRY(cudaEventElapsedTime(&ms4[k], ctx->ev[pairs[k][0]], ctx->ev[pairs[k][1]]));
+    }
+    return TREDSW_OK;
+}
+
+// Device timestamps (ms since a process-wide reference event) of the last timed call's marks, for timelines of
+// several contexts sharing one GPU: ms10[i] < 0 where mark i was not recorded.
+int tredsw_get_timeline(tredsw_ctx *ctx, float *ms10) {
+    if (!ctx || !ms10) return TREDSW_ERR_ARG;
+    static std::mutex mu;
+    static cudaEvent_t ref = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!ref) {
+            CUDA_TRY(cudaEventCreate(&ref));
+            CUDA_TRY(cudaEventRecord(ref, ctx->stream));
+            CUDA_TRY(cudaEventSynchronize(ref));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 10; ++k) {
+        ms10[k] = -1.f;
+        if (ctx->ev_valid[k] && cudaEventElapsedTime(&ms10[k], ref, ctx->ev[k]) != cudaSuccess) { cudaGetLastError(); ms10[k] = -1.f; }
     }
     return TREDSW_OK;
 }

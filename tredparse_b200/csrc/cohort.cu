@@ -256,6 +256,8 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     const bool dev = dev_ptrs(flags);
+    ctx->mark(8);
+    ctx->wait_before_sw = nullptr; ctx->record_sw_end = false;
     const int nr = c->nreads, np_ = c->nproblems, nf = c->nfamilies;
     int max_u = 0, min_period = 1 << 30;
     for (int f = 0; f < nf; ++f) {
@@ -275,6 +277,8 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     const bool packed4 = (c->input_flags & TREDSW_IN_READS_PACKED4) != 0, pe16 = (c->input_flags & TREDSW_IN_PE_LENS_I16) != 0;
     if (dev && packed4 && c->n_bases <= 0 && nr > 0) { tredsw_set_error("n_bases is required for packed reads in device memory"); return TREDSW_ERR_ARG; }
     const int64_t nbases = nr > 0 ? (dev ? c->n_bases : c->roff[nr]) : 0;
+    const uint32_t *unpack_src = nullptr; int64_t unpack_words = 0;
+    const int16_t *widen_src = nullptr;
     if (packed4 && nr > 0) {
         // rbuf holds nibbles: bring the packed words to the device, expand into the byte-per-base buffer
         const int64_t nwords = (nbases + 7) / 8;
@@ -285,8 +289,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
             d_pk = ctx->d_pk.as<uint32_t>();
         }
         if ((rc = ctx->d_q.ensure((size_t)nwords * 8))) return rc;
-        unpack_reads4_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(d_pk, nwords, ctx->d_q.as<uint32_t>());
-        ctx->launches += 1;
+        unpack_src = d_pk; unpack_words = nwords;            // launched below, once every input copy is queued
         d_rbuf = ctx->d_q.as<int8_t>();
     }
     if (!dev) {
@@ -297,8 +300,18 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
         }
         if ((rc = stage_in(ctx, ctx->d_prob, c->problems, (size_t)np_, 0u, &d_prob))) return rc;
     }
-    if ((rc = stage_in(ctx, ctx->d_fam, c->families, (size_t)nf, 0u, &d_fam))) return rc;
-    if ((rc = stage_in(ctx, ctx->d_t, c->loci, (size_t)nf, 0u, &d_loci))) return rc;
+    // the small per-call tables (always host pointers) travel through the context's page-locked staging buffer
+    const size_t b_step = (size_t)nf * NSTEP * sizeof(double);
+    size_t hoff[3];
+    {
+        const void *srcs[3] = {c->families, c->loci, c->step_pmf};
+        const size_t sizes[3] = {(size_t)nf * sizeof(tredsw_family), (size_t)nf * sizeof(tredsw_locus), b_step};
+        if ((rc = stage_small(ctx, ctx->h_in, srcs, sizes, 3, hoff))) return rc;
+    }
+    const unsigned char *hin = ctx->h_in.as<unsigned char>();
+    const size_t b_fam = hoff[1], b_loci = hoff[2] - hoff[1];
+    if ((rc = stage_in(ctx, ctx->d_fam, reinterpret_cast<const tredsw_family *>(hin), (size_t)nf, 0u, &d_fam))) return rc;
+    if ((rc = stage_in(ctx, ctx->d_t, reinterpret_cast<const tredsw_locus *>(hin + b_fam), (size_t)nf, 0u, &d_loci))) return rc;
     // ---- arenas ------------------------------------------------------------------------------------
     const int64_t slot_ints = 4 * (int64_t)KC + 2 * (int64_t)HL;
     const int64_t n_ipool = c->n_pe_lens + (int64_t)np_ * slot_ints;
@@ -311,8 +324,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
             CUDA_TRY(cudaMemcpyAsync(ctx->d_pe16.p, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
             d16 = ctx->d_pe16.as<int16_t>();
         }
-        widen_i16_kernel<<<(unsigned)((c->n_pe_lens + 255) / 256), 256, 0, ctx->stream>>>(d16, c->n_pe_lens, d_ipool);
-        ctx->launches += 1;
+        widen_src = d16;
     } else if (c->n_pe_lens > 0)
         CUDA_TRY(cudaMemcpyAsync(d_ipool, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int32_t),
                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
@@ -320,8 +332,34 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     const int64_t n_dpool = (int64_t)np_ * KDE_SPAN + (int64_t)nf * NSTEP;
     if ((rc = ctx->d_dpool.ensure((size_t)n_dpool * sizeof(double)))) return rc;
     double *d_dpool = ctx->d_dpool.as<double>();
-    CUDA_TRY(cudaMemcpyAsync(d_dpool + (int64_t)np_ * KDE_SPAN, c->step_pmf, (size_t)nf * NSTEP * sizeof(double),
+    CUDA_TRY(cudaMemcpyAsync(d_dpool + (int64_t)np_ * KDE_SPAN, hin + b_fam + b_loci, b_step,
                              cudaMemcpyHostToDevice, ctx->stream));
+    // ---- compute token (common.cuh: DeviceToken) ---------------------------------------------------------
+    // Every input copy of this call is queued by now and runs while earlier calls compute.  The kernels follow
+    // in two steps: the expansion / pre-filter / grouping kernels wait until the previous call's Smith-Waterman
+    // kernel has ended (they then share the GPU with that call's short finishing kernels instead of slowing its
+    // SW kernel down), and this call's SW kernel waits until the previous call has finished altogether.
+    DeviceToken &token = tredsw_device_token(ctx->device);
+    std::unique_lock<std::mutex> token_lock(token.mu, std::defer_lock);
+    static const bool no_token = getenv("TREDSW_NO_TOKEN") != nullptr;
+    if (!dev && !no_token) {
+        if (!ctx->done_ev) CUDA_TRY(cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming));
+        if (!ctx->sw_end_ev) CUDA_TRY(cudaEventCreateWithFlags(&ctx->sw_end_ev, cudaEventDisableTiming));
+        token_lock.lock();
+        if (token.ev && token.ev != ctx->done_ev) {
+            ctx->wait_before_sw = token.ev;
+            if (token.sw_end) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, token.sw_end, 0));
+        }
+        ctx->record_sw_end = true;
+    }
+    if (unpack_src) {
+        unpack_reads4_kernel<<<(unsigned)((unpack_words + 255) / 256), 256, 0, ctx->stream>>>(unpack_src, unpack_words, ctx->d_q.as<uint32_t>());
+        ctx->launches += 1;
+    }
+    if (widen_src) {
+        widen_i16_kernel<<<(unsigned)((c->n_pe_lens + 255) / 256), 256, 0, ctx->stream>>>(widen_src, c->n_pe_lens, d_ipool);
+        ctx->launches += 1;
+    }
     // surface arena: default search needs <= (#base) x (#ext) points per problem; start generous, grow on overflow
     long long per_problem = c->fullsearch ? (long long)c->maxinsert * c->maxinsert : 16LL * HL;
     long long surface_cap = (long long)np_ * per_problem;
@@ -387,31 +425,41 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     finalize_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
     CUDA_TRY(cudaGetLastError());
     ctx->mark(7);
+    if (token_lock.owns_lock()) {
+        if (ctx->record_sw_end) {                            // nr == 0: no SW launch recorded it
+            CUDA_TRY(cudaEventRecord(ctx->sw_end_ev, ctx->stream));
+            ctx->record_sw_end = false;
+        }
+        ctx->wait_before_sw = nullptr;
+        CUDA_TRY(cudaEventRecord(ctx->done_ev, ctx->stream));
+        token.ev = ctx->done_ev; token.sw_end = ctx->sw_end_ev;
+        token_lock.unlock();
+    }
     // ---- outputs -----------------------------------------------------------------------------------
+    // calls and counters come back through the page-locked staging buffer (see PinnedBuf); the optional bulky
+    // per-read / histogram outputs go straight to the caller's memory
+    const size_t b_calls = ((size_t)np_ * sizeof(tredsw_call) + 255) & ~(size_t)255;
+    if ((rc = ctx->h_out.ensure(b_calls + 12 * sizeof(unsigned long long)))) return rc;
+    unsigned char *hout = ctx->h_out.as<unsigned char>();
+    unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(hout + b_calls), *h_st = h_cnt + 8;
     if (!dev) {
-        CUDA_TRY(cudaMemcpyAsync(calls, d_calls, (size_t)np_ * sizeof(tredsw_call), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(hout, d_calls, (size_t)np_ * sizeof(tredsw_call), cudaMemcpyDeviceToHost, ctx->stream));
         if (read_out && nr > 0)
             CUDA_TRY(cudaMemcpyAsync(read_out, d_read_out, (size_t)nr * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (hist) CUDA_TRY(cudaMemcpyAsync(hist, cd.hist, sz_hist, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (stats) {
-        unsigned long long h_cnt[8], h_st[4];
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(h_st, d_stats, sizeof(h_st), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->mark(9);
+    if (stats || !dev) {
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        if (stats) CUDA_TRY(cudaMemcpyAsync(h_st, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h_st[i];
-        stats[4] = (int64_t)h_cnt[2]; stats[5] = (int64_t)h_cnt[1]; stats[6] = (int64_t)h_cnt[0]; stats[7] = 0;
+        if (!dev) memcpy(calls, hout, (size_t)np_ * sizeof(tredsw_call));
+        if (stats) {
+            for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h_st[i];
+            stats[4] = (int64_t)h_cnt[2]; stats[5] = (int64_t)h_cnt[1]; stats[6] = (int64_t)h_cnt[0]; stats[7] = 0;
+        }
         if (h_cnt[1]) {
             // the surface arena was too small for this batch: grow it for the next call and report
-            ctx->d_surface.ensure((size_t)(h_cnt[0] + h_cnt[0] / 4) * sizeof(double));
-            tredsw_set_error("likelihood surface arena overflow (%llu points needed); call again", h_cnt[0]);
-            return TREDSW_ERR_UNSUPPORTED;
-        }
-    } else if (!dev) {
-        unsigned long long h_cnt[8];
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (h_cnt[1]) {
             ctx->d_surface.ensure((size_t)(h_cnt[0] + h_cnt[0] / 4) * sizeof(double));
             tredsw_set_error("likelihood surface arena overflow (%llu points needed); call again", h_cnt[0]);
             return TREDSW_ERR_UNSUPPORTED;

@@ -53,13 +53,15 @@ __device__ __forceinline__ void kde_block(const int32_t *x, int n, double *out) 
     const double sd = sqrt(var * factor * factor);
     // compact the occupied histogram bins in ascending order (deterministic: the sums below run in the same
     // order as a plain scan over all bins); typically a few hundred of the 2048 bins are occupied
+    // (the compacted counts overwrite the histogram — every thread holds its bins in registers first — so the
+    // block needs 31 KB of shared memory and fits next to the Smith-Waterman CTAs of a concurrent call)
     __shared__ short cbin[2 * KDE_OFF];
-    __shared__ int ccnt[2 * KDE_OFF];
+    int *ccnt = hist;
     __shared__ int scan[KDE_THREADS];
     constexpr int PER = 2 * KDE_OFF / KDE_THREADS;
-    int mine_n = 0;
+    int mine_n = 0, mine_c[PER];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) mine_n += hist[tid * PER + k] != 0;
+    for (int k = 0; k < PER; ++k) { mine_c[k] = hist[tid * PER + k]; mine_n += mine_c[k] != 0; }
     scan[tid] = mine_n;
     __syncthreads();
     for (int d = 1; d < KDE_THREADS; d <<= 1) {
@@ -72,7 +74,7 @@ __device__ __forceinline__ void kde_block(const int32_t *x, int n, double *out) 
     int w = scan[tid] - mine_n;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-        const int c = hist[tid * PER + k];
+        const int c = mine_c[k];
         if (c != 0) { cbin[w] = (short)(tid * PER + k - KDE_OFF); ccnt[w] = c; ++w; }
     }
     __syncthreads();

@@ -825,7 +825,14 @@ int persistent_ctas(tredsw_ctx *ctx, size_t smem, bool need_fast, bool need_gene
     const int cap = env_cap > 0 ? env_cap : 8;
     if (per_sm > cap) per_sm = cap;
     if (per_sm < 1) per_sm = 1;
-    *out = per_sm * ctx->sm_count;
+    // Leave a few CTA slots of the GPU empty (spread over the SMs by the block scheduler): the short kernels that
+    // finish the PREVIOUS call of a pipeline (KDE, grid, reductions: up to ~35 KB of shared memory per block)
+    // need a place to run while this persistent kernel holds everything else, or that call — and the input copy
+    // of the one after it — waits for this kernel to drain (tools/e2e_probe.py --timeline).
+    static const int env_free = [] { const char *e = getenv("TREDSW_FREE_SLOTS"); return e ? atoi(e) : -1; }();
+    int free_slots = env_free >= 0 ? env_free : 0;
+    if (free_slots > per_sm * ctx->sm_count / 2) free_slots = per_sm * ctx->sm_count / 2;
+    *out = per_sm * ctx->sm_count - free_slots;
     return TREDSW_OK;
 }
 
@@ -872,7 +879,6 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.allow_fast = allow_fast ? 1 : 0;
     p.match = max_match > 0 ? max_match : 1;
     p.stats = d_stats;
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, mat25, 25, 0, cudaMemcpyHostToDevice, ctx->stream));
     const int nitems_bound = nreads / 32 + nfamilies + 1;
     int rc, nctas = 0;
     if ((rc = persistent_ctas(ctx, smem, need_fast, need_generic, &nctas))) return rc;
@@ -893,6 +899,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     p.counter = reinterpret_cast<int32_t *>(ctx->d_scratch.as<unsigned char>() + score_bytes + pot_bytes + gbnd_bytes);
     p.max_u = max_u;
     int32_t *d_perm = p.counter + 4;
+    std::vector<int32_t> h_perm;
     {   // Item order: families grouped by loop instantiation (measured: mixing instantiations on an SM costs far
         // more than any order could gain — they compete for the instruction cache), the groups with the fewest
         // families first: their items run cold code and are the slowest, so they must not form the tail of the
@@ -904,7 +911,7 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
             const int pa = instance_period(h_families[a].period), pb = instance_period(h_families[b].period);
             if (group_size[pa] != group_size[pb]) return group_size[pa] < group_size[pb];
             return pa < pb; });
-        CUDA_TRY(cudaMemcpyAsync(d_perm, perm.data(), nfamilies * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        h_perm.swap(perm);
     }
     p.fam_perm = d_perm;
     // q-gram pre-filter tables: per family 4096 x 2 bits (q-grams of all forward / all reverse-complement templates)
@@ -979,8 +986,17 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
             }
             if (too_many_n) info[f].q = 0;
         }
-        CUDA_TRY(cudaMemcpyAsync(d_qtab, tab.data(), qtab_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_qinfo, info.data(), nfamilies * sizeof(QgramInfo), cudaMemcpyHostToDevice, ctx->stream));
+        // perm | qtab | qinfo through the page-locked table staging (see stage_small): no pageable copy sits
+        // between the input transfer and the kernels of a call
+        const void *srcs[4] = {h_perm.data(), tab.data(), info.data(), mat25};
+        const size_t sizes[4] = {(size_t)nfamilies * sizeof(int32_t), qtab_bytes, (size_t)nfamilies * sizeof(QgramInfo), 25};
+        size_t offs[4];
+        if ((rc = stage_small(ctx, ctx->h_tab, srcs, sizes, 4, offs))) return rc;
+        const unsigned char *ht = ctx->h_tab.as<unsigned char>();
+        CUDA_TRY(cudaMemcpyToSymbolAsync(c_fmat25, ht + offs[3], 25, 0, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_perm, ht + offs[0], sizes[0], cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_qtab, ht + offs[1], sizes[1], cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_qinfo, ht + offs[2], sizes[2], cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->mark(0);
     prefilter_kernel<<<nb, tb, 0, ctx->stream>>>(d_rbuf, d_roff, nreads, d_read_family, nfamilies, d_families, d_qtab,
@@ -991,8 +1007,16 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 4;
     CUDA_TRY(cudaMemsetAsync(p.counter, 0, 2 * sizeof(int32_t), ctx->stream));
+    if (ctx->wait_before_sw) {            // compute token of the host-buffer pipeline (common.cuh: DeviceToken)
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->wait_before_sw, 0));
+        ctx->wait_before_sw = nullptr;
+    }
     if (need_generic) { if ((rc = launch_classify<false>(ctx, p, nctas, smem))) return rc; }
     if (need_fast) { if ((rc = launch_classify<true>(ctx, p, nctas, smem))) return rc; }
+    if (ctx->record_sw_end && ctx->sw_end_ev) {
+        CUDA_TRY(cudaEventRecord(ctx->sw_end_ev, ctx->stream));
+        ctx->record_sw_end = false;
+    }
     ctx->mark(1);
     return TREDSW_OK;
 }
