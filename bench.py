@@ -43,7 +43,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--samples", type=int, default=384, help="samples per GPU per step (x 30 loci)")
-    p.add_argument("--depth", type=int, default=4, help="host-buffer calls kept in flight by the e2e pipeline")
+    p.add_argument("--depth", type=int, default=2, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--streams", type=int, default=3, help="streams the device-resident steps alternate over "
                    "(2: the tail of one step's persistent SW kernel overlaps the head of the next step)")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
