@@ -26,7 +26,9 @@ def _models():
 
 
 CASES = [("DM1", (13, 1000), 250, 1000), ("DM1", (12, 500), 150, 1000), ("FXS", (30, 800), 150, 1000),
-         ("FXS", (250,), 250, 1200)]
+         ("FXS", (250,), 250, 1200),
+         ("DM1", (13, 1200), 250, 1500),      # config 5's larger grid: 1,125,750 points
+         ("DM1", (5, 700), 150, 2100)]        # > 2048 candidate columns: the reduction exchanges column sums in two rounds
 
 
 @pytest.fixture(scope="module")
