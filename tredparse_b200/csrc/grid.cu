@@ -47,6 +47,9 @@ struct GridParams {
 // as the general evaluation, on operands produced by the same device functions, hence the same bits: two
 // table reads instead of tens of logarithms.  On a --fullsearch / long-expansion grid (10^5 - 10^6 points)
 // > 90 % of the points are far, most of the rest mid.
+// Where the paired-end term is genuinely two-dimensional (i2 < fa2) its operands come from two more tables,
+// R1[t][i1] = rolled pdf of allele h1s[i1] at target length t and R2[t][i2] likewise for h2s[i2] (the values
+// pe_roll returns), so that a point costs two coalesced loads, the mixture and the logarithm per target pair.
 struct FarInfo {
     unsigned long long maxkey;   // ordered key of the surface maximum (atomicMax of the tiles kernel); 0 = no point
     long long off;               // ftab: rows[2 * n_h1] ({c12, pe} pairs), then rept[nd]
@@ -58,7 +61,7 @@ struct FarInfo {
     int sorted;                  // both candidate lists are non-decreasing (lets the reduction skip h1 > h2 chunks)
     int nd;                      // entries of rept[]
     int hrep;                    // a far allele (the largest h2)
-    int pad;
+    int npe;                     // paired-end tables present: R1[npe][n_h1], R2[npe][fa2] after rept[] (npe = n_target)
 };
 
 // order-preserving map double -> u64 (for atomicMax); 0 is below every value
@@ -230,6 +233,19 @@ __device__ __forceinline__ double ml_pe_term(const tredsw_grid_problem &P, const
     return acc;
 }
 
+// ml_pe_term from the tabulated operands (FarInfo.npe > 0, i2 < fa2): same mixture, same memo, same sum
+__device__ __forceinline__ double ml_pe_tab(const double *R1, const double *R2, int n1, int n2, int npe, int i1, int i2,
+                                            double eps, double log_small) {
+    double acc = 0.0;
+    LogMemo lg{-1.0, 0.0};
+    R1 += i1; R2 += i2;
+    for (int t = 0; t < npe; ++t) {
+        const double v = __dadd_rn(__dmul_rn(0.5, R1[(long long)t * n1]), __dmul_rn(0.5, R2[(long long)t * n2]));
+        acc = __dadd_rn(acc, lg(v, eps, log_small));
+    }
+    return acc;
+}
+
 __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, const TileShared &T) {
     double ml = ml_span_term(P, g, h1, h2);
     ml = __dadd_rn(ml, ml_part_term(P, g, h1, h2, T.sig_mp));
@@ -243,6 +259,8 @@ __device__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, in
 // problems are flattened into tiles of GRID_TILE points: tile_start = exclusive prefix sum of the tiles per
 // problem (device scan), then a persistent kernel strides over the tiles.
 constexpr int GRID_TILE = 256;
+constexpr int TILE_PTS = 4;                          // points per thread of grid_surface_tiles_kernel
+constexpr int TILE_POINTS = GRID_TILE * TILE_PTS;    // points per tile of a medium / large surface
 constexpr int GRID_CLUSTER = 8;       // CTAs per problem in the cluster variant of the reduction
 
 // Problem classes of the reductions, by number of surface points.
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_prob
     int nb = 0, nc = 0;
     for (int i = lo; i < hi; ++i) {
         const long long t = points_of(i);
-        if (t > GRID_WARP_LIMIT) ts += (t + GRID_TILE - 1) / GRID_TILE; else s += t;
+        if (t > GRID_WARP_LIMIT) ts += (t + TILE_POINTS - 1) / TILE_POINTS; else s += t;
         if (t > GRID_BLOCK_LIMIT) ++nc; else if (t > GRID_WARP_LIMIT) ++nb;
     }
     part[tid] = s; tpart[tid] = ts; pb[tid] = nb; pc[tid] = nc;
@@ -283,7 +301,7 @@ __global__ void __launch_bounds__(1024) grid_tiles_kernel(const tredsw_grid_prob
     for (int i = lo; i < hi; ++i) {
         const long long t = points_of(i);
         pt_start[i] = run; tile_start[i] = trun;
-        if (t > GRID_WARP_LIMIT) trun += (t + GRID_TILE - 1) / GRID_TILE; else run += t;
+        if (t > GRID_WARP_LIMIT) trun += (t + TILE_POINTS - 1) / TILE_POINTS; else run += t;
         if (t > GRID_BLOCK_LIMIT) lists[2 + nproblems + wc++] = i; else if (t > GRID_WARP_LIMIT) lists[2 + wb++] = i;
     }
     if (tid == 1023) { pt_start[nproblems] = part[1023]; tile_start[nproblems] = tpart[1023]; lists[0] = pb[1023]; lists[1] = pc[1023]; }
@@ -317,6 +335,7 @@ __device__ __forceinline__ int block_max_int(int v, int *s8) {
 // One block per medium / large surface (class lists of grid_tiles_kernel): per-problem constants, the
 // mid / far thresholds and the table allocation (FarInfo).  All scans are block-parallel.
 constexpr long long FAR_MIN_POINTS = 4096;     // tables only pay for at least this many mid + far points
+constexpr unsigned long long PE_TAB_MAX = 1ULL << 20;   // doubles per problem for the paired-end tables
 __global__ void __launch_bounds__(256) grid_setup_kernel(GridParams g, const int *lists, int nproblems) {
     __shared__ int s8[8];
     const int nb = lists[0], nc = lists[1];
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(256) grid_setup_kernel(GridParams g, const int
         l1 = block_max_int(l1, s8); l2 = block_max_int(l2, s8);
         if (tid == 0) {
             FarInfo f;
-            f.maxkey = 0; f.off = 0; f.ok = 0; f.pad = 0;
+            f.maxkey = 0; f.off = 0; f.ok = 0; f.npe = 0;
             f.lgamma_k1 = lgamma((double)P.n_rept + 1.0);
             f.sig_mp = sigma_h(P, P.max_partial);
             f.tmin = tmin;
@@ -358,9 +377,12 @@ __global__ void __launch_bounds__(256) grid_setup_kernel(GridParams g, const int
             f.hrep = mx2;
             f.nd = (two && P.n_h1 > 0) ? max(mx1 - P.readlen, 1) + max(mx2 - P.readlen, 1) - 1 : 0;
             if (two && P.n_h1 > 0 && (long long)(P.n_h2 - f.fam) * P.n_h1 >= FAR_MIN_POINTS) {
-                const unsigned long long need = ((unsigned long long)(2LL * P.n_h1 + f.nd) + 1ULL) & ~1ULL;   // even: rows stay 16-byte aligned
+                const unsigned long long base = (unsigned long long)(2LL * P.n_h1 + f.nd);
+                const unsigned long long pe = (P.run_pe && P.n_target > 0) ? (unsigned long long)P.n_target * (unsigned long long)(P.n_h1 + f.fa2) : 0ULL;
+                const bool want_pe = pe > 0 && pe <= PE_TAB_MAX;
+                const unsigned long long need = (base + (want_pe ? pe : 0ULL) + 1ULL) & ~1ULL;   // even: rows stay 16-byte aligned
                 const unsigned long long off = atomicAdd(g.fcursor, need);
-                if ((long long)(off + need) <= g.ftab_cap) { f.off = (long long)off; f.ok = 1; }
+                if ((long long)(off + need) <= g.ftab_cap) { f.off = (long long)off; f.ok = 1; f.npe = want_pe ? P.n_target : 0; }
             }
             g.far[pi] = f;
         }
@@ -381,23 +403,38 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(GridParams g, const int 
         double *rows = g.ftab + F.off, *rept = rows + 2 * (long long)P.n_h1;
         const int hrep = F.hrep, tmin = F.tmin;
         const double sig_mp = F.sig_mp, lgk = F.lgamma_k1;
-        const int n = P.n_h1 + F.nd;
+        const int nbase = P.n_h1 + F.nd, n1 = F.npe * P.n_h1, n = nbase + n1 + F.npe * F.fa2;
+        const int32_t *h2s = g.ipool + P.off_h2, *tl = g.ipool + P.off_target;
+        const double *pdf = g.dpool + P.off_pdf;
+        double *R1 = rept + F.nd, *R2 = R1 + n1;
         for (int e = part * 256 + threadIdx.x; e < n; e += 256 * FILL_SPLIT) {
             if (e < P.n_h1) {
                 const int h1 = h1s[e];
                 rows[2 * e] = __dadd_rn(ml_span_term(P, g, h1, hrep), ml_part_term(P, g, h1, hrep, sig_mp));
                 rows[2 * e + 1] = ml_pe_term(P, g, h1, hrep, tmin);
-            } else {
+            } else if (e < nbase) {
                 rept[e - P.n_h1] = ml_rept_term(P, e - P.n_h1 + 2, lgk);
+            } else {
+                // operands of the two-dimensional paired-end term, exactly as ml_pe_term obtains them
+                int idx = e - nbase;
+                const bool first = idx < n1;
+                if (!first) idx -= n1;
+                const int width = first ? P.n_h1 : F.fa2;
+                const int t = idx / width, i = idx - t * width;
+                int x = tl[t];
+                if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
+                (first ? R1 : R2)[idx] = pe_roll(pdf, first ? h1s[i] : h2s[i], P.pe_ref, P.pe_minpe, x, g.small_value);
             }
         }
     }
 }
 
-// Large and medium surfaces: persistent over their tiles.  Besides the surface, every tile contributes to the
-// maximum of its problem (ordered-key atomicMax — order independent, hence deterministic), so that the
-// reduction needs a single pass.
-__global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParams g, int nproblems, const long long *tile_start) {
+// Large and medium surfaces: persistent over their tiles of TILE_POINTS consecutive points (4 per thread, 256
+// apart: the per-tile work — tile -> problem search, index division, max reduction — is shared by 1024 points;
+// most points of a large surface are table look-ups, so that overhead is what they cost).  Besides the
+// surface, every tile contributes to the maximum of its problem (ordered-key atomicMax — order independent,
+// hence deterministic), so that the reduction needs a single pass.
+__global__ void __launch_bounds__(GRID_TILE, 4) grid_surface_tiles_kernel(GridParams g, int nproblems, const long long *tile_start) {
     const long long ntiles = tile_start[nproblems];
     __shared__ int s_pi;
     __shared__ unsigned long long s_wmax[GRID_TILE / 32];
@@ -414,38 +451,51 @@ __global__ void __launch_bounds__(GRID_TILE) grid_surface_tiles_kernel(GridParam
         const int pi = s_pi;
         const tredsw_grid_problem &P = g.prob[pi];
         const FarInfo &F = g.far[pi];
-        const long long total = (long long)P.n_h1 * P.n_h2;
-        const long long t = (tile - tile_start[pi]) * GRID_TILE + threadIdx.x;
-        unsigned long long key = 0;
+        const int n_h1 = P.n_h1, n_h2 = P.n_h2, readlen = P.readlen;
+        const bool haploid = P.ploidy == 1;
+        const long long total = (long long)n_h1 * n_h2;
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        double *surf = g.surface + P.off_surface;
+        const int f_ok = F.ok, fam = F.fam, fa2 = F.fa2, npe = F.npe;
+        const double *rows = g.ftab + F.off, *rept = rows + 2 * (long long)n_h1, *R1 = rept + F.nd;
+        TileShared T;
+        T.lgamma_k1 = F.lgamma_k1; T.sig_mp = F.sig_mp; T.tmin = F.tmin;
+        long long t = (tile - tile_start[pi]) * TILE_POINTS + threadIdx.x;
+        int i1 = 0, i2 = 0;
         if (t < total) {
-            const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-            int i1, i2;
-            if (total < 0x7fffffffLL) { i1 = (int)((unsigned)t / (unsigned)P.n_h2); i2 = (int)((unsigned)t - (unsigned)i1 * (unsigned)P.n_h2); }
-            else { i1 = (int)(t / P.n_h2); i2 = (int)(t % P.n_h2); }
+            if (total < 0x7fffffffLL) { i1 = (int)((unsigned)t / (unsigned)n_h2); i2 = (int)((unsigned)t - (unsigned)i1 * (unsigned)n_h2); }
+            else { i1 = (int)(t / n_h2); i2 = (int)(t % n_h2); }
+        }
+        unsigned long long key = 0;
+#pragma unroll 1
+        for (int k = 0; k < TILE_PTS && t < total; ++k, t += GRID_TILE) {
             const int h1 = h1s[i1];
-            const int h2 = (P.ploidy == 1) ? h1 : h2s[i2];
+            const int h2 = haploid ? h1 : h2s[i2];
             double ml = -INFINITY;
             if (h1 <= h2) {
-                TileShared T;
-                T.lgamma_k1 = F.lgamma_k1; T.sig_mp = F.sig_mp; T.tmin = F.tmin;
-                if (F.ok) {
-                    const double *rows = g.ftab + F.off;
-                    const double rp = rows[2 * (long long)P.n_h1 + (max(h1 - P.readlen, 1) + max(h2 - P.readlen, 1) - 2)];
-                    if (i2 >= F.fam) {
-                        const double2 row = reinterpret_cast<const double2 *>(rows)[i1];
-                        const double pe = (i2 >= F.fa2) ? row.y : ml_pe_term(P, g, h1, h2, T.tmin);
+                if (f_ok) {
+                    const double rp = rept[max(h1 - readlen, 1) + max(h2 - readlen, 1) - 2];
+                    const double2 row = reinterpret_cast<const double2 *>(rows)[i1];
+                    double pe;
+                    if (i2 >= fa2) pe = row.y;
+                    else if (npe > 0) pe = ml_pe_tab(R1, R1 + (long long)npe * n_h1, n_h1, fa2, npe, i1, i2, g.small_value, g.log_small);
+                    else pe = ml_pe_term(P, g, h1, h2, T.tmin);
+                    if (i2 >= fam) {
                         ml = __dadd_rn(__dadd_rn(row.x, rp), pe);
                     } else {
                         ml = __dadd_rn(ml_span_term(P, g, h1, h2), ml_part_term(P, g, h1, h2, T.sig_mp));
                         ml = __dadd_rn(ml, rp);
-                        ml = __dadd_rn(ml, ml_pe_term(P, g, h1, h2, T.tmin));
+                        ml = __dadd_rn(ml, pe);
                     }
                 } else {
                     ml = point_ml(P, g, h1, h2, T);
                 }
-                key = ord_key(ml);
+                key = max(key, ord_key(ml));
             }
-            g.surface[P.off_surface + t] = ml;
+            surf[t] = ml;
+            // next point of this thread: GRID_TILE further along the row-major order
+            if (n_h2 >= GRID_TILE) { i2 += GRID_TILE; if (i2 >= n_h2) { i2 -= n_h2; ++i1; } }
+            else { const int adv = i2 + GRID_TILE; const int q = adv / n_h2; i1 += q; i2 = adv - q * n_h2; }
         }
         key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
         key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
@@ -495,6 +545,12 @@ __device__ __forceinline__ bool better(const ArgMax &a, const ArgMax &b) {   // 
     return a.idx < b.idx;
 }
 
+// (u1, u2 = h1 / period, h2 / period: division is monotone, so min / max commute with it)
+__device__ __forceinline__ bool pathological_u(const tredsw_grid_problem &P, int u1, int u2) {
+    const int lo = min(u1, u2), hi = max(u1, u2);
+    if (P.expansion) return P.recessive ? (lo >= P.cutoff_risk) : (hi >= P.cutoff_risk);
+    return P.recessive ? (hi <= P.cutoff_risk) : (lo <= P.cutoff_risk);
+}
 __device__ __forceinline__ bool pathological(const tredsw_grid_problem &P, int h1, int h2) {
     const int lo = min(h1, h2) / P.period, hi = max(h1, h2) / P.period;
     if (P.expansion) return P.recessive ? (lo >= P.cutoff_risk) : (hi >= P.cutoff_risk);
@@ -549,13 +605,14 @@ __global__ void __launch_bounds__(256, 3) grid_reduce_kernel(GridParams g, const
             const int h2_last = sorted ? h2s[min(cb + RED_CHUNK, P.n_h2) - 1] : 0x7fffffff;
             int h2c[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const int c = cb + lane + 32 * j; h2c[j] = (P.ploidy != 1 && c < P.n_h2) ? h2s[c] : 0; }
+            for (int j = 0; j < 8; ++j) { const int c = cb + lane + 32 * j; h2c[j] = (P.ploidy != 1 && c < P.n_h2) ? h2s[c] / P.period : 0; }   // units
             double col[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) col[j] = 0.0;
             for (int i1 = row0; i1 < P.n_h1; i1 += rstep) {
                 const int h1 = h1s[i1];
                 if (h2_last < h1) continue;                               // the whole chunk has h1 > h2: not evaluated
+                const int u1 = h1 / P.period;
                 const long long row = (long long)i1 * P.n_h2;
                 double v[8];
 #pragma unroll
@@ -570,7 +627,7 @@ __global__ void __launch_bounds__(256, 3) grid_reduce_kernel(GridParams g, const
                     if (d < -746.0) continue;                             // exp(d) == 0 exactly
                     const double w = exp(d);
                     col[j] += w; racc += w;
-                    if (pathological(P, h1, (P.ploidy == 1) ? h1 : h2c[j])) raccp += w;
+                    if (pathological_u(P, u1, (P.ploidy == 1) ? u1 : h2c[j])) raccp += w;
                     if (d == 0.0) {
                         ArgMax c{ml, h1, row + cb + lane + 32 * j};
                         if (better(c, best)) best = c;
