@@ -43,6 +43,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--samples", type=int, default=384, help="samples per GPU per step (x 30 loci)")
+    p.add_argument("--no-grid-stress", action="store_true", help="skip the long-expansion grid measurement "
+                   "(BASELINE configs[4]) reported as roofline_grid_stress")
     p.add_argument("--depth", type=int, default=2, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--streams", type=int, default=3, help="streams the device-resident steps alternate over "
                    "(2: the tail of one step's persistent SW kernel overlaps the head of the next step)")
@@ -420,13 +422,31 @@ def _main(args):
                          "kernel_ms": stage["sw"], "share_of_step": stage["sw"] / max(stage["total"], 1e-9),
                          "executed_gcups": (int(st[1]) + int(st[2])) / sw_s / 1e9,
                          "algorithmic_gcups": int(st[0]) / sw_s / 1e9},
-            "roofline_grid": {"kernel": "grid_surface_kernel + grid_reduce_kernel", "bound": "hbm",
+            "roofline_grid": {"kernel": "grid_tiles/setup/fill + grid_surface_{points,tiles} + grid_reduce_{warp,<1>,<8>} (default search)", "bound": "hbm",
                               "achieved": grid_bytes / grid_s / 1e9, "peak": hbm, "unit": "GB/s",
                               "frac": grid_bytes / grid_s / 1e9 / hbm, "peak_source": hbm_src + " copy bandwidth",
                               "kernel_ms": stage["grid"], "points": int(st[4]),
                               "note": "FP64-log bound, not HBM bound: ~30-150 logs per 8-byte point (SURVEY 8d)"},
             "stage_ms": stage, "setup_s": {"simulate": t_gen},
         }
+        if not args.no_grid_stress:
+            # the grid kernels at the configuration their HBM roofline is quoted on (BASELINE configs[4]: 64
+            # problems x 500,500 points, --fullsearch, maxinsert 1000) — the cohort's default-search surfaces
+            # above are a few dozen points each and only measure launch latency
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import grid_stress
+                gs = grid_stress.run(problems=64, maxinsert=1000, readlen=150, reps=5, device=local_rank)
+                line["roofline_grid_stress"] = {
+                    "kernel": "grid_setup/fill + grid_surface_tiles + grid_reduce<8> (cluster of 8 CTAs per surface)",
+                    "workload": "long-expansion stress (BASELINE configs[4]): 64 problems x 500,500 points, fullsearch, maxinsert 1000, 150 bp",
+                    "bound": "hbm", "achieved": gs["algorithmic_GBps"], "peak": hbm, "unit": "GB/s",
+                    "frac": gs["algorithmic_GBps"] / hbm, "kernel_ms": gs["grid_ms"], "points": gs["points"],
+                    "bytes_per_point": 16, "traffic": 832e6 if gs["points"] == 32032000 else None,
+                    "note": "16 B/point algorithmic (8 written + 8 read by the reduction); traffic = dram bytes of the "
+                            "tiles + reduce kernels in profiles/r1_grid_stress_full.txt; FP64 log/exp bound (DESIGN 4.2)"}
+            except Exception as e:
+                line["roofline_grid_stress"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             try:
                 cores = os.cpu_count() or 1

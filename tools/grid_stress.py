@@ -13,6 +13,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def run(problems=8, maxinsert=1000, readlen=250, reps=5, device=0):
+    """-> dict with the best-of-`reps` device time of the grid stage and its algorithmic bandwidth."""
+    import torch
+    from tredparse_b200 import _lib, cohort, simulate
+    from tredparse_b200.meta import TREDsRepo
+    repo = TREDsRepo()
+    spec = [("DM1", (13, 1000)), ("FXS", (30, 800)), ("DM1", (12, 500)), ("HD", (17, 300))]
+    probs = [simulate.simulate_problem(repo[spec[i % 4][0]], spec[i % 4][1], readlen=readlen, seed=100 + i)
+             for i in range(problems)]
+    batch = cohort.CohortBatch(probs, maxinsert=maxinsert, fullsearch=True)
+    stream = torch.cuda.Stream(device=device)
+    ctx = _lib.Context(device, stream=stream.cuda_stream)
+    batch.to_device(device)
+    st = batch.run_host(ctx=ctx, want_stats=True)["stats"]
+    for _ in range(2):
+        batch.run_device(ctx)
+    ctx.enable_timing(True)
+    best = None
+    for _ in range(reps):
+        batch.run_device(ctx)
+        t = ctx.timing()
+        if best is None or t["grid"] < best["grid"]:
+            best = t
+    ctx.close()
+    pts = int(st[4])
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    gbs = 16.0 * pts / (best["grid"] * 1e-3) / 1e9
+    return {"problems": problems, "maxinsert": maxinsert, "readlen": readlen, "points": pts,
+            "grid_ms": best["grid"], "sw_ms": best["sw"], "kde_ms": best["kde"], "total_ms": best["total"],
+            "ns_per_point": best["grid"] * 1e6 / pts, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak,
+            "frac_of_hbm": gbs / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--problems", type=int, default=8)
@@ -20,35 +54,7 @@ def main():
     ap.add_argument("--readlen", type=int, default=250)
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
-    import torch
-    from tredparse_b200 import _lib, cohort, simulate
-    from tredparse_b200.meta import TREDsRepo
-    repo = TREDsRepo()
-    spec = [("DM1", (13, 1000)), ("FXS", (30, 800)), ("DM1", (12, 500)), ("HD", (17, 300))]
-    probs = [simulate.simulate_problem(repo[spec[i % 4][0]], spec[i % 4][1], readlen=a.readlen, seed=100 + i)
-             for i in range(a.problems)]
-    batch = cohort.CohortBatch(probs, maxinsert=a.maxinsert, fullsearch=True)
-    stream = torch.cuda.Stream()
-    ctx = _lib.Context(0, stream=stream.cuda_stream)
-    batch.to_device(0)
-    st = batch.run_host(ctx=ctx, want_stats=True)["stats"]
-    for _ in range(2):
-        batch.run_device(ctx)
-    ctx.enable_timing(True)
-    best = None
-    for _ in range(a.reps):
-        batch.run_device(ctx)
-        t = ctx.timing()
-        if best is None or t["grid"] < best["grid"]:
-            best = t
-    pts = int(st[4])
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    gbs = 16.0 * pts / (best["grid"] * 1e-3) / 1e9
-    print(json.dumps({"problems": a.problems, "maxinsert": a.maxinsert, "readlen": a.readlen, "points": pts,
-                      "grid_ms": best["grid"], "sw_ms": best["sw"], "kde_ms": best["kde"], "total_ms": best["total"],
-                      "ns_per_point": best["grid"] * 1e6 / pts, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak,
-                      "frac_of_hbm": gbs / peak}))
+    print(json.dumps(run(a.problems, a.maxinsert, a.readlen, a.reps)))
 
 
 if __name__ == "__main__":
