@@ -796,7 +796,6 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     g.small_value = exp(-10.0);
     g.really_small = exp(-100.0);
     g.log_small = log(g.small_value);
-    (void)points_hint;
     int rc;
     const size_t pt_bytes = (((size_t)nproblems + 1) * sizeof(long long) + 15) & ~(size_t)15;
     if ((rc = ctx->d_tiles.ensure(2 * pt_bytes + (2 + 2 * (size_t)nproblems) * sizeof(int)))) return rc;
@@ -807,8 +806,20 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     grid_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(d_prob, nproblems, d_pt, d_tl, d_lists);
     {   // per-problem constants and far-region tables of the medium / large surfaces
         const size_t far_bytes = (((size_t)nproblems * sizeof(FarInfo)) + 255) & ~(size_t)255;
-        const long long cap = 8LL << 20;                                   // doubles (64 MB): tables of ~1000 large surfaces
-        if ((rc = ctx->d_ftab.ensure(far_bytes + 256 + (size_t)cap * sizeof(double)))) return rc;
+        // table arena, in doubles: 64 MB serve ~250 long-expansion surfaces (a surface that finds it full is
+        // evaluated point by point — slower, same result); a cohort searched with --fullsearch has one large
+        // surface per problem, ~80 doubles of tables per candidate allele each
+        long long cap = 8LL << 20;
+        if (points_hint > 1024) {
+            const long long side = (long long)ceil(sqrt((double)points_hint));
+            const long long want = (long long)nproblems * 80 * side;
+            if (want > cap) cap = want < (1LL << 30) ? want : (1LL << 30);
+        }
+        if (ctx->d_ftab.ensure(far_bytes + 256 + (size_t)cap * sizeof(double)) != TREDSW_OK) {
+            cudaGetLastError();                                            // not enough memory for the big arena
+            cap = 8LL << 20;
+            if ((rc = ctx->d_ftab.ensure(far_bytes + 256 + (size_t)cap * sizeof(double)))) return rc;
+        }
         g.far = ctx->d_ftab.as<FarInfo>();
         g.fcursor = reinterpret_cast<unsigned long long *>(ctx->d_ftab.as<unsigned char>() + far_bytes);
         g.ftab = reinterpret_cast<double *>(ctx->d_ftab.as<unsigned char>() + far_bytes + 256);

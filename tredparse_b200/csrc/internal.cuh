@@ -12,7 +12,8 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                              const int8_t *h_mat25, int go, int ge, int32_t *d_work, int32_t *d_out,
                              unsigned long long *d_stats);
 
-// Likelihood surface + reductions (grid.cu).  points_hint sizes the x dimension of the launch only.
+// Likelihood surface + reductions (grid.cu).  points_hint (largest surface of the batch, or an upper bound)
+// sizes the arena of the far-region tables.
 int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int nproblems,
                          const int32_t *d_ipool, const double *d_dpool, double *d_surface, double *d_marg,
                          tredsw_grid_result *d_res, long long points_hint);
