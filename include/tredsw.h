@@ -326,6 +326,9 @@ typedef struct {
 
 /* bai_path NULL: <bam>.bai, then <bam without extension>.bai.  NULL + tredsw_last_error() on failure. */
 tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path);
+/* A second, independent handle on the same BAM for another host thread (handles are not thread-safe): own file
+ * descriptor and inflate state, the parsed index shared with `bam`.  Close each clone with tredsw_bam_close. */
+tredsw_bam *tredsw_bam_clone(tredsw_bam *bam);
 void tredsw_bam_close(tredsw_bam *bam);
 int32_t tredsw_bam_nref(tredsw_bam *bam);
 int32_t tredsw_bam_tid(tredsw_bam *bam, const char *contig);     /* -1 when unknown */

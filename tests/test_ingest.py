@@ -153,3 +153,56 @@ def test_gender_inference_from_chrY_depth(tmp_path):
         assert pre["inferredGender"] == want and pre["readLen"] == 100 and pre["depthY"] == (ym if want == "Male" else yf)
     pre = tredmod.presteps(male, repo, ["HD"], log)            # no X-linked locus requested: gender not inferred
     assert pre["inferredGender"] == "Unknown" and pre["depthY"] == -1
+
+
+# ---- loci dealt to host threads (tred.ingest_loci) ------------------------------------------------------------
+def _evidence_equal(a, b):
+    return (np.array_equal(a.reads, b.reads) and np.array_equal(a.roff, b.roff) and a.names == b.names and
+            np.array_equal(a.global_lens, b.global_lens) and np.array_equal(a.target_lens, b.target_lens) and
+            a.depth == b.depth)
+
+
+@pytest.mark.parametrize("sample,tredname,bam", BAMS, ids=[b[0] for b in BAMS])
+def test_threaded_ingest_equals_serial(sample, tredname, bam, repo):
+    from tredparse_b200 import tred as tredmod
+    log = logging.getLogger()
+    names = list(repo.names)
+    ev1, d1 = tredmod.ingest_loci(bam, repo, names, 150, True, False, log, threads=1)
+    ev4, d4 = tredmod.ingest_loci(bam, repo, names, 150, True, False, log, threads=4)
+    assert d1 == d4 and set(ev1) == set(ev4) and tredname in ev1
+    assert all(_evidence_equal(ev1[k], ev4[k]) for k in ev1)
+    assert ev1[tredname].nreads > 50 and d1[tredname] > 5
+    # clones are independent handles that share the index
+    with ingest.BamIngest(bam) as ing:
+        c = ing.clone()
+        a = ing.extract_locus(repo[tredname], 150, want_names=True)
+        b = c.extract_locus(repo[tredname], 150, want_names=True)
+        c.close()
+        assert _evidence_equal(a, b)
+        assert _evidence_equal(a, ing.extract_locus(repo[tredname], 150, want_names=True))   # the parent still works
+
+
+def test_run_wiring_without_the_gpu(monkeypatch, repo):
+    """tred.run up to the kernels: pre-steps, threaded ingest, one InputParams per locus with the locus depth
+    (tred.py:195-249); the batched GPU stage is replaced by a recorder."""
+    from tredparse_b200 import tred as tredmod
+    seen = {}
+
+    def fake_run_batched(ips, evidence=None):
+        seen["ips"], seen["evidence"] = ips, evidence
+        return [None] * len(ips)
+    monkeypatch.setattr(tredmod, "run_batched", fake_run_batched)
+    bam = os.path.join(GOLDEN, "t001.mini.bam")
+    names = ["HD", "DM1", "FXS"]
+    out = tredmod.run(("t001", bam, repo, names, 300, False, False, True, True, "INFO"))
+    assert out["samplekey"] == "t001" and out["bam"] == bam
+    calls = out["tredCalls"]
+    assert calls["readLen"] == 150 and calls["inferredGender"] == "Female" and calls["depthY"] == 0.0
+    assert not any(k.startswith("HD.") for k in calls)                   # the recorder returned no results
+    ips = seen["ips"]
+    assert [ip.tredName for ip in ips] == names and all(ip.READLEN == 150 and ip.gender == "Female" for ip in ips)
+    assert set(seen["evidence"]) == set(names)
+    hd = seen["evidence"]["HD"]
+    assert ips[0].depth == hd.depth > 5 and hd.nreads > 50
+    assert seen["evidence"]["DM1"].nreads == 0 and ips[1].depth == 0.0  # chr19: nothing in the chr4 mini BAM
+    assert ips[0].kwargs["maxinsert"] == 300 and ips[0].kwargs["fullsearch"] is False

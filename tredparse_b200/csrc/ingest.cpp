@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -121,7 +122,9 @@ struct tredsw_bam {
     std::vector<std::string> names;
     std::vector<int64_t> lengths;
     std::unordered_map<std::string, int32_t> tid_of;
-    std::vector<RefIndex> index;
+    // the parsed .bai (tens of MB for a whole-genome BAM) is immutable and shared by the clones of a handle
+    std::shared_ptr<const std::vector<RefIndex>> index_ptr;
+    std::string path;
     bool has_index = false;
     uint64_t first_record = 0;       // virtual offset of the first alignment record
     std::vector<unsigned char> rec;
@@ -164,8 +167,8 @@ struct tredsw_bam {
     // merged chunk list of an indexed region query (same rule as bamio.BAIIndex.chunks)
     std::vector<std::pair<uint64_t, uint64_t>> chunks(int tid, int64_t beg, int64_t end) const {
         std::vector<std::pair<uint64_t, uint64_t>> out;
-        if (tid < 0 || tid >= (int)index.size()) return out;
-        const RefIndex &ri = index[tid];
+        if (!index_ptr || tid < 0 || tid >= (int)index_ptr->size()) return out;
+        const RefIndex &ri = (*index_ptr)[tid];
         uint64_t min_off = 0;
         if (!ri.linear.empty()) { const size_t k = (size_t)(beg >> 14); min_off = k < ri.linear.size() ? ri.linear[k] : ri.linear.back(); }
         const int64_t e1 = end - 1;
@@ -232,6 +235,7 @@ tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
         b->tid_of[b->names.back()] = i;
     }
     b->first_record = b->bgzf.tell();
+    b->path = bam_path;
     // index: <bam>.bai, then <bam without extension>.bai (bamio.AlignmentFile)
     std::string cands[2];
     if (bai_path) cands[0] = bai_path;
@@ -257,7 +261,7 @@ tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
         int32_t nr = 0;
         memcpy(&nr, data.data() + off, 4); off += 4;
         bool good = true;
-        b->index.assign(nr > 0 ? nr : 0, RefIndex());
+        auto index = std::make_shared<std::vector<RefIndex>>(nr > 0 ? nr : 0);
         for (int i = 0; i < nr && good; ++i) {
             int32_t n_bin = 0;
             if (!need(4)) { good = false; break; }
@@ -267,7 +271,7 @@ tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
                 if (!need(8)) { good = false; break; }
                 memcpy(&bin, data.data() + off, 4); memcpy(&n_chunk, data.data() + off + 4, 4); off += 8;
                 if (n_chunk < 0 || !need((size_t)16 * n_chunk)) { good = false; break; }
-                auto &v = b->index[i].bins[bin];
+                auto &v = (*index)[i].bins[bin];
                 for (int c = 0; c < n_chunk; ++c) {
                     uint64_t s, e;
                     memcpy(&s, data.data() + off, 8); memcpy(&e, data.data() + off + 8, 8); off += 16;
@@ -278,14 +282,26 @@ tredsw_bam *tredsw_bam_open(const char *bam_path, const char *bai_path) {
             if (!good || !need(4)) { good = false; break; }
             memcpy(&n_intv, data.data() + off, 4); off += 4;
             if (n_intv < 0 || !need((size_t)8 * n_intv)) { good = false; break; }
-            b->index[i].linear.resize(n_intv);
-            if (n_intv) memcpy(b->index[i].linear.data(), data.data() + off, (size_t)8 * n_intv);
+            (*index)[i].linear.resize(n_intv);
+            if (n_intv) memcpy((*index)[i].linear.data(), data.data() + off, (size_t)8 * n_intv);
             off += (size_t)8 * n_intv;
         }
-        if (good) { b->has_index = true; break; }
-        b->index.clear();
+        if (good) { b->index_ptr = index; b->has_index = true; break; }
     }
     if (!b->has_index) { tredsw_set_error("no usable .bai index next to %s", bam_path); delete b; return nullptr; }
+    return b;
+}
+
+// A second handle on the same BAM for another host thread: its own file descriptor and inflate state, the
+// header tables copied, the parsed index shared.  Handles are not thread-safe; clones are independent.
+tredsw_bam *tredsw_bam_clone(tredsw_bam *src) {
+    if (!src) { tredsw_set_error("null handle"); return nullptr; }
+    tredsw_bam *b = new tredsw_bam();
+    b->bgzf.fh = fopen(src->path.c_str(), "rb");
+    if (!b->bgzf.fh) { tredsw_set_error("cannot open %s", src->path.c_str()); delete b; return nullptr; }
+    b->names = src->names; b->lengths = src->lengths; b->tid_of = src->tid_of;
+    b->index_ptr = src->index_ptr; b->has_index = src->has_index;
+    b->first_record = src->first_record; b->path = src->path;
     return b;
 }
 

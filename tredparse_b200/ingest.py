@@ -38,6 +38,8 @@ def _bind(lib):
         return
     lib.tredsw_bam_open.restype = ctypes.c_void_p
     lib.tredsw_bam_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    lib.tredsw_bam_clone.restype = ctypes.c_void_p
+    lib.tredsw_bam_clone.argtypes = [ctypes.c_void_p]
     lib.tredsw_bam_close.restype = None
     lib.tredsw_bam_close.argtypes = [ctypes.c_void_p]
     lib.tredsw_bam_nref.restype = ctypes.c_int32
@@ -80,6 +82,16 @@ class BamIngest:
         if not self.handle:
             raise IOError("tredsw_bam_open({}): {}".format(path, _lib.last_error()))
         self._caps = dict(reads=512, bases=512 * 256, pairs=8192, names=512 * 48)
+
+    def clone(self):
+        """An independent handle on the same BAM for another host thread (shares the parsed index)."""
+        other = object.__new__(BamIngest)
+        other.lib, other.path = self.lib, self.path
+        other.handle = self.lib.tredsw_bam_clone(self.handle)
+        if not other.handle:
+            raise IOError("tredsw_bam_clone({}): {}".format(self.path, _lib.last_error()))
+        other._caps = dict(self._caps)
+        return other
 
     def close(self):
         if getattr(self, "handle", None):

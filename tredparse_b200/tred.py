@@ -222,6 +222,62 @@ def run_batched(ips, evidence=None):
     return results
 
 
+INGEST_THREADS = int(os.environ.get("TREDSW_INGEST_THREADS", "0")) or min(8, os.cpu_count() or 1)
+
+
+def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None):
+    """Evidence and depth of every requested locus of one BAM.
+    Native ingest (csrc/ingest.cpp): one indexed pass per locus yields reads, pair distances AND depth; the loci
+    are dealt to `threads` host threads, each with its own clone of the BAM handle (own file descriptor, shared
+    index; ctypes releases the GIL during the pass).  The Python BAM reader (three passes per locus, like the
+    reference's pysam calls, tred.py:225-243) is the fallback for the depth when a BAM has no usable index or the
+    contig is missing; a locus whose extraction fails gets depth 30 like the reference (tred.py:236-240).
+    :return: ({tredName: ingest.LocusEvidence}, {tredName: depth})"""
+    ing = None
+    try:
+        from .ingest import BamIngest
+        ing = BamIngest(bam_path(bam))
+    except Exception as e:
+        logger.debug("native BAM ingest unavailable for `{}` ({}); using the Python reader".format(bam, e))
+    evidence, depths = {}, {}
+
+    def one(handle, tred):
+        xtred = repo[tred]
+        try:
+            if handle is not None and handle.tid(xtred.chr) >= 0:
+                ev = locus_evidence(handle, None, xtred, READLEN, alts, clip, repo.ref)
+                return tred, ev, ev.depth
+            bd = BamDepth(bam, repo.ref, logger)
+            return tred, None, bd.region_depth(xtred.chr, max(0, xtred.repeat_start - SPAN), xtred.repeat_end + SPAN)
+        except Exception as e:
+            logger.error("Exception on `{}` {} ({}). Set depth={}".format(bam, tred, e, 30))
+            return tred, None, 30
+
+    threads = max(1, min(threads or INGEST_THREADS, len(tredNames)))
+    if ing is None or threads == 1:
+        done = [one(ing, tred) for tred in tredNames]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        handles = [ing] + [ing.clone() for _ in range(threads - 1)]
+
+        def lane(k):
+            return [one(handles[k], tred) for tred in tredNames[k::threads]]
+        try:
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                done = [r for part in pool.map(lane, range(threads)) for r in part]
+        finally:
+            for h in handles[1:]:
+                h.close()
+    if ing is not None:
+        ing.close()
+    for tred, ev, depth in done:
+        if ev is not None:
+            evidence[tred] = ev
+        depths[tred] = depth
+        logger.debug("Inferred depth at locus {}: {}".format(tred, depth))
+    return evidence, depths
+
+
 def presteps(bam, repo, tredNames, logger):
     """The per-sample pre-steps of tred.run (tred.py:195-223): gender from the chrY depth — only when an X-linked
     locus is requested; 'Unknown' / -1 when the lookup fails — and the read length (150 when it cannot be read).
@@ -252,37 +308,10 @@ def run(arg):
     tredCalls.update(presteps(bam, repo, tredNames, logger))
     gender, READLEN = tredCalls["inferredGender"], tredCalls["readLen"]
 
-    # native ingest: one indexed pass per locus yields reads, pair distances AND depth (csrc/ingest.cpp); the
-    # Python BAM reader (three passes per locus, like the reference's pysam calls) is the fallback
-    ing = None
-    try:
-        from .ingest import BamIngest
-        ing = BamIngest(bam_path(bam))
-    except Exception as e:
-        logger.debug("native BAM ingest unavailable for `{}` ({}); using the Python reader".format(bam, e))
-    ips, depths, evidence = [], {}, {}
-    for tred in tredNames:
-        bd = BamDepth(bam, repo.ref, logger)
-        xtred = repo[tred]
-        WINDOW_START = max(0, xtred.repeat_start - SPAN)
-        WINDOW_END = xtred.repeat_end + SPAN
-        try:
-            if ing is not None and ing.tid(xtred.chr) >= 0:
-                evidence[tred] = locus_evidence(ing, None, xtred, READLEN, alts, clip, repo.ref)
-                depth = evidence[tred].depth
-            else:
-                depth = bd.region_depth(xtred.chr, WINDOW_START, WINDOW_END)
-        except Exception as e:
-            depth = 30
-            evidence.pop(tred, None)
-            logger.error("Exception on `{}` {} ({}). Set depth={}".format(bam, tred, e, depth))
-        logger.debug("Inferred depth at locus {}: {}".format(tred, depth))
-        depths[tred] = depth
-        ips.append(InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
-                               fullsearch=fullsearch, gender=gender, depth=depth, clip=clip, alts=alts,
-                               repeatpairs=repeatpairs, log=log))
-    if ing is not None:
-        ing.close()
+    evidence, depths = ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger)
+    ips = [InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
+                       fullsearch=fullsearch, gender=gender, depth=depths[tred], clip=clip, alts=alts,
+                       repeatpairs=repeatpairs, log=log) for tred in tredNames]
     try:
         results = run_batched(ips, evidence)
     except Exception as e:
