@@ -339,6 +339,11 @@ int tredsw_bam_extract_locus(tredsw_bam *bam, const tredsw_locus_query *q, int8_
                              int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
                              tredsw_locus_summary *out);
 
+/* BGZF blocks inflated so far by the library's own DEFLATE decoder (csrc/inflate_fast.h, every block CRC-checked)
+ * and by zlib (the fallback for streams the decoder refuses). */
+void tredsw_bam_inflate_stats(tredsw_bam *bam, int64_t *own_blocks, int64_t *zlib_blocks);
+/* The decoder on its own (test hook): 0 iff the raw DEFLATE stream `in` inflates to exactly out_len bytes. */
+int tredsw_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
 /* BamDepth.region_depth (tredparse/bam_parser.py:404-411): sum of pileup column depths over the reads
  * overlapping [start, end) / (end - start + 1); feeds half_depth of the repeat-only term and the chrY depth of
  * the gender inference (bam_parser.py:413-429). */

@@ -29,7 +29,7 @@ EXPORTS = [
     "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch",
     # native BAM ingest
     "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
-    "tredsw_bam_region_depth", "tredsw_bam_read_length", "tredsw_bam_clone",
+    "tredsw_bam_region_depth", "tredsw_bam_read_length", "tredsw_bam_clone", "tredsw_bam_inflate_stats", "tredsw_inflate_raw",
 ]
 
 

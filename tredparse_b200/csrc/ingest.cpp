@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/tredsw.h"
+#include "inflate_fast.h"
 
 void tredsw_set_error(const char *fmt, ...);
 
@@ -35,9 +36,12 @@ struct Bgzf {
     size_t pos = 0;
     z_stream zs;
     bool zs_init = false;
+    size_t blen = 0;                                  // inflated bytes of the current block (block has slack behind)
+    tredsw_inflate::FastInflater *fast = nullptr;     // own decoder (inflate_fast.h); zlib is the fallback
+    long long n_fast = 0, n_zlib = 0;                 // blocks inflated by either
 
     bool load(int64_t coffset) {
-        block.clear(); pos = 0; block_coffset = coffset; next_coffset = coffset;
+        blen = 0; pos = 0; block_coffset = coffset; next_coffset = coffset;
         if (fseeko(fh, coffset, SEEK_SET) != 0) return false;
         unsigned char head[18];
         if (fread(head, 1, 18, fh) != 18) return false;
@@ -58,15 +62,29 @@ struct Bgzf {
         if (clen > 0 && fread(cbuf.data(), 1, clen, fh) != (size_t)clen) return false;
         unsigned char tail[8];
         if (fread(tail, 1, 8, fh) != 8) return false;
+        const uint32_t crc = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
         const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
-        block.resize(isize);
+        if (block.size() < (size_t)isize + tredsw_inflate::FastInflater::SLACK) block.resize((size_t)isize + tredsw_inflate::FastInflater::SLACK);
+        blen = isize;
         if (isize > 0) {
-            if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) return false; zs_init = true; }
-            else inflateReset(&zs);
-            zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
-            zs.next_out = block.data(); zs.avail_out = isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END) return false;
+            static const bool zlib_only = getenv("TREDSW_ZLIB_INFLATE") != nullptr;
+            bool done = false;
+            if (!zlib_only && clen > 0) {
+                if (!fast) fast = new tredsw_inflate::FastInflater();
+                // the block's CRC-32 guards the result: anything else than a verified block goes to zlib
+                done = fast->inflate(cbuf.data(), (size_t)clen, block.data(), isize) &&
+                       (uint32_t)crc32(crc32(0L, Z_NULL, 0), block.data(), isize) == crc;
+                if (done) ++n_fast;
+            }
+            if (!done) {
+                if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) return false; zs_init = true; }
+                else inflateReset(&zs);
+                zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
+                zs.next_out = block.data(); zs.avail_out = isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END) return false;
+                ++n_zlib;
+            }
         }
         next_coffset = coffset + bsize + 1;
         return true;
@@ -77,19 +95,19 @@ struct Bgzf {
         pos = (size_t)(voffset & 0xffff);
     }
     uint64_t tell() const {
-        if (pos >= block.size() && block_coffset >= 0) return (uint64_t)next_coffset << 16;
+        if (pos >= blen && block_coffset >= 0) return (uint64_t)next_coffset << 16;
         return ((uint64_t)block_coffset << 16) | pos;
     }
     size_t read(void *dst, size_t n) {
         unsigned char *out = (unsigned char *)dst;
         size_t got = 0;
         while (n > 0) {
-            size_t avail = block.size() > pos ? block.size() - pos : 0;
+            size_t avail = blen > pos ? blen - pos : 0;
             if (avail == 0) {
                 const int64_t prev = block_coffset;
                 if (!load(next_coffset)) break;
-                if (block.empty()) { if (next_coffset == block_coffset || block_coffset == prev) break; continue; }
-                avail = block.size();
+                if (blen == 0) { if (next_coffset == block_coffset || block_coffset == prev) break; continue; }
+                avail = blen;
             }
             const size_t take = std::min(avail, n);
             memcpy(out + got, block.data() + pos, take);
@@ -97,7 +115,7 @@ struct Bgzf {
         }
         return got;
     }
-    ~Bgzf() { if (zs_init) inflateEnd(&zs); if (fh) fclose(fh); }
+    ~Bgzf() { if (zs_init) inflateEnd(&zs); if (fh) fclose(fh); delete fast; }
 };
 
 struct RefIndex {
@@ -306,6 +324,22 @@ tredsw_bam *tredsw_bam_clone(tredsw_bam *src) {
 }
 
 void tredsw_bam_close(tredsw_bam *b) { delete b; }
+
+// BGZF blocks inflated by this handle so far: by the library's own decoder / by zlib (the fallback).
+void tredsw_bam_inflate_stats(tredsw_bam *b, int64_t *own, int64_t *zlib_blocks) {
+    if (own) *own = b ? b->bgzf.n_fast : 0;
+    if (zlib_blocks) *zlib_blocks = b ? b->bgzf.n_zlib : 0;
+}
+
+// The raw-DEFLATE decoder on its own (test hook): 0 when `in` inflates to exactly out_len bytes.
+int tredsw_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len) {
+    if (!in || !out || in_len < 0 || out_len < 0) return TREDSW_ERR_ARG;
+    std::vector<uint8_t> buf((size_t)out_len + tredsw_inflate::FastInflater::SLACK);
+    tredsw_inflate::FastInflater dec;
+    if (!dec.inflate(in, (size_t)in_len, buf.data(), (size_t)out_len)) return TREDSW_ERR_UNSUPPORTED;
+    memcpy(out, buf.data(), (size_t)out_len);
+    return TREDSW_OK;
+}
 
 int32_t tredsw_bam_nref(tredsw_bam *b) { return b ? (int32_t)b->names.size() : 0; }
 

@@ -38,6 +38,10 @@ def _bind(lib):
         return
     lib.tredsw_bam_open.restype = ctypes.c_void_p
     lib.tredsw_bam_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    lib.tredsw_bam_inflate_stats.restype = None
+    lib.tredsw_bam_inflate_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    lib.tredsw_inflate_raw.restype = ctypes.c_int
+    lib.tredsw_inflate_raw.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
     lib.tredsw_bam_clone.restype = ctypes.c_void_p
     lib.tredsw_bam_clone.argtypes = [ctypes.c_void_p]
     lib.tredsw_bam_close.restype = None
@@ -82,6 +86,12 @@ class BamIngest:
         if not self.handle:
             raise IOError("tredsw_bam_open({}): {}".format(path, _lib.last_error()))
         self._caps = dict(reads=512, bases=512 * 256, pairs=8192, names=512 * 48)
+
+    def inflate_stats(self):
+        """(blocks inflated by the library's own decoder, blocks that fell back to zlib) for this handle."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        self.lib.tredsw_bam_inflate_stats(self.handle, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
 
     def clone(self):
         """An independent handle on the same BAM for another host thread (shares the parsed index)."""
