@@ -206,3 +206,66 @@ def test_run_wiring_without_the_gpu(monkeypatch, repo):
     assert ips[0].depth == hd.depth > 5 and hd.nreads > 50
     assert seen["evidence"]["DM1"].nreads == 0 and ips[1].depth == 0.0  # chr19: nothing in the chr4 mini BAM
     assert ips[0].kwargs["maxinsert"] == 300 and ips[0].kwargs["fullsearch"] is False
+
+
+# ---- corrupt input must not take the process down ---------------------------------------------------------------
+_FUZZ = r"""
+import os, sys, zlib, random
+sys.path.insert(0, {root!r})
+from tredparse_b200 import bamio, ingest
+from tredparse_b200.meta import TREDsRepo
+repo = TREDsRepo()
+src = bamio.AlignmentFile({bam!r})
+hd = repo["HD"]
+recs = [r for r in src.fetch(hd.chr, hd.repeat_start - 3000, hd.repeat_end + 3000)]
+refs = list(zip(src.references, src.lengths))
+src.close()
+path = os.path.join({tmp!r}, "stored.bam")
+bamio.write_bam(path, refs, recs, level=0)                 # stored blocks: content bytes sit in the file as they are
+good = open(path, "rb").read()
+with ingest.BamIngest(path) as ing:
+    base = ing.extract_locus(hd, 150, want_names=True)
+assert base.nreads > 50
+blocks, off = [], 0
+while off < len(good):
+    xlen = int.from_bytes(good[off + 10:off + 12], "little")
+    bsize = int.from_bytes(good[off + 16:off + 18], "little") + 1
+    blocks.append((off, xlen, bsize))
+    off += bsize
+rng = random.Random(3)
+ok = failed = 0
+for trial in range(150):
+    bad = bytearray(good)
+    off, xlen, bsize = blocks[rng.randrange(1, len(blocks) - 1)]      # not the header block, not the EOF block
+    lo, hi = off + 12 + xlen, off + bsize - 8
+    for _ in range(rng.randrange(1, 5)):
+        p = rng.randrange(lo, hi)
+        bad[p] = rng.randrange(256) if rng.random() < 0.5 else (bad[p] ^ (1 << rng.randrange(8)))
+    try:                                                   # keep the block's CRC valid where it still inflates:
+        data = zlib.decompress(bytes(bad[lo:hi]), -15)     # the damage must reach the record parser
+        bad[off + bsize - 8:off + bsize - 4] = (zlib.crc32(data) & 0xffffffff).to_bytes(4, "little")
+    except zlib.error:
+        pass
+    p2 = os.path.join({tmp!r}, "bad.bam")
+    open(p2, "wb").write(bytes(bad))
+    open(p2 + ".bai", "wb").write(open(path + ".bai", "rb").read())
+    try:
+        with ingest.BamIngest(p2) as ing:
+            ev = ing.extract_locus(hd, 150, alts=hd.alt, want_names=True)
+            ing.region_depth(hd.chr, hd.repeat_start - 1000, hd.repeat_end + 1000)
+            ing.read_length(100)
+        ok += 1
+    except Exception:
+        failed += 1
+print("survived", ok, failed)
+"""
+
+
+def test_corrupt_bam_records_do_not_crash_the_reader(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _FUZZ.format(root=root, bam=os.path.join(GOLDEN, "t001.mini.bam"), tmp=str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "survived" in r.stdout

@@ -149,7 +149,7 @@ struct tredsw_bam {
 
     bool read_record(Record &r) {
         int32_t bs;
-        if (bgzf.read(&bs, 4) != 4 || bs < 32) return false;
+        if (bgzf.read(&bs, 4) != 4 || bs < 32 || bs > (64 << 20)) return false;
         rec.resize(bs);
         if (bgzf.read(rec.data(), bs) != (size_t)bs) return false;
         const unsigned char *d = rec.data();
@@ -159,6 +159,8 @@ struct tredsw_bam {
         const int l_name = d[8];
         const int n_cigar = u16(12);
         r.flag = u16(14); r.l_seq = i32(16); r.next_tid = i32(20); r.next_pos = i32(24); r.tlen = i32(28);
+        // a record whose variable-length fields do not fit its block_size is corrupt: stop reading
+        if (r.l_seq < 0 || 32LL + l_name + 4LL * n_cigar + ((int64_t)r.l_seq + 1) / 2 + r.l_seq > (int64_t)bs) return false;
         int off = 32;
         r.name.assign((const char *)d + off, l_name > 0 ? l_name - 1 : 0);
         off += l_name;
