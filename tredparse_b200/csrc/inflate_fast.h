@@ -237,7 +237,11 @@ inline bool FastInflater::inflate(const uint8_t *in, size_t in_len, uint8_t *out
                 if (dist > (size_t)(op - out) || length > (size_t)(oend - op)) return false;
                 const uint8_t *src = op - dist;
                 uint8_t *const stop = op + length;
-                if (dist >= 8) {                       // word copies; may write up to 7 bytes past `stop` (SLACK)
+                if (dist >= 16) {                      // the common case (BAM: 98 % of matches, 88 % of them <= 16 bytes):
+                    memcpy(op, src, 16);               // one 16-byte move, more only for long matches; writes up to
+                    for (uint32_t k = 16; k < length; k += 16) memcpy(op + k, src + k, 16);   // 15 bytes past `stop` (SLACK)
+                    op = stop;
+                } else if (dist >= 8) {                // word copies of an overlapping match
                     do { uint64_t w; memcpy(&w, src, 8); memcpy(op, &w, 8); src += 8; op += 8; } while (op < stop);
                     op = stop;
                 } else if (dist == 1) {
