@@ -15,7 +15,7 @@ EPS, EPS2 = math.exp(-10), math.exp(-100)
 
 
 def closed_form_surface(inp, step, w):
-    """inp: the "inputs" dict of a tests/golden/likelihood_*.json document (units-keyed counts);
+    """inp: the "inputs" dict of a tests/golden/ref_likelihood_*.json document (units-keyed counts);
     returns ml(h1, h2, run_pe) -> [ml1, ml2, ml3, ml4] with h in bp."""
     K, L = inp["period"], inp["READLEN"]
     t1, t2 = L - 9, L - 18

@@ -14,9 +14,11 @@ The alignments themselves come from ``oracle.sw`` (engine="oracle": our C restat
 the reference's ssw.c compiled unmodified).  ``samfile`` arguments are anything with pysam's
 ``fetch`` / ``getrname`` interface.
 
-Parity status: evidence strings PINNED by the reference's README.md:77-86 table (FR / PR / RR of
-t001-HD and t002-DM1 reproduce exactly — tests/test_oracle_evidence.py); depth UNPINNED (pysam's
-pileup is restated, pysam is unavailable — SURVEY.md §8c).
+Parity status: PINNED to the reference's own code — tests/test_reference_pinned.py compares this module with
+the outputs of the reference's BamParser / PEextractor / tred.run (tests/golden/ref_tred_*.json,
+ref_problems.json.gz, made through oracle/refshim.py), defaults and --useclippedreads / --norepeatpairs /
+--noalts; the README.md:77-86 evidence strings reproduce exactly.  pysam itself is unavailable: fetch / pileup
+semantics are restated (oracle/pysam_stub.py lists the pileup readings; tests/golden/ref_depth_dm1.json).
 """
 import math
 from collections import defaultdict
@@ -174,12 +176,26 @@ class EvidenceOracle:
                             self._parse_read(read, keep_pairs)
                     except Exception:
                         continue
+        return self._finish()
+
+    def _finish(self):
+        """Tail of BamParser.parse (bam_parser.py:248-258): REPT-pair removal, tallies, rept."""
         if not (self.repeatpairs or self.clip):
             self.remove_pairs_of_rept()
         for x in self.details:
             self.counts[x["tag"]][x["h"]] += 1
         self.rept = sum(self.counts["REPT"].values()) if self.counts["REPT"] else 0
         return self
+
+    def parse_reads(self, seqs, names):
+        """The same for reads given as strings (synthetic problems: no BAM in between)."""
+        class _R(object):
+            __slots__ = ("query_sequence", "query_name")
+        for s, n in zip(seqs, names):
+            r = _R()
+            r.query_sequence, r.query_name = s, n
+            self._parse_read(r)
+        return self._finish()
 
     def remove_pairs_of_rept(self):
         seen = defaultdict(int)

@@ -10,6 +10,18 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def golden_module(name):
+    """Import tests/golden/<name>.py (the fixture generators double as helper libraries for the tests)."""
+    import importlib.util
+    key = "golden_" + name
+    if key not in sys.modules:
+        spec = importlib.util.spec_from_file_location(key, os.path.join(GOLDEN, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[key] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[key]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -23,10 +23,9 @@ Outputs (all under tests/golden/):
         Random / simulated / adversarial (read, template) pairs (150 & 250 bp, indels, N, >=250 scores,
         pure-repeat ties, tiny and ragged lengths) with the reference library's outputs.
 
-  likelihood_<sample>_<tred>[_variant].json
-        Inputs (counts, depth, PE lengths, ...) and outputs of oracle/likelihood_oracle.py: the surface
-        (ml1..ml4, ml per grid point, evaluation order), call, CI, PP, label, P_h1/P_h2/P_h1h2.
-        These are ORACLE outputs (the reference's Python layer is Python-2 only and cannot run here).
+
+The likelihood / pipeline goldens (ref_*.json) are made by tests/golden/make_ref_fixtures.py from the
+reference's own Python code.
 """
 import json
 import os
@@ -38,7 +37,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from oracle import sw, evidence_oracle as evo, likelihood_oracle as lko  # noqa: E402
+from oracle import sw, evidence_oracle as evo  # noqa: E402
 from tredparse_b200 import bamio  # noqa: E402
 from tredparse_b200.meta import TREDsRepo  # noqa: E402
 
@@ -109,44 +108,6 @@ def evidence_case(sample, tredname, repo, bam):
                         period=len(tred.repeat))
     pe = evo.PEOracle(sam, tred.chr, tred.repeat_start, tred.repeat_end)
     return ev, pe, READLEN, depth
-
-
-class _PE:
-    def __init__(self, g, t, ref, minpe):
-        self.global_lens, self.target_lens, self.ref, self.MINPE = g, t, ref, minpe
-
-
-def likelihood_case(tag, tred, period, READLEN, counts, rept, ploidy, depth, pe, step, weights,
-                    maxinsert=300, fullsearch=False, keep_surface=True):
-    lk = lko.LikelihoodOracle(tred, period, READLEN, counts, rept, ploidy, depth, pe, step, weights,
-                              maxinsert=maxinsert, fullsearch=fullsearch)
-    lk.call()
-    doc = {
-        "inputs": {"tred": tred.name, "period": period, "READLEN": READLEN,
-                   "FULL": {str(k): int(v) for k, v in counts["FULL"].items()},
-                   "PREF": {str(k): int(v) for k, v in counts["PREF"].items()},
-                   "rept": int(rept), "ploidy": ploidy, "depth": depth,
-                   "global_lens": [int(x) for x in pe.global_lens] if pe else [],
-                   "target_lens": [int(x) for x in pe.target_lens] if pe else [],
-                   "pe_ref": pe.ref if pe else 0, "MINPE": pe.MINPE if pe else 0,
-                   "maxinsert": maxinsert, "fullsearch": fullsearch},
-        "outputs": {"alleles": [int(x) for x in lk.alleles], "lik": float(lk.lik), "PP": float(lk.PP),
-                    "CI": lk.CI, "label": lk.label, "PEDP": lk.PEDP, "PEG": lk.PEG, "PET": lk.PET,
-                    "P_PEG": lk.P_PEG, "P_PET": lk.P_PET,
-                    "P_h1": lk.P_h1, "P_h2": lk.P_h2, "P_h1h2": lk.P_h1h2,
-                    "run_pe": bool(getattr(lk, "run_pe", False)),
-                    "h1range": [int(x) for x in getattr(lk, "h1range", [])],
-                    "h2range": [int(x) for x in getattr(lk, "h2range", [])],
-                    "n_points": len(lk.surface)},
-    }
-    if keep_surface:
-        doc["outputs"]["surface"] = [[float(a), float(b), float(c), float(d), float(e), int(h1), int(h2)]
-                                     for (a, b, c, d, e, h1, h2) in lk.surface]
-    with open(os.path.join(HERE, "likelihood_{}.json".format(tag)), "w") as fw:
-        json.dump(doc, fw)
-    print("  likelihood", tag, "alleles", lk.alleles, "PP", lk.PP, "CI", lk.CI, "label", lk.label,
-          "points", len(lk.surface), "lik", lk.lik)
-    return lk
 
 
 def synthetic_pairs():
@@ -244,33 +205,10 @@ def synthetic_pairs():
 def main():
     sw.build(REFERENCE)
     repo = TREDsRepo()
-    with open(os.path.join(ROOT, "tredparse_b200", "data", "models.json")) as fp:
-        md = json.load(fp)
-    step = {int(k): np.array(v) for k, v in md["step_size_by_period"].items()}
-    for i in range(6, 18):
-        step[i] = step[6]
-    weights = md["stutter_weights"]
-    # the product's JSON must say what the reference's model files say
-    ref_step = lko.load_step_model(os.path.join(REFERENCE, "tredparse/data/illumina_v3.pcrfree.stepmodel"))
-    ref_w = lko.load_noise_model(os.path.join(REFERENCE, "tredparse/data/illumina_v3.pcrfree.stuttermodel"))
-    assert ref_w == weights and all(np.array_equal(ref_step[k], step[k]) for k in ref_step)
-
     for sample, tredname in CASES:
         tred = repo[tredname]
         bam = trim_bam(sample, tred)
-        ev, pe, READLEN, depth = evidence_case(sample, tredname, repo, bam)
-        counts = {"FULL": dict(ev.counts["FULL"]), "PREF": dict(ev.counts["PREF"])}
-        tag = "{}_{}".format(sample, tredname)
-        likelihood_case(tag, tred, ev.period, READLEN, counts, ev.rept, ev.ploidy, depth, pe, step, weights)
-        # variants: no PE model, haploid, full search (smaller maxinsert keeps the file small), and a
-        # long-expansion range beyond SPAN (quirk Q7)
-        likelihood_case(tag + "_nope", tred, ev.period, READLEN, counts, ev.rept, ev.ploidy, depth,
-                        None, step, weights)
-        likelihood_case(tag + "_haploid", tred, ev.period, READLEN, counts, ev.rept, 1, depth, pe, step, weights)
-        likelihood_case(tag + "_full60", tred, ev.period, READLEN, counts, ev.rept, ev.ploidy, depth, pe,
-                        step, weights, maxinsert=60, fullsearch=True)
-        likelihood_case(tag + "_max1200", tred, ev.period, READLEN, counts, ev.rept, ev.ploidy, depth, pe,
-                        step, weights, maxinsert=1200, keep_surface=True)
+        evidence_case(sample, tredname, repo, bam)
     synthetic_pairs()
 
 

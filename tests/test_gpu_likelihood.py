@@ -37,8 +37,8 @@ def _run_case(doc):
     return batch, batch.summarize(0), tred, period
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "likelihood_*.json"))),
-                         ids=lambda p: os.path.basename(p)[11:-5])
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_likelihood_*.json"))),
+                         ids=lambda p: os.path.basename(p)[15:-5])
 def test_surface_and_call_match_golden(path):
     doc = json.load(open(path))
     out = doc["outputs"]
@@ -80,7 +80,7 @@ def test_kde_matches_scipy():
     rng = np.random.default_rng(3)
     sets = [np.clip(rng.normal(350, 75, 2800).astype(int), 0, 999),
             np.clip(rng.normal(420, 90, 150).astype(int), -50, 999),
-            json.load(open(os.path.join(GOLDEN, "likelihood_t001_HD.json")))["inputs"]["global_lens"]]
+            json.load(open(os.path.join(GOLDEN, "ref_likelihood_t001_HD.json")))["inputs"]["global_lens"]]
     got = models.pe_kde(sets)
     for x, g in zip(sets, got):
         pdf = gaussian_kde(np.asarray(x, dtype=float)).evaluate(np.arange(1000))
@@ -93,7 +93,7 @@ def test_batched_problems_equal_single_problem_runs():
     """Many problems in one launch give the same numbers as one launch each (pool offsets)."""
     from tredparse_b200 import models
     from tredparse_b200.meta import TREDsRepo
-    docs = [json.load(open(p)) for p in sorted(glob.glob(os.path.join(GOLDEN, "likelihood_*.json")))]
+    docs = [json.load(open(p)) for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_likelihood_*.json")))]
     singles = [_run_case(d)[1] for d in docs]
     batch = models.GridBatch()
     repo = TREDsRepo()

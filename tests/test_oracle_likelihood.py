@@ -14,7 +14,7 @@ from tredparse_b200.meta import TREDsRepo
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FILES = sorted(glob.glob(os.path.join(GOLDEN, "likelihood_*.json")))
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "ref_likelihood_*.json")))
 EPS, EPS2 = math.exp(-10), math.exp(-100)
 
 
@@ -44,7 +44,7 @@ def _oracle(doc):
     return lk
 
 
-@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p)[11:-5])
+@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p)[15:-5])
 def test_oracle_reproduces_golden(path):
     doc = json.load(open(path))
     out = doc["outputs"]
@@ -65,7 +65,7 @@ def test_oracle_reproduces_golden(path):
 
 
 def test_reference_readme_call_t001_HD():
-    doc = json.load(open(os.path.join(GOLDEN, "likelihood_t001_HD.json")))
+    doc = json.load(open(os.path.join(GOLDEN, "ref_likelihood_t001_HD.json")))
     lk = _oracle(doc)
     assert [int(x) for x in lk.alleles] == [15, 41]            # README.md:79
     assert round(lk.PP, 6) == 1.0 and lk.label == "risk"
@@ -77,7 +77,7 @@ from oracle.closed_form import closed_form_surface as _closed_form_surface  # no
 
 @pytest.mark.parametrize("name", ["t001_HD", "t002_DM1", "t002_DM1_max1200", "t001_HD_haploid", "t001_HD_nope"])
 def test_dense_oracle_equals_closed_form(name):
-    doc = json.load(open(os.path.join(GOLDEN, "likelihood_{}.json".format(name))))
+    doc = json.load(open(os.path.join(GOLDEN, "ref_likelihood_{}.json".format(name))))
     inp, out = doc["inputs"], doc["outputs"]
     step, w = _models()
     ml = _closed_form_surface(inp, step, w)
@@ -94,7 +94,7 @@ def test_dense_oracle_equals_closed_form(name):
 
 def test_candidate_list_keeps_duplicates_quirk_Q9():
     """extended_range = base + range(...) is a list: spanning keys above max_partial appear twice."""
-    doc = json.load(open(os.path.join(GOLDEN, "likelihood_t002_DM1.json")))
+    doc = json.load(open(os.path.join(GOLDEN, "ref_likelihood_t002_DM1.json")))
     h2 = doc["outputs"]["h2range"]
     assert len(h2) >= len(set(h2))
     assert doc["outputs"]["n_points"] == sum(1 for a in doc["outputs"]["h1range"] for b in h2 if a <= b)
@@ -108,7 +108,7 @@ def test_separability_the_far_region_tables_rely_on(name):
         terms do not depend on h2;
       * h2 >= H2 = max(H1, pe_ref + 1000 - min{target length >= MINPE}): nor does the paired-end term;
       * everywhere: the repeat-only term depends on max(h1-L,1) + max(h2-L,1) only."""
-    doc = json.load(open(os.path.join(GOLDEN, "likelihood_{}.json".format(name))))
+    doc = json.load(open(os.path.join(GOLDEN, "ref_likelihood_{}.json".format(name))))
     inp, out = doc["inputs"], doc["outputs"]
     step, w = _models()
     ml = _closed_form_surface(inp, step, w)

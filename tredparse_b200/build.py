@@ -6,6 +6,7 @@ Build libtredsw.so (the sm_100a CUDA library behind include/tredsw.h) in-tree wi
 nvcc cross-compiles without a GPU; the resulting tredparse_b200/libtredsw.so is git-ignored but
 travels with the source tree to the GPU box.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtredsw.so")
 SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu", "ingest.cpp"]
-HEADERS = ["common.cuh", "sw_sweep.cuh", "internal.cuh", "kde.cuh", os.path.join("..", "..", "include", "tredsw.h")]
+INCLUDE = os.path.abspath(os.path.join(HERE, "..", "include"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -30,8 +31,10 @@ def up_to_date():
     if not os.path.exists(OUT):
         return False
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+    # every file under csrc/ and include/ is a dependency (a header list kept by hand went stale once)
+    deps = [p for p in glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(INCLUDE, "*"))
+            if not p.endswith(".o")] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
 
 
 def build(force=False, verbose=False):

@@ -31,6 +31,9 @@ class Problem:
     __slots__ = ("tred", "readlen", "ploidy", "depth", "reads", "roff", "global_lens", "target_lens",
                  "alleles", "names")
 
+    def name_strings(self):
+        return ["f{}".format(int(x)) for x in self.names]
+
     @property
     def nreads(self):
         return len(self.roff) - 1
@@ -54,8 +57,8 @@ def simulate_problem(tred, alleles, readlen=150, cov_per_hap=15.0, error=0.005, 
     prefix, suffix, motif = encode(tred.prefix), encode(tred.suffix), encode(tred.repeat)
     P = len(motif)
     ref_copy = tred.ref_copy
-    reads, target = [], []
-    for h in alleles:
+    reads, target, names = [], [], []
+    for hap_idx, h in enumerate(alleles):
         rep = np.tile(motif, h)
         nmask = rep == 4                               # 'N' in the motif (GCN loci): any base
         if nmask.any():
@@ -79,8 +82,10 @@ def simulate_problem(tred, alleles, readlen=150, cov_per_hap=15.0, error=0.005, 
         idx = np.arange(readlen)
         r1 = hap[s1[k1][:, None] + idx]
         r2 = _COMP[hap[s2[k2][:, None] + idx]][:, ::-1]
-        for block in (r1, r2):
+        for block, kept in ((r1, k1), (r2, k2)):
             if block.size:
+                # mates share a name: <haplotype>.<fragment> (remove_pairs_of_rept pairs reads by name)
+                names.append(hap_idx * 1000000 + np.nonzero(kept)[0])
                 err = rng.random(block.shape) < error
                 block = np.where(err, rng.integers(0, 4, block.shape), block).astype(np.int8)
                 reads.append(block)
@@ -97,7 +102,7 @@ def simulate_problem(tred, alleles, readlen=150, cov_per_hap=15.0, error=0.005, 
     pr.global_lens = _fragment_lengths(rng, N_GLOBAL).astype(np.int32)
     pr.target_lens = (np.concatenate(target) if target else np.zeros(0)).astype(np.int32)
     pr.depth = float(depth) if depth is not None else cov_per_hap * len(alleles)
-    pr.names = None
+    pr.names = (np.concatenate(names)[order] if names else np.zeros(0, dtype=np.int64)).astype(np.int64)
     return pr
 
 
@@ -113,11 +118,12 @@ def draw_allele(rng, tred, risk_fraction=0.01):
     return int(rng.choice(keys, p=p / p.sum()))
 
 
-def simulate_cohort(repo, names, nsamples, readlen=150, seed=20240000, maxunits=None):
-    """nsamples x len(names) problems, alleles drawn per sample from each locus' allele_freq; gender
-    50/50 (X-linked loci are haploid in males); depth ~ N(35, 5^2)."""
-    problems = []
-    for s in range(nsamples):
+def cohort_specs(repo, names, nsamples, readlen=150, seed=20240000, maxunits=None, first_sample=0):
+    """Specs (keyword arguments of ``simulate_from_spec``) of nsamples x len(names) problems: alleles drawn per
+    sample from each locus' allele_freq; gender 50/50 (X-linked loci are haploid in males); depth ~ N(35, 5^2).
+    Sample ``s`` depends on ``seed + s`` only, so ranks can simulate disjoint sample ranges independently."""
+    specs = []
+    for s in range(first_sample, first_sample + nsamples):
         rng = np.random.default_rng(seed + s)
         male = rng.random() < 0.5
         depth = float(np.clip(rng.normal(35, 5), 15, 60))
@@ -127,6 +133,17 @@ def simulate_cohort(repo, names, nsamples, readlen=150, seed=20240000, maxunits=
             alleles = tuple(sorted(draw_allele(rng, tred) for _ in range(ploidy)))
             if maxunits:
                 alleles = tuple(min(a, maxunits) for a in alleles)
-            problems.append(simulate_problem(tred, alleles, readlen=readlen, cov_per_hap=depth / 2.0,
-                                             seed=0xB200 + 1000 * li + 7919 * s))
-    return problems
+            specs.append({"tred": name, "alleles": [int(a) for a in alleles], "readlen": readlen,
+                          "cov_per_hap": depth / 2.0, "seed": 0xB200 + 1000 * li + 7919 * s, "sample": s})
+    return specs
+
+
+def simulate_from_spec(repo, spec):
+    return simulate_problem(repo[spec["tred"]], tuple(spec["alleles"]), readlen=spec.get("readlen", 150),
+                            cov_per_hap=spec.get("cov_per_hap", 15.0), error=spec.get("error", 0.005),
+                            seed=spec["seed"], depth=spec.get("depth"))
+
+
+def simulate_cohort(repo, names, nsamples, readlen=150, seed=20240000, maxunits=None, first_sample=0):
+    return [simulate_from_spec(repo, sp) for sp in
+            cohort_specs(repo, names, nsamples, readlen, seed, maxunits, first_sample)]
