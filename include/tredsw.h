@@ -77,6 +77,7 @@ uint32_t cigar_int_to_len(uint32_t cigar_int);
 #define TREDSW_NO_BEGIN 4u       /* skip the reverse pass (ref_begin/query_begin = -1), flag==0 of ssw_align */
 #define TREDSW_CIGAR 8u          /* also produce CIGARs (banded_sw restatement) */
 #define TREDSW_FORCE_WORD 16u    /* behave like ssw_init(score_size=1): 16-bit kernel conventions only */
+#define TREDSW_GRID_NO_SURFACE 32u /* tredsw_likelihood_grid with device pointers: `surface` is scratch only */
 
 typedef struct tredsw_ctx tredsw_ctx;
 
@@ -109,7 +110,8 @@ int tredsw_int_pipe_peak(tredsw_ctx *ctx, double *giga_lane_instr_per_s);
 
 /* Tags of a classified read (tredparse/bam_parser.py:157-168). */
 enum { TREDSW_TAG_NONE = 0, TREDSW_TAG_FULL = 1, TREDSW_TAG_PREF = 2, TREDSW_TAG_POST = 3,
-       TREDSW_TAG_REPT = 4, TREDSW_TAG_HANG = 5 };
+       TREDSW_TAG_REPT = 4, TREDSW_TAG_HANG = 5,
+       TREDSW_TAG_REPT_PAIR = 6 /* tredsw_genotype_batch + norepeatpairs: a read removed with its REPT pair */ };
 
 /* Generic batch of independent (query, template) alignments == a batch of
  * ssw_init -> ssw_align(flag=1) -> destroy calls (src/ssw_wrap.py:186-224).
@@ -193,15 +195,30 @@ typedef struct {
     double sum_path;            /* same over pathological points */
     int32_t arg_i1;             /* indices into the h1/h2 candidate lists of the call (Q10) */
     int32_t arg_i2;
-    int32_t n_points;
+    int32_t n_points;           /* -1: the table arena was too small for this surface (call again) */
     int32_t pad;
+    double sum_uniq;            /* sum_all without the second occurrences of duplicated candidates (Q9) = the
+                                   total of the joint posterior dict P_h1h2 (models.py:285,304-317) */
 } tredsw_grid_result;
+
+/* One entry of a sparsified posterior (models.py:304-317: entries below e^-10 are dropped, the rest divided
+ * by the full total).  a / b are alleles in repeat units.  JOINT entries carry the un-normalised weight
+ * exp(ml - max ml); the JOINT_TOTAL entry of the same problem carries their divisor. */
+typedef struct {
+    int32_t problem;
+    int32_t kind;               /* TREDSW_POST_* */
+    int32_t a, b;               /* P_h1: a = h1; P_h2: a = h2; joint: (a, b) = (h1, h2) */
+    double p;
+} tredsw_posterior;
+enum { TREDSW_POST_H1 = 1, TREDSW_POST_H2 = 2, TREDSW_POST_JOINT = 3, TREDSW_POST_JOINT_TOTAL = 4 };
 
 /* Evaluate the log-likelihood surface of `nproblems` problems and reduce it.
  * ipool: int32 pool holding, per problem, the observed spanning / partial keys and counts, the target
  * pair lengths (already wrapped into 0..999 like a numpy index) and the h1 / h2 candidate lists;
  * dpool: double pool holding the KDE pdfs (1000 each) and step PMFs (37 each);
- * surface / marg: output pools (surface may be NULL in host mode to skip copying it back).
+ * surface / marg: output pools.  The reductions do not need the surface: it is materialised (every point,
+ * -inf where h1 > h2) only when asked for — host mode: `surface` non-NULL; device mode: unless
+ * TREDSW_GRID_NO_SURFACE (the buffer is then scratch for the near-allele part of large surfaces).
  * For ploidy 1 the caller passes n_h2 = 1 and the kernel evaluates h2 = h1 (models.py:261). */
 int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem *problems, int32_t nproblems,
                            const int32_t *ipool, int64_t n_ipool, const double *dpool, int64_t n_dpool,
@@ -219,7 +236,8 @@ int tredsw_pe_kde(tredsw_ctx *ctx, const int32_t *lens, const int64_t *off, int3
  * Whole (sample, locus) problems in one call: reads -> Smith-Waterman + classification -> tallies ->
  * candidate ranges -> KDE -> likelihood grid -> call / CI / PP / label, everything on the device.
  * == the body of tred.run's per-locus loop (tredparse/tred.py:225-275) for a whole cohort shard,
- * minus BAM I/O.  Only the CLI defaults repeatpairs=True, clip=False are supported here.
+ * minus BAM I/O.  --useclippedreads: set tredsw_family.clip (per-read max_units, bam_parser.py:154-155);
+ * --norepeatpairs: set tredsw_cohort.norepeatpairs and pass read_name (bam_parser.py:248-249,270-287).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t family;             /* index into families / loci */
@@ -265,8 +283,11 @@ typedef struct {
     int8_t pad_[3];
     int32_t gap_open, gap_extend;
     uint32_t input_flags;       /* TREDSW_IN_* below: compact transfer formats, expanded on the device */
-    int32_t reserved_;
+    int32_t norepeatpairs;      /* 1: drop every read whose name occurs on more than one REPT read of its problem
+                                   (remove_pairs_of_rept, bam_parser.py:270-287; ignored for clip families, :248) */
     int64_t n_bases;            /* total bases in rbuf (= roff[nreads]); required with TREDSW_DEVICE_PTRS + PACKED4 */
+    const int32_t *read_name;   /* nreads name ids (equal id within a problem = same query name); needed only
+                                   with norepeatpairs, may be NULL otherwise */
 } tredsw_cohort;
 
 /* tredsw_cohort.input_flags — halve the host->device bytes of a call; the buffers are expanded into the
@@ -291,6 +312,15 @@ typedef struct {
  * tredsw_classify_reads, [4] grid points evaluated, [5] surface arena overflow (0 = ok). */
 int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
                           int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats);
+
+/* The same, also returning the sparsified posteriors P_h1 / P_h2 / P_h1h2 the reference writes into its JSON
+ * (models.py:292-294,304-317) as one flat list of entries in no particular order.  `post` (host or device
+ * according to `flags`) holds post_cap entries; *n_post (same memory space, 64-bit) receives the number of
+ * entries produced — when it exceeds post_cap the list is truncated and the call should be repeated with a
+ * larger buffer. */
+int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
+                             int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats,
+                             tredsw_posterior *post, int64_t post_cap, int64_t *n_post);
 
 /* ------------------------------------------------------------------------------------------------
  * (C) native BAM ingest (host code, zlib) — replaces the three pysam passes per locus of the reference:

@@ -49,7 +49,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(SAlign) == 40 and SAlign.cigar.offset == 24
     assert ctypes.sizeof(_lib.Family) == 128 == _lib.FAMILY_DTYPE.itemsize
     assert ctypes.sizeof(_lib.GridProblem) == 16 * 4 + 5 * 8 + 10 * 8 == _lib.GRID_PROBLEM_DTYPE.itemsize
-    assert ctypes.sizeof(_lib.GridResult) == 40 == _lib.GRID_RESULT_DTYPE.itemsize
+    assert ctypes.sizeof(_lib.GridResult) == 48 == _lib.GRID_RESULT_DTYPE.itemsize
+    assert _lib.POSTERIOR_DTYPE.itemsize == 24
     assert cohort.PROBLEM_DTYPE.itemsize == 40 and cohort.LOCUS_DTYPE.itemsize == 32
     assert cohort.CALL_DTYPE.itemsize == 64
     assert ctypes.sizeof(cohort.Cohort) % 8 == 0
@@ -90,3 +91,37 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_python_mirrors_equal_the_compiled_header(tmp_path):
+    """sizeof / offsetof as gcc sees include/tredsw.h == the ctypes / numpy mirrors the host side marshals with."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "tredsw.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(s_align), sizeof(tredsw_family), sizeof(tredsw_grid_problem),
+           sizeof(tredsw_grid_result), sizeof(tredsw_posterior), sizeof(tredsw_problem), sizeof(tredsw_locus),
+           sizeof(tredsw_cohort), sizeof(tredsw_call));
+    printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(tredsw_cohort, families), offsetof(tredsw_cohort, stutter_w),
+           offsetof(tredsw_cohort, input_flags), offsetof(tredsw_cohort, norepeatpairs), offsetof(tredsw_cohort, n_bases),
+           offsetof(tredsw_cohort, read_name));
+    printf("%zu %zu\\n", offsetof(tredsw_grid_result, sum_uniq), offsetof(tredsw_posterior, p));
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    lines = subprocess.check_output([str(exe)]).decode().split("\n")
+    sizes = [int(x) for x in lines[0].split()]
+    C = cohort.Cohort
+    assert sizes == [40, ctypes.sizeof(_lib.Family), ctypes.sizeof(_lib.GridProblem), ctypes.sizeof(_lib.GridResult),
+                     _lib.POSTERIOR_DTYPE.itemsize, cohort.PROBLEM_DTYPE.itemsize, cohort.LOCUS_DTYPE.itemsize,
+                     ctypes.sizeof(C), cohort.CALL_DTYPE.itemsize]
+    assert [int(x) for x in lines[1].split()] == [C.families.offset, C.stutter_w.offset, C.input_flags.offset,
+                                                  C.norepeatpairs.offset, C.n_bases.offset, C.read_name.offset]
+    assert [int(x) for x in lines[2].split()] == [_lib.GRID_RESULT_DTYPE.fields["sum_uniq"][1],
+                                                  _lib.POSTERIOR_DTYPE.fields["p"][1]]

@@ -170,15 +170,38 @@ def _materialise(docs):
     return problems
 
 
-@pytest.mark.parametrize("group", ["cohort", "sweep", "listed", "readlen250"])
+TAGNAME = {1: "FULL", 2: "PREF", 3: "POST", 4: "REPT"}
+
+
+@pytest.mark.parametrize("group", ["cohort", "sweep", "listed", "readlen250", "clip", "norepeatpairs"])
 def test_cohort_pipeline_equals_reference_on_synthetic_problems(group):
     """BASELINE configs[2] / configs[3] / configs[4]-style problems: the cohort shard of 4 samples x 30 loci, the
-    paper's "20/h" sweep (h = 5..300) at HD, the listed HD / DM1 / FXS pairs incl. full expansions, 250-bp reads."""
+    paper's "20/h" sweep (h = 5..300) at HD, the listed HD / DM1 / FXS pairs incl. full expansions, 250-bp reads,
+    and the non-default flags --useclippedreads (ragged read lengths) / --norepeatpairs on the device pipeline:
+    evidence strings, per-read details, call, CI, PP, lik, label and the sparse posteriors P_h1 / P_h2 / P_h1h2
+    equal the reference's BamParser.parse + IntegratedCaller.call."""
     from tredparse_b200 import cohort
     docs = [d for d in _load_problems() if d["spec"]["group"] == group]
     assert docs
     for readlen in sorted({d["spec"]["readlen"] for d in docs}):
         sub = [d for d in docs if d["spec"]["readlen"] == readlen]
         problems = _materialise(sub)
-        out = cohort.CohortBatch(problems).run_host(want_hist=True, want_reads=True, packed=True)
-        _check_against_reference(sub, problems, out)
+        batch = cohort.CohortBatch(problems, clip=(group == "clip"), repeatpairs=(group != "norepeatpairs"))
+        out = batch.run_host(want_hist=True, want_reads=True, packed=True, want_post=True)
+        post = cohort.posteriors(out["post"], len(problems))
+        r0 = [0]
+
+        def extra(i, d, pr, c):
+            rows = out["reads"][r0[0]:r0[0] + pr.nreads]
+            r0[0] += pr.nreads
+            names = pr.name_strings()
+            details = [[TAGNAME[int(t)], int(h), names[k]] for k, (t, h) in enumerate(rows[:, :2]) if int(t) in TAGNAME]
+            assert details == d["ref"]["details"], d["spec"]
+            hang = int(np.sum(rows[:, 0] == 5))
+            kept = len(details) + hang + int(np.sum(rows[:, 0] == 6))
+            assert kept == d["ref"]["hang"], d["spec"]          # counts["HANG"] counts every classified read
+            for name in ("P_h1", "P_h2", "P_h1h2"):
+                close(post[i][name], d["ref"][name], RTOL, "{} {}".format(d["spec"], name))
+        _check_against_reference(sub, problems, out, extra)
+        if group == "norepeatpairs":
+            assert any(int(np.sum(out["reads"][:, 0] == 6)) > 0 for _ in [0]), "no REPT pair was removed: the case is vacuous"

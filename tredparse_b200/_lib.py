@@ -26,7 +26,7 @@ EXPORTS = [
     "tredsw_version", "tredsw_device_count", "tredsw_last_error", "tredsw_create", "tredsw_destroy",
     "tredsw_synchronize", "tredsw_sm_count", "tredsw_launch_count", "tredsw_enable_timing",
     "tredsw_get_timing", "tredsw_get_timeline", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
-    "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch",
+    "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch", "tredsw_genotype_batch_ex",
     # native BAM ingest
     "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
     "tredsw_bam_region_depth", "tredsw_bam_read_length", "tredsw_bam_clone", "tredsw_bam_inflate_stats", "tredsw_inflate_raw",
@@ -60,7 +60,7 @@ class GridResult(ctypes.Structure):
     """tredsw_grid_result (include/tredsw.h)"""
     _fields_ = [("max_ml", ctypes.c_double), ("sum_all", ctypes.c_double), ("sum_path", ctypes.c_double),
                 ("arg_i1", ctypes.c_int32), ("arg_i2", ctypes.c_int32), ("n_points", ctypes.c_int32),
-                ("pad", ctypes.c_int32)]
+                ("pad", ctypes.c_int32), ("sum_uniq", ctypes.c_double)]
 
 
 GRID_PROBLEM_DTYPE = np.dtype(
@@ -71,7 +71,10 @@ GRID_PROBLEM_DTYPE = np.dtype(
     [(n, "<i8") for n in ("off_span", "off_part", "off_target", "off_h1", "off_h2", "off_pdf",
                           "off_step", "off_surface", "off_ph1", "off_ph2")])
 GRID_RESULT_DTYPE = np.dtype([("max_ml", "<f8"), ("sum_all", "<f8"), ("sum_path", "<f8"),
-                              ("arg_i1", "<i4"), ("arg_i2", "<i4"), ("n_points", "<i4"), ("pad", "<i4")])
+                              ("arg_i1", "<i4"), ("arg_i2", "<i4"), ("n_points", "<i4"), ("pad", "<i4"),
+                              ("sum_uniq", "<f8")])
+POSTERIOR_DTYPE = np.dtype([("problem", "<i4"), ("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("p", "<f8")])
+POST_H1, POST_H2, POST_JOINT, POST_JOINT_TOTAL = 1, 2, 3, 4
 FAMILY_DTYPE = np.dtype([("prefix", "i1", 32), ("suffix", "i1", 32), ("repeat", "i1", 32),
                          ("prefix_len", "<i4"), ("suffix_len", "<i4"), ("period", "<i4"),
                          ("max_units", "<i4"), ("clip", "<i4"), ("reserved", "<i4", 3)])

@@ -36,8 +36,8 @@ class Cohort(ctypes.Structure):
                 ("step_pmf", ctypes.c_void_p), ("stutter_w", ctypes.c_double * 5), ("gc", ctypes.c_double),
                 ("score", ctypes.c_double), ("maxinsert", ctypes.c_int32), ("fullsearch", ctypes.c_int32),
                 ("mat25", ctypes.c_int8 * 25), ("pad_", ctypes.c_int8 * 3), ("gap_open", ctypes.c_int32),
-                ("gap_extend", ctypes.c_int32), ("input_flags", ctypes.c_uint32), ("reserved_", ctypes.c_int32),
-                ("n_bases", ctypes.c_int64)]
+                ("gap_extend", ctypes.c_int32), ("input_flags", ctypes.c_uint32), ("norepeatpairs", ctypes.c_int32),
+                ("n_bases", ctypes.c_int64), ("read_name", ctypes.c_void_p)]
 
 
 IN_READS_PACKED4, IN_PE_LENS_I16 = 1, 2          # tredsw_cohort.input_flags
@@ -52,6 +52,9 @@ def _bind(lib):
         lib.tredsw_genotype_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(Cohort), ctypes.c_uint32,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int32, ctypes.c_void_p]
+        lib.tredsw_genotype_batch_ex.restype = ctypes.c_int
+        lib.tredsw_genotype_batch_ex.argtypes = lib.tredsw_genotype_batch.argtypes + [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         lib._cohort_bound = True
 
 
@@ -60,15 +63,19 @@ class CohortBatch:
     global_lens, target_lens — see simulate.Problem)."""
 
     def __init__(self, problems, maxinsert=300, fullsearch=False, score=1.0, gc=.68, match=1, mismatch=5,
-                 gap_open=7, gap_extend=2):
+                 gap_open=7, gap_extend=2, clip=False, repeatpairs=True):
+        """clip / repeatpairs: --useclippedreads / not --norepeatpairs (tred.py:75-81; note that InputParams
+        defaults repeatpairs to False while the CLI passes True).  Without repeatpairs every problem needs
+        ``names`` (read names or ids: mates share one)."""
         self.maxinsert, self.fullsearch = maxinsert, fullsearch
+        self.clip, self.repeatpairs = bool(clip), bool(repeatpairs)
         self.score, self.gc = score, gc
         self.match, self.mismatch, self.gap_open, self.gap_extend = match, mismatch, gap_open, gap_extend
         fam_index, fams, loci, step_rows = {}, [], [], []
         step = StepModel()
         n = len(problems)
         P = np.zeros(n, dtype=PROBLEM_DTYPE)
-        rbufs, roffs, rprob, pe = [], [np.zeros(1, dtype=np.int64)], [], []
+        rbufs, roffs, rprob, pe, rname = [], [np.zeros(1, dtype=np.int64)], [], [], []
         rbase, pebase, max_len = 0, 0, 1
         for i, pr in enumerate(problems):
             t = pr.tred
@@ -76,7 +83,7 @@ class CohortBatch:
             if key not in fam_index:
                 period = len(t.repeat)
                 fam_index[key] = len(fams)
-                fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, -(-pr.readlen // period)))
+                fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, -(-pr.readlen // period), clip=self.clip))
                 L = np.zeros(1, dtype=LOCUS_DTYPE)
                 ref = t.repeat_end - t.repeat_start + 1
                 L["period"], L["readlen"], L["pe_ref"], L["pe_minpe"] = period, pr.readlen, ref, ref - 1 + 2 * 9 + 2
@@ -92,6 +99,13 @@ class CohortBatch:
             roffs.append(roff[1:] + rbase)
             rbase += int(roff[-1])
             rprob.append(np.full(nr, i, dtype=np.int32))
+            if not self.repeatpairs and not self.clip:
+                names = getattr(pr, "names", None)
+                if names is None or len(names) != nr:
+                    raise ValueError("repeatpairs=False needs the read names of every problem")
+                ids = {}
+                rname.append(np.array([ids.setdefault(x, len(ids)) for x in
+                                       (names.tolist() if hasattr(names, "tolist") else names)], dtype=np.int32))
             if nr:
                 max_len = max(max_len, int(np.max(np.diff(roff))))
             g = np.asarray(pr.global_lens, dtype=np.int32)
@@ -105,6 +119,7 @@ class CohortBatch:
         self.roff = np.ascontiguousarray(np.concatenate(roffs), dtype=np.int64)
         self.read_problem = np.ascontiguousarray(np.concatenate(rprob) if rprob else np.zeros(0, np.int32), dtype=np.int32)
         self.pe_lens = np.ascontiguousarray(np.concatenate(pe) if pe else np.zeros(0, np.int32), dtype=np.int32)
+        self.read_name = np.ascontiguousarray(np.concatenate(rname), dtype=np.int32) if rname else None
         self.nreads = len(self.roff) - 1
         self.max_read_len = max_len
         self.families = np.ascontiguousarray(np.concatenate(fams))
@@ -132,7 +147,7 @@ class CohortBatch:
         return self
 
     # ---- descriptor -----------------------------------------------------------------------------------
-    def _descriptor(self, rbuf, roff, rprob, problems, pe_lens, input_flags=0):
+    def _descriptor(self, rbuf, roff, rprob, problems, pe_lens, input_flags=0, read_name=None):
         c = Cohort()
         c.input_flags, c.n_bases = input_flags, int(len(self.rbuf))
         c.rbuf, c.roff, c.read_problem, c.problems, c.pe_lens = rbuf, roff, rprob, problems, pe_lens
@@ -147,10 +162,15 @@ class CohortBatch:
         for i in range(25):
             c.mat25[i] = int(mat[i])
         c.gap_open, c.gap_extend = self.gap_open, self.gap_extend
+        if self.read_name is not None:
+            c.norepeatpairs = 1
+            c.read_name = read_name if read_name is not None else self.read_name.ctypes.data
         return c
 
     # ---- host buffers through the C ABI (H2D + kernels + D2H inside the call) -------------------------
-    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False, packed=False):
+    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False, packed=False, want_post=False):
+        """want_post: also return the sparsified posteriors (``posteriors()`` turns them into the reference's
+        P_h1 / P_h2 / P_h1h2 dicts)."""
         ctx = ctx or _lib.default_context()
         _bind(ctx.lib)
         calls = np.zeros(self.nproblems, dtype=CALL_DTYPE)
@@ -166,9 +186,16 @@ class CohortBatch:
             rbuf, pe, flags_in = self.rbuf, self.pe_lens, 0
         c = self._descriptor(rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
                              self.problems.ctypes.data, pe.ctypes.data, flags_in)
-        for attempt in range(2):
-            rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), 0, _lib.ptr(calls), _lib.ptr(read_out),
-                                               _lib.ptr(hist), self.hist_units, _lib.ptr(stats))
+        post_cap = max(4096, 64 * self.nproblems) if want_post else 0
+        n_post = np.zeros(1, dtype=np.int64)
+        for attempt in range(4):
+            post = np.zeros(post_cap, dtype=_lib.POSTERIOR_DTYPE) if want_post else None
+            rc = ctx.lib.tredsw_genotype_batch_ex(ctx.handle, ctypes.byref(c), 0, _lib.ptr(calls), _lib.ptr(read_out),
+                                                  _lib.ptr(hist), self.hist_units, _lib.ptr(stats), _lib.ptr(post),
+                                                  post_cap, _lib.ptr(n_post) if want_post else None)
+            if rc == 0 and want_post and int(n_post[0]) > post_cap:
+                post_cap = int(n_post[0]) + 1024          # the entry list was truncated: once more with room for it
+                continue
             if rc == 0 or "arena overflow" not in _lib.last_error():
                 break
         _lib.check(rc, "tredsw_genotype_batch")
@@ -182,6 +209,8 @@ class CohortBatch:
             out["hist"] = hist
         if want_stats:
             out["stats"] = stats
+        if want_post:
+            out["post"] = post[:int(n_post[0])]
         return out
 
     # ---- device-resident buffers (torch = memory + stream plumbing only) ------------------------------
@@ -195,6 +224,8 @@ class CohortBatch:
             "pe_lens": t(self.pe_lens, np.int32),
             "calls": torch.zeros(self.nproblems * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev),
         }
+        if self.read_name is not None:
+            self._dev["read_name"] = t(self.read_name, np.int32)
         return self
 
     def run_device(self, ctx):
@@ -202,13 +233,19 @@ class CohortBatch:
         _bind(ctx.lib)
         d = self._dev
         c = self._descriptor(d["rbuf"].data_ptr(), d["roff"].data_ptr(), d["rprob"].data_ptr(),
-                             d["problems"].data_ptr(), d["pe_lens"].data_ptr())
+                             d["problems"].data_ptr(), d["pe_lens"].data_ptr(),
+                             read_name=d["read_name"].data_ptr() if "read_name" in d else None)
         rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), _lib.DEVICE_PTRS, d["calls"].data_ptr(),
                                            None, None, 0, None)
         _lib.check(rc, "tredsw_genotype_batch")
 
     def calls_from_device(self):
-        return self._dev["calls"].cpu().numpy().view(CALL_DTYPE)
+        calls = self._dev["calls"].cpu().numpy().view(CALL_DTYPE)
+        if len(calls) and int(calls["n_points"].min()) < 0:
+            # a likelihood arena was too small for some problem of this batch (the library has grown it on the
+            # way when it could see the counters); the caller re-runs the batch
+            raise _lib.TredswError("likelihood arena overflow in a device-resident batch; run it again")
+        return calls
 
 
 class HostPipeline:
@@ -260,6 +297,22 @@ class HostPipeline:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def posteriors(post, nproblems):
+    """Entry list of tredsw_genotype_batch_ex -> per problem {"P_h1": {...}, "P_h2": {...}, "P_h1h2": {...}} with the
+    reference's keys ("15", "15,41") and values (models.py:304-317)."""
+    out = [{"P_h1": {}, "P_h2": {}, "P_h1h2": {}} for _ in range(nproblems)]
+    totals = {int(e["problem"]): float(e["p"]) for e in post[post["kind"] == _lib.POST_JOINT_TOTAL]}
+    for e in post:
+        k, p = int(e["kind"]), int(e["problem"])
+        if k == _lib.POST_H1:
+            out[p]["P_h1"][str(int(e["a"]))] = float(e["p"])
+        elif k == _lib.POST_H2:
+            out[p]["P_h2"][str(int(e["a"]))] = float(e["p"])
+        elif k == _lib.POST_JOINT:
+            out[p]["P_h1h2"]["{},{}".format(int(e["a"]), int(e["b"]))] = float(e["p"]) / totals[p]
+    return out
 
 
 def decode_call(call, period=None):

@@ -39,6 +39,14 @@ struct CohortDev {
     long long surface_cap;
     int maxinsert, fullsearch;
     double w0, w1, w2, w3, w4, gc, score;
+    const int32_t *read_name;    // name ids (norepeatpairs) or NULL
+    int32_t *read_rw;            // read_out, writable (REPT-pair removal rewrites tags)
+    int8_t *drop;                // nreads flags: read removed with its REPT pair
+    int norepeatpairs;
+    tredsw_posterior *post;      // sparse posterior entries (optional)
+    long long post_cap;
+    unsigned long long *post_cursor;
+    double small_value;
 };
 
 __global__ void read_family_kernel(const int32_t *read_problem, const tredsw_problem *problems, int nreads,
@@ -63,13 +71,38 @@ __global__ void widen_i16_kernel(const int16_t *in, int64_t n, int32_t *out) {
     if (i < n) out[i] = (int32_t)in[i];
 }
 
+// remove_pairs_of_rept (bam_parser.py:270-287): a name carried by more than one REPT read of a problem is
+// removed from the evidence altogether — every read of that name that made it into `details` (any tag but HANG).
+// Reads of a problem are contiguous, so each read scans its problem's neighbourhood (~10^2 reads).  Clip families
+// skip this (bam_parser.py:248: `if not (self.repeatpairs or self.clip)`).
+__global__ void rept_pairs_mark_kernel(CohortDev c) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c.nreads) return;
+    c.drop[r] = 0;
+    const int tag = c.read_out[(int64_t)r * 8];
+    const int p = c.read_problem[r];
+    if (tag <= 0 || tag == TREDSW_TAG_HANG || p < 0 || p >= c.nproblems) return;
+    if (c.families[c.problems[p].family].clip) return;
+    const int name = c.read_name[r];
+    int n_rept = 0;
+    for (int j = r; j >= 0 && c.read_problem[j] == p; --j)
+        if (c.read_name[j] == name && c.read_out[(int64_t)j * 8] == TREDSW_TAG_REPT) ++n_rept;
+    for (int j = r + 1; j < c.nreads && c.read_problem[j] == p; ++j)
+        if (c.read_name[j] == name && c.read_out[(int64_t)j * 8] == TREDSW_TAG_REPT) ++n_rept;
+    if (n_rept > 1) c.drop[r] = 1;
+}
+__global__ void rept_pairs_apply_kernel(CohortDev c) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < c.nreads && c.drop[r]) c.read_rw[(int64_t)r * 8] = TREDSW_TAG_REPT_PAIR;
+}
+
 __global__ void tally_kernel(CohortDev c) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= c.nreads) return;
     const int32_t *o = c.read_out + (int64_t)r * 8;
     const int tag = o[0], h = o[1];
     const int p = c.read_problem[r];
-    if (p < 0 || p >= c.nproblems || tag <= 0 || tag == TREDSW_TAG_HANG || h < 0 || h > c.HU) return;
+    if (p < 0 || p >= c.nproblems || tag <= 0 || tag == TREDSW_TAG_HANG || tag == TREDSW_TAG_REPT_PAIR || h < 0 || h > c.HU) return;
     // PREF and POST share one histogram (bam_parser.py:77)
     const int which = tag == TREDSW_TAG_FULL ? 0 : (tag == TREDSW_TAG_REPT ? 2 : 1);
     atomicAdd(&c.hist[((int64_t)p * 3 + which) * (c.HU + 1) + h], 1);
@@ -166,13 +199,16 @@ __global__ void __launch_bounds__(KDE_THREADS) cohort_kde_kernel(CohortDev c, co
 // 95% interval over the merged, sorted keys of a marginal (models.py:319-340).  The candidate list is a
 // sorted base part [0, nb) followed by an ascending extension [nb, n); equal keys are summed (the
 // reference's defaultdict); entries failing `used` never became keys.
+// With `c.post` the sparsified marginal (models.py:304-317: entries >= e^-10, divided by the full total) is
+// emitted on the way — the merge walks every key, the interval stops moving once it is found.
 template <class Used>
-__device__ void ci_of(const int32_t *hs, const double *w, int n, int nb, Used used, int &lo, int &hi) {
+__device__ void ci_of(const CohortDev &c, int p, int kind, int period, const int32_t *hs, const double *w, int n, int nb,
+                      Used used, int &lo, int &hi) {
     double total = 0.0;
     for (int i = 0; i < n; ++i) if (used(hs[i])) total += w[i];
     int a = 0, b = nb;
     double cum = 0.0;
-    bool in_range = false, any = false;
+    bool in_range = false, any = false, done = false;
     int k = 0;
     lo = 0; hi = 0;
     while (a < nb || b < n) {
@@ -182,11 +218,20 @@ __device__ void ci_of(const int32_t *hs, const double *w, int n, int nb, Used us
         while (a < nb && hs[a] == key) { v += w[a]; ++a; }
         while (b < n && hs[b] == key) { v += w[b]; ++b; }
         if (!used(key)) continue;
+        if (c.post && v >= c.small_value) {
+            const unsigned long long at = atomicAdd(c.post_cursor, 1ULL);
+            if ((long long)at < c.post_cap) {
+                tredsw_posterior e;
+                e.problem = p; e.kind = kind; e.a = key / period; e.b = 0; e.p = v / total;
+                c.post[at] = e;
+            }
+        }
+        if (done) continue;
         any = true;
         k = key;
         cum += v;
         if (!in_range && cum > .025 * total) { in_range = true; lo = key; }
-        if (cum > .975 * total) break;
+        if (cum > .975 * total) { done = true; if (!c.post) break; }
     }
     hi = any ? k : 0;
 }
@@ -203,10 +248,10 @@ __global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tred
     for (int k = 0; k <= c.HU; ++k) { fdp += hf[k]; pdp += hf[(c.HU + 1) + k]; }
     out.fdp = fdp; out.pdp = pdp; out.rdp = g.n_rept; out.run_pe = g.run_pe;
     int a1 = -1, a2 = -1;
-    if (g.n_h1 == 0 || res[p].n_points == 0) {
+    if (g.n_h1 == 0 || res[p].n_points <= 0) {
         out.allele1 = out.allele2 = -1;
         out.ci[0] = out.ci[1] = out.ci[2] = out.ci[3] = -1;
-        out.pp = -1; out.lik = -1; out.n_points = (g.n_h2 < 0) ? -1 : 0;   // -1: surface arena overflow
+        out.pp = -1; out.lik = -1; out.n_points = (g.n_h2 < 0 || res[p].n_points < 0) ? -1 : 0;   // -1: an arena overflowed
     } else {
         const tredsw_grid_result r = res[p];
         const int32_t *h1s = c.ipool + g.off_h1, *h2s = c.ipool + g.off_h2;
@@ -219,14 +264,23 @@ __global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tred
         const double *ph1 = c.marg + g.off_ph1, *ph2 = c.marg + g.off_ph2;
         int lo1, hi1, lo2, hi2;
         if (g.ploidy == 1) {
-            ci_of(h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo1, hi1);
+            ci_of(c, p, TREDSW_POST_H1, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo1, hi1);
+            if (c.post) ci_of(c, p, TREDSW_POST_H2, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo2, hi2);
             lo2 = lo1; hi2 = hi1;
         } else {
             int mx2 = h2s[0], mn1 = h1s[0];
             for (int i = 1; i < g.n_h2; ++i) mx2 = max(mx2, h2s[i]);
             for (int i = 1; i < g.n_h1; ++i) mn1 = min(mn1, h1s[i]);
-            ci_of(h1s, ph1, g.n_h1, c.nbase[2 * p], [mx2](int h) { return h <= mx2; }, lo1, hi1);
-            ci_of(h2s, ph2, g.n_h2, c.nbase[2 * p + 1], [mn1](int h) { return h >= mn1; }, lo2, hi2);
+            ci_of(c, p, TREDSW_POST_H1, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [mx2](int h) { return h <= mx2; }, lo1, hi1);
+            ci_of(c, p, TREDSW_POST_H2, g.period, h2s, ph2, g.n_h2, c.nbase[2 * p + 1], [mn1](int h) { return h >= mn1; }, lo2, hi2);
+        }
+        if (c.post) {                                    // divisor of this problem's joint entries
+            const unsigned long long at = atomicAdd(c.post_cursor, 1ULL);
+            if ((long long)at < c.post_cap) {
+                tredsw_posterior e;
+                e.problem = p; e.kind = TREDSW_POST_JOINT_TOTAL; e.a = 0; e.b = 0; e.p = r.sum_uniq;
+                c.post[at] = e;
+            }
         }
         out.ci[0] = lo1 / g.period; out.ci[1] = hi1 / g.period; out.ci[2] = lo2 / g.period; out.ci[3] = hi2 / g.period;
         atomicAdd(&c.counters[2], (unsigned long long)r.n_points);
@@ -250,7 +304,15 @@ __global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tred
 
 extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
                                      int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats) {
+    return tredsw_genotype_batch_ex(ctx, c, flags, calls, read_out, hist, hist_units, stats, nullptr, 0, nullptr);
+}
+
+extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c, uint32_t flags, tredsw_call *calls,
+                                        int32_t *read_out, int32_t *hist, int32_t hist_units, int64_t *stats,
+                                        tredsw_posterior *post, int64_t post_cap, int64_t *n_post) {
     if (!ctx || !c || !calls) { tredsw_set_error("null argument"); return TREDSW_ERR_ARG; }
+    if (post && (post_cap <= 0 || !n_post)) { tredsw_set_error("post needs post_cap > 0 and n_post"); return TREDSW_ERR_ARG; }
+    if (c->norepeatpairs && c->nreads > 0 && !c->read_name) { tredsw_set_error("norepeatpairs needs read_name"); return TREDSW_ERR_ARG; }
     if (c->nproblems <= 0 || c->nreads < 0 || c->nfamilies <= 0 || !c->families || !c->loci || !c->step_pmf ||
         c->max_read_len <= 0 || c->maxinsert < 1) { tredsw_set_error("bad cohort descriptor"); return TREDSW_ERR_ARG; }
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -263,7 +325,6 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     for (int f = 0; f < nf; ++f) {
         if (c->families[f].max_units > max_u) max_u = c->families[f].max_units;
         if (c->loci[f].period < min_period) min_period = c->loci[f].period;
-        if (c->families[f].clip) { tredsw_set_error("clip mode is not supported by tredsw_genotype_batch"); return TREDSW_ERR_UNSUPPORTED; }
     }
     const int HU = max_u;
     if (hist && hist_units != HU) { tredsw_set_error("hist_units must equal the largest max_units (%d)", HU); return TREDSW_ERR_ARG; }
@@ -273,6 +334,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     // ---- inputs ------------------------------------------------------------------------------------
     const int8_t *d_rbuf = c->rbuf; const int64_t *d_roff = c->roff; const int32_t *d_rp = c->read_problem;
     const tredsw_problem *d_prob = c->problems; const int32_t *d_pe = c->pe_lens;
+    const int32_t *d_rname = c->read_name;
     const tredsw_family *d_fam; const tredsw_locus *d_loci;
     const bool packed4 = (c->input_flags & TREDSW_IN_READS_PACKED4) != 0, pe16 = (c->input_flags & TREDSW_IN_PE_LENS_I16) != 0;
     if (dev && packed4 && c->n_bases <= 0 && nr > 0) { tredsw_set_error("n_bases is required for packed reads in device memory"); return TREDSW_ERR_ARG; }
@@ -297,6 +359,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
             if (!packed4 && (rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
             if ((rc = stage_in(ctx, ctx->d_qoff, c->roff, (size_t)nr + 1, 0u, &d_roff))) return rc;
             if ((rc = stage_in(ctx, ctx->d_qidx, c->read_problem, (size_t)nr, 0u, &d_rp))) return rc;
+            if (c->norepeatpairs && (rc = stage_in(ctx, ctx->d_tidx, c->read_name, (size_t)nr, 0u, &d_rname))) return rc;
         }
         if ((rc = stage_in(ctx, ctx->d_prob, c->problems, (size_t)np_, 0u, &d_prob))) return rc;
     }
@@ -375,7 +438,7 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     const size_t o_gp = carve(sz_gp), o_nb = carve((size_t)np_ * 2 * sizeof(int32_t)), o_hist = carve(sz_hist),
                  o_rf = carve((size_t)(nr + 1) * sizeof(int32_t)), o_ro = carve((size_t)(nr + 1) * 8 * sizeof(int32_t)),
                  o_calls = carve((size_t)np_ * sizeof(tredsw_call)), o_cnt = carve(8 * sizeof(unsigned long long)),
-                 o_stats = carve(4 * sizeof(unsigned long long));
+                 o_stats = carve(4 * sizeof(unsigned long long)), o_drop = carve((size_t)nr + 1);
     if ((rc = ctx->d_misc.ensure(off))) return rc;
     unsigned char *mb = ctx->d_misc.as<unsigned char>();
     if ((rc = ctx->d_work.ensure(((size_t)4 * nf + 2 + nr + 1) * sizeof(int32_t)))) return rc;
@@ -393,9 +456,19 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     cd.maxinsert = c->maxinsert; cd.fullsearch = c->fullsearch;
     cd.w0 = c->stutter_w[0]; cd.w1 = c->stutter_w[1]; cd.w2 = c->stutter_w[2]; cd.w3 = c->stutter_w[3]; cd.w4 = c->stutter_w[4];
     cd.gc = c->gc; cd.score = c->score;
+    cd.small_value = exp(-10.0);
+    cd.norepeatpairs = c->norepeatpairs; cd.read_name = d_rname;
+    cd.drop = reinterpret_cast<int8_t *>(mb + o_drop);
+    // sparse posteriors: device arena of post_cap entries; counters[3] is its cursor
+    tredsw_posterior *d_post = nullptr;
+    if (post) {
+        if (dev) d_post = post;
+        else { if ((rc = ctx->d_cigar.ensure((size_t)post_cap * sizeof(tredsw_posterior)))) return rc; d_post = ctx->d_cigar.as<tredsw_posterior>(); }
+    }
+    cd.post = d_post; cd.post_cap = post_cap; cd.post_cursor = cd.counters + 3;
     int32_t *d_read_family = reinterpret_cast<int32_t *>(mb + o_rf);
     int32_t *d_read_out = (dev && read_out) ? read_out : reinterpret_cast<int32_t *>(mb + o_ro);
-    cd.read_out = d_read_out;
+    cd.read_out = d_read_out; cd.read_rw = d_read_out;
     tredsw_call *d_calls = dev ? calls : reinterpret_cast<tredsw_call *>(mb + o_calls);
     unsigned long long *d_stats = reinterpret_cast<unsigned long long *>(mb + o_stats);
     CUDA_TRY(cudaMemsetAsync(cd.hist, 0, sz_hist, ctx->stream));
@@ -410,6 +483,11 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
         if ((rc = tredsw_internal_classify(ctx, d_rbuf, d_roff, nr, d_read_family, d_fam, c->families, nf,
                                            c->max_read_len, c->mat25, c->gap_open, c->gap_extend,
                                            ctx->d_work.as<int32_t>(), d_read_out, stats ? d_stats : nullptr))) return rc;
+        if (c->norepeatpairs) {
+            rept_pairs_mark_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
+            rept_pairs_apply_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
+            ctx->launches += 2;
+        }
         tally_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
     }
     plan_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd);
@@ -420,8 +498,10 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     ctx->mark(5);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 3;
+    unsigned long long *d_tab_flag = nullptr;
     if ((rc = tredsw_internal_grid(ctx, cd.gp, np_, d_ipool, d_dpool, ctx->d_surface.as<double>(), cd.marg,
-                                   ctx->d_res.as<tredsw_grid_result>(), c->fullsearch ? per_problem : 1024))) return rc;
+                                   ctx->d_res.as<tredsw_grid_result>(), c->fullsearch ? per_problem : 4LL * HL, 0,
+                                   d_post, post_cap, cd.post_cursor, &d_tab_flag))) return rc;
     finalize_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
     CUDA_TRY(cudaGetLastError());
     ctx->mark(7);
@@ -439,9 +519,10 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     // calls and counters come back through the page-locked staging buffer (see PinnedBuf); the optional bulky
     // per-read / histogram outputs go straight to the caller's memory
     const size_t b_calls = ((size_t)np_ * sizeof(tredsw_call) + 255) & ~(size_t)255;
-    if ((rc = ctx->h_out.ensure(b_calls + 12 * sizeof(unsigned long long)))) return rc;
+    if ((rc = ctx->h_out.ensure(b_calls + 14 * sizeof(unsigned long long)))) return rc;
     unsigned char *hout = ctx->h_out.as<unsigned char>();
-    unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(hout + b_calls), *h_st = h_cnt + 8;
+    unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(hout + b_calls), *h_st = h_cnt + 8, *h_tab = h_cnt + 12;
+    if (dev && post) CUDA_TRY(cudaMemcpyAsync(n_post, cd.post_cursor, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     if (!dev) {
         CUDA_TRY(cudaMemcpyAsync(hout, d_calls, (size_t)np_ * sizeof(tredsw_call), cudaMemcpyDeviceToHost, ctx->stream));
         if (read_out && nr > 0)
@@ -452,8 +533,17 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
     if (stats || !dev) {
         CUDA_TRY(cudaMemcpyAsync(h_cnt, cd.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         if (stats) CUDA_TRY(cudaMemcpyAsync(h_st, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_tab, d_tab_flag, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (!dev) memcpy(calls, hout, (size_t)np_ * sizeof(tredsw_call));
+        if (!dev && post) {
+            *n_post = (int64_t)h_cnt[3];
+            const size_t n = (size_t)(h_cnt[3] < (unsigned long long)post_cap ? h_cnt[3] : (unsigned long long)post_cap);
+            if (n) {
+                CUDA_TRY(cudaMemcpyAsync(post, d_post, n * sizeof(tredsw_posterior), cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            }
+        }
         if (stats) {
             for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h_st[i];
             stats[4] = (int64_t)h_cnt[2]; stats[5] = (int64_t)h_cnt[1]; stats[6] = (int64_t)h_cnt[0]; stats[7] = 0;
@@ -462,6 +552,12 @@ extern "C" int tredsw_genotype_batch(tredsw_ctx *ctx, const tredsw_cohort *c, ui
             // the surface arena was too small for this batch: grow it for the next call and report
             ctx->d_surface.ensure((size_t)(h_cnt[0] + h_cnt[0] / 4) * sizeof(double));
             tredsw_set_error("likelihood surface arena overflow (%llu points needed); call again", h_cnt[0]);
+            return TREDSW_ERR_UNSUPPORTED;
+        }
+        if (h_tab[1]) {
+            // likewise the table / reduction-scratch arena of the large surfaces (grid.cu)
+            ctx->d_ftab.ensure(ctx->d_ftab.cap + (size_t)(h_tab[0] + h_tab[0] / 4) * sizeof(double));
+            tredsw_set_error("likelihood table arena overflow (%llu doubles needed); call again", h_tab[0]);
             return TREDSW_ERR_UNSUPPORTED;
         }
     }

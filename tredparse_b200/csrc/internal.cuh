@@ -13,7 +13,11 @@ int tredsw_internal_classify(tredsw_ctx *ctx, const int8_t *d_rbuf, const int64_
                              unsigned long long *d_stats);
 
 // Likelihood surface + reductions (grid.cu).  points_hint (largest surface of the batch, or an upper bound)
-// sizes the arena of the far-region tables.
+// sizes the table arena.  d_surface: per-problem slots (scratch; the full surface when `materialise`).
+// d_post / post_cap / d_post_cursor: optional arena for the sparse joint-posterior entries.
+// *d_overflow_flag receives a device pointer to {doubles needed, overflow flag} of the table arena.
 int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int nproblems,
                          const int32_t *d_ipool, const double *d_dpool, double *d_surface, double *d_marg,
-                         tredsw_grid_result *d_res, long long points_hint);
+                         tredsw_grid_result *d_res, long long points_hint, int materialise,
+                         tredsw_posterior *d_post, long long post_cap, unsigned long long *d_post_cursor,
+                         unsigned long long **d_overflow_flag);
