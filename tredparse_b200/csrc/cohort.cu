@@ -333,7 +333,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     int rc;
     // ---- inputs ------------------------------------------------------------------------------------
     const int8_t *d_rbuf = c->rbuf; const int64_t *d_roff = c->roff; const int32_t *d_rp = c->read_problem;
-    const tredsw_problem *d_prob = c->problems; const int32_t *d_pe = c->pe_lens;
+    const tredsw_problem *d_prob = c->problems;
     const int32_t *d_rname = c->read_name;
     const tredsw_family *d_fam; const tredsw_locus *d_loci;
     const bool packed4 = (c->input_flags & TREDSW_IN_READS_PACKED4) != 0, pe16 = (c->input_flags & TREDSW_IN_PE_LENS_I16) != 0;
@@ -391,7 +391,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     } else if (c->n_pe_lens > 0)
         CUDA_TRY(cudaMemcpyAsync(d_ipool, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int32_t),
                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    (void)d_pe;
+
     const int64_t n_dpool = (int64_t)np_ * KDE_SPAN + (int64_t)nf * NSTEP;
     if ((rc = ctx->d_dpool.ensure((size_t)n_dpool * sizeof(double)))) return rc;
     double *d_dpool = ctx->d_dpool.as<double>();

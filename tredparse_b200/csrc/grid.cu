@@ -17,8 +17,9 @@
 //
 // THE SURFACE IS NOT MATERIALISED (unless the caller asks for it).  What the caller of the reference gets are
 // the call, the marginals P_h1 / P_h2, the sparse joint P_h1h2 and the PP sums; so:
-//   * small surfaces (<= 2048 points, every haploid problem): one warp per problem evaluates, reduces and emits
-//     in one kernel (grid_small_kernel), the ml values parked in the problem's scratch slot (L1/L2);
+//   * small surfaces (<= 4096 points, every haploid problem) are cut into work items of 256 points — one warp per
+//     item, whatever the mix of sizes — that park the ml values in the problem's scratch slot (L1/L2); one warp
+//     per problem then reduces and emits;
 //   * large surfaces: row-structured.  A warp owns rows (one h1), its lanes walk the columns (h2) in chunks of
 //     256; everything that depends on h1 only is hoisted out of the columns.  Where the longer allele lies
 //     beyond every observed key, the partial clamp and the read length (column index >= fam, the MID region)
@@ -28,10 +29,12 @@
 //     point is  ml = (c12 + rept[dsum]) + pe  — on a --fullsearch / long-expansion grid > 90 % of the points —
 //     and its weight exp(ml - max) = exp(c12 + pe - max) * exp(rept[dsum]): one multiply with a per-row factor
 //     and a tabulated exp(rept) (rept lies in [-100, 0], so neither factor can overflow).
-//     Pass A (grid_rows_eval_kernel) evaluates the near / mid points into the scratch slot and finds the
-//     maximum; pass B (grid_rows_reduce_kernel) accumulates row sums, column sums (registers -> shared memory ->
-//     per-CTA partials, summed by the last CTA of the problem in rank order: deterministic), the PP sums, the
-//     arg-max (Q10) and emits the joint-posterior entries >= e^-10.
+//     Pass A (rows_eval) evaluates the near / mid points into the scratch slot — the paired-end term of 8 columns
+//     per lane at once, pair lengths outer: 8 independent product chains fed by one uniform and 8 coalesced loads
+//     — and finds the maximum and the arg-max (Q10); pass B (grid_rows_reduce_kernel) accumulates row sums, column
+//     sums (registers -> shared memory -> per-CTA partials, summed by the last CTA of the problem in rank order:
+//     deterministic), the PP sums and emits the joint-posterior entries >= e^-10.
+// Four launches per call: classify | {point items, table setup} | {small reductions, pass A} | pass B.
 // DRAM traffic is the near-region scratch (a few % of the surface, L2-resident) plus the tables.
 #include "internal.cuh"
 #include "kde.cuh"
@@ -42,15 +45,16 @@ namespace {
 constexpr int SPAN = 1000;
 constexpr int NSTEP = 37;
 constexpr int DEV = 18;
-constexpr long long SMALL_LIMIT = 2048;   // <= : one warp per problem
+constexpr long long SMALL_LIMIT = 4096;   // <= : point items + one warp for the reductions
+constexpr int ITEM_POINTS = 256;          // points per work item of a small surface (8 per lane)
+constexpr int ITEM_MAX = 16;              // items per small surface (an item strides when there are more chunks)
 constexpr int NC_MAX = 32;                // CTAs per large surface (rows are dealt round-robin in groups of 8)
 constexpr int CHUNK = 256;                // columns per chunk: 8 per lane
 constexpr int FILL_SPLIT = 8;             // blocks per large surface filling its tables
+constexpr int PE_BLOCK = 64;              // factors per flush of the paired-end product
 
-// per large surface: constants, thresholds, table layout, cross-CTA reduction state (zeroed every call)
+// per large surface: constants, thresholds, table layout (written by the classify / setup kernels)
 struct BigInfo {
-    unsigned long long maxkey;   // ordered key of the surface maximum (pass A, atomicMax); 0 = no point
-    unsigned long long argkey;   // pass B: min over the points at the maximum of (h1 << 40 | row-major index)
     long long off;               // table arena offset (doubles)
     double lgamma_k1;            // lgamma(n_rept + 1)
     double sig_mp;               // sigma(max_partial)
@@ -59,15 +63,14 @@ struct BigInfo {
     int ok;                      // row / rept / sigma tables present
     int npe;                     // paired-end operand tables present (= n_target)
     int sorted;                  // both candidate lists non-decreasing: rows skip the h1 > h2 columns wholesale
-    int nd;                      // entries of rept2[]
+    int nd;                      // entries of rept[] / erept[]
     int hrep;                    // a far allele (the largest h2)
     int mx1;                     // largest h1
-    int nc;                      // CTAs working on this surface
+    int nc;                      // CTA slots allocated for this surface
+    int nce;                     // CTAs actually working on it (chosen once the number of large surfaces is known)
     int nb1, nb2;                // length of the sorted base part of the h1 / h2 list (duplicates live beyond it)
-    int npoints;                 // evaluated points (pass A)
+    int patho_mode;              // the PP predicate for h1 <= h2: 0 = by column (h2), 1 = by row (h1)
     unsigned int done_b;         // CTAs of pass B that have finished
-    int alloc_fail;              // the table arena was too small even for the mandatory part
-    int pad_;
 };
 
 struct GridParams {
@@ -82,43 +85,38 @@ struct GridParams {
     int materialise;             // write every point (and -inf where h1 > h2) into the surface slots
     BigInfo *big;                // [nproblems]
     int *lists;                  // [0] number of large surfaces, [1 + i] their problem indices
+    int *items;                  // point items of the small surfaces: (problem, chunk, nitems) triples
+    unsigned int *counters;      // [0] items, [1] work cursor pass A, [2] work cursor pass B
     double *ftab;                // table arena
     long long ftab_cap;
     unsigned long long *fcursor; // [0] arena cursor, [1] overflow flag
     tredsw_posterior *post;      // sparse joint-posterior entries (optional)
     long long post_cap;
     unsigned long long *post_cursor;
+    int nblk_small;              // horizontally fused launches: blocks [0, nblk_small) work on the small surfaces
+    int target_ctas;             // CTAs the row kernels should spread the large surfaces over
 };
 
 // table layout of one large surface, in doubles from BigInfo.off
 struct Tab {
-    long long rows, sig1, sig2, rept2, dup, R1, R2, colpart, partial, end;
+    long long colpart, partial, pa, dup, rows, sig1, sig2, rept, erept, R1, R2, end;
 };
 __host__ __device__ inline Tab tab_layout(int n1, int n2, int nd, int npe, int nc, bool with_tables) {
     Tab t;
     long long o = 0;
-    t.colpart = o; o += (long long)nc * n2;
-    t.partial = o; o += (long long)nc * 4;
+    t.colpart = o; o += (long long)nc * n2;                  // pass B: column sums of each CTA
+    t.partial = o; o += (long long)nc * 4;                   // pass B: {sum_all, sum_path, sum_dup} of each CTA
+    t.pa = o; o += (long long)nc * 4;                        // pass A: {max ml, arg key, points} of each CTA
     t.dup = o; o += ((long long)n1 + n2 + 1) / 2;            // int32 flags, two per double
     t.rows = o; if (with_tables) o += 3LL * n1;              // {c12, pe_far, f} per row
     t.sig1 = o; if (with_tables) o += n1;
     t.sig2 = o; if (with_tables) o += n2;
-    o = (o + 1) & ~1LL;                                      // 16-byte aligned pairs
-    t.rept2 = o; if (with_tables) o += 2LL * nd;             // {rept, exp(rept)} per dsum
-    t.R1 = o; if (with_tables) o += (long long)npe * n1;
-    t.R2 = o; if (with_tables) o += (long long)npe * n2;
+    t.rept = o; if (with_tables) o += nd;                    // repeat-only term per dsum
+    t.erept = o; if (with_tables) o += nd;                   // exp of it
+    t.R1 = o; if (with_tables) o += (long long)npe * n1;     // 0.5 * rolled pdf of h1 at pair length t
+    t.R2 = o; if (with_tables) o += (long long)npe * n2;     // 0.5 * rolled pdf of h2 (stride fa2)
     t.end = (o + 1) & ~1LL;
     return t;
-}
-
-// order-preserving map double -> u64 (for atomicMax); 0 is below every value
-__device__ __forceinline__ unsigned long long ord_key(double x) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
-}
-__device__ __forceinline__ double ord_val(unsigned long long k) {
-    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
-    return __longlong_as_double((long long)b);
 }
 
 __device__ __forceinline__ double sigma_h(const tredsw_grid_problem &P, int h) {
@@ -153,7 +151,7 @@ __device__ __forceinline__ double pe_roll(const double *pdf, int h, int ref, int
     return pdf[y];
 }
 
-// sum_k c_k log(v_k) as the log of a running product; every factor lies in [eps, 1], so 64 of them stay above
+// sum_k c_k log(v_k) as the log of a running product; every factor lies in (eps, 1], so 64 of them stay above
 // e^-640.  The explicit intrinsics keep the compiler from contracting differently in different call sites: the
 // table-driven and the direct evaluation of a point have to give the same bits.
 struct LogProd {
@@ -202,8 +200,12 @@ __device__ __forceinline__ double term_span(const tredsw_grid_problem &P, const 
     return __dadd_rn(lp.done(), __dmul_rn((double)nfloor, g.log_small));
 }
 
-// sgc1 / sgc2: sigma of the alleles clamped to max_partial (negative = compute on first use).  A partial key
-// below both clamped alleles by more than 18 sees alpha*c1 + (1-alpha)*c2, one above both sees 0.
+// sgc1 / sgc2: sigma of the alleles clamped to max_partial (negative = compute on first use).
+// With A <= B the clamped alleles, a partial key k sees (models.py:170-180: c [k < hc] + c PS(hc)[k])
+//   k < A-18        : alpha_A c_A + alpha_B c_B         (below both, no stutter mass)            "bulk"
+//   A+18 < k < B-18 : alpha_A 0   + alpha_B c_B         (past A altogether, still below B)       "between"
+//   k > B+18        : 0                                  -> floored
+// and only the keys within 18 of A or B need the stutter pdf.  Same products and sums as the plain formula.
 __device__ __forceinline__ double term_part(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2,
                                             double sgc1, double sgc2, double sig_mp) {
     if (P.n_part <= 0) return 0.0;
@@ -216,14 +218,17 @@ __device__ __forceinline__ double term_part(const tredsw_grid_problem &P, const 
     const double b = 1.0 - a;
     const int hc1 = min(h1, P.max_partial), hc2 = min(h2, P.max_partial);
     const double c1 = 1.0 / (double)(hc1 + 1), c2 = 1.0 / (double)(hc2 + 1);
-    const int lo = min(hc1, hc2) - DEV, hi = max(hc1, hc2) + DEV;
+    const int A = min(hc1, hc2), B = max(hc1, hc2);
     const double v_bulk = __dadd_rn(__dmul_rn(a, c1), __dmul_rn(b, c2));   // p1 = c1 + c1 * 0, p2 = c2 + c2 * 0
+    // between: the smaller clamped allele contributes 0, the larger its plateau
+    const double v_btw = hc1 <= hc2 ? __dadd_rn(__dmul_rn(a, 0.0), __dmul_rn(b, c2)) : __dadd_rn(__dmul_rn(a, c1), __dmul_rn(b, 0.0));
     LogProd lp;
-    int nfloor = 0, nbulk = 0;
+    int nfloor = 0, nbulk = 0, nbtw = 0;
     for (int i = 0; i < P.n_part; ++i) {
         const int k = pkey[i], c = pcnt[i];
-        if (k < lo) { nbulk += c; continue; }
-        if (k > hi) { nfloor += c; continue; }
+        if (k < A - DEV) { nbulk += c; continue; }
+        if (k > B + DEV) { nfloor += c; continue; }
+        if (k > A + DEV && k < B - DEV) { nbtw += c; continue; }
         if (sgc1 < 0.0) sgc1 = hc1 == P.max_partial ? sig_mp : sigma_h(P, hc1);
         if (sgc2 < 0.0) sgc2 = hc2 == P.max_partial ? sig_mp : sigma_h(P, hc2);
         const double v = __dadd_rn(__dmul_rn(a, pdf_part(step, hc1, sgc1, c1, k)), __dmul_rn(b, pdf_part(step, hc2, sgc2, c2, k)));
@@ -234,6 +239,10 @@ __device__ __forceinline__ double term_part(const tredsw_grid_problem &P, const 
     if (nbulk) {
         if (v_bulk <= eps) nfloor += nbulk;
         else acc = __dadd_rn(acc, __dmul_rn((double)nbulk, log(v_bulk)));
+    }
+    if (nbtw) {
+        if (v_btw <= eps) nfloor += nbtw;
+        else acc = __dadd_rn(acc, __dmul_rn((double)nbtw, log(v_btw)));
     }
     return __dadd_rn(acc, __dmul_rn((double)nfloor, g.log_small));
 }
@@ -249,38 +258,40 @@ __device__ __forceinline__ double term_rept(const tredsw_grid_problem &P, int ds
     return pk > -100.0 ? pk : -100.0;
 }
 
+// paired-end term: sum_t log(max(.5 R(h1)[x_t] + .5 R(h2)[x_t], eps)) as the log of the product of the floored
+// mixtures, flushed every PE_BLOCK pairs (64 factors >= e^-10 stay above e^-640); the row kernels evaluate the
+// same blocks from tabulated halves, 8 columns at a time
 __device__ __forceinline__ double term_pe(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2, int tmin) {
     if (!P.run_pe) return 0.0;
     const double eps = g.small_value;
-    const long long off1 = (long long)h1 - P.pe_ref, off2 = (long long)h2 - P.pe_ref;
-    // every pair length is below MINPE or shifted past the end of the support: 0.5*eps + 0.5*eps = eps
-    if (tmin == 0x7fffffff || (tmin + off1 >= SPAN && tmin + off2 >= SPAN)) return __dmul_rn((double)P.n_target, g.log_small);
     const double *pdf = g.dpool + P.off_pdf;
     const int32_t *tl = g.ipool + P.off_target;
-    LogProd lp;
-    int nfloor = 0;
-    for (int i = 0; i < P.n_target; ++i) {
-        int x = tl[i];
-        if (x < 0) x += SPAN;                   // numpy negative-index wrap (models.py:473)
-        const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
-        const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
-        const double v = __dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2));
-        if (v <= eps) ++nfloor; else lp.mul(v);
+    double acc = 0.0;
+    const long long off1 = (long long)h1 - P.pe_ref, off2 = (long long)h2 - P.pe_ref;
+    if (tmin == 0x7fffffff || (tmin + off1 >= SPAN && tmin + off2 >= SPAN)) {
+        // every pair length is below MINPE or shifted past the end of the support: every factor is eps
+        // (.5 eps + .5 eps); the same blocks of products as below, without touching the pdf
+        for (int t0 = 0; t0 < P.n_target; t0 += PE_BLOCK) {
+            double prod = 1.0;
+            const int t1 = min(t0 + PE_BLOCK, P.n_target);
+            for (int i = t0; i < t1; ++i) prod = __dmul_rn(prod, eps);
+            acc = __dadd_rn(acc, log(prod));
+        }
+        return acc;
     }
-    return __dadd_rn(lp.done(), __dmul_rn((double)nfloor, g.log_small));
-}
-
-// term_pe from the tabulated operands R1[t][i1] / R2[t][i2] (exactly what pe_roll returns)
-__device__ __forceinline__ double term_pe_tab(const double *R1, const double *R2, int n1, int n2, int npe, int i1, int i2,
-                                              double eps, double log_small) {
-    LogProd lp;
-    int nfloor = 0;
-    R1 += i1; R2 += i2;
-    for (int t = 0; t < npe; ++t) {
-        const double v = __dadd_rn(__dmul_rn(0.5, R1[(long long)t * n1]), __dmul_rn(0.5, R2[(long long)t * n2]));
-        if (v <= eps) ++nfloor; else lp.mul(v);
+    for (int t0 = 0; t0 < P.n_target; t0 += PE_BLOCK) {
+        double prod = 1.0;
+        const int t1 = min(t0 + PE_BLOCK, P.n_target);
+        for (int i = t0; i < t1; ++i) {
+            int x = tl[i];
+            if (x < 0) x += SPAN;               // numpy negative-index wrap (models.py:473)
+            const double r1 = pe_roll(pdf, h1, P.pe_ref, P.pe_minpe, x, eps);
+            const double r2 = pe_roll(pdf, h2, P.pe_ref, P.pe_minpe, x, eps);
+            prod = __dmul_rn(prod, fmax(__dadd_rn(__dmul_rn(0.5, r1), __dmul_rn(0.5, r2)), eps));
+        }
+        acc = __dadd_rn(acc, log(prod));
     }
-    return __dadd_rn(lp.done(), __dmul_rn((double)nfloor, log_small));
+    return acc;
 }
 
 struct ProblemConsts {
@@ -290,19 +301,19 @@ struct ProblemConsts {
 };
 
 __device__ __forceinline__ double point_ml(const tredsw_grid_problem &P, const GridParams &g, int h1, int h2,
-                                           const ProblemConsts &T, double sg1, double sg2, double sgc1, double sgc2) {
-    double ml = term_span(P, g, h1, h2, sg1, sg2);
-    ml = __dadd_rn(ml, term_part(P, g, h1, h2, sgc1, sgc2, T.sig_mp));
+                                           const ProblemConsts &T) {
+    double ml = term_span(P, g, h1, h2, -1.0, -1.0);
+    ml = __dadd_rn(ml, term_part(P, g, h1, h2, -1.0, -1.0, T.sig_mp));
     ml = __dadd_rn(ml, term_rept(P, max(h1 - P.readlen, 1) + max(h2 - P.readlen, 1), T.lgamma_k1));
     ml = __dadd_rn(ml, term_pe(P, g, h1, h2, T.tmin));
     return ml;
 }
 
-// (u1, u2 = h1 / period, h2 / period: division is monotone, so min / max commute with it)
-__device__ __forceinline__ bool pathological_u(const tredsw_grid_problem &P, int u1, int u2) {
-    const int lo = min(u1, u2), hi = max(u1, u2);
-    if (P.expansion) return P.recessive ? (lo >= P.cutoff_risk) : (hi >= P.cutoff_risk);
-    return P.recessive ? (hi <= P.cutoff_risk) : (lo <= P.cutoff_risk);
+// PP predicate of a point (models.py:351-364) on alleles in bp (h >= 0): floor(h / K) >= c  <=>  h >= c K;
+// floor(h / K) <= c  <=>  h < (c + 1) K
+__device__ __forceinline__ bool pathological_h(const tredsw_grid_problem &P, int hlo, int hhi) {
+    if (P.expansion) return (P.recessive ? hlo : hhi) >= P.cutoff_risk * P.period;
+    return (P.recessive ? hhi : hlo) < (P.cutoff_risk + 1) * P.period;
 }
 
 // A candidate list is a sorted base part [0, nb) followed by an ascending extension (models.py:250-257; with
@@ -332,59 +343,7 @@ __device__ __forceinline__ void emit_joint(const GridParams &g, int pi, int u1, 
     }
 }
 
-// ==========================================================================================================
-// small surfaces: one warp per problem — evaluate, reduce, emit.  Large ones are registered for the row kernels.
-// ==========================================================================================================
-__global__ void __launch_bounds__(256) grid_small_kernel(GridParams g) {
-    const int lane = threadIdx.x & 31;
-    const int pi = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (pi >= g.nproblems) return;
-    const tredsw_grid_problem &P = g.prob[pi];
-    const int n1 = P.n_h1, n2 = P.n_h2;
-    const long long total = n2 > 0 ? (long long)n1 * n2 : 0;
-    const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
-    const bool haploid = P.ploidy == 1;
-    if (!haploid && total > SMALL_LIMIT) {
-        // ---- register a large surface: list slot, list maxima, table allocation --------------------------
-        int mx1 = -0x7fffffff, mx2 = -0x7fffffff;
-        for (int i = lane; i < n1; i += 32) mx1 = max(mx1, h1s[i]);
-        for (int i = lane; i < n2; i += 32) mx2 = max(mx2, h2s[i]);
-        mx1 = __reduce_max_sync(0xffffffffu, mx1); mx2 = __reduce_max_sync(0xffffffffu, mx2);
-        const int nb1 = base_len(h1s, n1, lane), nb2 = base_len(h2s, n2, lane);
-        if (lane == 0) {
-            BigInfo B;
-            memset(&B, 0, sizeof(B));
-            B.argkey = ~0ULL;
-            B.mx1 = mx1; B.hrep = mx2; B.nb1 = nb1; B.nb2 = nb2;
-            B.nd = max(mx1 - P.readlen, 1) + max(mx2 - P.readlen, 1) - 1;
-            B.nc = min(NC_MAX, max(1, (n1 + 31) / 32));
-            const int npe = (P.run_pe && P.n_target > 0) ? P.n_target : 0;
-            const Tab full = tab_layout(n1, n2, B.nd, npe, B.nc, true), nope = tab_layout(n1, n2, B.nd, 0, B.nc, true),
-                      bare = tab_layout(n1, n2, B.nd, 0, B.nc, false);
-            // the reduction scratch is mandatory; the tables are taken when the arena has room for them
-            unsigned long long off = atomicAdd(&g.fcursor[0], (unsigned long long)full.end);
-            if ((long long)(off + full.end) <= g.ftab_cap) { B.ok = 1; B.npe = npe; }
-            else {
-                off = atomicAdd(&g.fcursor[0], (unsigned long long)nope.end);
-                if ((long long)(off + nope.end) <= g.ftab_cap) { B.ok = 1; B.npe = 0; }
-                else {
-                    off = atomicAdd(&g.fcursor[0], (unsigned long long)bare.end);
-                    if ((long long)(off + bare.end) > g.ftab_cap) { B.alloc_fail = 1; atomicExch(&g.fcursor[1], 1ULL); off = 0; }
-                }
-            }
-            B.off = (long long)off;
-            g.big[pi] = B;
-            if (!B.alloc_fail) { const int slot = atomicAdd(&g.lists[0], 1); g.lists[1 + slot] = pi; }
-            else {
-                tredsw_grid_result r;
-                memset(&r, 0, sizeof(r));
-                r.arg_i1 = r.arg_i2 = -1; r.n_points = -1;
-                g.res[pi] = r;
-            }
-        }
-        return;
-    }
-    // ---- evaluate --------------------------------------------------------------------------------------
+__device__ __forceinline__ ProblemConsts problem_consts(const tredsw_grid_problem &P, const GridParams &g, int lane) {
     ProblemConsts T;
     T.lgamma_k1 = lgamma((double)P.n_rept + 1.0);
     T.sig_mp = sigma_h(P, P.max_partial);
@@ -395,66 +354,161 @@ __global__ void __launch_bounds__(256) grid_small_kernel(GridParams g) {
         tmin = __reduce_min_sync(0xffffffffu, tmin);
     }
     T.tmin = tmin;
-    double *surf = g.surface + P.off_surface;
-    double best_ml = -INFINITY;
-    int best_h1 = 0x7fffffff, best_t = 0x7fffffff, cnt = 0;
-    for (long long tt = lane; tt < total; tt += 32) {
-        const int t = (int)tt;
-        const int i1 = t / n2, i2 = t - i1 * n2;
-        const int h1 = h1s[i1];
-        const int h2 = haploid ? h1 : h2s[i2];
-        double ml = -INFINITY;
-        if (h1 <= h2) {
-            ml = point_ml(P, g, h1, h2, T, -1.0, -1.0, -1.0, -1.0);
-            ++cnt;
-            if (ml > best_ml || (ml == best_ml && (h1 < best_h1 || (h1 == best_h1 && t < best_t)))) { best_ml = ml; best_h1 = h1; best_t = t; }
+    return T;
+}
+
+// ==========================================================================================================
+// K1  classify: one warp per problem.  Small surfaces (<= 4096 points, every haploid problem) are cut into work
+//     items of 256 points; large ones are registered for the row kernels and get their table space.
+// ==========================================================================================================
+__global__ void __launch_bounds__(256) grid_classify_kernel(GridParams g) {
+    const int lane = threadIdx.x & 31;
+    const int pi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pi >= g.nproblems) return;
+    const tredsw_grid_problem &P = g.prob[pi];
+    const int n1 = P.n_h1, n2 = P.n_h2;
+    const long long total = n2 > 0 ? (long long)n1 * n2 : 0;
+    if (P.ploidy == 1 || total <= SMALL_LIMIT) {
+        if (lane == 0 && total > 0) {
+            const int chunks = (int)((total + ITEM_POINTS - 1) / ITEM_POINTS);
+            const int n = min(chunks, ITEM_MAX);
+            const unsigned at = atomicAdd(&g.counters[0], (unsigned)n);
+            for (int i = 0; i < n; ++i) { g.items[3 * (at + i)] = pi; g.items[3 * (at + i) + 1] = i; g.items[3 * (at + i) + 2] = n; }
         }
-        surf[t] = ml;
+        return;
     }
-    for (int d = 16; d > 0; d >>= 1) {
-        const double oml = __shfl_xor_sync(0xffffffffu, best_ml, d);
-        const int oh = __shfl_xor_sync(0xffffffffu, best_h1, d), ot = __shfl_xor_sync(0xffffffffu, best_t, d);
-        if (oml > best_ml || (oml == best_ml && (oh < best_h1 || (oh == best_h1 && ot < best_t)))) { best_ml = oml; best_h1 = oh; best_t = ot; }
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    }
-    __syncwarp();
-    // ---- reduce ----------------------------------------------------------------------------------------
-    double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
-    for (int i2 = lane; i2 < n2; i2 += 32) ph2[i2] = 0.0;
-    const int nb1 = cnt ? base_len(h1s, n1, lane) : n1;
-    const int nb2 = (cnt && !haploid) ? base_len(h2s, n2, lane) : n2;
-    double sum_all = 0.0, sum_path = 0.0, sum_uniq = 0.0;
-    const double eps = g.small_value;
-    for (int i1 = 0; i1 < n1; ++i1) {
-        const int h1 = h1s[i1], u1 = h1 / P.period;
-        const bool dup1 = is_second_occurrence(h1s, nb1, i1);
-        double acc = 0.0, accp = 0.0, accu = 0.0;
-        for (int i2 = lane; i2 < n2; i2 += 32) {           // column i2 always belongs to lane i2 % 32: the plain
-            const double ml = surf[i1 * n2 + i2];          // read-modify-write of ph2 below is race-free and ordered
-            if (ml == -INFINITY) continue;
-            const double w = exp(ml - best_ml);
-            const int u2 = haploid ? u1 : h2s[i2] / P.period;
-            acc += w; ph2[i2] += w;
-            if (pathological_u(P, u1, u2)) accp += w;
-            if (!(dup1 || (!haploid && is_second_occurrence(h2s, nb2, i2)))) {
-                accu += w;
-                if (w >= eps) emit_joint(g, pi, u1, u2, w);
+    const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+    int mx1 = -0x7fffffff, mx2 = -0x7fffffff;
+    for (int i = lane; i < n1; i += 32) mx1 = max(mx1, h1s[i]);
+    for (int i = lane; i < n2; i += 32) mx2 = max(mx2, h2s[i]);
+    mx1 = __reduce_max_sync(0xffffffffu, mx1); mx2 = __reduce_max_sync(0xffffffffu, mx2);
+    const int nb1 = base_len(h1s, n1, lane), nb2 = base_len(h2s, n2, lane);
+    if (lane == 0) {
+        BigInfo B;
+        memset(&B, 0, sizeof(B));
+        B.mx1 = mx1; B.hrep = mx2; B.nb1 = nb1; B.nb2 = nb2;
+        B.nd = max(mx1 - P.readlen, 1) + max(mx2 - P.readlen, 1) - 1;
+        B.nc = min(NC_MAX, max(1, (n1 + 7) / 8)); B.nce = B.nc;
+        // for h1 <= h2: expansion-dominant and contraction-recessive look at the longer allele (column),
+        // expansion-recessive and contraction-dominant at the shorter one (row)
+        B.patho_mode = (P.expansion != 0) == (P.recessive != 0) ? 1 : 0;
+        const int npe = (P.run_pe && P.n_target > 0) ? P.n_target : 0;
+        const Tab full = tab_layout(n1, n2, B.nd, npe, B.nc, true), nope = tab_layout(n1, n2, B.nd, 0, B.nc, true),
+                  bare = tab_layout(n1, n2, B.nd, 0, B.nc, false);
+        // the reduction scratch is mandatory; the tables are taken when the arena has room for them
+        bool fail = false;
+        unsigned long long off = atomicAdd(&g.fcursor[0], (unsigned long long)full.end);
+        if ((long long)(off + full.end) <= g.ftab_cap) { B.ok = 1; B.npe = npe; }
+        else {
+            off = atomicAdd(&g.fcursor[0], (unsigned long long)nope.end);
+            if ((long long)(off + nope.end) <= g.ftab_cap) { B.ok = 1; B.npe = 0; }
+            else {
+                off = atomicAdd(&g.fcursor[0], (unsigned long long)bare.end);
+                if ((long long)(off + bare.end) > g.ftab_cap) { fail = true; atomicExch(&g.fcursor[1], 1ULL); off = 0; }
             }
         }
-        for (int d = 16; d > 0; d >>= 1) {
-            acc += __shfl_down_sync(0xffffffffu, acc, d);
-            accp += __shfl_down_sync(0xffffffffu, accp, d);
-            accu += __shfl_down_sync(0xffffffffu, accu, d);
+        B.off = (long long)off;
+        g.big[pi] = B;
+        if (!fail) { const int slot = atomicAdd(&g.lists[0], 1); g.lists[1 + slot] = pi; }
+        else {
+            tredsw_grid_result r;
+            memset(&r, 0, sizeof(r));
+            r.arg_i1 = r.arg_i2 = -1; r.n_points = -1;
+            g.res[pi] = r;
         }
-        if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; sum_uniq += accu; }
     }
-    if (lane == 0) {
-        tredsw_grid_result r;
-        r.max_ml = best_ml; r.sum_all = sum_all; r.sum_path = sum_path; r.sum_uniq = sum_uniq;
-        r.arg_i1 = cnt ? best_t / n2 : -1;
-        r.arg_i2 = cnt ? best_t % n2 : -1;
-        r.n_points = cnt; r.pad = 0;
-        g.res[pi] = r;
+}
+
+// ---- small surfaces, part 1: one warp per item evaluates its points into the scratch slot ---------------------
+__device__ __forceinline__ void small_points(const GridParams &g, int first_warp, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    const unsigned nitems = g.counters[0];
+    for (unsigned it = first_warp; it < nitems; it += nwarps) {
+        const int pi = g.items[3 * it], chunk0 = g.items[3 * it + 1], stride = g.items[3 * it + 2];
+        const tredsw_grid_problem &P = g.prob[pi];
+        const int n2 = P.n_h2;
+        const long long total = (long long)P.n_h1 * n2;
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const bool haploid = P.ploidy == 1;
+        const ProblemConsts T = problem_consts(P, g, lane);
+        double *surf = g.surface + P.off_surface;
+        for (long long c0 = (long long)chunk0 * ITEM_POINTS; c0 < total; c0 += (long long)stride * ITEM_POINTS)
+            for (int q = lane; q < ITEM_POINTS; q += 32) {
+                const long long t = c0 + q;
+                if (t >= total) break;
+                const int i1 = (int)(t / n2), i2 = (int)(t - (long long)i1 * n2);
+                const int h1 = h1s[i1];
+                const int h2 = haploid ? h1 : h2s[i2];
+                surf[t] = h1 <= h2 ? point_ml(P, g, h1, h2, T) : -INFINITY;
+            }
+    }
+}
+
+// ---- small surfaces, part 2: one warp per problem reduces its scratch slot ------------------------------------
+__device__ __forceinline__ void small_reduce(const GridParams &g, int first_warp, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    for (int pi = first_warp; pi < g.nproblems; pi += nwarps) {
+        const tredsw_grid_problem &P = g.prob[pi];
+        const int n1 = P.n_h1, n2 = P.n_h2;
+        const long long total = n2 > 0 ? (long long)n1 * n2 : 0;
+        const bool haploid = P.ploidy == 1;
+        if (!haploid && total > SMALL_LIMIT) continue;
+        const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const double *surf = g.surface + P.off_surface;
+        double best_ml = -INFINITY;
+        int best_h1 = 0x7fffffff, cnt = 0;
+        long long best_t = 0x7fffffffffffffffLL;
+        for (long long t = lane; t < total; t += 32) {
+            const double ml = surf[t];
+            if (ml == -INFINITY) continue;
+            ++cnt;
+            const int h1 = h1s[t / n2];
+            if (ml > best_ml || (ml == best_ml && (h1 < best_h1 || (h1 == best_h1 && t < best_t)))) { best_ml = ml; best_h1 = h1; best_t = t; }
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            const double oml = __shfl_xor_sync(0xffffffffu, best_ml, d);
+            const int oh = __shfl_xor_sync(0xffffffffu, best_h1, d);
+            const long long ot = __shfl_xor_sync(0xffffffffu, best_t, d);
+            if (oml > best_ml || (oml == best_ml && (oh < best_h1 || (oh == best_h1 && ot < best_t)))) { best_ml = oml; best_h1 = oh; best_t = ot; }
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        }
+        double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+        for (int i2 = lane; i2 < n2; i2 += 32) ph2[i2] = 0.0;
+        const int nb1 = cnt ? base_len(h1s, n1, lane) : n1;
+        const int nb2 = (cnt && !haploid) ? base_len(h2s, n2, lane) : n2;
+        double sum_all = 0.0, sum_path = 0.0, sum_uniq = 0.0;
+        const double eps = g.small_value;
+        for (int i1 = 0; i1 < n1; ++i1) {
+            const int h1 = h1s[i1];
+            const bool dup1 = is_second_occurrence(h1s, nb1, i1);
+            double acc = 0.0, accp = 0.0, accu = 0.0;
+            for (int i2 = lane; i2 < n2; i2 += 32) {           // column i2 always belongs to lane i2 % 32: the plain
+                const double ml = surf[(long long)i1 * n2 + i2];   // read-modify-write of ph2 is race-free and ordered
+                if (ml == -INFINITY) continue;
+                const double w = exp(ml - best_ml);
+                const int h2 = haploid ? h1 : h2s[i2];
+                acc += w; ph2[i2] += w;
+                if (pathological_h(P, h1, h2)) accp += w;            // (evaluated points have h1 <= h2)
+                if (!(dup1 || (!haploid && is_second_occurrence(h2s, nb2, i2)))) {
+                    accu += w;
+                    if (w >= eps) emit_joint(g, pi, h1 / P.period, h2 / P.period, w);
+                }
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                acc += __shfl_down_sync(0xffffffffu, acc, d);
+                accp += __shfl_down_sync(0xffffffffu, accp, d);
+                accu += __shfl_down_sync(0xffffffffu, accu, d);
+            }
+            if (lane == 0) { ph1[i1] = acc; sum_all += acc; sum_path += accp; sum_uniq += accu; }
+        }
+        if (lane == 0) {
+            tredsw_grid_result r;
+            r.max_ml = best_ml; r.sum_all = sum_all; r.sum_path = sum_path; r.sum_uniq = sum_uniq;
+            r.arg_i1 = cnt ? (int)(best_t / n2) : -1;
+            r.arg_i2 = cnt ? (int)(best_t % n2) : -1;
+            r.n_points = cnt; r.pad = 0;
+            g.res[pi] = r;
+        }
     }
 }
 
@@ -475,11 +529,11 @@ __device__ __forceinline__ int block_max_int(int v, int *s8) {
 
 // FILL_SPLIT blocks per large surface: each derives the thresholds (cheap, block-parallel scans — no block waits
 // for another), part 0 publishes them, all fill their share of the tables.
-__global__ void __launch_bounds__(256) grid_big_setup_kernel(GridParams g) {
+__device__ __forceinline__ void big_setup(const GridParams &g, int first_block, int nblocks) {
     __shared__ int s8[8];
     const int nbig = g.lists[0];
     const int tid = threadIdx.x;
-    for (int kk = blockIdx.x; kk < nbig * FILL_SPLIT; kk += gridDim.x) {
+    for (int kk = first_block; kk < nbig * FILL_SPLIT; kk += nblocks) {
         const int pi = g.lists[1 + kk / FILL_SPLIT], part = kk % FILL_SPLIT;
         const tredsw_grid_problem &P = g.prob[pi];
         BigInfo &B = g.big[pi];
@@ -507,6 +561,9 @@ __global__ void __launch_bounds__(256) grid_big_setup_kernel(GridParams g) {
         const double lgk = lgamma((double)P.n_rept + 1.0), sig_mp = sigma_h(P, P.max_partial);
         if (part == 0 && tid == 0) {
             B.lgamma_k1 = lgk; B.sig_mp = sig_mp; B.tmin = tmin; B.fam = fam; B.fa2 = fa2; B.sorted = unsorted ? 0 : 1;
+            // few large surfaces: many CTAs each (latency); many: few CTAs each, so that a warp keeps its column
+            // registers over many rows (throughput)
+            B.nce = max(1, min(B.nc, (g.target_ctas + nbig - 1) / nbig));
         }
         const Tab tb = tab_layout(n1, n2, B.nd, B.npe, B.nc, B.ok != 0);
         double *tab = g.ftab + B.off;
@@ -516,7 +573,7 @@ __global__ void __launch_bounds__(256) grid_big_setup_kernel(GridParams g) {
         if (!B.ok) continue;
         const int hrep = B.hrep, npe = B.npe, nd = B.nd;
         const double *pdf = g.dpool + P.off_pdf;
-        const long long o_s1 = 0, o_s2 = o_s1 + n1, o_rows = o_s2 + n2, o_rept = o_rows + n1, o_R1 = o_rept + nd,
+        const long long o_s2 = n1, o_rows = o_s2 + n2, o_rept = o_rows + n1, o_R1 = o_rept + nd,
                         o_R2 = o_R1 + (long long)npe * n1, n_all = o_R2 + (long long)npe * fa2;
         for (long long e = part * 256 + tid; e < n_all; e += 256 * FILL_SPLIT) {
             if (e < o_s2) tab[tb.sig1 + e] = sigma_h(P, h1s[e]);
@@ -526,17 +583,17 @@ __global__ void __launch_bounds__(256) grid_big_setup_kernel(GridParams g) {
                 const int hc1 = min(h1, P.max_partial);
                 const double s1 = sigma_h(P, h1), sc1 = hc1 == P.max_partial ? sig_mp : s1;
                 // (for a far column the second allele's sigma is never used: every key is farther than 18 from it;
-                //  sig_mp stands in for the clamped one)
+                //  sig_mp is the clamped one)
                 tab[tb.rows + 3LL * i1] = __dadd_rn(term_span(P, g, h1, hrep, s1, 0.5), term_part(P, g, h1, hrep, sc1, sig_mp, sig_mp));
                 tab[tb.rows + 3LL * i1 + 1] = term_pe(P, g, h1, hrep, tmin);
                 tab[tb.rows + 3LL * i1 + 2] = 0.0;
             } else if (e < o_R1) {
                 const int d = (int)(e - o_rept);
                 const double r = term_rept(P, d + 2, lgk);
-                tab[tb.rept2 + 2LL * d] = r;
-                tab[tb.rept2 + 2LL * d + 1] = exp(r);
+                tab[tb.rept + d] = r;
+                tab[tb.erept + d] = exp(r);
             } else {
-                // operands of the two-dimensional paired-end term, exactly as term_pe obtains them
+                // halved operands of the two-dimensional paired-end term (0.5 * what pe_roll returns: exact)
                 long long idx = e - o_R1;
                 const bool first = e < o_R2;
                 if (!first) idx = e - o_R2;
@@ -544,51 +601,80 @@ __global__ void __launch_bounds__(256) grid_big_setup_kernel(GridParams g) {
                 const int t = (int)(idx / width), i = (int)(idx - (long long)t * width);
                 int x = tl[t];
                 if (x < 0) x += SPAN;
-                tab[(first ? tb.R1 : tb.R2) + idx] = pe_roll(pdf, first ? h1s[i] : h2s[i], P.pe_ref, P.pe_minpe, x, g.small_value);
+                tab[(first ? tb.R1 : tb.R2) + idx] = __dmul_rn(0.5, pe_roll(pdf, first ? h1s[i] : h2s[i], P.pe_ref, P.pe_minpe, x, g.small_value));
             }
         }
     }
 }
 
+// K2 = { point items of the small surfaces | table setup of the large ones }
+__global__ void __launch_bounds__(256) grid_points_setup_kernel(GridParams g) {
+    if ((int)blockIdx.x < g.nblk_small) small_points(g, blockIdx.x * 8 + (threadIdx.x >> 5), g.nblk_small * 8);
+    else big_setup(g, blockIdx.x - g.nblk_small, gridDim.x - g.nblk_small);
+}
+
 struct RowTables {
-    const double *rows, *sig1, *sig2, *rept2, *R1, *R2;
+    const double *rows, *sig1, *sig2, *rept, *erept, *R1, *R2;
     const int32_t *dup;
-    double *colpart, *partial;
+    double *colpart, *partial, *pa;
 };
 __device__ __forceinline__ RowTables row_tables(const GridParams &g, const BigInfo &B, int n1, int n2) {
     const Tab tb = tab_layout(n1, n2, B.nd, B.npe, B.nc, B.ok != 0);
     double *tab = g.ftab + B.off;
     RowTables r;
-    r.rows = tab + tb.rows; r.sig1 = tab + tb.sig1; r.sig2 = tab + tb.sig2; r.rept2 = tab + tb.rept2;
+    r.rows = tab + tb.rows; r.sig1 = tab + tb.sig1; r.sig2 = tab + tb.sig2; r.rept = tab + tb.rept; r.erept = tab + tb.erept;
     r.R1 = tab + tb.R1; r.R2 = tab + tb.R2; r.dup = reinterpret_cast<const int32_t *>(tab + tb.dup);
-    r.colpart = tab + tb.colpart; r.partial = tab + tb.partial;
+    r.colpart = tab + tb.colpart; r.partial = tab + tb.partial; r.pa = tab + tb.pa;
     return r;
 }
 
-// Pass A: near / mid points into the scratch slot, the maximum and the point count of every large surface.
-// Work item = (surface, CTA rank c < nc): the row groups g = c, c + nc, ... of 8 rows (one per warp) — near rows
-// (expensive) and far rows (cheap) are dealt evenly.
-__global__ void __launch_bounds__(256) grid_rows_eval_kernel(GridParams g) {
+struct Best {                       // running arg-max with the reference's tie rule (ml, -h1, evaluation order): Q10
+    double ml;
+    unsigned long long key;         // h1 << 40 | row-major index
+    __device__ __forceinline__ void take(double m, int h1, long long idx) {
+        if (m >= ml) {
+            const unsigned long long k = ((unsigned long long)h1 << 40) | (unsigned long long)idx;
+            if (m > ml || k < key) { ml = m; key = k; }
+        }
+    }
+    __device__ __forceinline__ void merge(double m, unsigned long long k) {
+        if (m > ml || (m == ml && k < key)) { ml = m; key = k; }
+    }
+};
+
+// Pass A: near / mid points into the scratch slot; maximum, arg-max and point count of this CTA's rows.
+// Work item = (surface, CTA rank c < nc): the row groups g = c, c + nc, ... of 8 rows (one per warp); items are
+// taken from an atomic cursor, rank-major, so the ranks holding the expensive near rows start first.
+__device__ __forceinline__ void rows_eval(const GridParams &g) {
+    __shared__ double s_ml[8];
     __shared__ unsigned long long s_key[8];
     __shared__ int s_cnt[8];
+    __shared__ unsigned s_item;
     const int nbig = g.lists[0];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int item = blockIdx.x; item < nbig * NC_MAX; item += gridDim.x) {
-        const int pi = g.lists[1 + item / NC_MAX], c = item % NC_MAX;
-        BigInfo &B = g.big[pi];
-        const int nc = B.nc;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&g.counters[1], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= (unsigned)nbig * NC_MAX) break;
+        const int pi = g.lists[1 + item % nbig], c = item / nbig;
+        const BigInfo &B = g.big[pi];
+        const int nc = B.nce;
         if (c >= nc) continue;
         const tredsw_grid_problem &P = g.prob[pi];
         const int n1 = P.n_h1, n2 = P.n_h2, L = P.readlen;
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
         double *surf = g.surface + P.off_surface, *ph1 = g.marg + P.off_ph1;
+        // sorted lists: the last near / mid allele; a row beyond it has far columns only
+        const int h2_mid_last = (B.sorted && B.ok && B.fa2 > 0) ? h2s[B.fa2 - 1] : 0x7fffffff;
         const RowTables R = row_tables(g, B, n1, n2);
         const int ok = B.ok, fam = B.fam, fa2 = B.fa2, npe = B.npe, sorted = B.sorted;
         const bool mat = g.materialise != 0;
         ProblemConsts T;
         T.lgamma_k1 = B.lgamma_k1; T.sig_mp = B.sig_mp; T.tmin = B.tmin;
-        const double eps = g.small_value, log_small = g.log_small;
-        double mx = -INFINITY;
+        const double eps = g.small_value;
+        Best best{-INFINITY, ~0ULL};
         int cnt = 0;
         for (int grp = c; grp * 8 < n1; grp += nc) {
             const int i1 = grp * 8 + warp;
@@ -596,8 +682,16 @@ __global__ void __launch_bounds__(256) grid_rows_eval_kernel(GridParams g) {
         }
         for (int cb = 0; cb < n2; cb += CHUNK) {
             const int cend = min(cb + CHUNK, n2);
+            const int jmax = (cend - cb + 31) >> 5;
             const int h2_last = sorted ? h2s[cend - 1] : 0x7fffffff;
             const bool all_far = ok && cb >= fa2;
+            int h2v[8], dh2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = cb + lane + 32 * j;
+                h2v[j] = col < cend ? h2s[col] : -0x40000000;
+                dh2[j] = max(h2v[j] - L, 1);
+            }
             for (int grp = c; grp * 8 < n1; grp += nc) {
                 const int i1 = grp * 8 + warp;
                 if (i1 >= n1) continue;
@@ -607,88 +701,131 @@ __global__ void __launch_bounds__(256) grid_rows_eval_kernel(GridParams g) {
                     if (mat) for (int col = cb + lane; col < cend; col += 32) surf[row + col] = -INFINITY;
                     continue;
                 }
-                const int dh1 = max(h1 - L, 1);
+                const int dh1 = max(h1 - L, 1) - 2;
                 double c12 = 0.0, pe_far = 0.0, sg1 = -1.0, sgc1 = -1.0;
                 if (ok) {
                     c12 = R.rows[3LL * i1]; pe_far = R.rows[3LL * i1 + 1]; sg1 = R.sig1[i1];
                     sgc1 = min(h1, P.max_partial) == P.max_partial ? T.sig_mp : sg1;
                 }
-                if (all_far) {
+                if (all_far || (ok && h1 > h2_mid_last)) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
+                        if (j >= jmax) break;
                         const int col = cb + lane + 32 * j;
-                        if (col >= cend) continue;
-                        const int h2 = h2s[col];
                         double ml = -INFINITY;
-                        if (h1 <= h2) {
-                            ml = __dadd_rn(__dadd_rn(c12, R.rept2[2LL * (dh1 + max(h2 - L, 1) - 2)]), pe_far);
-                            mx = fmax(mx, ml); ++cnt;
+                        if (h1 <= h2v[j]) {
+                            ml = __dadd_rn(__dadd_rn(c12, R.rept[dh1 + dh2[j]]), pe_far);
+                            best.take(ml, h1, row + col); ++cnt;
                         }
-                        if (mat) surf[row + col] = ml;
+                        if (mat && col < cend) surf[row + col] = ml;
                     }
                     continue;
                 }
-#pragma unroll 1
-                for (int col = cb + lane; col < cend; col += 32) {
-                    const int h2 = h2s[col];
+                // column groups [jlo, jhi) of this chunk hold near / mid columns the row evaluates
+                int jlo = 0;
+                const int jhi = ok ? min(jmax, (min(fa2, cend) - cb + 31) >> 5) : jmax;
+                if (sorted) while (jlo < jhi && h2s[min(cb + 32 * jlo + 31, cend - 1)] < h1) ++jlo;
+                // ---- a chunk with near / mid columns: the paired-end term of its 8 columns per lane at once
+                // (pair lengths outer, columns inner: 8 independent product chains, one uniform + 8 coalesced loads)
+                double pe[8];
+                if (ok && npe > 0) {
+                    int cj[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { pe[j] = 0.0; cj[j] = min(cb + lane + 32 * j, fa2 - 1); }
+                    const double *r1p = R.R1 + i1;
+                    for (int t0 = 0; t0 < npe; t0 += PE_BLOCK) {
+                        double prod[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) prod[j] = 1.0;
+                        const int t1 = min(t0 + PE_BLOCK, npe);
+                        for (int t = t0; t < t1; ++t) {
+                            const double r1 = r1p[(long long)t * n1];
+                            const double *r2p = R.R2 + (long long)t * fa2;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (j < jlo) continue;
+                                if (j >= jhi) break;
+                                prod[j] = __dmul_rn(prod[j], fmax(__dadd_rn(r1, r2p[cj[j]]), eps));
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { if (j < jlo) continue; if (j >= jhi) break; pe[j] = __dadd_rn(pe[j], log(prod[j])); }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j >= jmax) break;
+                    const int col = cb + lane + 32 * j;
+                    if (col >= cend) continue;
+                    const int h2 = h2v[j];
                     double ml = -INFINITY;
                     if (h1 <= h2) {
                         if (ok) {
-                            const double rp = R.rept2[2LL * (dh1 + max(h2 - L, 1) - 2)];
+                            const double rp = R.rept[dh1 + dh2[j]];
                             if (col >= fa2) ml = __dadd_rn(__dadd_rn(c12, rp), pe_far);
                             else {
-                                const double pe = npe > 0 ? term_pe_tab(R.R1, R.R2, n1, fa2, npe, i1, col, eps, log_small)
-                                                          : term_pe(P, g, h1, h2, T.tmin);
-                                if (col >= fam) ml = __dadd_rn(__dadd_rn(c12, rp), pe);
+                                const double pej = npe > 0 ? pe[j] : term_pe(P, g, h1, h2, T.tmin);
+                                if (col >= fam) ml = __dadd_rn(__dadd_rn(c12, rp), pej);
                                 else {
                                     const double sg2 = R.sig2[col];
                                     const double sgc2 = min(h2, P.max_partial) == P.max_partial ? T.sig_mp : sg2;
                                     ml = __dadd_rn(term_span(P, g, h1, h2, sg1, sg2), term_part(P, g, h1, h2, sgc1, sgc2, T.sig_mp));
-                                    ml = __dadd_rn(__dadd_rn(ml, rp), pe);
+                                    ml = __dadd_rn(__dadd_rn(ml, rp), pej);
                                 }
                             }
                         } else {
-                            ml = point_ml(P, g, h1, h2, T, -1.0, -1.0, -1.0, -1.0);
+                            ml = point_ml(P, g, h1, h2, T);
                         }
-                        mx = fmax(mx, ml); ++cnt;
+                        best.take(ml, h1, row + col); ++cnt;
                         if (!(ok && col >= fa2) || mat) surf[row + col] = ml;
                     } else if (mat) surf[row + col] = ml;
                 }
             }
         }
-        unsigned long long key = cnt ? ord_key(mx) : 0ULL;
         for (int d = 16; d > 0; d >>= 1) {
-            key = max(key, __shfl_xor_sync(0xffffffffu, key, d));
+            best.merge(__shfl_xor_sync(0xffffffffu, best.ml, d), __shfl_xor_sync(0xffffffffu, best.key, d));
             cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         }
-        __syncthreads();
-        if (lane == 0) { s_key[warp] = key; s_cnt[warp] = cnt; }
+        if (lane == 0) { s_ml[warp] = best.ml; s_key[warp] = best.key; s_cnt[warp] = cnt; }
         __syncthreads();
         if (tid == 0) {
-            unsigned long long m = s_key[0];
+            Best b{s_ml[0], s_key[0]};
             int n = s_cnt[0];
 #pragma unroll
-            for (int w = 1; w < 8; ++w) { m = max(m, s_key[w]); n += s_cnt[w]; }
-            if (m) atomicMax(&B.maxkey, m);
-            if (n) atomicAdd(&B.npoints, n);
+            for (int w = 1; w < 8; ++w) { b.merge(s_ml[w], s_key[w]); n += s_cnt[w]; }
+            R.pa[4LL * c] = b.ml;
+            R.pa[4LL * c + 1] = __longlong_as_double((long long)b.key);
+            R.pa[4LL * c + 2] = (double)n;
         }
     }
 }
 
-// Pass B: weights exp(ml - max) of every point -> row sums (P_h1), column sums (P_h2), PP sums, arg-max, joint
-// entries.  Column sums: registers (8 columns per lane over the warp's rows) -> shared memory (8 warps, in warp
-// order) -> this CTA's slice of colpart; the last CTA of a surface to finish adds the slices in rank order.
-__global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
+// K3 = { reductions of the small surfaces | pass A of the large ones }
+__global__ void __launch_bounds__(256, 2) grid_reduce_eval_kernel(GridParams g) {
+    if ((int)blockIdx.x < g.nblk_small) small_reduce(g, blockIdx.x * 8 + (threadIdx.x >> 5), g.nblk_small * 8);
+    else rows_eval(g);
+}
+
+// K4  pass B: weights exp(ml - max) of every point -> row sums (P_h1), column sums (P_h2), PP sums, joint entries.
+// A far point costs a multiply (per-row factor x tabulated exp of the repeat-only term) and two additions.
+// Column sums: registers (8 columns per lane over the warp's rows) -> shared memory (8 warps, in warp order) ->
+// this CTA's slice of colpart; the last CTA of a surface to finish adds the slices in rank order.
+__global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) {
     __shared__ double s_col[8][CHUNK];
     __shared__ double s_sum[8][3];
-    __shared__ unsigned long long s_arg[8];
     __shared__ int s_last;
+    __shared__ unsigned s_item;
     const int nbig = g.lists[0];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int item = blockIdx.x; item < nbig * NC_MAX; item += gridDim.x) {
-        const int pi = g.lists[1 + item / NC_MAX], c = item % NC_MAX;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&g.counters[2], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= (unsigned)nbig * NC_MAX) break;
+        const int pi = g.lists[1 + item % nbig], c = item / nbig;
         BigInfo &B = g.big[pi];
-        const int nc = B.nc;
+        const int nc = B.nce;
         if (c >= nc) continue;
         const tredsw_grid_problem &P = g.prob[pi];
         const int n1 = P.n_h1, n2 = P.n_h2, L = P.readlen, K = P.period;
@@ -697,10 +834,16 @@ __global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
         double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
         const RowTables R = row_tables(g, B, n1, n2);
         double *rows_w = const_cast<double *>(R.rows);
-        const int ok = B.ok, fa2 = B.fa2, sorted = B.sorted;
+        const int ok = B.ok, fa2 = B.fa2, sorted = B.sorted, prow_mode = B.patho_mode;
         const double eps = g.small_value;
-        const unsigned long long maxkey = B.maxkey;
-        const double M = maxkey ? ord_val(maxkey) : INFINITY;          // no point at all: nothing compares equal
+        // the surface maximum: pass A's per-CTA results in rank order
+        Best top{-INFINITY, ~0ULL};
+        long long npoints = 0;
+        for (int r = 0; r < nc; ++r) {
+            top.merge(R.pa[4LL * r], (unsigned long long)__double_as_longlong(R.pa[4LL * r + 1]));
+            npoints += (long long)R.pa[4LL * r + 2];
+        }
+        const double M = npoints ? top.ml : INFINITY;
         // per-row factor of the far weights
         if (ok)
             for (int grp = c; grp * 8 < n1; grp += nc) {
@@ -708,18 +851,26 @@ __global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
                 if (i1 < n1 && lane == 0) rows_w[3LL * i1 + 2] = exp(__dadd_rn(R.rows[3LL * i1], R.rows[3LL * i1 + 1]) - M);
             }
         __syncwarp();
-        double sum_all = 0.0, sum_path = 0.0, sum_uniq = 0.0;          // lane 0 of every warp
-        unsigned long long argkey = ~0ULL;
+        double sum_all = 0.0, sum_path = 0.0, sum_dup = 0.0;          // lane 0 of every warp
         for (int cb = 0; cb < n2; cb += CHUNK) {
             const int cend = min(cb + CHUNK, n2);
+            const int jmax = (cend - cb + 31) >> 5;
             const int h2_last = sorted ? h2s[cend - 1] : 0x7fffffff;
-            int h2v[8], dup2 = 0;
+            const bool all_far = ok && cb >= fa2;
+            int h2v[8], dh2[8], dup2 = 0, pcol = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int col = cb + lane + 32 * j;
-                h2v[j] = col < cend ? h2s[col] : -0x7fffffff;
-                if (col < cend && R.dup[n1 + col]) dup2 |= 1 << j;
+                h2v[j] = col < cend ? h2s[col] : -0x40000000;
+                dh2[j] = max(h2v[j] - L, 1);
+                if (col < cend) {
+                    if (R.dup[n1 + col]) dup2 |= 1 << j;
+                    // column mode: the PP predicate looks at the longer allele only
+                    if (!prow_mode && pathological_h(P, h2v[j], h2v[j])) pcol |= 1 << j;
+                }
             }
+            const int h2_first = h2s[cb];
+            const bool full_chunk = cend - cb == CHUNK;
             double colacc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) colacc[j] = 0.0;
@@ -728,43 +879,59 @@ __global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
                 if (i1 >= n1) continue;
                 const int h1 = h1s[i1];
                 if (h2_last < h1) continue;
-                const int u1 = h1 / K, dh1 = max(h1 - L, 1);
+                const int dh1 = max(h1 - L, 1) - 2;
                 const bool dup1 = R.dup[i1] != 0;
+                const bool prow = prow_mode && pathological_h(P, h1, h1);
                 const long long row = (long long)i1 * n2;
-                double c12 = 0.0, pe_far = 0.0, f = 0.0;
-                if (ok) { c12 = R.rows[3LL * i1]; pe_far = R.rows[3LL * i1 + 1]; f = R.rows[3LL * i1 + 2]; }
-                double racc = 0.0, raccp = 0.0, raccu = 0.0;
+                const double f = ok ? R.rows[3LL * i1 + 2] : 0.0;
+                // a far weight is f * exp(rept) <= f: below e^-10 none of them enters the joint posterior
+                const bool may_emit = g.post != nullptr && !dup1 && f >= eps;
+                double racc = 0.0, raccp = 0.0, raccd = 0.0;
+                if (all_far && full_chunk && sorted && h1 <= h2_first && !dup1 && dup2 == 0 && !may_emit) {
+                    // the common case of a long-expansion grid: 8 valid far columns, nothing to test
+                    const double *er = R.erept + dh1;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int h2 = h2v[j];
-                    if (h1 > h2) continue;                                // not evaluated, or past the chunk
-                    const int col = cb + lane + 32 * j;
-                    double ml, w;
-                    if (ok && col >= fa2) {
-                        const double2 r = *reinterpret_cast<const double2 *>(R.rept2 + 2LL * (dh1 + max(h2 - L, 1) - 2));
-                        ml = __dadd_rn(__dadd_rn(c12, r.x), pe_far);
-                        w = f * r.y;
-                    } else {
-                        ml = surf[row + col];
-                        const double d = ml - M;
-                        w = d < -746.0 ? 0.0 : exp(d);
+                    for (int j = 0; j < 8; ++j) {
+                        const double w = f * er[dh2[j]];
+                        colacc[j] += w; racc += w;
+                        if ((pcol >> j) & 1) raccp += w;
                     }
-                    colacc[j] += w; racc += w;
-                    const int u2 = h2 / K;
-                    if (pathological_u(P, u1, u2)) raccp += w;
-                    if (!(dup1 || ((dup2 >> j) & 1))) {
-                        raccu += w;
-                        if (w >= eps) emit_joint(g, pi, u1, u2, w);
+                } else if (all_far) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= jmax) break;
+                        if (h1 > h2v[j]) continue;                        // not evaluated, or past the chunk
+                        const double w = f * R.erept[dh1 + dh2[j]];
+                        colacc[j] += w; racc += w;
+                        if ((pcol >> j) & 1) raccp += w;
+                        if (dup1 || ((dup2 >> j) & 1)) raccd += w;
+                        else if (may_emit && w >= eps) emit_joint(g, pi, h1 / K, h2v[j] / K, w);
                     }
-                    if (ml == M) argkey = min(argkey, ((unsigned long long)h1 << 40) | (unsigned long long)(row + col));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= jmax) break;
+                        if (h1 > h2v[j]) continue;
+                        const int col = cb + lane + 32 * j;
+                        double w;
+                        if (ok && col >= fa2) w = f * R.erept[dh1 + dh2[j]];
+                        else {
+                            const double d = surf[row + col] - M;
+                            w = d < -746.0 ? 0.0 : exp(d);
+                        }
+                        colacc[j] += w; racc += w;
+                        if ((pcol >> j) & 1) raccp += w;
+                        if (dup1 || ((dup2 >> j) & 1)) raccd += w;
+                        else if (w >= eps) emit_joint(g, pi, h1 / K, h2v[j] / K, w);
+                    }
                 }
                 if (__any_sync(0xffffffffu, racc != 0.0)) {
                     for (int d = 16; d > 0; d >>= 1) {
                         racc += __shfl_down_sync(0xffffffffu, racc, d);
                         raccp += __shfl_down_sync(0xffffffffu, raccp, d);
-                        raccu += __shfl_down_sync(0xffffffffu, raccu, d);
+                        raccd += __shfl_down_sync(0xffffffffu, raccd, d);
                     }
-                    if (lane == 0) { ph1[i1] += racc; sum_all += racc; sum_path += raccp; sum_uniq += raccu; }
+                    if (lane == 0) { ph1[i1] += racc; sum_all += racc; sum_path += prow ? racc : raccp; sum_dup += raccd; }
                 }
             }
 #pragma unroll
@@ -776,15 +943,12 @@ __global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
             if (cb + tid < n2) R.colpart[(long long)c * n2 + cb + tid] = cs;
             __syncthreads();
         }
-        for (int d = 16; d > 0; d >>= 1) argkey = min(argkey, __shfl_xor_sync(0xffffffffu, argkey, d));
-        if (lane == 0) { s_sum[warp][0] = sum_all; s_sum[warp][1] = sum_path; s_sum[warp][2] = sum_uniq; s_arg[warp] = argkey; }
+        if (lane == 0) { s_sum[warp][0] = sum_all; s_sum[warp][1] = sum_path; s_sum[warp][2] = sum_dup; }
         __syncthreads();
         if (tid == 0) {
             double a = 0.0, p = 0.0, u = 0.0;
-            unsigned long long k = ~0ULL;
-            for (int w = 0; w < 8; ++w) { a += s_sum[w][0]; p += s_sum[w][1]; u += s_sum[w][2]; k = min(k, s_arg[w]); }
+            for (int w = 0; w < 8; ++w) { a += s_sum[w][0]; p += s_sum[w][1]; u += s_sum[w][2]; }
             R.partial[4LL * c] = a; R.partial[4LL * c + 1] = p; R.partial[4LL * c + 2] = u;
-            if (k != ~0ULL) atomicMin(&B.argkey, k);
             __threadfence();
             s_last = (atomicAdd(&B.done_b, 1u) == (unsigned)(nc - 1));
         }
@@ -799,18 +963,15 @@ __global__ void __launch_bounds__(256) grid_rows_reduce_kernel(GridParams g) {
             if (tid == 0) {
                 double a = 0.0, p = 0.0, u = 0.0;
                 for (int r = 0; r < nc; ++r) { a += __ldcg(R.partial + 4LL * r); p += __ldcg(R.partial + 4LL * r + 1); u += __ldcg(R.partial + 4LL * r + 2); }
-                const unsigned long long k = *(volatile unsigned long long *)&B.argkey;
-                const int npoints = *(volatile int *)&B.npoints;
                 tredsw_grid_result r;
-                r.max_ml = maxkey ? M : -INFINITY; r.sum_all = a; r.sum_path = p; r.sum_uniq = u;
-                const long long idx = (long long)(k & ((1ULL << 40) - 1));
-                r.arg_i1 = (npoints && k != ~0ULL) ? (int)(idx / n2) : -1;
-                r.arg_i2 = (npoints && k != ~0ULL) ? (int)(idx % n2) : -1;
-                r.n_points = npoints; r.pad = 0;
+                r.max_ml = npoints ? top.ml : -INFINITY; r.sum_all = a; r.sum_path = p; r.sum_uniq = a - u;
+                const long long idx = (long long)(top.key & ((1ULL << 40) - 1));
+                r.arg_i1 = npoints ? (int)(idx / n2) : -1;
+                r.arg_i2 = npoints ? (int)(idx % n2) : -1;
+                r.n_points = (int)npoints; r.pad = 0;
                 g.res[pi] = r;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -822,6 +983,20 @@ __global__ void __launch_bounds__(KDE_THREADS) pe_kde_kernel(const int32_t *lens
 }
 
 }  // namespace
+
+// device-side bookkeeping area of one grid call, at the start of ctx->d_ftab
+struct GridArea {
+    size_t big_bytes, ctr_off, list_off, item_off, tab_off;
+};
+static GridArea grid_area(int nproblems) {
+    GridArea a;
+    a.big_bytes = (((size_t)nproblems * sizeof(BigInfo)) + 255) & ~(size_t)255;
+    a.ctr_off = a.big_bytes;                                                         // fcursor[2] | counters[4] | lists[0]
+    a.list_off = a.ctr_off + 32;
+    a.item_off = (a.list_off + ((size_t)nproblems + 1) * sizeof(int) + 255) & ~(size_t)255;
+    a.tab_off = (a.item_off + (size_t)nproblems * ITEM_MAX * 3 * sizeof(int) + 255) & ~(size_t)255;
+    return a;
+}
 
 int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int nproblems,
                          const int32_t *d_ipool, const double *d_dpool, double *d_surface, double *d_marg,
@@ -836,40 +1011,45 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     g.post = d_post; g.post_cap = post_cap; g.post_cursor = d_post_cursor;
     int rc;
     ctx->mark(2);
-    // [BigInfo x np | cursor, overflow (256 B) | lists (1 + np ints) | table arena]
-    const size_t big_bytes = (((size_t)nproblems * sizeof(BigInfo)) + 255) & ~(size_t)255;
-    const size_t list_bytes = (((size_t)nproblems + 1) * sizeof(int) + 255) & ~(size_t)255;
+    const GridArea ar = grid_area(nproblems);
     // table arena, in doubles: 128 MB serve ~250 long-expansion surfaces; a cohort searched with --fullsearch has
-    // one large surface per problem, ~(60 + n_target) doubles of tables per candidate allele each.  A surface
-    // that finds the arena short of its tables is evaluated point by point (slower, same result); one that
-    // cannot even get its reduction scratch is reported through the overflow flag and the call is repeated
-    // with a larger arena.
+    // one large surface per problem, ~(100 + n_target) doubles of tables and reduction scratch per candidate
+    // allele each.  A surface that finds the arena short of its tables is evaluated point by point (slower, same
+    // result); one that cannot even get its reduction scratch is reported through the overflow flag and the
+    // call is repeated with a larger arena.
     long long cap = 16LL << 20;
     if (points_hint > SMALL_LIMIT) {
         const long long side = (long long)ceil(sqrt((double)points_hint));
         const long long want = (long long)nproblems * 160 * side;
         if (want > cap) cap = want < (1LL << 30) ? want : (1LL << 30);
     }
-    if ((long long)(ctx->d_ftab.cap / sizeof(double)) - (long long)((big_bytes + 256 + list_bytes) / sizeof(double)) > cap)
-        cap = (long long)(ctx->d_ftab.cap / sizeof(double)) - (long long)((big_bytes + 256 + list_bytes) / sizeof(double));
-    if (ctx->d_ftab.ensure(big_bytes + 256 + list_bytes + (size_t)cap * sizeof(double)) != TREDSW_OK) {
+    const long long have = ((long long)ctx->d_ftab.cap - (long long)ar.tab_off) / (long long)sizeof(double);
+    if (have > cap) cap = have;
+    if (ctx->d_ftab.ensure(ar.tab_off + (size_t)cap * sizeof(double)) != TREDSW_OK) {
         cudaGetLastError();                                            // not enough memory for the big arena
         cap = 16LL << 20;
-        if ((rc = ctx->d_ftab.ensure(big_bytes + 256 + list_bytes + (size_t)cap * sizeof(double)))) return rc;
+        if ((rc = ctx->d_ftab.ensure(ar.tab_off + (size_t)cap * sizeof(double)))) return rc;
     }
     unsigned char *base = ctx->d_ftab.as<unsigned char>();
     g.big = reinterpret_cast<BigInfo *>(base);
-    g.fcursor = reinterpret_cast<unsigned long long *>(base + big_bytes);
-    g.lists = reinterpret_cast<int *>(base + big_bytes + 256);
-    g.ftab = reinterpret_cast<double *>(base + big_bytes + 256 + list_bytes);
+    g.fcursor = reinterpret_cast<unsigned long long *>(base + ar.ctr_off);
+    g.counters = reinterpret_cast<unsigned int *>(base + ar.ctr_off + 16);
+    g.lists = reinterpret_cast<int *>(base + ar.list_off);
+    g.items = reinterpret_cast<int *>(base + ar.item_off);
+    g.ftab = reinterpret_cast<double *>(base + ar.tab_off);
     g.ftab_cap = cap;
     if (d_overflow_flag) *d_overflow_flag = g.fcursor;                 // [0] doubles needed, [1] overflow
-    CUDA_TRY(cudaMemsetAsync(g.fcursor, 0, 256 + sizeof(int), ctx->stream));   // cursor, flag, lists[0]
-    grid_small_kernel<<<(nproblems + 7) / 8, 256, 0, ctx->stream>>>(g);
-    const int nsetup = ctx->sm_count * 8, nrows = ctx->sm_count * 4;
-    grid_big_setup_kernel<<<nsetup, 256, 0, ctx->stream>>>(g);
-    grid_rows_eval_kernel<<<nrows, 256, 0, ctx->stream>>>(g);
-    grid_rows_reduce_kernel<<<nrows, 256, 0, ctx->stream>>>(g);
+    CUDA_TRY(cudaMemsetAsync(base + ar.ctr_off, 0, 32 + sizeof(int), ctx->stream));   // cursors, counters, lists[0]
+    grid_classify_kernel<<<(nproblems + 7) / 8, 256, 0, ctx->stream>>>(g);
+    // fused launches: a share of the blocks serves the small surfaces, the rest the large ones
+    const int per_sm = 8;
+    int nsmall = (nproblems + 7) / 8;
+    if (nsmall > ctx->sm_count * per_sm / 2) nsmall = ctx->sm_count * per_sm / 2;
+    g.nblk_small = nsmall;
+    g.target_ctas = ctx->sm_count * 6;
+    grid_points_setup_kernel<<<nsmall + ctx->sm_count * per_sm / 2, 256, 0, ctx->stream>>>(g);
+    grid_reduce_eval_kernel<<<nsmall + ctx->sm_count * 4, 256, 0, ctx->stream>>>(g);
+    grid_rows_reduce_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g);
     CUDA_TRY(cudaGetLastError());
     ctx->mark(3);
     ctx->launches += 4;
@@ -925,9 +1105,7 @@ extern "C" int tredsw_likelihood_grid(tredsw_ctx *ctx, const tredsw_grid_problem
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (!h_flag[1]) break;
         if (attempt == 1) { tredsw_set_error("likelihood table arena overflow (%llu doubles needed)", h_flag[0]); return TREDSW_ERR_UNSUPPORTED; }
-        const size_t big_bytes = (((size_t)nproblems * sizeof(BigInfo)) + 255) & ~(size_t)255;
-        const size_t list_bytes = (((size_t)nproblems + 1) * sizeof(int) + 255) & ~(size_t)255;
-        if ((rc = ctx->d_ftab.ensure(big_bytes + 256 + list_bytes + (size_t)(h_flag[0] + h_flag[0] / 8) * sizeof(double)))) return rc;
+        if ((rc = ctx->d_ftab.ensure(grid_area(nproblems).tab_off + (size_t)(h_flag[0] + h_flag[0] / 8) * sizeof(double)))) return rc;
     }
     if (surface && n_surface > 0)
         CUDA_TRY(cudaMemcpyAsync(surface, g.surface, (size_t)n_surface * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
