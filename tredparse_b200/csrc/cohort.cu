@@ -108,9 +108,10 @@ __global__ void tally_kernel(CohortDev c) {
     atomicAdd(&c.hist[((int64_t)p * 3 + which) * (c.HU + 1) + h], 1);
 }
 
-// one thread per problem
-__global__ void plan_kernel(CohortDev c) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per problem: histogram bins -> observed keys (ordered compaction by ballot), run_pe, candidate lists.
+__global__ void __launch_bounds__(256) plan_kernel(CohortDev c) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (p >= c.nproblems) return;
     const tredsw_problem pr = c.problems[p];
     const tredsw_locus L = c.loci[pr.family];
@@ -121,32 +122,71 @@ __global__ void plan_kernel(CohortDev c) {
     int32_t *slot = c.ipool + c.slot_base + (int64_t)p * (4 * c.KC + 2 * c.HL);
     int32_t *skey = slot, *scnt = slot + c.KC, *pkey = slot + 2 * c.KC, *pcnt = slot + 3 * c.KC;
     int32_t *h1s = slot + 4 * c.KC, *h2s = h1s + c.HL;
+    const unsigned lt = (1u << lane) - 1u;
     int ns = 0, np_ = 0, max_full = 0, max_partial = 0, n_rept = 0;
-    for (int k = 0; k <= c.HU; ++k) {
-        if (hf[k] > 0 && ns < c.KC) { skey[ns] = k * P; scnt[ns] = hf[k]; ++ns; max_full = k * P; }
-        if (hp[k] > 0 && np_ < c.KC) { pkey[np_] = k * P; pcnt[np_] = hp[k]; ++np_; max_partial = k * P; }
-        n_rept += hr[k];
+    for (int k0 = 0; k0 <= c.HU; k0 += 32) {
+        const int k = k0 + lane;
+        const int f = k <= c.HU ? hf[k] : 0, q = k <= c.HU ? hp[k] : 0, r = k <= c.HU ? hr[k] : 0;
+        const unsigned mf = __ballot_sync(0xffffffffu, f > 0), mq = __ballot_sync(0xffffffffu, q > 0);
+        const int pf = ns + __popc(mf & lt), pq = np_ + __popc(mq & lt);
+        if (f > 0 && pf < c.KC) { skey[pf] = k * P; scnt[pf] = f; }
+        if (q > 0 && pq < c.KC) { pkey[pq] = k * P; pcnt[pq] = q; }
+        if (mf) max_full = (k0 + 31 - __clz(mf)) * P;
+        if (mq) max_partial = (k0 + 31 - __clz(mq)) * P;
+        ns = min(ns + __popc(mf), c.KC); np_ = min(np_ + __popc(mq), c.KC);
+        n_rept += __reduce_add_sync(0xffffffffu, r);
     }
-    // scnt / pcnt must directly follow the keys for the grid kernel (keys[n] then counts[n])
-    for (int i = 0; i < ns; ++i) skey[ns + i] = scnt[i];
-    for (int i = 0; i < np_; ++i) pkey[np_ + i] = pcnt[i];
+    __syncwarp();
+    // counts directly after the keys (keys[n] then counts[n]); the two regions may overlap: read, then write
+    {
+        int vs[8], vp[8];                                    // KC <= 256 (checked by the caller)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = lane + 32 * j; vs[j] = i < ns ? scnt[i] : 0; vp[j] = i < np_ ? pcnt[i] : 0; }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = lane + 32 * j; if (i < ns) skey[ns + i] = vs[j]; if (i < np_) pkey[np_ + i] = vp[j]; }
+        __syncwarp();
+    }
     int above = 0;
-    for (int i = 0; i < np_; ++i) if (pkey[i] > max_full + P) above += pkey[np_ + i];
+    for (int i = lane; i < np_; i += 32) if (pkey[i] > max_full + P) above += pkey[np_ + i];
+    above = __reduce_add_sync(0xffffffffu, above);
     const bool has_pe = pr.n_global >= 100 && pr.n_target >= 5;
     const bool run_pe = max_partial >= t3 && above > 1 && has_pe;
     int mp_model = t2;
     if (np_ > 0 && max_partial > mp_model) mp_model = max_partial;
-    // base = sorted(set(span keys) U {max_partial})
+    // base = sorted(set(span keys) U {max_partial}), built by lane 0 (<= KC entries)
     int nb = 0;
-    int32_t *base = h1s;    // build in place, copy below
-    bool placed = (np_ == 0);
-    for (int i = 0; i < ns; ++i) {
-        const int k = skey[i];
-        if (!placed && max_partial < k) { base[nb++] = max_partial; placed = true; }
-        if (!placed && max_partial == k) placed = true;
-        base[nb++] = k;
+    if (lane == 0) {
+        bool placed = (np_ == 0);
+        for (int i = 0; i < ns; ++i) {
+            const int k = skey[i];
+            if (!placed && max_partial < k) { h1s[nb++] = max_partial; placed = true; }
+            if (!placed && max_partial == k) placed = true;
+            h1s[nb++] = k;
+        }
+        if (!placed) h1s[nb++] = max_partial;
     }
-    if (!placed) base[nb++] = max_partial;
+    nb = __shfl_sync(0xffffffffu, nb, 0);
+    __syncwarp();
+    int n1 = 0, n2 = 0, nb1 = 0, nb2 = 0;
+    if (nb > 0) {
+        if (c.fullsearch) {
+            n1 = min(c.maxinsert, c.HL);
+            for (int i = lane; i < n1; i += 32) { h1s[i] = P * (i + 1); h2s[i] = P * (i + 1); }
+            n2 = n1; nb1 = n1; nb2 = n2;
+        } else {
+            const bool ext1 = (max_full == 0), ext2 = (n_rept > 0 || run_pe);
+            for (int i = lane; i < nb; i += 32) h2s[i] = h1s[i];
+            // extension: max_partial + P, max_partial + 2P, ..., P * maxinsert
+            const int next = max(0, c.maxinsert - max_partial / P);
+            const int e1 = ext1 ? min(next, c.HL - nb) : 0, e2 = ext2 ? min(next, c.HL - nb) : 0;
+            for (int j = lane; j < e1; j += 32) h1s[nb + j] = max_partial + P * (j + 1);
+            for (int j = lane; j < e2; j += 32) h2s[nb + j] = max_partial + P * (j + 1);
+            n1 = nb + e1; n2 = nb + e2; nb1 = nb; nb2 = nb;
+        }
+        if (pr.ploidy == 1) { n2 = 1; nb2 = 1; }
+    }
+    if (lane != 0) return;
     tredsw_grid_problem g;
     memset(&g, 0, sizeof(g));
     g.period = P; g.readlen = L.readlen; g.ploidy = pr.ploidy; g.n_rept = n_rept;
@@ -160,22 +200,6 @@ __global__ void plan_kernel(CohortDev c) {
     g.off_pdf = run_pe ? (int64_t)p * KDE_SPAN : -1;
     g.off_step = c.step_base + (int64_t)pr.family * NSTEP;
     g.off_ph1 = (int64_t)p * 2 * c.HL; g.off_ph2 = g.off_ph1 + c.HL;
-    int n1 = 0, n2 = 0, nb1 = 0, nb2 = 0;
-    if (nb > 0) {
-        if (c.fullsearch) {
-            for (int h = P; h <= P * c.maxinsert && n1 < c.HL; h += P) { h1s[n1] = h; h2s[n1] = h; ++n1; }
-            n2 = n1; nb1 = n1; nb2 = n2;
-        } else {
-            const bool ext1 = (max_full == 0), ext2 = (n_rept > 0 || run_pe);
-            for (int i = 0; i < nb; ++i) h2s[i] = base[i];       // base was built in h1s
-            n1 = nb; n2 = nb; nb1 = nb; nb2 = nb;
-            for (int h = max_partial + P; h <= P * c.maxinsert; h += P) {
-                if (ext1 && n1 < c.HL) h1s[n1++] = h;
-                if (ext2 && n2 < c.HL) h2s[n2++] = h;
-            }
-        }
-        if (pr.ploidy == 1) { n2 = 1; nb2 = 1; }
-    }
     g.n_h1 = n1; g.n_h2 = n2;
     const long long need = (long long)n1 * n2;
     long long off = 0;
@@ -196,29 +220,61 @@ __global__ void __launch_bounds__(KDE_THREADS) cohort_kde_kernel(CohortDev c, co
     }
 }
 
-// 95% interval over the merged, sorted keys of a marginal (models.py:319-340).  The candidate list is a
-// sorted base part [0, nb) followed by an ascending extension [nb, n); equal keys are summed (the
-// reference's defaultdict); entries failing `used` never became keys.
-// With `c.post` the sparsified marginal (models.py:304-317: entries >= e^-10, divided by the full total) is
-// emitted on the way — the merge walks every key, the interval stops moving once it is found.
-template <class Used>
-__device__ void ci_of(const CohortDev &c, int p, int kind, int period, const int32_t *hs, const double *w, int n, int nb,
-                      Used used, int &lo, int &hi) {
-    double total = 0.0;
-    for (int i = 0; i < n; ++i) if (used(hs[i])) total += w[i];
-    int a = 0, b = nb;
-    double cum = 0.0;
-    bool in_range = false, any = false, done = false;
-    int k = 0;
+// 95% interval over the merged, sorted keys of a marginal (models.py:319-340) and its sparsified form
+// (models.py:304-317), by one warp.  The candidate list is a sorted base part [0, nb) followed by an ascending
+// extension [nb, n); equal keys are one key of the reference's defaultdict (their weights add up); entries outside
+// [ulo, uhi] never became keys (an h1 above every h2, an h2 below every h1: no evaluated point uses them).
+// cum(x) = sum of the weights of the keys <= x is evaluated by the whole warp; the interval ends are the smallest
+// keys with cum > 2.5 % / 97.5 % of the total — found by bisection in each sorted part, no serial merge.
+struct Marginal {
+    const int32_t *hs;
+    const double *w;
+    int n, nb, ulo, uhi;
+    __device__ __forceinline__ bool used(int h) const { return h >= ulo && h <= uhi; }
+    __device__ __forceinline__ double cum(int x, int lane) const {
+        double a = 0.0;
+        for (int i = lane; i < n; i += 32) { const int h = hs[i]; if (h <= x && used(h)) a += w[i]; }
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        return a;
+    }
+    // smallest used key of the sorted part [a, b) with cum(key) > thr; INT_MAX when there is none
+    __device__ __forceinline__ int first_above(int a, int b, double thr, int lane) const {
+        int lo = a, hi = b;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum(hs[mid], lane) > thr) hi = mid; else lo = mid + 1;
+        }
+        return (lo < b && used(hs[lo])) ? hs[lo] : 0x7fffffff;
+    }
+};
+
+__device__ void ci_of(const CohortDev &c, int p, int kind, int period, const Marginal &m, int lane, int &lo, int &hi) {
+    const double total = m.cum(0x7fffffff, lane);
+    int last = -0x7fffffff;
+    for (int i = lane; i < m.n; i += 32) if (m.used(m.hs[i])) last = max(last, m.hs[i]);
+    last = __reduce_max_sync(0xffffffffu, last);
     lo = 0; hi = 0;
-    while (a < nb || b < n) {
-        int key;
-        if (a < nb && (b >= n || hs[a] <= hs[b])) key = hs[a]; else key = hs[b];
-        double v = 0.0;
-        while (a < nb && hs[a] == key) { v += w[a]; ++a; }
-        while (b < n && hs[b] == key) { v += w[b]; ++b; }
-        if (!used(key)) continue;
-        if (c.post && v >= c.small_value) {
+    if (last != -0x7fffffff) {
+        const int l = min(m.first_above(0, m.nb, .025 * total, lane), m.first_above(m.nb, m.n, .025 * total, lane));
+        const int h = min(m.first_above(0, m.nb, .975 * total, lane), m.first_above(m.nb, m.n, .975 * total, lane));
+        lo = l == 0x7fffffff ? 0 : l;
+        hi = h == 0x7fffffff ? last : h;
+    }
+    if (!c.post) return;
+    for (int i = lane; i < m.n; i += 32) {
+        const int key = m.hs[i];
+        if (!m.used(key)) continue;
+        double v = m.w[i];
+        if (i >= m.nb) {
+            bool second = false;                                   // already a key of the base part?
+            if (m.nb > 0 && key <= m.hs[m.nb - 1]) for (int j = 0; j < m.nb; ++j) if (m.hs[j] == key) second = true;
+            if (second) continue;
+        } else {
+            int a = m.nb, b = m.n;                                 // the same key among the extension
+            while (a < b) { const int mid = (a + b) >> 1; if (m.hs[mid] < key) a = mid + 1; else b = mid; }
+            if (a < m.n && m.hs[a] == key) v += m.w[a];
+        }
+        if (v >= c.small_value) {
             const unsigned long long at = atomicAdd(c.post_cursor, 1ULL);
             if ((long long)at < c.post_cap) {
                 tredsw_posterior e;
@@ -226,18 +282,13 @@ __device__ void ci_of(const CohortDev &c, int p, int kind, int period, const int
                 c.post[at] = e;
             }
         }
-        if (done) continue;
-        any = true;
-        k = key;
-        cum += v;
-        if (!in_range && cum > .025 * total) { in_range = true; lo = key; }
-        if (cum > .975 * total) { done = true; if (!c.post) break; }
     }
-    hi = any ? k : 0;
 }
 
-__global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tredsw_call *calls) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per problem
+__global__ void __launch_bounds__(256) finalize_kernel(CohortDev c, const tredsw_grid_result *res, tredsw_call *calls) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (p >= c.nproblems) return;
     const tredsw_grid_problem g = c.gp[p];
     const tredsw_locus L = c.loci[c.problems[p].family];
@@ -245,8 +296,9 @@ __global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tred
     tredsw_call out;
     memset(&out, 0, sizeof(out));
     int fdp = 0, pdp = 0;
-    for (int k = 0; k <= c.HU; ++k) { fdp += hf[k]; pdp += hf[(c.HU + 1) + k]; }
-    out.fdp = fdp; out.pdp = pdp; out.rdp = g.n_rept; out.run_pe = g.run_pe;
+    for (int k = lane; k <= c.HU; k += 32) { fdp += hf[k]; pdp += hf[(c.HU + 1) + k]; }
+    out.fdp = __reduce_add_sync(0xffffffffu, fdp); out.pdp = __reduce_add_sync(0xffffffffu, pdp);
+    out.rdp = g.n_rept; out.run_pe = g.run_pe;
     int a1 = -1, a2 = -1;
     if (g.n_h1 == 0 || res[p].n_points <= 0) {
         out.allele1 = out.allele2 = -1;
@@ -264,27 +316,34 @@ __global__ void finalize_kernel(CohortDev c, const tredsw_grid_result *res, tred
         const double *ph1 = c.marg + g.off_ph1, *ph2 = c.marg + g.off_ph2;
         int lo1, hi1, lo2, hi2;
         if (g.ploidy == 1) {
-            ci_of(c, p, TREDSW_POST_H1, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo1, hi1);
-            if (c.post) ci_of(c, p, TREDSW_POST_H2, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [](int) { return true; }, lo2, hi2);
+            const Marginal m{h1s, ph1, g.n_h1, c.nbase[2 * p], -0x7fffffff, 0x7fffffff};
+            ci_of(c, p, TREDSW_POST_H1, g.period, m, lane, lo1, hi1);
+            if (c.post) ci_of(c, p, TREDSW_POST_H2, g.period, m, lane, lo2, hi2);      // h2 = h1: the same marginal
             lo2 = lo1; hi2 = hi1;
         } else {
-            int mx2 = h2s[0], mn1 = h1s[0];
-            for (int i = 1; i < g.n_h2; ++i) mx2 = max(mx2, h2s[i]);
-            for (int i = 1; i < g.n_h1; ++i) mn1 = min(mn1, h1s[i]);
-            ci_of(c, p, TREDSW_POST_H1, g.period, h1s, ph1, g.n_h1, c.nbase[2 * p], [mx2](int h) { return h <= mx2; }, lo1, hi1);
-            ci_of(c, p, TREDSW_POST_H2, g.period, h2s, ph2, g.n_h2, c.nbase[2 * p + 1], [mn1](int h) { return h >= mn1; }, lo2, hi2);
-        }
-        if (c.post) {                                    // divisor of this problem's joint entries
-            const unsigned long long at = atomicAdd(c.post_cursor, 1ULL);
-            if ((long long)at < c.post_cap) {
-                tredsw_posterior e;
-                e.problem = p; e.kind = TREDSW_POST_JOINT_TOTAL; e.a = 0; e.b = 0; e.p = r.sum_uniq;
-                c.post[at] = e;
-            }
+            int mx2 = -0x7fffffff, mn1 = 0x7fffffff;
+            for (int i = lane; i < g.n_h2; i += 32) mx2 = max(mx2, h2s[i]);
+            for (int i = lane; i < g.n_h1; i += 32) mn1 = min(mn1, h1s[i]);
+            mx2 = __reduce_max_sync(0xffffffffu, mx2); mn1 = __reduce_min_sync(0xffffffffu, mn1);
+            const Marginal m1{h1s, ph1, g.n_h1, c.nbase[2 * p], -0x7fffffff, mx2};
+            const Marginal m2{h2s, ph2, g.n_h2, c.nbase[2 * p + 1], mn1, 0x7fffffff};
+            ci_of(c, p, TREDSW_POST_H1, g.period, m1, lane, lo1, hi1);
+            ci_of(c, p, TREDSW_POST_H2, g.period, m2, lane, lo2, hi2);
         }
         out.ci[0] = lo1 / g.period; out.ci[1] = hi1 / g.period; out.ci[2] = lo2 / g.period; out.ci[3] = hi2 / g.period;
-        atomicAdd(&c.counters[2], (unsigned long long)r.n_points);
+        if (lane == 0) {
+            atomicAdd(&c.counters[2], (unsigned long long)r.n_points);
+            if (c.post) {                                    // divisor of this problem's joint entries
+                const unsigned long long at = atomicAdd(c.post_cursor, 1ULL);
+                if ((long long)at < c.post_cap) {
+                    tredsw_posterior e;
+                    e.problem = p; e.kind = TREDSW_POST_JOINT_TOTAL; e.a = 0; e.b = 0; e.p = r.sum_uniq;
+                    c.post[at] = e;
+                }
+            }
+        }
     }
+    if (lane != 0) return;
     // label (models.py:370-392)
     int label = (a1 != -1) ? 0 : 3;
     if (L.expansion) {
@@ -329,6 +388,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     const int HU = max_u;
     if (hist && hist_units != HU) { tredsw_set_error("hist_units must equal the largest max_units (%d)", HU); return TREDSW_ERR_ARG; }
     const int KC = HU + 2;
+    if (KC > 256) { tredsw_set_error("max_units %d too large (<= 254)", HU); return TREDSW_ERR_UNSUPPORTED; }
     const int HL = c->maxinsert + KC + 2;
     int rc;
     // ---- inputs ------------------------------------------------------------------------------------
@@ -490,7 +550,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
         }
         tally_kernel<<<(nr + tb - 1) / tb, tb, 0, ctx->stream>>>(cd);
     }
-    plan_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd);
+    plan_kernel<<<(np_ + 7) / 8, 256, 0, ctx->stream>>>(cd);
     ctx->mark(4);
     // one block per problem (most exit at once: only problems with run_pe need the KDE); the hardware block
     // scheduler balances the sparse, uneven survivors better than a strided loop would
@@ -502,7 +562,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     if ((rc = tredsw_internal_grid(ctx, cd.gp, np_, d_ipool, d_dpool, ctx->d_surface.as<double>(), cd.marg,
                                    ctx->d_res.as<tredsw_grid_result>(), c->fullsearch ? per_problem : 4LL * HL, 0,
                                    d_post, post_cap, cd.post_cursor, &d_tab_flag))) return rc;
-    finalize_kernel<<<(np_ + 127) / 128, 128, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
+    finalize_kernel<<<(np_ + 7) / 8, 256, 0, ctx->stream>>>(cd, ctx->d_res.as<tredsw_grid_result>(), d_calls);
     CUDA_TRY(cudaGetLastError());
     ctx->mark(7);
     if (token_lock.owns_lock()) {

@@ -17,7 +17,7 @@
 //
 // THE SURFACE IS NOT MATERIALISED (unless the caller asks for it).  What the caller of the reference gets are
 // the call, the marginals P_h1 / P_h2, the sparse joint P_h1h2 and the PP sums; so:
-//   * small surfaces (<= 4096 points, every haploid problem) are cut into work items of 256 points — one warp per
+//   * small surfaces (<= 512 points, every haploid problem) are cut into work items of 256 points — one warp per
 //     item, whatever the mix of sizes — that park the ml values in the problem's scratch slot (L1/L2); one warp
 //     per problem then reduces and emits;
 //   * large surfaces: row-structured.  A warp owns rows (one h1), its lanes walk the columns (h2) in chunks of
@@ -45,9 +45,9 @@ namespace {
 constexpr int SPAN = 1000;
 constexpr int NSTEP = 37;
 constexpr int DEV = 18;
-constexpr long long SMALL_LIMIT = 4096;   // <= : point items + one warp for the reductions
+constexpr long long SMALL_LIMIT = 512;    // <= : point items + one warp for the reductions
 constexpr int ITEM_POINTS = 256;          // points per work item of a small surface (8 per lane)
-constexpr int ITEM_MAX = 16;              // items per small surface (an item strides when there are more chunks)
+constexpr int ITEM_MAX = 12;              // items per small surface (an item strides when there are more chunks)
 constexpr int NC_MAX = 32;                // CTAs per large surface (rows are dealt round-robin in groups of 8)
 constexpr int CHUNK = 256;                // columns per chunk: 8 per lane
 constexpr int FILL_SPLIT = 8;             // blocks per large surface filling its tables
@@ -70,6 +70,9 @@ struct BigInfo {
     int nce;                     // CTAs actually working on it (chosen once the number of large surfaces is known)
     int nb1, nb2;                // length of the sorted base part of the h1 / h2 list (duplicates live beyond it)
     int patho_mode;              // the PP predicate for h1 <= h2: 0 = by column (h2), 1 = by row (h1)
+    int far_arith;               // the far columns are an arithmetic sequence above the read length:
+    int far_d0, far_step;        //   max(h2s[col] - L, 1) = far_d0 + far_step * (col - fa2)  (no list load per point)
+    int has_dup;                 // a candidate occurs twice (Q9)
     unsigned int done_b;         // CTAs of pass B that have finished
 };
 
@@ -86,7 +89,7 @@ struct GridParams {
     BigInfo *big;                // [nproblems]
     int *lists;                  // [0] number of large surfaces, [1 + i] their problem indices
     int *items;                  // point items of the small surfaces: (problem, chunk, nitems) triples
-    unsigned int *counters;      // [0] items, [1] work cursor pass A, [2] work cursor pass B
+    unsigned int *counters;      // [0] items, [1] work cursor pass A, [2] work cursor pass B, [3] item cursor
     double *ftab;                // table arena
     long long ftab_cap;
     unsigned long long *fcursor; // [0] arena cursor, [1] overflow flag
@@ -358,7 +361,7 @@ __device__ __forceinline__ ProblemConsts problem_consts(const tredsw_grid_proble
 }
 
 // ==========================================================================================================
-// K1  classify: one warp per problem.  Small surfaces (<= 4096 points, every haploid problem) are cut into work
+// K1  classify: one warp per problem.  Small surfaces (<= 512 points, every haploid problem) are cut into work
 //     items of 256 points; large ones are registered for the row kernels and get their table space.
 // ==========================================================================================================
 __global__ void __launch_bounds__(256) grid_classify_kernel(GridParams g) {
@@ -369,6 +372,14 @@ __global__ void __launch_bounds__(256) grid_classify_kernel(GridParams g) {
     const int n1 = P.n_h1, n2 = P.n_h2;
     const long long total = n2 > 0 ? (long long)n1 * n2 : 0;
     if (P.ploidy == 1 || total <= SMALL_LIMIT) {
+        // the stutter probability of every candidate, once per problem instead of up to four times per point;
+        // parked in the marginal slots (P_h1 / P_h2 are written by the reduction, after the points are done)
+        {
+            const int32_t *a1 = g.ipool + P.off_h1, *a2 = g.ipool + P.off_h2;
+            double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
+            for (int i = lane; i < n1; i += 32) ph1[i] = sigma_h(P, a1[i]);
+            if (P.ploidy != 1) for (int i = lane; i < n2; i += 32) ph2[i] = sigma_h(P, a2[i]);
+        }
         if (lane == 0 && total > 0) {
             const int chunks = (int)((total + ITEM_POINTS - 1) / ITEM_POINTS);
             const int n = min(chunks, ITEM_MAX);
@@ -420,15 +431,21 @@ __global__ void __launch_bounds__(256) grid_classify_kernel(GridParams g) {
 }
 
 // ---- small surfaces, part 1: one warp per item evaluates its points into the scratch slot ---------------------
-__device__ __forceinline__ void small_points(const GridParams &g, int first_warp, int nwarps) {
+// (items come from an atomic cursor: their cost varies by two orders of magnitude)
+__device__ __forceinline__ void small_points(const GridParams &g) {
     const int lane = threadIdx.x & 31;
     const unsigned nitems = g.counters[0];
-    for (unsigned it = first_warp; it < nitems; it += nwarps) {
+    for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(&g.counters[3], 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= nitems) break;
         const int pi = g.items[3 * it], chunk0 = g.items[3 * it + 1], stride = g.items[3 * it + 2];
         const tredsw_grid_problem &P = g.prob[pi];
         const int n2 = P.n_h2;
         const long long total = (long long)P.n_h1 * n2;
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
+        const double *sg1s = g.marg + P.off_ph1, *sg2s = g.marg + P.off_ph2;
         const bool haploid = P.ploidy == 1;
         const ProblemConsts T = problem_consts(P, g, lane);
         double *surf = g.surface + P.off_surface;
@@ -439,7 +456,16 @@ __device__ __forceinline__ void small_points(const GridParams &g, int first_warp
                 const int i1 = (int)(t / n2), i2 = (int)(t - (long long)i1 * n2);
                 const int h1 = h1s[i1];
                 const int h2 = haploid ? h1 : h2s[i2];
-                surf[t] = h1 <= h2 ? point_ml(P, g, h1, h2, T) : -INFINITY;
+                double ml = -INFINITY;
+                if (h1 <= h2) {
+                    const double s1 = sg1s[i1], s2 = haploid ? s1 : sg2s[i2];
+                    const double sc1 = h1 >= P.max_partial ? T.sig_mp : s1, sc2 = h2 >= P.max_partial ? T.sig_mp : s2;
+                    ml = term_span(P, g, h1, h2, s1, s2);
+                    ml = __dadd_rn(ml, term_part(P, g, h1, h2, sc1, sc2, T.sig_mp));
+                    ml = __dadd_rn(ml, term_rept(P, max(h1 - P.readlen, 1) + max(h2 - P.readlen, 1), T.lgamma_k1));
+                    ml = __dadd_rn(ml, term_pe(P, g, h1, h2, T.tmin));
+                }
+                surf[t] = ml;
             }
     }
 }
@@ -478,6 +504,28 @@ __device__ __forceinline__ void small_reduce(const GridParams &g, int first_warp
         const int nb2 = (cnt && !haploid) ? base_len(h2s, n2, lane) : n2;
         double sum_all = 0.0, sum_path = 0.0, sum_uniq = 0.0;
         const double eps = g.small_value;
+        if (haploid) {
+            // one point per candidate (h2 = h1): lanes over the candidates
+            double acc = 0.0, accp = 0.0, accu = 0.0;
+            for (int i1 = lane; i1 < n1; i1 += 32) {
+                const double ml = surf[i1];
+                const int h1 = h1s[i1];
+                const double w = exp(ml - best_ml);
+                ph1[i1] = w; acc += w;
+                if (pathological_h(P, h1, h1)) accp += w;
+                if (!is_second_occurrence(h1s, nb1, i1)) {
+                    accu += w;
+                    if (w >= eps) emit_joint(g, pi, h1 / P.period, h1 / P.period, w);
+                }
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                accp += __shfl_xor_sync(0xffffffffu, accp, d);
+                accu += __shfl_xor_sync(0xffffffffu, accu, d);
+            }
+            sum_all = acc; sum_path = accp; sum_uniq = accu;
+            if (lane == 0 && n2 > 0) ph2[0] = acc;
+        } else
         for (int i1 = 0; i1 < n1; ++i1) {
             const int h1 = h1s[i1];
             const bool dup1 = is_second_occurrence(h1s, nb1, i1);
@@ -559,7 +607,15 @@ __device__ __forceinline__ void big_setup(const GridParams &g, int first_block, 
         l1 = block_max_int(l1, s8); l2 = block_max_int(l2, s8);
         const int fam = B.ok ? l1 + 1 : n2, fa2 = B.ok ? l2 + 1 : n2;
         const double lgk = lgamma((double)P.n_rept + 1.0), sig_mp = sigma_h(P, P.max_partial);
+        int notarith = 0, anydup = 0;
+        const int fstep = fa2 + 1 < n2 ? h2s[fa2 + 1] - h2s[fa2] : 0, fd0 = fa2 < n2 ? h2s[fa2] - P.readlen : 1;
+        for (int i = fa2 + tid; i < n2; i += 256) if (h2s[i] != h2s[fa2] + (i - fa2) * fstep) notarith = 1;
+        if (fd0 < 1) notarith = 1;
+        for (int i = tid; i < n1 + n2; i += 256)
+            if (i < n1 ? is_second_occurrence(h1s, B.nb1, i) : is_second_occurrence(h2s, B.nb2, i - n1)) anydup = 1;
+        notarith = block_max_int(notarith, s8); anydup = block_max_int(anydup, s8);
         if (part == 0 && tid == 0) {
+            B.far_arith = notarith ? 0 : 1; B.far_d0 = fd0; B.far_step = fstep; B.has_dup = anydup;
             B.lgamma_k1 = lgk; B.sig_mp = sig_mp; B.tmin = tmin; B.fam = fam; B.fa2 = fa2; B.sorted = unsorted ? 0 : 1;
             // few large surfaces: many CTAs each (latency); many: few CTAs each, so that a warp keeps its column
             // registers over many rows (throughput)
@@ -609,7 +665,7 @@ __device__ __forceinline__ void big_setup(const GridParams &g, int first_block, 
 
 // K2 = { point items of the small surfaces | table setup of the large ones }
 __global__ void __launch_bounds__(256) grid_points_setup_kernel(GridParams g) {
-    if ((int)blockIdx.x < g.nblk_small) small_points(g, blockIdx.x * 8 + (threadIdx.x >> 5), g.nblk_small * 8);
+    if ((int)blockIdx.x < g.nblk_small) small_points(g);
     else big_setup(g, blockIdx.x - g.nblk_small, gridDim.x - g.nblk_small);
 }
 
@@ -643,8 +699,83 @@ struct Best {                       // running arg-max with the reference's tie 
 };
 
 // Pass A: near / mid points into the scratch slot; maximum, arg-max and point count of this CTA's rows.
-// Work item = (surface, CTA rank c < nc): the row groups g = c, c + nc, ... of 8 rows (one per warp); items are
+// Work item = (surface, CTA rank c < nce): the row groups g = c, c + nce, ... of 8 rows (one per warp); items are
 // taken from an atomic cursor, rank-major, so the ranks holding the expensive near rows start first.
+// A warp walks one row at a time, left to right: column groups of 32 with near / mid columns go through
+// mixed_batch<NJ> (NJ = 4, 2, 1 groups at a time: the paired-end products of NJ columns per lane run as NJ
+// independent chains over the pair lengths, fed by one uniform and NJ coalesced loads per length), the far
+// columns through a loop of two additions per point.
+struct RowCtx {
+    const tredsw_grid_problem *P;
+    const GridParams *g;
+    const int32_t *h2s;
+    double *surf;                 // row base
+    const double *rept_row;       // rept + max(h1 - L, 1) - 2
+    const double *R1row, *R2, *sig2;
+    double c12, pe_far, sg1, sgc1, eps;
+    int h1, i1, n1, n2, L, fam, fa2, npe, ok, c0, tmin;
+    long long rowbase;
+    bool mat, strict;
+};
+
+template <int NJ>
+__device__ __forceinline__ void mixed_batch(const RowCtx &x, const ProblemConsts &T, int gb, int lane, Best &best, int &cnt) {
+    const tredsw_grid_problem &P = *x.P;
+    double pe[NJ];
+    int col[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) { col[q] = 32 * (gb + q) + lane; pe[q] = 0.0; }
+    if (x.ok && x.npe > 0) {
+        int cj[NJ];
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) cj[q] = min(col[q], x.fa2 - 1);
+        for (int t0 = 0; t0 < x.npe; t0 += PE_BLOCK) {
+            double prod[NJ];
+#pragma unroll
+            for (int q = 0; q < NJ; ++q) prod[q] = 1.0;
+            const int t1 = min(t0 + PE_BLOCK, x.npe);
+#pragma unroll 2
+            for (int t = t0; t < t1; ++t) {
+                const double r1 = x.R1row[(long long)t * x.n1];
+                const double *r2p = x.R2 + (long long)t * x.fa2;
+#pragma unroll
+                for (int q = 0; q < NJ; ++q) prod[q] = __dmul_rn(prod[q], fmax(__dadd_rn(r1, r2p[cj[q]]), x.eps));
+            }
+#pragma unroll
+            for (int q = 0; q < NJ; ++q) pe[q] = __dadd_rn(pe[q], log(prod[q]));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+        const int c = col[q];
+        if (c >= x.n2) continue;
+        const int h2 = x.h2s[c];
+        double ml = -INFINITY;
+        if (x.h1 <= h2) {
+            if (x.ok) {
+                const double rp = x.rept_row[max(h2 - x.L, 1)];
+                if (c >= x.fa2) ml = __dadd_rn(__dadd_rn(x.c12, rp), x.pe_far);
+                else {
+                    const double pej = x.npe > 0 ? pe[q] : term_pe(P, *x.g, x.h1, h2, x.tmin);
+                    if (c >= x.fam) ml = __dadd_rn(__dadd_rn(x.c12, rp), pej);
+                    else {
+                        const double sg2 = x.sig2[c];
+                        const double sgc2 = min(h2, P.max_partial) == P.max_partial ? T.sig_mp : sg2;
+                        ml = __dadd_rn(term_span(P, *x.g, x.h1, h2, x.sg1, sg2), term_part(P, *x.g, x.h1, h2, x.sgc1, sgc2, T.sig_mp));
+                        ml = __dadd_rn(__dadd_rn(ml, rp), pej);
+                    }
+                }
+            } else {
+                ml = point_ml(P, *x.g, x.h1, h2, T);
+            }
+            if (x.strict) { if (ml > best.ml) { best.ml = ml; best.key = ((unsigned long long)x.h1 << 40) | (unsigned long long)(x.rowbase + c); } }
+            else best.take(ml, x.h1, x.rowbase + c);
+            ++cnt;
+            if (!(x.ok && c >= x.fa2) || x.mat) x.surf[c] = ml;
+        } else if (x.mat) x.surf[c] = ml;
+    }
+}
+
 __device__ __forceinline__ void rows_eval(const GridParams &g) {
     __shared__ double s_ml[8];
     __shared__ unsigned long long s_key[8];
@@ -666,119 +797,68 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
         const int n1 = P.n_h1, n2 = P.n_h2, L = P.readlen;
         const int32_t *h1s = g.ipool + P.off_h1, *h2s = g.ipool + P.off_h2;
         double *surf = g.surface + P.off_surface, *ph1 = g.marg + P.off_ph1;
-        // sorted lists: the last near / mid allele; a row beyond it has far columns only
-        const int h2_mid_last = (B.sorted && B.ok && B.fa2 > 0) ? h2s[B.fa2 - 1] : 0x7fffffff;
         const RowTables R = row_tables(g, B, n1, n2);
-        const int ok = B.ok, fam = B.fam, fa2 = B.fa2, npe = B.npe, sorted = B.sorted;
-        const bool mat = g.materialise != 0;
         ProblemConsts T;
         T.lgamma_k1 = B.lgamma_k1; T.sig_mp = B.sig_mp; T.tmin = B.tmin;
-        const double eps = g.small_value;
+        RowCtx x;
+        x.P = &P; x.g = &g; x.h2s = h2s; x.R2 = R.R2; x.sig2 = R.sig2; x.eps = g.small_value;
+        x.n1 = n1; x.n2 = n2; x.L = L; x.fam = B.fam; x.fa2 = B.fa2; x.npe = B.npe; x.ok = B.ok; x.tmin = B.tmin;
+        x.mat = g.materialise != 0; x.strict = B.sorted != 0;
+        const bool sorted = B.sorted != 0, arith = B.far_arith != 0 && B.ok;
+        const int ngroups = (n2 + 31) >> 5;
+        const int g_mid_end = B.ok ? (min(B.fa2, n2) + 31) >> 5 : ngroups;     // groups [.., g_mid_end) hold near / mid columns
         Best best{-INFINITY, ~0ULL};
         int cnt = 0;
         for (int grp = c; grp * 8 < n1; grp += nc) {
             const int i1 = grp * 8 + warp;
-            if (i1 < n1 && lane == 0) ph1[i1] = 0.0;
-        }
-        for (int cb = 0; cb < n2; cb += CHUNK) {
-            const int cend = min(cb + CHUNK, n2);
-            const int jmax = (cend - cb + 31) >> 5;
-            const int h2_last = sorted ? h2s[cend - 1] : 0x7fffffff;
-            const bool all_far = ok && cb >= fa2;
-            int h2v[8], dh2[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = cb + lane + 32 * j;
-                h2v[j] = col < cend ? h2s[col] : -0x40000000;
-                dh2[j] = max(h2v[j] - L, 1);
+            if (i1 >= n1) continue;
+            if (lane == 0) ph1[i1] = 0.0;
+            const int h1 = h1s[i1];
+            x.h1 = h1; x.i1 = i1; x.rowbase = (long long)i1 * n2; x.surf = surf + x.rowbase;
+            x.c12 = 0.0; x.pe_far = 0.0; x.sg1 = -1.0; x.sgc1 = -1.0;
+            x.rept_row = R.rept + (max(h1 - L, 1) - 2);
+            x.R1row = R.R1 + i1;
+            if (B.ok) {
+                x.c12 = R.rows[3LL * i1]; x.pe_far = R.rows[3LL * i1 + 1]; x.sg1 = R.sig1[i1];
+                x.sgc1 = min(h1, P.max_partial) == P.max_partial ? T.sig_mp : x.sg1;
             }
-            for (int grp = c; grp * 8 < n1; grp += nc) {
-                const int i1 = grp * 8 + warp;
-                if (i1 >= n1) continue;
-                const int h1 = h1s[i1];
-                const long long row = (long long)i1 * n2;
-                if (h2_last < h1) {                              // the whole chunk has h1 > h2: not evaluated
-                    if (mat) for (int col = cb + lane; col < cend; col += 32) surf[row + col] = -INFINITY;
-                    continue;
-                }
-                const int dh1 = max(h1 - L, 1) - 2;
-                double c12 = 0.0, pe_far = 0.0, sg1 = -1.0, sgc1 = -1.0;
-                if (ok) {
-                    c12 = R.rows[3LL * i1]; pe_far = R.rows[3LL * i1 + 1]; sg1 = R.sig1[i1];
-                    sgc1 = min(h1, P.max_partial) == P.max_partial ? T.sig_mp : sg1;
-                }
-                if (all_far || (ok && h1 > h2_mid_last)) {
+            // first column the row evaluates (sorted lists: lower bound of h1)
+            int c0 = 0;
+            if (sorted) {
+                int lo = 0, hi = n2;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (h2s[mid] < h1) lo = mid + 1; else hi = mid; }
+                c0 = lo;
+            }
+            x.c0 = c0;
+            if (x.mat) for (int col = lane; col < c0; col += 32) x.surf[col] = -INFINITY;
+            int gb = c0 >> 5;
+            while (gb < g_mid_end) {
+                const int left = g_mid_end - gb;
+                if (left >= 4) { mixed_batch<4>(x, T, gb, lane, best, cnt); gb += 4; }
+                else if (left >= 2) { mixed_batch<2>(x, T, gb, lane, best, cnt); gb += 2; }
+                else { mixed_batch<1>(x, T, gb, lane, best, cnt); gb += 1; }
+            }
+            // far columns: two additions per point
+            const double c12 = x.c12, pe_far = x.pe_far;
+            const double *rr = x.rept_row;
+            const unsigned long long keybase = ((unsigned long long)h1 << 40) | (unsigned long long)x.rowbase;
+            for (; gb < ngroups; gb += 4) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j >= jmax) break;
-                        const int col = cb + lane + 32 * j;
-                        double ml = -INFINITY;
-                        if (h1 <= h2v[j]) {
-                            ml = __dadd_rn(__dadd_rn(c12, R.rept[dh1 + dh2[j]]), pe_far);
-                            best.take(ml, h1, row + col); ++cnt;
-                        }
-                        if (mat && col < cend) surf[row + col] = ml;
-                    }
-                    continue;
-                }
-                // column groups [jlo, jhi) of this chunk hold near / mid columns the row evaluates
-                int jlo = 0;
-                const int jhi = ok ? min(jmax, (min(fa2, cend) - cb + 31) >> 5) : jmax;
-                if (sorted) while (jlo < jhi && h2s[min(cb + 32 * jlo + 31, cend - 1)] < h1) ++jlo;
-                // ---- a chunk with near / mid columns: the paired-end term of its 8 columns per lane at once
-                // (pair lengths outer, columns inner: 8 independent product chains, one uniform + 8 coalesced loads)
-                double pe[8];
-                if (ok && npe > 0) {
-                    int cj[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { pe[j] = 0.0; cj[j] = min(cb + lane + 32 * j, fa2 - 1); }
-                    const double *r1p = R.R1 + i1;
-                    for (int t0 = 0; t0 < npe; t0 += PE_BLOCK) {
-                        double prod[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) prod[j] = 1.0;
-                        const int t1 = min(t0 + PE_BLOCK, npe);
-                        for (int t = t0; t < t1; ++t) {
-                            const double r1 = r1p[(long long)t * n1];
-                            const double *r2p = R.R2 + (long long)t * fa2;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (j < jlo) continue;
-                                if (j >= jhi) break;
-                                prod[j] = __dmul_rn(prod[j], fmax(__dadd_rn(r1, r2p[cj[j]]), eps));
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { if (j < jlo) continue; if (j >= jhi) break; pe[j] = __dadd_rn(pe[j], log(prod[j])); }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j >= jmax) break;
-                    const int col = cb + lane + 32 * j;
-                    if (col >= cend) continue;
-                    const int h2 = h2v[j];
+                for (int q = 0; q < 4; ++q) {
+                    const int col = 32 * (gb + q) + lane;
+                    if (col >= n2) continue;
+                    int d2;
+                    bool valid;
+                    if (arith) { d2 = B.far_d0 + B.far_step * (col - B.fa2); valid = h1 <= L + d2; }      // (h2 = L + d2 there)
+                    else { const int h2 = h2s[col]; d2 = max(h2 - L, 1); valid = h1 <= h2; }
                     double ml = -INFINITY;
-                    if (h1 <= h2) {
-                        if (ok) {
-                            const double rp = R.rept[dh1 + dh2[j]];
-                            if (col >= fa2) ml = __dadd_rn(__dadd_rn(c12, rp), pe_far);
-                            else {
-                                const double pej = npe > 0 ? pe[j] : term_pe(P, g, h1, h2, T.tmin);
-                                if (col >= fam) ml = __dadd_rn(__dadd_rn(c12, rp), pej);
-                                else {
-                                    const double sg2 = R.sig2[col];
-                                    const double sgc2 = min(h2, P.max_partial) == P.max_partial ? T.sig_mp : sg2;
-                                    ml = __dadd_rn(term_span(P, g, h1, h2, sg1, sg2), term_part(P, g, h1, h2, sgc1, sgc2, T.sig_mp));
-                                    ml = __dadd_rn(__dadd_rn(ml, rp), pej);
-                                }
-                            }
-                        } else {
-                            ml = point_ml(P, g, h1, h2, T);
-                        }
-                        best.take(ml, h1, row + col); ++cnt;
-                        if (!(ok && col >= fa2) || mat) surf[row + col] = ml;
-                    } else if (mat) surf[row + col] = ml;
+                    if (valid) {
+                        ml = __dadd_rn(__dadd_rn(c12, rr[d2]), pe_far);
+                        if (x.strict) { if (ml > best.ml) { best.ml = ml; best.key = keybase + (unsigned)col; } }
+                        else best.take(ml, h1, x.rowbase + col);
+                        ++cnt;
+                    }
+                    if (x.mat) x.surf[col] = ml;
                 }
             }
         }
@@ -802,7 +882,8 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
 
 // K3 = { reductions of the small surfaces | pass A of the large ones }
 __global__ void __launch_bounds__(256, 2) grid_reduce_eval_kernel(GridParams g) {
-    if ((int)blockIdx.x < g.nblk_small) small_reduce(g, blockIdx.x * 8 + (threadIdx.x >> 5), g.nblk_small * 8);
+    const int nrows_blocks = (int)gridDim.x - g.nblk_small;       // the row blocks come first: they are the long pole
+    if ((int)blockIdx.x >= nrows_blocks) small_reduce(g, (blockIdx.x - nrows_blocks) * 8 + (threadIdx.x >> 5), g.nblk_small * 8);
     else rows_eval(g);
 }
 
@@ -834,7 +915,7 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
         double *ph1 = g.marg + P.off_ph1, *ph2 = g.marg + P.off_ph2;
         const RowTables R = row_tables(g, B, n1, n2);
         double *rows_w = const_cast<double *>(R.rows);
-        const int ok = B.ok, fa2 = B.fa2, sorted = B.sorted, prow_mode = B.patho_mode;
+        const int ok = B.ok, fa2 = B.fa2, sorted = B.sorted, prow_mode = B.patho_mode, has_dup = B.has_dup;
         const double eps = g.small_value;
         // the surface maximum: pass A's per-CTA results in rank order
         Best top{-INFINITY, ~0ULL};
@@ -864,7 +945,7 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
                 h2v[j] = col < cend ? h2s[col] : -0x40000000;
                 dh2[j] = max(h2v[j] - L, 1);
                 if (col < cend) {
-                    if (R.dup[n1 + col]) dup2 |= 1 << j;
+                    if (has_dup && R.dup[n1 + col]) dup2 |= 1 << j;
                     // column mode: the PP predicate looks at the longer allele only
                     if (!prow_mode && pathological_h(P, h2v[j], h2v[j])) pcol |= 1 << j;
                 }
@@ -880,7 +961,7 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
                 const int h1 = h1s[i1];
                 if (h2_last < h1) continue;
                 const int dh1 = max(h1 - L, 1) - 2;
-                const bool dup1 = R.dup[i1] != 0;
+                const bool dup1 = has_dup && R.dup[i1] != 0;
                 const bool prow = prow_mode && pathological_h(P, h1, h1);
                 const long long row = (long long)i1 * n2;
                 const double f = ok ? R.rows[3LL * i1 + 2] : 0.0;
