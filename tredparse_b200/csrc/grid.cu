@@ -89,7 +89,8 @@ struct GridParams {
     BigInfo *big;                // [nproblems]
     int *lists;                  // [0] number of large surfaces, [1 + i] their problem indices
     int *items;                  // point items of the small surfaces: (problem, chunk, nitems) triples
-    unsigned int *counters;      // [0] items, [1] work cursor pass A, [2] work cursor pass B, [3] item cursor
+    int *row_items;              // work items of the row kernels: (problem, CTA rank) pairs
+    unsigned int *counters;      // [0] items, [1] work cursor pass A, [2] work cursor pass B, [3] item cursor, [4] row items
     double *ftab;                // table arena
     long long ftab_cap;
     unsigned long long *fcursor; // [0] arena cursor, [1] overflow flag
@@ -620,6 +621,8 @@ __device__ __forceinline__ void big_setup(const GridParams &g, int first_block, 
             // few large surfaces: many CTAs each (latency); many: few CTAs each, so that a warp keeps its column
             // registers over many rows (throughput)
             B.nce = max(1, min(B.nc, (g.target_ctas + nbig - 1) / nbig));
+            const unsigned at = atomicAdd(&g.counters[4], (unsigned)B.nce);
+            for (int r = 0; r < B.nce; ++r) { g.row_items[2 * (at + r)] = pi; g.row_items[2 * (at + r) + 1] = r; }
         }
         const Tab tb = tab_layout(n1, n2, B.nd, B.npe, B.nc, B.ok != 0);
         double *tab = g.ftab + B.off;
@@ -664,7 +667,7 @@ __device__ __forceinline__ void big_setup(const GridParams &g, int first_block, 
 }
 
 // K2 = { point items of the small surfaces | table setup of the large ones }
-__global__ void __launch_bounds__(256) grid_points_setup_kernel(GridParams g) {
+__global__ void __launch_bounds__(256, 3) grid_points_setup_kernel(GridParams g) {
     if ((int)blockIdx.x < g.nblk_small) small_points(g);
     else big_setup(g, blockIdx.x - g.nblk_small, gridDim.x - g.nblk_small);
 }
@@ -781,15 +784,14 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
     __shared__ unsigned long long s_key[8];
     __shared__ int s_cnt[8];
     __shared__ unsigned s_item;
-    const int nbig = g.lists[0];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&g.counters[1], 1u);
         __syncthreads();
         const unsigned item = s_item;
-        if (item >= (unsigned)nbig * NC_MAX) break;
-        const int pi = g.lists[1 + item % nbig], c = item / nbig;
+        if (item >= g.counters[4]) break;
+        const int pi = g.row_items[2 * item], c = g.row_items[2 * item + 1];
         const BigInfo &B = g.big[pi];
         const int nc = B.nce;
         if (c >= nc) continue;
@@ -896,15 +898,14 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
     __shared__ double s_sum[8][3];
     __shared__ int s_last;
     __shared__ unsigned s_item;
-    const int nbig = g.lists[0];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(&g.counters[2], 1u);
         __syncthreads();
         const unsigned item = s_item;
-        if (item >= (unsigned)nbig * NC_MAX) break;
-        const int pi = g.lists[1 + item % nbig], c = item / nbig;
+        if (item >= g.counters[4]) break;
+        const int pi = g.row_items[2 * item], c = g.row_items[2 * item + 1];
         BigInfo &B = g.big[pi];
         const int nc = B.nce;
         if (c >= nc) continue;
@@ -1067,15 +1068,16 @@ __global__ void __launch_bounds__(KDE_THREADS) pe_kde_kernel(const int32_t *lens
 
 // device-side bookkeeping area of one grid call, at the start of ctx->d_ftab
 struct GridArea {
-    size_t big_bytes, ctr_off, list_off, item_off, tab_off;
+    size_t big_bytes, ctr_off, list_off, item_off, row_off, tab_off;
 };
 static GridArea grid_area(int nproblems) {
     GridArea a;
     a.big_bytes = (((size_t)nproblems * sizeof(BigInfo)) + 255) & ~(size_t)255;
-    a.ctr_off = a.big_bytes;                                                         // fcursor[2] | counters[4] | lists[0]
-    a.list_off = a.ctr_off + 32;
+    a.ctr_off = a.big_bytes;                                                         // fcursor[2] | counters[8] | lists[0]
+    a.list_off = a.ctr_off + 48;
     a.item_off = (a.list_off + ((size_t)nproblems + 1) * sizeof(int) + 255) & ~(size_t)255;
-    a.tab_off = (a.item_off + (size_t)nproblems * ITEM_MAX * 3 * sizeof(int) + 255) & ~(size_t)255;
+    a.row_off = (a.item_off + (size_t)nproblems * ITEM_MAX * 3 * sizeof(int) + 255) & ~(size_t)255;
+    a.tab_off = (a.row_off + (size_t)nproblems * NC_MAX * 2 * sizeof(int) + 255) & ~(size_t)255;
     return a;
 }
 
@@ -1117,10 +1119,11 @@ int tredsw_internal_grid(tredsw_ctx *ctx, const tredsw_grid_problem *d_prob, int
     g.counters = reinterpret_cast<unsigned int *>(base + ar.ctr_off + 16);
     g.lists = reinterpret_cast<int *>(base + ar.list_off);
     g.items = reinterpret_cast<int *>(base + ar.item_off);
+    g.row_items = reinterpret_cast<int *>(base + ar.row_off);
     g.ftab = reinterpret_cast<double *>(base + ar.tab_off);
     g.ftab_cap = cap;
     if (d_overflow_flag) *d_overflow_flag = g.fcursor;                 // [0] doubles needed, [1] overflow
-    CUDA_TRY(cudaMemsetAsync(base + ar.ctr_off, 0, 32 + sizeof(int), ctx->stream));   // cursors, counters, lists[0]
+    CUDA_TRY(cudaMemsetAsync(base + ar.ctr_off, 0, 48 + sizeof(int), ctx->stream));   // cursors, counters, lists[0]
     grid_classify_kernel<<<(nproblems + 7) / 8, 256, 0, ctx->stream>>>(g);
     // fused launches: a share of the blocks serves the small surfaces, the rest the large ones
     const int per_sm = 8;
