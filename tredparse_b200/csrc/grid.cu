@@ -73,6 +73,7 @@ struct BigInfo {
     int far_arith;               // the far columns are an arithmetic sequence above the read length:
     int far_d0, far_step;        //   max(h2s[col] - L, 1) = far_d0 + far_step * (col - fa2)  (no list load per point)
     int has_dup;                 // a candidate occurs twice (Q9)
+    int h2_arith, h2_a0, h2_step; // the whole h2 list is h2_a0 + h2_step * col (step > 0): lower bounds need no search
     unsigned int done_b;         // CTAs of pass B that have finished
 };
 
@@ -614,9 +615,14 @@ __device__ __forceinline__ void big_setup(const GridParams &g, int first_block, 
         if (fd0 < 1) notarith = 1;
         for (int i = tid; i < n1 + n2; i += 256)
             if (i < n1 ? is_second_occurrence(h1s, B.nb1, i) : is_second_occurrence(h2s, B.nb2, i - n1)) anydup = 1;
-        notarith = block_max_int(notarith, s8); anydup = block_max_int(anydup, s8);
+        int notall = 0;
+        const int astep = n2 > 1 ? h2s[1] - h2s[0] : 1;
+        for (int i = tid; i < n2; i += 256) if (h2s[i] != h2s[0] + i * astep) notall = 1;
+        if (astep <= 0) notall = 1;
+        notarith = block_max_int(notarith, s8); anydup = block_max_int(anydup, s8); notall = block_max_int(notall, s8);
         if (part == 0 && tid == 0) {
             B.far_arith = notarith ? 0 : 1; B.far_d0 = fd0; B.far_step = fstep; B.has_dup = anydup;
+            B.h2_arith = notall ? 0 : 1; B.h2_a0 = h2s[0]; B.h2_step = astep;
             B.lgamma_k1 = lgk; B.sig_mp = sig_mp; B.tmin = tmin; B.fam = fam; B.fa2 = fa2; B.sorted = unsorted ? 0 : 1;
             // few large surfaces: many CTAs each (latency); many: few CTAs each, so that a warp keeps its column
             // registers over many rows (throughput)
@@ -826,7 +832,8 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
             }
             // first column the row evaluates (sorted lists: lower bound of h1)
             int c0 = 0;
-            if (sorted) {
+            if (B.h2_arith) c0 = min(n2, max(0, (h1 - B.h2_a0 + B.h2_step - 1) / B.h2_step));
+            else if (sorted) {
                 int lo = 0, hi = n2;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (h2s[mid] < h1) lo = mid + 1; else hi = mid; }
                 c0 = lo;
@@ -844,6 +851,32 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
             const double c12 = x.c12, pe_far = x.pe_far;
             const double *rr = x.rept_row;
             const unsigned long long keybase = ((unsigned long long)h1 << 40) | (unsigned long long)x.rowbase;
+            const bool mat = x.mat, strict = x.strict;
+            if (arith && strict && !mat) {
+                // sorted lists, arithmetic far columns: every column from max(32 gb, c0) on is evaluated, its table
+                // index is linear in the column — one load, two additions and a compare per point
+                const int cf = max(32 * gb, c0);
+                const int step32 = 32 * B.far_step;
+                const double *pp = rr + (B.far_d0 + B.far_step * (cf + lane - B.fa2));
+                double bm = best.ml;
+                int bc = -1;
+                int col = cf + lane;
+                for (; col + 96 < n2; col += 128, pp += 4 * step32) {
+                    const double v0 = pp[0], v1 = pp[step32], v2 = pp[2 * step32], v3 = pp[3 * step32];
+                    const double m0 = __dadd_rn(__dadd_rn(c12, v0), pe_far), m1 = __dadd_rn(__dadd_rn(c12, v1), pe_far);
+                    const double m2 = __dadd_rn(__dadd_rn(c12, v2), pe_far), m3 = __dadd_rn(__dadd_rn(c12, v3), pe_far);
+                    if (m0 > bm) { bm = m0; bc = col; }
+                    if (m1 > bm) { bm = m1; bc = col + 32; }
+                    if (m2 > bm) { bm = m2; bc = col + 64; }
+                    if (m3 > bm) { bm = m3; bc = col + 96; }
+                }
+                for (; col < n2; col += 32, pp += step32) {
+                    const double m0 = __dadd_rn(__dadd_rn(c12, pp[0]), pe_far);
+                    if (m0 > bm) { bm = m0; bc = col; }
+                }
+                if (bc >= 0) { best.ml = bm; best.key = keybase + (unsigned)bc; }
+                if (cf + lane < n2) cnt += (n2 - 1 - cf - lane) / 32 + 1;
+            } else
             for (; gb < ngroups; gb += 4) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -856,11 +889,11 @@ __device__ __forceinline__ void rows_eval(const GridParams &g) {
                     double ml = -INFINITY;
                     if (valid) {
                         ml = __dadd_rn(__dadd_rn(c12, rr[d2]), pe_far);
-                        if (x.strict) { if (ml > best.ml) { best.ml = ml; best.key = keybase + (unsigned)col; } }
+                        if (strict) { if (ml > best.ml) { best.ml = ml; best.key = keybase + (unsigned)col; } }
                         else best.take(ml, h1, x.rowbase + col);
                         ++cnt;
                     }
-                    if (x.mat) x.surf[col] = ml;
+                    if (mat) x.surf[col] = ml;
                 }
             }
         }
@@ -928,11 +961,14 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
         const double M = npoints ? top.ml : INFINITY;
         // per-row factor of the far weights
         if (ok)
-            for (int grp = c; grp * 8 < n1; grp += nc) {
-                const int i1 = grp * 8 + warp;
-                if (i1 < n1 && lane == 0) rows_w[3LL * i1 + 2] = exp(__dadd_rn(R.rows[3LL * i1], R.rows[3LL * i1 + 1]) - M);
+            for (int g0 = c; g0 * 8 < n1; g0 += 32 * nc) {            // lane r: the r-th row of this warp
+                const int i1 = (g0 + lane * nc) * 8 + warp;
+                if (i1 < n1) rows_w[3LL * i1 + 2] = exp(__dadd_rn(R.rows[3LL * i1], R.rows[3LL * i1 + 1]) - M);
             }
         __syncwarp();
+        // PP predicate as thresholds on the allele in bp (pathological_h)
+        const int pp_thr = P.expansion ? P.cutoff_risk * K : (P.cutoff_risk + 1) * K;
+        const bool pp_ge = P.expansion != 0;
         double sum_all = 0.0, sum_path = 0.0, sum_dup = 0.0;          // lane 0 of every warp
         for (int cb = 0; cb < n2; cb += CHUNK) {
             const int cend = min(cb + CHUNK, n2);
@@ -948,7 +984,7 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
                 if (col < cend) {
                     if (has_dup && R.dup[n1 + col]) dup2 |= 1 << j;
                     // column mode: the PP predicate looks at the longer allele only
-                    if (!prow_mode && pathological_h(P, h2v[j], h2v[j])) pcol |= 1 << j;
+                    if (!prow_mode && (pp_ge ? h2v[j] >= pp_thr : h2v[j] < pp_thr)) pcol |= 1 << j;
                 }
             }
             const int h2_first = h2s[cb];
@@ -963,7 +999,7 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
                 if (h2_last < h1) continue;
                 const int dh1 = max(h1 - L, 1) - 2;
                 const bool dup1 = has_dup && R.dup[i1] != 0;
-                const bool prow = prow_mode && pathological_h(P, h1, h1);
+                const bool prow = prow_mode && (pp_ge ? h1 >= pp_thr : h1 < pp_thr);
                 const long long row = (long long)i1 * n2;
                 const double f = ok ? R.rows[3LL * i1 + 2] : 0.0;
                 // a far weight is f * exp(rept) <= f: below e^-10 none of them enters the joint posterior
@@ -978,11 +1014,20 @@ __global__ void __launch_bounds__(256, 3) grid_rows_reduce_kernel(GridParams g) 
                         colacc[j] += w; racc += w;
                         if ((pcol >> j) & 1) raccp += w;
                     }
+                } else if (all_far && !dup1 && dup2 == 0 && !may_emit) {
+                    const double *er = R.erept + dh1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (h1 > h2v[j]) continue;                        // not evaluated, or past the chunk
+                        const double w = f * er[dh2[j]];
+                        colacc[j] += w; racc += w;
+                        if ((pcol >> j) & 1) raccp += w;
+                    }
                 } else if (all_far) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (j >= jmax) break;
-                        if (h1 > h2v[j]) continue;                        // not evaluated, or past the chunk
+                        if (h1 > h2v[j]) continue;
                         const double w = f * R.erept[dh1 + dh2[j]];
                         colacc[j] += w; racc += w;
                         if ((pcol >> j) & 1) raccp += w;
