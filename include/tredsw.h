@@ -295,6 +295,11 @@ typedef struct {
 #define TREDSW_IN_READS_PACKED4 1u   /* rbuf holds two base codes per byte: base i in bits 4*(i&1).. of byte i>>1 */
 #define TREDSW_IN_PE_LENS_I16 2u     /* pe_lens points to int16_t values (pair lengths kept are < 1000) */
 
+/* The transfer formats on the host side: base codes (one per byte) -> TREDSW_IN_READS_PACKED4, int32 lengths ->
+ * TREDSW_IN_PE_LENS_I16.  `out` holds (n + 1) / 2 bytes / n values; `threads` host threads share the packing. */
+int tredsw_pack_reads4(const int8_t *codes, int64_t n, uint8_t *out, int threads);
+int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out);
+
 typedef struct {
     int32_t allele1, allele2;   /* units, sorted; -1/-1 when there is no evidence */
     int32_t ci[4];              /* h1_lo, h1_hi, h2_lo, h2_hi (units); -1 when missing */

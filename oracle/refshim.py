@@ -39,15 +39,17 @@ that ``__file__`` into a scratch directory holding a symlink named ``libssw.so``
 library: INTEGRATION.md level 0, an unmodified ``Aligner`` on the drop-in).
 
 /root/reference does not exist on the GPU box.  ``build()`` (run here by ``__graft_entry__.build``)
-therefore also writes the *compiled code objects* of the transformed modules to ``oracle/_ref/refpy/*.bin``
-(git-ignored build artefacts, like ``libssw_ref.so``); ``load()`` falls back to them when the source tree is
-absent.  Only ``ssw`` is usable there (the others need the reference's data files).
+therefore also writes the *compiled code objects* of the transformed modules to ``oracle/_ref/refpy/*.bin`` and
+the data tables they read (catalogue, alt regions, step / stutter model) to ``oracle/_ref/refpy/data/`` —
+git-ignored build artefacts that travel with the snapshot like ``libssw_ref.so``; ``load()`` falls back to them
+when the source tree is absent, so ``bench.py``'s reference arm runs the reference's own code there too.
 """
 import ast
 import builtins
 import marshal
 import os
 import re
+import shutil
 import sys
 import tempfile
 import types
@@ -77,6 +79,12 @@ def available():
 
 def cached(name="ssw"):
     return os.path.exists(os.path.join(CACHE, name + ".bin"))
+
+
+def usable():
+    """The whole reference package can be loaded: the source tree is mounted, or build() left the code objects and
+    the reference's data tables under oracle/_ref/refpy/."""
+    return available() or (all(cached(m) for m in MODULES) and os.path.isdir(os.path.join(CACHE, "data")))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,6 +201,12 @@ def build():
         ver = re.search(r'__version__\s*=\s*"([^"]+)"', fp.read()).group(1)
     with open(os.path.join(CACHE, "VERSION"), "w") as fp:
         fp.write(ver + "\n")
+    # the tables the reference's modules read at run time (catalogue, alt regions, step / stutter model, chrY regions)
+    os.makedirs(os.path.join(CACHE, "data"), exist_ok=True)
+    src = os.path.join(REFERENCE, "tredparse", "data")
+    for name in os.listdir(src):
+        if name.endswith((".csv", ".stepmodel", ".stuttermodel", ".gc")):
+            shutil.copyfile(os.path.join(src, name), os.path.join(CACHE, "data", name))
     return True
 
 
@@ -224,7 +238,7 @@ def load(libssw=None, modules=None):
     if not os.path.exists(libssw):
         raise IOError("libssw-compatible library not found: {}".format(libssw))
     if modules is None:
-        modules = list(MODULES) if available() else ["ssw"]
+        modules = list(MODULES) if usable() else ["ssw"]
     key = (libssw, tuple(modules))
     if key in _loaded:
         return _loaded[key]
@@ -253,8 +267,10 @@ def load(libssw=None, modules=None):
             mod.__package__ = pkgname
             if name == "ssw":
                 mod.__file__ = os.path.join(scratch, "ssw_wrap.py")
-            else:
+            elif available():
                 mod.__file__ = os.path.join(REFERENCE, MODULES[name])
+            else:
+                mod.__file__ = os.path.join(CACHE, name + ".py")       # utils.datafile() -> oracle/_ref/refpy/data
             mod.__dict__.update(_py2div=_py2div, range=_py2range)
             sys.modules[mod.__name__] = mod
             code = _code(name)

@@ -101,3 +101,57 @@ def test_single_process_helpers_are_identities():
     assert out.tolist() == [[2, 3], [0, 0], [4, 5], [0, 0], [0, 1]]
     assert dist.reduce_max_sum([1.5], [2, 3]) == ([1.5], [2.0, 3.0])
     dist.barrier()
+
+
+def test_cost_sorted_deal_balances_and_partitions():
+    sys.path.insert(0, ROOT)
+    from tredparse_b200 import dist
+    rng = np.random.default_rng(3)
+    costs = rng.gamma(2.0, 100.0, 30011)
+    for world in (1, 2, 4, 8):
+        owner = dist.shard_by_cost(costs, world)
+        assert owner.min() == 0 and owner.max() == world - 1 and len(owner) == len(costs)
+        loads = np.array([costs[owner == r].sum() for r in range(world)])
+        assert loads.max() - loads.min() <= costs.max()                     # serpentine deal of the sorted costs
+        assert np.array_equal(owner, dist.shard_by_cost(costs.copy(), world))  # deterministic: no communication needed
+
+
+def _tensor_gather_worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        sys.path.insert(0, ROOT)
+        from tredparse_b200 import dist
+        dist.init("gloo")
+        n = 1001
+        costs = np.arange(n, dtype=float) % 17 + 1
+        owner = dist.shard_by_cost(costs, world)
+        mine = np.nonzero(owner == rank)[0]
+        rec = np.zeros(len(mine), dtype=[("a", "<i4"), ("b", "<f8")])
+        rec["a"], rec["b"] = mine * 3, mine / 7.0
+        counts = np.bincount(owner, minlength=world)
+        out, seen = dist.gather_records(rec, mine, n, all_counts=counts, return_seen=True)
+        ok = True
+        if rank == 0:
+            ok = bool(seen.all() and np.array_equal(out["a"], np.arange(n) * 3) and np.allclose(out["b"], np.arange(n) / 7.0))
+        else:
+            ok = out is None
+        q.put(("rank%d" % rank, ok))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put(("error", traceback.format_exc() + repr(e)))
+
+
+def test_two_rank_gloo_tensor_gather_of_records():
+    """bench.py's final gather: padded uint8 tensors, counts known to every rank from the deterministic partition."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tensor_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert "error" not in got, got.get("error")
+    assert got == {"rank0": True, "rank1": True}

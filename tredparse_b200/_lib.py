@@ -26,7 +26,7 @@ EXPORTS = [
     "tredsw_version", "tredsw_device_count", "tredsw_last_error", "tredsw_create", "tredsw_destroy",
     "tredsw_synchronize", "tredsw_sm_count", "tredsw_launch_count", "tredsw_enable_timing",
     "tredsw_get_timing", "tredsw_get_timeline", "tredsw_int_pipe_peak", "tredsw_align_pairs", "tredsw_classify_reads",
-    "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch", "tredsw_genotype_batch_ex",
+    "tredsw_likelihood_grid", "tredsw_pe_kde", "tredsw_genotype_batch", "tredsw_genotype_batch_ex", "tredsw_pack_reads4", "tredsw_narrow_i16",
     # native BAM ingest
     "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
     "tredsw_bam_region_depth", "tredsw_bam_read_length", "tredsw_bam_clone", "tredsw_bam_inflate_stats", "tredsw_inflate_raw",
@@ -127,6 +127,10 @@ def load():
                                                _vp, ctypes.c_uint32]
         lib.tredsw_pe_kde.restype = ctypes.c_int
         lib.tredsw_pe_kde.argtypes = [_vp, _vp, _vp, ctypes.c_int32, _vp, ctypes.c_uint32]
+        lib.tredsw_pack_reads4.restype = ctypes.c_int
+        lib.tredsw_pack_reads4.argtypes = [_vp, ctypes.c_int64, _vp, ctypes.c_int]
+        lib.tredsw_narrow_i16.restype = ctypes.c_int
+        lib.tredsw_narrow_i16.argtypes = [_vp, ctypes.c_int64, _vp]
         _lib = lib
         return lib
 

@@ -63,7 +63,7 @@ class CohortBatch:
     global_lens, target_lens — see simulate.Problem)."""
 
     def __init__(self, problems, maxinsert=300, fullsearch=False, score=1.0, gc=.68, match=1, mismatch=5,
-                 gap_open=7, gap_extend=2, clip=False, repeatpairs=True):
+                 gap_open=7, gap_extend=2, clip=False, repeatpairs=True, family_keys=None):
         """clip / repeatpairs: --useclippedreads / not --norepeatpairs (tred.py:75-81; note that InputParams
         defaults repeatpairs to False while the CLI passes True).  Without repeatpairs every problem needs
         ``names`` (read names or ids: mates share one)."""
@@ -73,6 +73,23 @@ class CohortBatch:
         self.match, self.mismatch, self.gap_open, self.gap_extend = match, mismatch, gap_open, gap_extend
         fam_index, fams, loci, step_rows = {}, [], [], []
         step = StepModel()
+
+        def add_family(t, readlen):
+            period = len(t.repeat)
+            fam_index[(t.name, readlen)] = len(fams)
+            fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, -(-readlen // period), clip=self.clip))
+            L = np.zeros(1, dtype=LOCUS_DTYPE)
+            ref = t.repeat_end - t.repeat_start + 1
+            L["period"], L["readlen"], L["pe_ref"], L["pe_minpe"] = period, readlen, ref, ref - 1 + 2 * 9 + 2
+            L["expansion"], L["recessive"] = int(t.is_expansion), int(t.is_recessive)
+            L["cutoff_prerisk"], L["cutoff_risk"] = int(t.cutoff_prerisk), int(t.cutoff_risk)
+            loci.append(L)
+            step_rows.append(step.step_size_by_period[period])
+
+        # family_keys: [(tred, readlen)] — a fixed family table for every batch of a cohort (otherwise families are
+        # numbered in order of first appearance in this batch)
+        for t, readlen in (family_keys or []):
+            add_family(t, readlen)
         n = len(problems)
         P = np.zeros(n, dtype=PROBLEM_DTYPE)
         rbufs, roffs, rprob, pe, rname = [], [np.zeros(1, dtype=np.int64)], [], [], []
@@ -81,16 +98,7 @@ class CohortBatch:
             t = pr.tred
             key = (t.name, pr.readlen)
             if key not in fam_index:
-                period = len(t.repeat)
-                fam_index[key] = len(fams)
-                fams.append(ssw.make_family(t.prefix, t.repeat, t.suffix, -(-pr.readlen // period), clip=self.clip))
-                L = np.zeros(1, dtype=LOCUS_DTYPE)
-                ref = t.repeat_end - t.repeat_start + 1
-                L["period"], L["readlen"], L["pe_ref"], L["pe_minpe"] = period, pr.readlen, ref, ref - 1 + 2 * 9 + 2
-                L["expansion"], L["recessive"] = int(t.is_expansion), int(t.is_recessive)
-                L["cutoff_prerisk"], L["cutoff_risk"] = int(t.cutoff_prerisk), int(t.cutoff_risk)
-                loci.append(L)
-                step_rows.append(step.step_size_by_period[period])
+                add_family(t, pr.readlen)
             f = fam_index[key]
             reads = np.asarray(pr.reads, dtype=np.int8)
             roff = np.asarray(pr.roff, dtype=np.int64)
@@ -130,21 +138,25 @@ class CohortBatch:
         self._dev = None
         self._packed = None
 
-    def pack_inputs(self):
+    def pack_inputs(self, out=None, threads=4, keep=True):
         """Compact transfer formats (TREDSW_IN_READS_PACKED4 | TREDSW_IN_PE_LENS_I16): two base codes per byte
-        and int16 pair lengths — half the host->device bytes; the library expands them on the device.  Done
-        once per batch, like the base encoding itself; run_host(packed=True) then sends these buffers."""
-        codes = self.rbuf.view(np.uint8)
-        n = len(codes)
-        pad = (-n) % 8
-        if pad:
-            codes = np.concatenate([codes, np.zeros(pad, np.uint8)])
-        packed = (codes[0::2] & 15) | ((codes[1::2] & 15) << 4)
-        if len(self.pe_lens) and (self.pe_lens.min() < -32768 or self.pe_lens.max() > 32767):
-            raise ValueError("paired-end lengths do not fit int16")
-        self._packed = {"rbuf": np.ascontiguousarray(packed, dtype=np.uint8),
-                        "pe_lens": np.ascontiguousarray(self.pe_lens.astype(np.int16))}
-        return self
+        and int16 pair lengths — half the host->device bytes; the library expands them on the device.
+        Native host code (tredsw_pack_reads4 / tredsw_narrow_i16; ctypes releases the GIL): the per-batch cost of a
+        cohort pipeline between ingest and the copy.  `out`: optional dict of preallocated (e.g. pinned) arrays
+        {"rbuf": uint8[(n+7)//8*4...], "pe_lens": int16[n]} to pack into; run_host(packed=True) sends them."""
+        lib = _lib.load()
+        n = len(self.rbuf)
+        nbytes = ((n + 7) // 8) * 4                      # whole 32-bit words of 8 bases
+        if out is None:
+            out = {"rbuf": np.zeros(nbytes, dtype=np.uint8), "pe_lens": np.zeros(len(self.pe_lens), dtype=np.int16)}
+        if len(out["rbuf"]) < nbytes or len(out["pe_lens"]) < len(self.pe_lens):
+            raise ValueError("pack_inputs: output buffers too small")
+        _lib.check(lib.tredsw_pack_reads4(_lib.ptr(self.rbuf), n, _lib.ptr(out["rbuf"]), int(threads)), "tredsw_pack_reads4")
+        _lib.check(lib.tredsw_narrow_i16(_lib.ptr(self.pe_lens), len(self.pe_lens), _lib.ptr(out["pe_lens"])), "tredsw_narrow_i16")
+        if keep:
+            self._packed = out
+            return self
+        return out                                      # (several threads may pack one batch into different buffers)
 
     # ---- descriptor -----------------------------------------------------------------------------------
     def _descriptor(self, rbuf, roff, rprob, problems, pe_lens, input_flags=0, read_name=None):
@@ -178,9 +190,13 @@ class CohortBatch:
         hist = np.zeros((self.nproblems, 3, self.hist_units + 1), dtype=np.int32) if want_hist else None
         stats = np.zeros(8, dtype=np.int64) if want_stats else None
         if packed:
-            if self._packed is None:
-                self.pack_inputs()
-            rbuf, pe = self._packed["rbuf"], self._packed["pe_lens"]
+            if isinstance(packed, dict):
+                bufs = packed                                # buffers filled by pack_inputs(out=..., keep=False)
+            else:
+                if self._packed is None:
+                    self.pack_inputs()
+                bufs = self._packed
+            rbuf, pe = bufs["rbuf"], bufs["pe_lens"]
             flags_in = IN_READS_PACKED4 | IN_PE_LENS_I16
         else:
             rbuf, pe, flags_in = self.rbuf, self.pe_lens, 0
@@ -199,8 +215,10 @@ class CohortBatch:
             if rc == 0 or "arena overflow" not in _lib.last_error():
                 break
         _lib.check(rc, "tredsw_genotype_batch")
-        self.h2d_bytes = (rbuf.nbytes + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
-                          pe.nbytes + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
+        n_rbuf = (len(self.rbuf) + 1) // 2 if packed else self.rbuf.nbytes       # bytes the call copies
+        n_pe = len(self.pe_lens) * (2 if packed else 4)
+        self.h2d_bytes = (n_rbuf + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
+                          n_pe + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
         self.d2h_bytes = calls.nbytes + (read_out.nbytes if want_reads else 0) + (hist.nbytes if want_hist else 0)
         out = {"calls": calls}
         if want_reads:

@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+#include <thread>
 
 #include "../../include/tredsw.h"
 #include "inflate_fast.h"
@@ -467,6 +468,54 @@ int tredsw_bam_extract_locus(tredsw_bam *b, const tredsw_locus_query *q, int8_t 
     out->nreads = nreads; out->nbases = nbases; out->name_bytes = name_bytes;
     out->n_global = ng; out->n_target = nt;
     out->depth = (double)depth_sum * 1.0 / (double)(WIN_E - WIN_S + 1);
+    return TREDSW_OK;
+}
+
+
+// ---- host-side transfer formats (tredsw_cohort.input_flags) ------------------------------------------------------
+// Two base codes per byte / int16 pair lengths: what a cohort pipeline does to every batch between ingest and the
+// host-to-device copy.  Plain loops (the compiler vectorises them), split over `threads` std::threads.
+int tredsw_pack_reads4(const int8_t *codes, int64_t n, uint8_t *out, int threads) {
+    if ((!codes && n > 0) || !out || n < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    const int64_t nbytes = (n + 1) / 2;
+    // 8 codes (one 64-bit word) -> 4 bytes with shifts and masks only, so that the loop vectorises
+    auto work = [&](int64_t b0, int64_t b1) {                    // output bytes [b0, b1), b0 a multiple of 4
+        int64_t b = b0;
+        for (; b + 4 <= b1 && 2 * b + 8 <= n; b += 4) {
+            uint64_t x;
+            memcpy(&x, codes + 2 * b, 8);
+            x &= 0x0F0F0F0F0F0F0F0FULL;
+            x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;         // bytes 0, 2, 4, 6: lo | hi << 4
+            x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+            x = (x | (x >> 16));
+            const uint32_t y = (uint32_t)x;
+            memcpy(out + b, &y, 4);
+        }
+        for (; b < b1; ++b) {
+            const int64_t i = 2 * b;
+            const unsigned lo = (unsigned)codes[i] & 15u, hi = (i + 1 < n) ? ((unsigned)codes[i + 1] & 15u) : 0u;
+            out[b] = (uint8_t)(lo | (hi << 4));
+        }
+    };
+    if (threads <= 1 || nbytes < (1 << 20)) { work(0, nbytes); return TREDSW_OK; }
+    try {
+        std::vector<std::thread> pool;
+        const int64_t per = ((nbytes + threads - 1) / threads + 3) & ~(int64_t)3;
+        for (int t = 0; t < threads; ++t) {
+            const int64_t b0 = (int64_t)t * per, b1 = std::min(nbytes, b0 + per);
+            if (b0 < b1) pool.emplace_back(work, b0, b1);
+        }
+        for (auto &th : pool) th.join();
+    } catch (const std::exception &e) { tredsw_set_error("tredsw_pack_reads4: %s", e.what()); return TREDSW_ERR_ARG; }
+    return TREDSW_OK;
+}
+
+int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out) {
+    if ((!in && n > 0) || !out || n < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    for (int64_t i = 0; i < n; ++i) {
+        if (in[i] < -32768 || in[i] > 32767) { tredsw_set_error("pair length %d does not fit int16", in[i]); return TREDSW_ERR_ARG; }
+        out[i] = (int16_t)in[i];
+    }
     return TREDSW_OK;
 }
 

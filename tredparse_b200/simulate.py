@@ -138,6 +138,45 @@ def cohort_specs(repo, names, nsamples, readlen=150, seed=20240000, maxunits=Non
     return specs
 
 
+def sample_header(seed, s):
+    """(male, depth) of cohort sample `s`: gender 50/50, depth ~ N(35, 5^2) clipped to [15, 60]."""
+    rng = np.random.default_rng(seed + s)
+    male = bool(rng.random() < 0.5)
+    return male, float(np.clip(rng.normal(35, 5), 15, 60))
+
+
+def problem_spec(repo, names, s, li, readlen=150, seed=20240000, maxunits=None):
+    """Spec of the (sample s, locus li) problem of the cohort, independent of every other problem (own random
+    stream), so that a rank can materialise exactly the problems it owns — same distribution as cohort_specs."""
+    male, depth = sample_header(seed, s)
+    tred = repo[names[li]]
+    ploidy = 1 if (male and tred.is_xlinked) else 2
+    rng = np.random.default_rng([seed + s, li, 0xA11E1E])
+    alleles = tuple(sorted(draw_allele(rng, tred) for _ in range(ploidy)))
+    if maxunits:
+        alleles = tuple(min(a, maxunits) for a in alleles)
+    return {"tred": names[li], "alleles": [int(a) for a in alleles], "readlen": readlen, "cov_per_hap": depth / 2.0,
+            "seed": 0xB200 + 1000 * li + 7919 * s, "sample": s, "locus": li}
+
+
+def problem_costs(repo, names, nsamples, readlen=150, seed=20240000, first_sample=0):
+    """A-priori cost of every (sample, locus) problem, float64 [nsamples, nloci]: expected reads (depth x ploidy)
+    x forward cells of the locus' template family — what a scheduler knows before reading a BAM."""
+    cells = np.zeros(len(names))
+    xl = np.zeros(len(names), dtype=bool)
+    for li, n in enumerate(names):
+        t = repo[n]
+        P, flank = len(t.repeat), len(t.prefix) + len(t.suffix)
+        mu = -(-readlen // P)
+        cells[li] = 2.0 * readlen * sum(flank + P * u for u in range(1, mu + 1))
+        xl[li] = t.is_xlinked
+    out = np.zeros((nsamples, len(names)))
+    for k in range(nsamples):
+        male, depth = sample_header(seed, first_sample + k)
+        out[k] = depth * np.where(xl & male, 0.5, 1.0) * cells
+    return out
+
+
 def simulate_from_spec(repo, spec):
     return simulate_problem(repo[spec["tred"]], tuple(spec["alleles"]), readlen=spec.get("readlen", 150),
                             cov_per_hap=spec.get("cov_per_hap", 15.0), error=spec.get("error", 0.005),
