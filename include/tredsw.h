@@ -298,7 +298,7 @@ typedef struct {
 /* The transfer formats on the host side: base codes (one per byte) -> TREDSW_IN_READS_PACKED4, int32 lengths ->
  * TREDSW_IN_PE_LENS_I16.  `out` holds (n + 1) / 2 bytes / n values; `threads` host threads share the packing. */
 int tredsw_pack_reads4(const int8_t *codes, int64_t n, uint8_t *out, int threads);
-int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out);
+int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out, int threads);
 
 typedef struct {
     int32_t allele1, allele2;   /* units, sorted; -1/-1 when there is no evidence */

@@ -130,7 +130,7 @@ def load():
         lib.tredsw_pack_reads4.restype = ctypes.c_int
         lib.tredsw_pack_reads4.argtypes = [_vp, ctypes.c_int64, _vp, ctypes.c_int]
         lib.tredsw_narrow_i16.restype = ctypes.c_int
-        lib.tredsw_narrow_i16.argtypes = [_vp, ctypes.c_int64, _vp]
+        lib.tredsw_narrow_i16.argtypes = [_vp, ctypes.c_int64, _vp, ctypes.c_int]
         _lib = lib
         return lib
 

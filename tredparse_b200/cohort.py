@@ -152,11 +152,20 @@ class CohortBatch:
         if len(out["rbuf"]) < nbytes or len(out["pe_lens"]) < len(self.pe_lens):
             raise ValueError("pack_inputs: output buffers too small")
         _lib.check(lib.tredsw_pack_reads4(_lib.ptr(self.rbuf), n, _lib.ptr(out["rbuf"]), int(threads)), "tredsw_pack_reads4")
-        _lib.check(lib.tredsw_narrow_i16(_lib.ptr(self.pe_lens), len(self.pe_lens), _lib.ptr(out["pe_lens"])), "tredsw_narrow_i16")
+        _lib.check(lib.tredsw_narrow_i16(_lib.ptr(self.pe_lens), len(self.pe_lens), _lib.ptr(out["pe_lens"]), int(threads)),
+                   "tredsw_narrow_i16")
         if keep:
             self._packed = out
             return self
         return out                                      # (several threads may pack one batch into different buffers)
+
+    def pack_reads4(self, out, threads=4):
+        """Only the reads (for producers that already write int16 pair lengths): base codes -> `out`, 4 bit/base."""
+        n = len(self.rbuf)
+        if len(out) < ((n + 7) // 8) * 4:
+            raise ValueError("pack_reads4: output buffer too small")
+        _lib.check(_lib.load().tredsw_pack_reads4(_lib.ptr(self.rbuf), n, _lib.ptr(out), int(threads)), "tredsw_pack_reads4")
+        return out
 
     # ---- descriptor -----------------------------------------------------------------------------------
     def _descriptor(self, rbuf, roff, rprob, problems, pe_lens, input_flags=0, read_name=None):

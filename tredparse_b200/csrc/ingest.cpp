@@ -472,6 +472,32 @@ int tredsw_bam_extract_locus(tredsw_bam *b, const tredsw_locus_query *q, int8_t 
 }
 
 
+}  // extern "C"
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+// 64 codes -> 32 bytes per iteration: maddubs(lo, hi) x (1, 16) = lo | hi << 4 in every 16-bit lane, then pack
+__attribute__((target("avx2"))) static int64_t pack4_avx2(const int8_t *codes, int64_t nbytes_out, uint8_t *out) {
+    const __m256i mask = _mm256_set1_epi8(0x0F), mul = _mm256_set1_epi16(0x1001);
+    int64_t b = 0;
+    for (; b + 32 <= nbytes_out; b += 32) {
+        __m256i x0 = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(codes + 2 * b)), mask);
+        __m256i x1 = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(codes + 2 * b + 32)), mask);
+        x0 = _mm256_maddubs_epi16(x0, mul);
+        x1 = _mm256_maddubs_epi16(x1, mul);
+        const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(x0, x1), 0xD8);
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(out + b), p);
+    }
+    return b;
+}
+static bool have_avx2() { static const bool v = __builtin_cpu_supports("avx2"); return v; }
+#else
+static int64_t pack4_avx2(const int8_t *, int64_t, uint8_t *) { return 0; }
+static bool have_avx2() { return false; }
+#endif
+
+extern "C" {
+
 // ---- host-side transfer formats (tredsw_cohort.input_flags) ------------------------------------------------------
 // Two base codes per byte / int16 pair lengths: what a cohort pipeline does to every batch between ingest and the
 // host-to-device copy.  Plain loops (the compiler vectorises them), split over `threads` std::threads.
@@ -481,6 +507,7 @@ int tredsw_pack_reads4(const int8_t *codes, int64_t n, uint8_t *out, int threads
     // 8 codes (one 64-bit word) -> 4 bytes with shifts and masks only, so that the loop vectorises
     auto work = [&](int64_t b0, int64_t b1) {                    // output bytes [b0, b1), b0 a multiple of 4
         int64_t b = b0;
+        if (have_avx2() && 2 * b1 <= n) b += pack4_avx2(codes + 2 * b0, b1 - b0, out + b0);
         for (; b + 4 <= b1 && 2 * b + 8 <= n; b += 4) {
             uint64_t x;
             memcpy(&x, codes + 2 * b, 8);
@@ -510,12 +537,33 @@ int tredsw_pack_reads4(const int8_t *codes, int64_t n, uint8_t *out, int threads
     return TREDSW_OK;
 }
 
-int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out) {
+int tredsw_narrow_i16(const int32_t *in, int64_t n, int16_t *out, int threads) {
     if ((!in && n > 0) || !out || n < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
-    for (int64_t i = 0; i < n; ++i) {
-        if (in[i] < -32768 || in[i] > 32767) { tredsw_set_error("pair length %d does not fit int16", in[i]); return TREDSW_ERR_ARG; }
-        out[i] = (int16_t)in[i];
+    // branch-free body (vectorises); the range check is an OR over the block
+    auto work = [&](int64_t a, int64_t b, int *bad) {
+        int32_t acc = 0;
+        for (int64_t i = a; i < b; ++i) {
+            const int32_t v = in[i];
+            acc |= (v + 32768) & ~0xFFFF;
+            out[i] = (int16_t)v;
+        }
+        *bad = acc != 0;
+    };
+    int nt = (threads <= 1 || n < (1 << 20)) ? 1 : threads;
+    std::vector<int> bad((size_t)nt, 0);
+    if (nt == 1) work(0, n, &bad[0]);
+    else {
+        try {
+            std::vector<std::thread> pool;
+            const int64_t per = (n + nt - 1) / nt;
+            for (int t = 0; t < nt; ++t) {
+                const int64_t a = (int64_t)t * per, b = std::min(n, a + per);
+                if (a < b) pool.emplace_back(work, a, b, &bad[(size_t)t]);
+            }
+            for (auto &th : pool) th.join();
+        } catch (const std::exception &e) { tredsw_set_error("tredsw_narrow_i16: %s", e.what()); return TREDSW_ERR_ARG; }
     }
+    for (int b : bad) if (b) { tredsw_set_error("a pair length does not fit int16"); return TREDSW_ERR_ARG; }
     return TREDSW_OK;
 }
 
