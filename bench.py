@@ -63,6 +63,9 @@ def parse_args():
     p.add_argument("--depth", type=int, default=3, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--streams", type=int, default=3, help="streams the device-resident steps alternate over "
                    "(the tail of one step's persistent SW kernel overlaps the head of the next step)")
+    p.add_argument("--transfer", default="bytes", choices=("bytes", "packed4"),
+                   help="e2e leg: copy the reads as ingest leaves them (one byte per base, pinned), or pack them to "
+                        "4 bit/base on the host first (inside the timed region) — less PCIe traffic, more host work")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
     p.add_argument("--cpu-sample", type=int, default=0, help="samples in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -539,17 +542,22 @@ def _main(args):
             setattr(b, name, pin(getattr(b, name)))
     # pair lengths: the producer's format is int16 already (what is kept is < 1000, bam_parser.py:356-357) — pinned
     # once, like the offsets; the base codes arrive one byte per base and are packed per step
+    packing = args.transfer == "packed4"
     for b in batches:
         b.pe16 = pin(b.pe_lens.astype(np.int16))
+        if not packing:
+            b.rbuf = pin(b.rbuf)                                   # ingest writes into caller-owned pinned buffers
     depth = max(1, args.depth)
     max_bases = max(len(b.rbuf) for b in batches)
-    slots = [pin(np.zeros(((max_bases + 7) // 8) * 4, np.uint8)) for _ in range(depth)]
+    slots = [pin(np.zeros(((max_bases + 7) // 8) * 4, np.uint8)) if packing else None for _ in range(depth)]
     pipe = cohort.HostPipeline(local_rank, depth=depth)
     pack_threads = max(1, min(4, (os.cpu_count() or 1) // max(1, world * depth)))
 
     def step_e2e(ctx_slot, b):
         cx, slot = ctx_slot
-        return b.run_host(ctx=cx, packed={"rbuf": b.pack_reads4(slot, pack_threads), "pe_lens": b.pe16})["calls"]
+        if packing:
+            return b.run_host(ctx=cx, packed={"rbuf": b.pack_reads4(slot, pack_threads), "pe_lens": b.pe16})["calls"]
+        return b.run_host(ctx=cx, packed={"pe_lens": b.pe16})["calls"]
 
     import queue
     from concurrent.futures import ThreadPoolExecutor
@@ -567,6 +575,9 @@ def _main(args):
     with ThreadPoolExecutor(max_workers=depth) as tp:
         for _ in tp.map(worker, warm + warm[:depth]):
             pass
+        # the gather path once, untimed (NCCL sets up the channels of a collective on its first use)
+        tdist.gather_records(np.zeros(timed_counts[rank], dtype=cohort.CALL_DTYPE), timed_idx, nsamples * nloci,
+                             all_counts=timed_counts, require_all=False, return_seen=True)
         barrier()
         e2e_launch0 = pipe.launches
         t0 = time.perf_counter()
@@ -635,9 +646,12 @@ def _main(args):
             "e2e": {"value": nprob / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                     "ms_per_step": 1e3 * t_e2e / len(timed), "calls_in_flight": depth,
-                    "includes": "per step: native packing of the batch's base codes (1 byte/base as ingest leaves them -> 4 bit/base, "
-                                "{} host threads), H2D from pinned memory, kernels, D2H of the calls; at the end the gather of the "
-                                "{} call records on rank 0.  Pair lengths are int16 from the producer.".format(pack_threads, int(seen.sum()))},
+                    "transfer": args.transfer,
+                    "includes": ("per step: native packing of the batch's base codes (1 byte/base as ingest leaves them -> "
+                                 "4 bit/base, {} host threads), ".format(pack_threads) if packing else
+                                 "per step: the batch's reads as ingest leaves them (1 byte/base, no host-side repacking), ") +
+                                "H2D from pinned memory, kernels, D2H of the calls; at the end the gather of the {} call records "
+                                "on rank 0.  Pair lengths are int16 from the producer (kept lengths are < 1000).".format(int(seen.sum()))},
             "gpu_launches": int(launches) + int(e2e_launches),
             "clocks": clocks,
             "roofline": {"kernel": "classify_kernel<P> (sw_family.cu), all period instantiations of one step",

@@ -71,6 +71,7 @@ uint32_t cigar_int_to_len(uint32_t cigar_int);
 #define TREDSW_ERR_CUDA (-1)     /* CUDA runtime / driver error, or no device */
 #define TREDSW_ERR_ARG (-2)      /* invalid argument */
 #define TREDSW_ERR_UNSUPPORTED (-3)
+#define TREDSW_ERR_IO (-4)       /* BAM ingest: truncated / corrupt file, read error (never partial evidence) */
 
 #define TREDSW_DEVICE_PTRS 1u    /* all buffer arguments are device pointers; enqueue only */
 #define TREDSW_SCORE2 2u         /* also produce score2 / ref_end2 exactly like ssw.c (ghost rows) */

@@ -269,3 +269,50 @@ def test_corrupt_bam_records_do_not_crash_the_reader(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "survived" in r.stdout
+
+
+def _damaged_copies(tmp_path):
+    """The fixture truncated to half its size, and with one byte flipped in the middle of a compressed block."""
+    import shutil
+    src = os.path.join(GOLDEN, "t001.mini.bam")
+    data = open(src, "rb").read()
+    out = []
+    for name, blob in (("truncated.bam", data[:len(data) // 2]),
+                       ("flipped.bam", data[:len(data) // 2] + bytes([data[len(data) // 2] ^ 0x5A]) + data[len(data) // 2 + 1:])):
+        p = str(tmp_path / name)
+        with open(p, "wb") as fw:
+            fw.write(blob)
+        shutil.copy(src + ".bai", p + ".bai")
+        out.append(p)
+    return out
+
+
+def test_truncated_or_corrupt_bam_is_an_error_not_partial_evidence(tmp_path):
+    """A BGZF stream that ends early or fails its CRC must surface as an error from every native entry point — never
+    as 'fewer reads' (pysam raises on such files; a silent partial result would become a plausible wrong genotype)."""
+    from tredparse_b200 import ingest, _lib
+    from tredparse_b200.meta import TREDsRepo
+    hd = TREDsRepo()["HD"]
+    with ingest.BamIngest(os.path.join(GOLDEN, "t001.mini.bam")) as good:
+        ev = good.extract_locus(hd, 150, alts=())
+        assert ev.nreads == 68 and abs(ev.depth - 29.3) < 0.1
+    for path in _damaged_copies(tmp_path):
+        with ingest.BamIngest(path) as ing:
+            with pytest.raises(_lib.TredswError):
+                ing.extract_locus(hd, 150, alts=())
+            with pytest.raises(_lib.TredswError):
+                ing.region_depth(hd.chr, hd.repeat_start - 1000, hd.repeat_end + 1000)
+
+
+@pytest.mark.gpu
+def test_run_reports_no_call_for_a_damaged_bam(tmp_path):
+    """tred.run on a damaged BAM: the locus is skipped with an error logged (the reference's `except: continue`,
+    tred.py:245-249), no genotype is invented."""
+    from tredparse_b200 import tred as T
+    from tredparse_b200.meta import TREDsRepo
+    for path in _damaged_copies(tmp_path):
+        try:
+            res = T.run(("x", path, TREDsRepo(), ["HD"], 300, False, False, True, True, "INFO"))
+        except Exception:
+            continue                                     # raising is fine too
+        assert "HD.1" not in res["tredCalls"] or res["tredCalls"]["HD.1"] == -1

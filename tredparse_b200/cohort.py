@@ -205,8 +205,9 @@ class CohortBatch:
                 if self._packed is None:
                     self.pack_inputs()
                 bufs = self._packed
-            rbuf, pe = bufs["rbuf"], bufs["pe_lens"]
-            flags_in = IN_READS_PACKED4 | IN_PE_LENS_I16
+            # (a dict may carry only one of the two compact formats: e.g. int16 pair lengths, reads one byte per base)
+            rbuf, pe = bufs.get("rbuf", self.rbuf), bufs.get("pe_lens", self.pe_lens)
+            flags_in = (IN_READS_PACKED4 if "rbuf" in bufs else 0) | (IN_PE_LENS_I16 if "pe_lens" in bufs else 0)
         else:
             rbuf, pe, flags_in = self.rbuf, self.pe_lens, 0
         c = self._descriptor(rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
@@ -224,8 +225,8 @@ class CohortBatch:
             if rc == 0 or "arena overflow" not in _lib.last_error():
                 break
         _lib.check(rc, "tredsw_genotype_batch")
-        n_rbuf = (len(self.rbuf) + 1) // 2 if packed else self.rbuf.nbytes       # bytes the call copies
-        n_pe = len(self.pe_lens) * (2 if packed else 4)
+        n_rbuf = (len(self.rbuf) + 1) // 2 if (flags_in & IN_READS_PACKED4) else self.rbuf.nbytes   # bytes the call copies
+        n_pe = len(self.pe_lens) * (2 if (flags_in & IN_PE_LENS_I16) else 4)
         self.h2d_bytes = (n_rbuf + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
                           n_pe + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
         self.d2h_bytes = calls.nbytes + (read_out.nbytes if want_reads else 0) + (hist.nbytes if want_hist else 0)

@@ -40,31 +40,39 @@ struct Bgzf {
     size_t blen = 0;                                  // inflated bytes of the current block (block has slack behind)
     tredsw_inflate::FastInflater *fast = nullptr;     // own decoder (inflate_fast.h); zlib is the fallback
     long long n_fast = 0, n_zlib = 0;                 // blocks inflated by either
+    // Sticky: set on I/O or format failure (a truncated or corrupt file) — NOT on a clean end of file.  Every
+    // entry point that read through this handle checks it and reports TREDSW_ERR_IO instead of partial evidence.
+    const char *err = nullptr;
+    bool fail(const char *why) { if (!err) err = why; return false; }
 
     bool load(int64_t coffset) {
         blen = 0; pos = 0; block_coffset = coffset; next_coffset = coffset;
-        if (fseeko(fh, coffset, SEEK_SET) != 0) return false;
+        if (fseeko(fh, coffset, SEEK_SET) != 0) return fail("seek failed");
         unsigned char head[18];
-        if (fread(head, 1, 18, fh) != 18) return false;
-        if (head[0] != 31 || head[1] != 139 || !(head[3] & 4)) return false;
+        const size_t nhead = fread(head, 1, 18, fh);
+        if (nhead == 0 && feof(fh)) return false;                          // clean end of file
+        if (nhead != 18) return fail("truncated BGZF block header");
+        if (head[0] != 31 || head[1] != 139 || !(head[3] & 4)) return fail("not a BGZF block");
         const int xlen = head[10] | (head[11] << 8);
         std::vector<unsigned char> extra(xlen);
         memcpy(extra.data(), head + 12, std::min(6, xlen));
-        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fh) != (size_t)(xlen - 6)) return false;
+        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fh) != (size_t)(xlen - 6)) return fail("truncated BGZF block header");
         int bsize = -1;
         for (int off = 0; off + 4 <= xlen;) {
             const int slen = extra[off + 2] | (extra[off + 3] << 8);
             if (extra[off] == 66 && extra[off + 1] == 67 && off + 6 <= xlen) bsize = extra[off + 4] | (extra[off + 5] << 8);
             off += 4 + slen;
         }
-        if (bsize < 0) return false;
+        if (bsize < 0) return fail("BGZF block without a BC field");
         const int clen = bsize - xlen - 19;
+        if (clen < 0) return fail("bad BGZF block size");
         cbuf.resize(clen > 0 ? clen : 0);
-        if (clen > 0 && fread(cbuf.data(), 1, clen, fh) != (size_t)clen) return false;
+        if (clen > 0 && fread(cbuf.data(), 1, clen, fh) != (size_t)clen) return fail("truncated BGZF block");
         unsigned char tail[8];
-        if (fread(tail, 1, 8, fh) != 8) return false;
+        if (fread(tail, 1, 8, fh) != 8) return fail("truncated BGZF block");
         const uint32_t crc = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
         const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        if (isize > 65536) return fail("BGZF block larger than 64 KiB");   // (the format's limit; also bounds the resize)
         if (block.size() < (size_t)isize + tredsw_inflate::FastInflater::SLACK) block.resize((size_t)isize + tredsw_inflate::FastInflater::SLACK);
         blen = isize;
         if (isize > 0) {
@@ -78,12 +86,13 @@ struct Bgzf {
                 if (done) ++n_fast;
             }
             if (!done) {
-                if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) return false; zs_init = true; }
+                if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) { blen = 0; return fail("zlib init failed"); } zs_init = true; }
                 else inflateReset(&zs);
                 zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
                 zs.next_out = block.data(); zs.avail_out = isize;
                 const int rc = inflate(&zs, Z_FINISH);
-                if (rc != Z_STREAM_END) return false;
+                if (rc != Z_STREAM_END || zs.total_out != isize ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), block.data(), isize) != crc) { blen = 0; return fail("corrupt BGZF block (inflate / length / CRC-32)"); }
                 ++n_zlib;
             }
         }
@@ -150,9 +159,12 @@ struct tredsw_bam {
 
     bool read_record(Record &r) {
         int32_t bs;
-        if (bgzf.read(&bs, 4) != 4 || bs < 32 || bs > (64 << 20)) return false;
+        const size_t nbs = bgzf.read(&bs, 4);
+        if (nbs == 0) return false;                                          // end of file (or bgzf.err)
+        if (nbs != 4) return bgzf.fail("truncated BAM record");
+        if (bs < 32 || bs > (64 << 20)) return bgzf.fail("bad BAM record size");
         rec.resize(bs);
-        if (bgzf.read(rec.data(), bs) != (size_t)bs) return false;
+        if (bgzf.read(rec.data(), bs) != (size_t)bs) return bgzf.fail("truncated BAM record");
         const unsigned char *d = rec.data();
         auto i32 = [&](int o) { int32_t v; memcpy(&v, d + o, 4); return v; };
         auto u16 = [&](int o) { uint16_t v; memcpy(&v, d + o, 2); return v; };
@@ -161,7 +173,7 @@ struct tredsw_bam {
         const int n_cigar = u16(12);
         r.flag = u16(14); r.l_seq = i32(16); r.next_tid = i32(20); r.next_pos = i32(24); r.tlen = i32(28);
         // a record whose variable-length fields do not fit its block_size is corrupt: stop reading
-        if (r.l_seq < 0 || 32LL + l_name + 4LL * n_cigar + ((int64_t)r.l_seq + 1) / 2 + r.l_seq > (int64_t)bs) return false;
+        if (r.l_seq < 0 || 32LL + l_name + 4LL * n_cigar + ((int64_t)r.l_seq + 1) / 2 + r.l_seq > (int64_t)bs) return bgzf.fail("corrupt BAM record");
         int off = 32;
         r.name.assign((const char *)d + off, l_name > 0 ? l_name - 1 : 0);
         off += l_name;
@@ -361,10 +373,14 @@ int tredsw_bam_region_depth(tredsw_bam *b, int32_t tid, int64_t start, int64_t e
     if (tid < 0 || tid >= (int)b->names.size()) { tredsw_set_error("contig id %d out of range", tid); return TREDSW_ERR_ARG; }
     if (end < start) { tredsw_set_error("empty region"); return TREDSW_ERR_ARG; }
     int64_t total = 0;
-    b->fetch(tid, start, end, [&](const Record &r) {
-        if ((r.flag & (4 | 256 | 512 | 1024)) || !r.has_cigar) return;
-        total += r.ref_len;
-    });
+    b->bgzf.err = nullptr;
+    try {
+        b->fetch(tid, start, end, [&](const Record &r) {
+            if ((r.flag & (4 | 256 | 512 | 1024)) || !r.has_cigar) return;
+            total += r.ref_len;
+        });
+    } catch (const std::exception &e) { tredsw_set_error("tredsw_bam_region_depth: %s", e.what()); return TREDSW_ERR_IO; }
+    if (b->bgzf.err) { tredsw_set_error("%s: %s", b->path.c_str(), b->bgzf.err); return TREDSW_ERR_IO; }
     *depth = (double)total * 1.0 / (double)(end - start + 1);
     return TREDSW_OK;
 }
@@ -373,24 +389,48 @@ int tredsw_bam_region_depth(tredsw_bam *b, int32_t tid, int64_t start, int64_t e
 // file (the reference breaks after len(rls) > firstN); min_out may be NULL.
 int tredsw_bam_read_length(tredsw_bam *b, int32_t first_n, int32_t *max_out, int32_t *min_out) {
     if (!b || !max_out || first_n < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
-    b->bgzf.seek(b->first_record);
-    Record r;
     int32_t n = 0, mx = -1, mn = 0x7fffffff;
-    while (n <= first_n && b->read_record(r)) {
-        mx = std::max(mx, r.l_seq); mn = std::min(mn, r.l_seq);
-        ++n;
-    }
+    b->bgzf.err = nullptr;
+    try {
+        b->bgzf.seek(b->first_record);
+        Record r;
+        while (n <= first_n && b->read_record(r)) {
+            mx = std::max(mx, r.l_seq); mn = std::min(mn, r.l_seq);
+            ++n;
+        }
+    } catch (const std::exception &e) { tredsw_set_error("tredsw_bam_read_length: %s", e.what()); return TREDSW_ERR_IO; }
+    if (b->bgzf.err) { tredsw_set_error("%s: %s", b->path.c_str(), b->bgzf.err); return TREDSW_ERR_IO; }
     if (n == 0) { tredsw_set_error("no records"); return TREDSW_ERR_ARG; }
     *max_out = mx;
     if (min_out) *min_out = mn;
     return TREDSW_OK;
 }
 
+static int extract_locus_impl(tredsw_bam *b, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
+                              int64_t *roff, int32_t reads_cap, int32_t *global_lens, int32_t global_cap,
+                              int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
+                              tredsw_locus_summary *out);
+
 int tredsw_bam_extract_locus(tredsw_bam *b, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
                              int64_t *roff, int32_t reads_cap, int32_t *global_lens, int32_t global_cap,
                              int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
                              tredsw_locus_summary *out) {
     if (!b || !q || !out || !roff || reads_cap < 0) { tredsw_set_error("bad arguments"); return TREDSW_ERR_ARG; }
+    b->bgzf.err = nullptr;
+    int rc;
+    try {
+        rc = extract_locus_impl(b, q, rbuf, rbuf_cap, roff, reads_cap, global_lens, global_cap, target_lens, target_cap,
+                                names, names_cap, out);
+    } catch (const std::exception &e) { tredsw_set_error("tredsw_bam_extract_locus: %s", e.what()); return TREDSW_ERR_IO; }
+    // a truncated or corrupt file must not come back as "fewer reads": no partial evidence
+    if (rc == TREDSW_OK && b->bgzf.err) { tredsw_set_error("%s: %s", b->path.c_str(), b->bgzf.err); memset(out, 0, sizeof(*out)); return TREDSW_ERR_IO; }
+    return rc;
+}
+
+static int extract_locus_impl(tredsw_bam *b, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
+                              int64_t *roff, int32_t reads_cap, int32_t *global_lens, int32_t global_cap,
+                              int32_t *target_lens, int32_t target_cap, char *names, int64_t names_cap,
+                              tredsw_locus_summary *out) {
     if (q->tid < 0 || q->tid >= (int)b->names.size()) { tredsw_set_error("contig id %d out of range", q->tid); return TREDSW_ERR_ARG; }
     static const int8_t NIB[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};   // "=ACMGRSVTWYHKDBN"
     memset(out, 0, sizeof(*out));

@@ -72,6 +72,23 @@ struct ClassifyParams {
 
 __constant__ int8_t c_fmat25[25];
 
+// Base codes of one read, one byte per base at an arbitrary byte address: the unaligned head byte by byte, the body
+// with 16-byte loads (LDG.128), then the tail — f(j, code) is called for j = 0..m-1 in order.
+template <class F>
+__device__ __forceinline__ void for_each_base(const int8_t *s, int m, F f) {
+    int j = 0;
+    const int head = min(m, (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(s) & 15u)) & 15u));
+    for (; j < head; ++j) f(j, (int)s[j]);
+    for (; j + 16 <= m; j += 16) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(s + j));
+        const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f(j + k, (int)(int8_t)((v[k >> 2] >> ((k & 3) * 8)) & 0xffu));
+    }
+    for (; j < m; ++j) f(j, (int)s[j]);
+}
+
+
 __device__ __forceinline__ int fam_code(const FamilySmem &F, int u, int strand, int n, int i) {
     int k = strand ? (n - 1 - i) : i;
     int c;
@@ -534,7 +551,9 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
     unsigned char *slot = reinterpret_cast<unsigned char *>(p.score_buf) + (size_t)blockIdx.x * (2 * p.max_u) * 32 * sizeof(uint16_t);
     score_t *scores = reinterpret_cast<score_t *>(slot);                           // [2U][32]
     uint8_t *runs = slot + (size_t)(2 * p.max_u) * 32;                             // [2U][32] (packed kernel only)
-    uint32_t *pot = p.pot_buf + (size_t)blockIdx.x * R * 32;                       // [R][32]
+    // suffix potentials [R][32]: phase 1 only, so in the packed kernel they live in the shared-memory column that
+    // phase 2 later uses for its boundary staging (LDS instead of an L2 round trip per row pair and strip)
+    uint32_t *pot = FAST ? bnd : p.pot_buf + (size_t)blockIdx.x * R * 32;
     uint32_t *gbnd = p.gbnd_buf + (size_t)blockIdx.x * (p.nslots + 1) * R * 32;    // [nslots + 1][R][32]
     const uint32_t one = p.one;
     sw_build_lut(&lut, c_fmat25, lane, 32);
@@ -572,7 +591,7 @@ __global__ void __launch_bounds__(32) classify_kernel(ClassifyParams p) {
         if (valid) { q = p.rbuf + p.roff[r]; m = (int)(p.roff[r + 1] - p.roff[r]); }
         bool too_long = m > p.max_rows;
         if (too_long) m = 0;
-        for (int j = 0; j < m; ++j) { int c = q[j]; codes[j * 32 + lane] = (uint8_t)((c < 0 || c > 4) ? 4 : c); }
+        if (m > 0) for_each_base(q, m, [&](int j, int c) { codes[j * 32 + lane] = (uint8_t)((c < 0 || c > 4) ? 4 : c); });
         const int m_warp = __reduce_max_sync(0xffffffffu, m);
         __syncwarp();
 
@@ -734,15 +753,14 @@ __global__ void prefilter_kernel(const int8_t *rbuf, const int64_t *roff, int nr
             const int8_t *s = rbuf + roff[r];
             const int m = (int)(roff[r + 1] - roff[r]);
             uint32_t code = 0; int run = 0, nN = 0, hf = 0, hr = 0;
-            for (int j = 0; j < m; ++j) {
-                const int c = s[j];
-                if (c < 0 || c > 3) { ++nN; run = 0; continue; }
+            for_each_base(s, m, [&](int, int c) {
+                if (c < 0 || c > 3) { ++nN; run = 0; return; }
                 code = ((code << 2) | (uint32_t)c) & mask;
                 if (++run >= q) {
                     const uint32_t e = (tab[code >> 4] >> ((code & 15u) * 2u)) & 3u;
                     hf += e & 1u; hr += e >> 1;
                 }
-            }
+            });
             const int thr = qinfo[f].min_score - (q - 1) * (nN + 1);
             if (hf < thr && hr < thr) {
                 if (stats) {
