@@ -66,6 +66,8 @@ def parse_args():
     p.add_argument("--transfer", default="bytes", choices=("bytes", "packed4"),
                    help="e2e leg: copy the reads as ingest leaves them (one byte per base, pinned), or pack them to "
                         "4 bit/base on the host first (inside the timed region) — less PCIe traffic, more host work")
+    p.add_argument("--from-bam", type=int, default=8, help="samples of the from-BAM leg (N = 1 only; 0 = skip): synthetic "
+                   "whole-sample BAMs (+-10 kb windows at 30 loci) through tred.run_chunk, native ingest included")
     p.add_argument("--impl", default="tredsw", choices=("tredsw", "reference"))
     p.add_argument("--cpu-sample", type=int, default=0, help="samples in the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,6 +218,37 @@ def batch_from_arrays(cohort, template, arr):
     return b
 
 
+def _write_bam(job):
+    from tredparse_b200 import simulate, bamio
+    from tredparse_b200.meta import TREDsRepo
+    path, sample = job
+    repo = TREDsRepo()
+    names = distinct_loci(repo)
+    sam = bamio.AlignmentFile(os.path.join(ROOT, "tests", "golden", "t001.mini.bam"))
+    refs = list(zip(sam.references, sam.lengths))
+    sam.close()
+    simulate.write_sample_bam(path, repo, names, refs, sample, READLEN, COHORT_SEED)
+    return path
+
+
+def make_bams(nsamples, workers):
+    """Synthetic whole-sample BAMs of the first `nsamples` cohort samples (written once per box under /tmp)."""
+    import multiprocessing as mp
+    d = os.path.join("/tmp", "tredsw_bench_bams")
+    os.makedirs(d, exist_ok=True)
+    jobs = [(os.path.join(d, "s{:04d}.bam".format(s)), s) for s in range(nsamples)]
+    todo = [j for j in jobs if not (os.path.exists(j[0]) and os.path.exists(j[0] + ".bai"))]
+    if todo:
+        with mp.get_context("fork").Pool(processes=max(1, min(workers, len(todo)))) as pool:
+            pool.map(_write_bam, todo, chunksize=1)
+    return [j[0] for j in jobs]
+
+
+def _ref_run_bam(job):
+    from oracle import refdrive
+    return refdrive.run_bam(job)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the reference's CPU path (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------
@@ -258,6 +291,11 @@ class ReferencePool:
         from oracle import refdrive
         t0 = time.perf_counter()
         res = self.pool.map(refdrive.genotype_problem, tasks, chunksize=1)
+        return res, time.perf_counter() - t0
+
+    def run_bams(self, jobs):
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_run_bam, jobs, chunksize=1)
         return res, time.perf_counter() - t0
 
     def close(self):
@@ -444,6 +482,11 @@ def _main(args):
     workers = max(1, min(16, (os.cpu_count() or 1) // max(1, min(world, 8))))
     arrays = build_batches(chunks, workers)
     t_gen = time.perf_counter() - t_gen
+    bams = []
+    if rank == 0 and world == 1 and args.from_bam > 0:
+        t_b = time.perf_counter()
+        bams = make_bams(args.from_bam, workers)
+        t_bams = time.perf_counter() - t_b
     # the CPU baseline's process pool is forked here, before CUDA / NCCL exist in this process (rank 0, N = 1 only)
     ref_pool, ref_pool_error = None, "not requested"
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -705,7 +748,6 @@ def _main(args):
                 res, dt1 = pool.run(tasks)
                 res, dt2 = pool.run(tasks)
                 res, dt3 = pool.run(tasks)
-                pool.close()
                 med = float(np.median([dt1, dt2, dt3]))
                 # the sample doubles as a parity check of the GPU calls: calls, CI, PP, label and the tallies
                 agree = compared = 0
@@ -730,6 +772,43 @@ def _main(args):
                     "ssw_c_loop": ssw_c_loop_ceiling(tasks, cores)}
             except Exception as e:  # the GPU line must still be printed
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        if bams:
+            # ---- from BAM: native ingest (host threads) + the fused device call, through the product's tred.run_chunk
+            try:
+                from tredparse_b200 import tred as T
+                tasks_b = [("s{:04d}".format(i), p, repo, list(names), 300, False, False, True, True, "INFO")
+                           for i, p in enumerate(bams)]
+                T.run_chunk(tasks_b[:1])                                           # warm (library, arenas, page cache)
+                t0 = time.perf_counter()
+                got = T.run_chunk(tasks_b)
+                dt = time.perf_counter() - t0
+                fb = {"value": len(bams) * nloci / dt, "unit": UNIT, "samples": len(bams), "loci": nloci, "seconds": dt,
+                      "bam_mb_per_sample": os.path.getsize(bams[0]) / 1e6, "host_threads": T.INGEST_THREADS,
+                      "what": "tred.run_chunk on synthetic whole-sample BAMs (+-10 kb windows, ~35x, 30 loci): BGZF inflate + "
+                              "record parsing + read selection + pair lengths + depth on host threads (csrc/ingest.cpp), then "
+                              "ONE fused device call for all loci of all samples; pre-steps (gender, read length) included",
+                      "setup_write_bams_s": t_bams}
+                if ref_pool is not None:
+                    jobs = [("s{:04d}".format(i), p, list(names)) for i, p in enumerate(bams)]
+                    res_b, dt_b = ref_pool.run_bams(jobs)
+                    same = total = 0
+                    for mine_r, theirs in zip(got, res_b):
+                        for n in names:
+                            total += 1
+                            keys = (".1", ".2", ".CI", ".label", ".FR", ".PR", ".RR", ".FDP", ".PDP", ".RDP", ".PEDP", ".PEG", ".PET")
+                            ok = all(mine_r["tredCalls"].get(n + k) == theirs.get(n + k) for k in keys)
+                            ok = ok and abs(float(mine_r["tredCalls"].get(n + ".PP", -9)) - float(theirs.get(n + ".PP", -8))) < 1e-9
+                            ok = ok and abs(float(mine_r["tredCalls"].get(n + ".DP", -9)) - float(theirs.get(n + ".DP", -8))) < 1e-9
+                            same += int(ok)
+                    fb["reference"] = {"value": len(bams) * nloci / dt_b, "unit": UNIT, "cores": ref_pool.cores, "seconds": dt_b,
+                                       "what": "the reference's own tred.run (oracle/refshim.py) on the same BAM files, one sample per "
+                                               "process; its pysam calls are served by the repo's pure-Python BAM reader",
+                                       "identical_to_gpu": "{}/{} loci: alleles, CI, PP, label, FR/PR/RR, depths, PE summaries".format(same, total)}
+                line["from_bam"] = fb
+            except Exception as e:
+                line["from_bam"] = {"error": repr(e)}
+        if ref_pool is not None:
+            ref_pool.close()
         emit(line)
     if world > 1:
         dist.barrier()

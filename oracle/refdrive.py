@@ -122,3 +122,22 @@ def genotype_problem(args):
 def usable():
     from . import sw
     return refshim.usable() and os.path.exists(sw.REF_SO)
+
+
+def run_bam(args):
+    """The reference's own ``tred.run`` (tred.py:180-278) on a BAM file through the pysam stand-in
+    (oracle/pysam_stub.py over the repo's Python BAM reader) — the from-BAM CPU arm.
+    args = (samplekey, bam path, [tred names]) -> tredCalls"""
+    import tempfile
+    global _repo
+    ref = reference()
+    if _repo is None:
+        _repo = ref.meta.TREDsRepo()
+    samplekey, bam, treds = args
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="reftred_"))
+    try:
+        out = ref.tred.run((samplekey, bam, _repo, list(treds), 300, False, False, True, True, "INFO"))
+    finally:
+        os.chdir(cwd)
+    return out["tredCalls"]

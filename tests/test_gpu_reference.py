@@ -205,3 +205,39 @@ def test_cohort_pipeline_equals_reference_on_synthetic_problems(group):
         _check_against_reference(sub, problems, out, extra)
         if group == "norepeatpairs":
             assert any(int(np.sum(out["reads"][:, 0] == 6)) > 0 for _ in [0]), "no REPT pair was removed: the case is vacuous"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# from BAM: native ingest + fused device call == the reference's tred.run on the same file
+# ---------------------------------------------------------------------------------------------------------
+def test_run_chunk_equals_run_sample_by_sample():
+    """Several samples through ONE fused device call give what each gives alone."""
+    from tredparse_b200 import tred as T
+    from tredparse_b200.meta import TREDsRepo
+    repo = TREDsRepo()
+    args = [(s, os.path.join(GOLDEN, s + ".mini.bam"), repo, ["HD", "DM1", "FXS", "SCA17"], 300, False, False, True, True, "INFO")
+            for s in ("t001", "t002")]
+    both = T.run_chunk(args)
+    for a, got in zip(args, both):
+        alone = T.run(a)
+        close(json.loads(json.dumps(got)), json.loads(json.dumps(alone)), 1e-12)
+
+
+def test_tred_run_on_a_synthetic_sample_bam_equals_the_reference(tmp_path):
+    """A simulated whole-sample BAM (reads placed around several loci, expansions included): the product's
+    tred.run (native ingest -> fused device pipeline) against the reference's own tred.run on the same file."""
+    from oracle import refdrive
+    if not refdrive.usable():
+        pytest.skip("the reference package is not loadable here (oracle/_ref/ not built)")
+    from tredparse_b200 import tred as T, simulate, bamio
+    from tredparse_b200.meta import TREDsRepo
+    repo = TREDsRepo()
+    names = ["HD", "DM1", "FXS", "FRDA", "SCA10", "ULD", "OPMD", "AR"]
+    sam = bamio.AlignmentFile(os.path.join(GOLDEN, "t001.mini.bam"))
+    refs = list(zip(sam.references, sam.lengths))
+    path = str(tmp_path / "s.bam")
+    truth = simulate.write_sample_bam(path, repo, names, refs, 3, flank=2000)
+    mine = T.run(("s", path, repo, names, 300, False, False, True, True, "INFO"))["tredCalls"]
+    theirs = refdrive.run_bam(("s", path, names))
+    close(json.loads(json.dumps(mine)), json.loads(json.dumps(theirs, default=float)))
+    assert any(mine[n + ".1"] > 0 for n in names)

@@ -141,6 +141,8 @@ class BGZFReader:
         head = self.fh.read(18)
         if len(head) < 18:
             self._block, self._block_coffset, self._next_coffset, self._pos = b"", coffset, coffset, 0
+            if len(head):
+                raise IOError("truncated BGZF block header at offset {}".format(coffset))
             return False
         id1, id2, cm, flg, _mtime, _xfl, _os, xlen = struct.unpack("<BBBBIBBH", head[:12])
         if id1 != 31 or id2 != 139 or not (flg & 4):
@@ -157,8 +159,14 @@ class BGZFReader:
             raise ValueError("BGZF block without BC subfield")
         cdata_len = bsize - xlen - 19
         cdata = self.fh.read(cdata_len)
-        self.fh.read(8)  # crc32 + isize
+        tail = self.fh.read(8)  # crc32 + isize
+        if len(cdata) < cdata_len or len(tail) < 8:
+            raise IOError("truncated BGZF block at offset {}".format(coffset))
+        crc, isize = struct.unpack("<II", tail)
         self._block = zlib.decompress(cdata, -15) if cdata_len > 0 else b""
+        # htslib / pysam verify both: a damaged block is an error, not data
+        if len(self._block) != isize or (zlib.crc32(self._block) & 0xFFFFFFFF) != crc:
+            raise IOError("corrupt BGZF block at offset {} (length / CRC-32)".format(coffset))
         self._block_coffset = coffset
         self._next_coffset = coffset + bsize + 1
         self._pos = 0

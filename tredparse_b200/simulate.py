@@ -186,3 +186,80 @@ def simulate_from_spec(repo, spec):
 def simulate_cohort(repo, names, nsamples, readlen=150, seed=20240000, maxunits=None, first_sample=0):
     return [simulate_from_spec(repo, sp) for sp in
             cohort_specs(repo, names, nsamples, readlen, seed, maxunits, first_sample)]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the same simulation as aligned records: synthetic whole-sample BAMs for the from-BAM path
+# ---------------------------------------------------------------------------------------------------------
+def locus_records(tred, tid, alleles, readlen=150, cov_per_hap=15.0, error=0.005, seed=0, tag="", flank=FLANK_BP):
+    """Paired reads of one locus as ``bamio.AlignedSegment`` records placed on the reference: haplotype coordinates are
+    mapped onto the locus (flanks one to one, the repeat clamped to the reference's copy number), every read gets a
+    ``<readlen>M`` CIGAR and proper-pair flags — what an aligner reports for reads around a repeat whose length
+    differs from the reference.  Same haplotypes, fragments and errors as ``simulate_problem`` with the same seed."""
+    from .bamio import AlignedSegment
+    rng = np.random.default_rng(seed)
+    prefix, suffix, motif = encode(tred.prefix), encode(tred.suffix), encode(tred.repeat)
+    P = len(motif)
+    lut = np.array(list("ACGTN"))
+    recs = []
+    ref_rep_len = tred.repeat_end - tred.repeat_start + 1
+    for hap_idx, h in enumerate(alleles):
+        rep = np.tile(motif, h)
+        nmask = rep == 4
+        if nmask.any():
+            rep = rep.copy()
+            rep[nmask] = rng.integers(0, 4, int(nmask.sum()))
+        hap = np.concatenate([rng.integers(0, 4, flank).astype(np.int8), prefix, rep.astype(np.int8), suffix,
+                              rng.integers(0, 4, flank).astype(np.int8)])
+        rep_start = flank + len(prefix)
+        rep_end = rep_start + P * h
+        L = len(hap)
+        nfrag = int(round(cov_per_hap * L / (2.0 * readlen)))
+        frag = _fragment_lengths(rng, nfrag)
+        start = rng.integers(0, L - frag + 1)
+        end = start + frag
+
+        def to_ref(x):        # haplotype coordinate -> 0-based reference coordinate
+            x = np.asarray(x)
+            left = (tred.repeat_start - 1) - (rep_start - x)
+            inside = (tred.repeat_start - 1) + np.minimum(x - rep_start, ref_rep_len - 1)
+            right = tred.repeat_end + (x - rep_end)
+            return np.where(x < rep_start, left, np.where(x < rep_end, inside, right))
+        s1, s2 = start, end - readlen
+        p1, p2 = to_ref(s1), to_ref(s2)
+        e2 = to_ref(end - 1) + 1
+        idx = np.arange(readlen)
+        r1 = hap[s1[:, None] + idx]
+        r2 = hap[s2[:, None] + idx]                     # stored on the forward strand, flagged reverse
+        for block in (r1, r2):
+            err = rng.random(block.shape) < error
+            block[err] = rng.integers(0, 4, int(err.sum()))
+        for k in range(nfrag):
+            name = "{}h{}f{}".format(tag, hap_idx, k)
+            tl = int(e2[k] - p1[k])
+            recs.append(AlignedSegment(name, 0x1 | 0x2 | 0x20 | 0x40, tid, int(p1[k]), 60, [(0, readlen)], tid, int(p2[k]),
+                                       tl, "".join(lut[r1[k]])))
+            recs.append(AlignedSegment(name, 0x1 | 0x2 | 0x10 | 0x80, tid, int(p2[k]), 60, [(0, readlen)], tid, int(p1[k]),
+                                       -tl, "".join(lut[r2[k]])))
+    return recs
+
+
+def write_sample_bam(path, repo, names, references, sample, readlen=150, seed=20240000, flank=10000):
+    """One synthetic sample as an indexed BAM: paired reads in a +-`flank` window (default 10 kb: the reference's
+    paired-end window, bam_parser.py:31) around every locus of `names`,
+    alleles / gender / depth as in ``problem_spec``.  references: [(contig, length)] of the header.
+    :return: {tred name: alleles} (the truth)"""
+    from .bamio import write_bam
+    tid = {n: i for i, (n, _) in enumerate(references)}
+    recs, truth = [], {}
+    for li, name in enumerate(names):
+        sp = problem_spec(repo, names, sample, li, readlen, seed)
+        t = repo[name]
+        if t.chr not in tid:
+            continue
+        truth[name] = sp["alleles"]
+        recs += locus_records(t, tid[t.chr], tuple(sp["alleles"]), readlen, sp["cov_per_hap"], seed=sp["seed"],
+                              tag="s{}l{}".format(sample, li), flank=flank)
+    recs.sort(key=lambda r: (r.reference_id, r.reference_start))
+    write_bam(path, references, recs, level=1)
+    return truth

@@ -222,10 +222,60 @@ def run_batched(ips, evidence=None):
     return results
 
 
+TAGNAME = {1: "FULL", 2: "PREF", 3: "POST", 4: "REPT"}
+
+
+def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeatpairs=True, ctx=None):
+    """The fused device path for loci whose evidence came from the native ingest: ONE ``tredsw_genotype_batch_ex``
+    call (Smith-Waterman + classification -> tallies -> candidate ranges -> KDE -> likelihood grid -> call / CI / PP
+    / label -> sparse posteriors) over any number of (sample, locus) problems, then the reference's per-locus
+    result fields (tred.py:251-275) assembled from what comes back.
+    :param items: list of (tred, READLEN, gender, depth, ingest.LocusEvidence)
+    :return: list of dicts keyed like the ``<T>.xxx`` entries of tredCalls, without the prefix."""
+    from . import cohort
+    from .simulate import Problem
+    if not items:
+        return []
+    problems = []
+    for tred, readlen, gender, depth, ev in items:
+        pr = Problem()
+        pr.tred, pr.readlen = tred, readlen
+        pr.ploidy = 1 if (gender == "Male" and tred.is_xlinked) else tred.ploidy
+        pr.depth, pr.reads, pr.roff = depth, ev.reads, ev.roff
+        pr.global_lens, pr.target_lens = ev.global_lens, ev.target_lens
+        pr.alleles, pr.names = None, ev.names
+        problems.append(pr)
+    batch = cohort.CohortBatch(problems, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
+    out = batch.run_host(ctx=ctx, want_reads=True, want_hist=True, want_post=True)
+    post = cohort.posteriors(out["post"], len(problems))
+    results, r0 = [], 0
+    for i, (tred, readlen, gender, depth, ev) in enumerate(items):
+        c = cohort.decode_call(out["calls"][i])
+        if c["n_points"] < 0:
+            raise RuntimeError("likelihood arena overflow")          # (run_host repeats the call; not expected)
+        rows = out["reads"][r0:r0 + ev.nreads]
+        r0 += ev.nreads
+        seqs, names = ev.read_strings(), ev.names or [""] * ev.nreads
+        details = [{"tag": TAGNAME[int(t)], "h": int(h), "id": names[k], "seq": seqs[k]}
+                   for k, (t, h) in enumerate(rows[:, :2]) if int(t) in TAGNAME]
+        hist = out["hist"][i]
+        cs = lambda row: ";".join("{}|{}".format(k, int(v)) for k, v in enumerate(row) if v)
+        missing = c["alleles"][0] < 0
+        g, t = [int(x) for x in ev.global_lens], [int(x) for x in ev.target_lens]
+        results.append({
+            "1": c["alleles"][0], "2": c["alleles"][1], "FR": cs(hist[0]), "PR": cs(hist[1]), "RR": cs(hist[2]),
+            "DP": depth, "FDP": c["FDP"], "PDP": c["PDP"], "RDP": c["RDP"], "PEDP": len(t),
+            "PEG": mean_std(g), "PET": mean_std(t), "CI": c["CI"], "PP": c["PP"], "label": c["label"],
+            "details": details,
+            "P_h1": "" if missing else post[i]["P_h1"], "P_h2": "" if missing else post[i]["P_h2"],
+            "P_h1h2": "" if missing else post[i]["P_h1h2"], "P_PEG": histogram(g), "P_PET": histogram(t)})
+    return results
+
+
 INGEST_THREADS = int(os.environ.get("TREDSW_INGEST_THREADS", "0")) or min(8, os.cpu_count() or 1)
 
 
-def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None):
+def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None, want_names=True):
     """Evidence and depth of every requested locus of one BAM.
     Native ingest (csrc/ingest.cpp): one indexed pass per locus yields reads, pair distances AND depth; the loci
     are dealt to `threads` host threads, each with its own clone of the BAM handle (own file descriptor, shared
@@ -243,13 +293,19 @@ def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None)
 
     def one(handle, tred):
         xtred = repo[tred]
+        native = handle is not None and handle.tid(xtred.chr) >= 0
         try:
-            if handle is not None and handle.tid(xtred.chr) >= 0:
+            if native:
                 ev = locus_evidence(handle, None, xtred, READLEN, alts, clip, repo.ref)
                 return tred, ev, ev.depth
             bd = BamDepth(bam, repo.ref, logger)
             return tred, None, bd.region_depth(xtred.chr, max(0, xtred.repeat_start - SPAN), xtred.repeat_end + SPAN)
         except Exception as e:
+            if native:
+                # the window could not be read (truncated / corrupt BAM): no evidence, no call — the reference's
+                # `except Exception: continue` (tred.py:245-249); reading it again with another reader is pointless
+                logger.error("Exception on `{}` {} ({})".format(bam, tred, e))
+                return tred, None, FAILED
             logger.error("Exception on `{}` {} ({}). Set depth={}".format(bam, tred, e, 30))
             return tred, None, 30
 
@@ -299,58 +355,87 @@ def presteps(bam, repo, tredNames, logger):
     return {"inferredGender": gender, "depthY": ydepth, "readLen": READLEN}
 
 
+FAILED = object()        # depth marker of a locus whose BAM window could not be read (corrupt / truncated file)
+
+
+def result_fields(tpResult, depth):
+    """BamParserResults -> the per-locus entries of tredCalls (tred.py:251-275), without the '<T>.' prefix."""
+    a = tpResult.alleles
+    return {"1": a[0], "2": a[1], "FR": counter_s(tpResult.counts["FULL"]), "PR": counter_s(tpResult.counts["PREF"]),
+            "RR": counter_s(tpResult.counts["REPT"]), "DP": depth, "FDP": tpResult.FDP, "PDP": tpResult.PDP,
+            "RDP": tpResult.RDP, "PEDP": tpResult.PEDP, "PEG": tpResult.PEG, "PET": tpResult.PET, "CI": tpResult.CI,
+            "PP": tpResult.PP, "label": tpResult.label, "details": tpResult.details, "P_h1": tpResult.P_h1,
+            "P_h2": tpResult.P_h2, "P_h1h2": tpResult.P_h1h2, "P_PEG": tpResult.P_PEG, "P_PET": tpResult.P_PET}
+
+
 def run(arg):
     """Run the TRED caller on a list of TREDs for one sample.  :return: dict of calls"""
-    samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
-    tredCalls = {"inferredGender": "Unknown", "depthY": -1}
-    if check_bam(bam) is None:
-        return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
-    tredCalls.update(presteps(bam, repo, tredNames, logger))
-    gender, READLEN = tredCalls["inferredGender"], tredCalls["readLen"]
+    return run_chunk([arg])[0]
 
-    evidence, depths = ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger)
-    ips = [InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
-                       fullsearch=fullsearch, gender=gender, depth=depths[tred], clip=clip, alts=alts,
-                       repeatpairs=repeatpairs, log=log) for tred in tredNames]
-    try:
-        results = run_batched(ips, evidence)
-    except Exception as e:
-        # keep the reference's per-locus isolation (tred.py:245-249): retry one locus at a time
-        logger.error("Batched run failed on `{}` ({}); falling back to per-locus calls".format(bam, e))
-        results = []
-        for ip in ips:
-            try:
-                results.append(runBam(ip))
-            except Exception as e2:
-                logger.error("Exception on `{}` {} ({})".format(bam, ip.tredName, e2))
-                results.append(None)
 
-    for tred, tpResult in zip(tredNames, results):
-        if tpResult is None:
+def run_chunk(args, only=None):
+    """Several samples at once: per-sample pre-steps and native ingest on the host (threads), then the loci of ALL
+    the samples through ONE fused device call.  Same results as ``run`` sample by sample.
+    :param args: list of ``run`` argument tuples (same maxinsert / fullsearch / clip / repeatpairs for all)
+    :param only: optional list, per sample, of the TRED names to process (a rank's share of a sharded cohort);
+                 the other requested names of that sample are left out of its tredCalls
+    :return: list of {"samplekey", "bam", "tredCalls"}"""
+    out, items, where = [], [], []
+    for si, arg in enumerate(args):
+        samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
+        tredCalls = {"inferredGender": "Unknown", "depthY": -1}
+        out.append({"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls, "_fields": {}, "_names": list(tredNames)})
+        if check_bam(bam) is None:
             continue
-        alleles = tpResult.alleles
-        tredCalls[tred + ".1"] = alleles[0]
-        tredCalls[tred + ".2"] = alleles[1]
-        tredCalls[tred + ".FR"] = counter_s(tpResult.counts["FULL"])
-        tredCalls[tred + ".PR"] = counter_s(tpResult.counts["PREF"])
-        tredCalls[tred + ".RR"] = counter_s(tpResult.counts["REPT"])
-        tredCalls[tred + ".DP"] = depths[tred]
-        tredCalls[tred + ".FDP"] = tpResult.FDP
-        tredCalls[tred + ".PDP"] = tpResult.PDP
-        tredCalls[tred + ".RDP"] = tpResult.RDP
-        tredCalls[tred + ".PEDP"] = tpResult.PEDP
-        tredCalls[tred + ".PEG"] = tpResult.PEG
-        tredCalls[tred + ".PET"] = tpResult.PET
-        tredCalls[tred + ".CI"] = tpResult.CI
-        tredCalls[tred + ".PP"] = tpResult.PP
-        tredCalls[tred + ".label"] = tpResult.label
-        tredCalls[tred + ".details"] = tpResult.details
-        tredCalls[tred + ".P_h1"] = tpResult.P_h1
-        tredCalls[tred + ".P_h2"] = tpResult.P_h2
-        tredCalls[tred + ".P_h1h2"] = tpResult.P_h1h2
-        tredCalls[tred + ".P_PEG"] = tpResult.P_PEG
-        tredCalls[tred + ".P_PET"] = tpResult.P_PET
-    return {"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls}
+        tredCalls.update(presteps(bam, repo, tredNames, logger))          # (gender looks at every requested locus)
+        gender, READLEN = tredCalls["inferredGender"], tredCalls["readLen"]
+        wanted = [t for t in tredNames if only is None or t in only[si]]
+        out[-1]["_names"] = wanted
+        evidence, depths = ingest_loci(bam, repo, wanted, READLEN, alts, clip, logger, want_names=True)
+        out[-1].update(_depths=depths, _gender=gender, _readlen=READLEN)
+        for t in wanted:
+            if t in evidence:
+                items.append((repo[t], READLEN, gender, depths[t], evidence[t]))
+                where.append((si, t))
+    if not args:
+        return []
+    _, _, repo, _, maxinsert, fullsearch, clip, alts, repeatpairs, log = args[0]
+    # loci whose evidence came from the native one-pass ingest: the fused device pipeline, all of them in one call
+    try:
+        res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
+        for (si, t), r in zip(where, res):
+            out[si]["_fields"][t] = r
+    except Exception as e:
+        logger.error("Fused run failed ({}); falling back to the per-stage path".format(e))
+    for o, arg in zip(out, args):
+        samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
+        fields, depths = o.pop("_fields"), o.pop("_depths", {})
+        wanted, gender, READLEN = o.pop("_names"), o.pop("_gender", "Unknown"), o.pop("_readlen", 150)
+        # the rest (no usable index, contig missing, ...): Python BAM reader + per-stage kernels
+        rest = [t for t in wanted if t not in fields and t in depths and depths[t] is not FAILED]
+        if rest:
+            ips = [InputParams(bam=bam, READLEN=READLEN, tredName=tred, repo=repo, maxinsert=maxinsert,
+                               fullsearch=fullsearch, gender=gender, depth=depths[tred], clip=clip, alts=alts,
+                               repeatpairs=repeatpairs, log=log) for tred in rest]
+            try:
+                results = run_batched(ips, {})
+            except Exception as e:
+                # keep the reference's per-locus isolation (tred.py:245-249): retry one locus at a time
+                logger.error("Batched run failed on `{}` ({}); falling back to per-locus calls".format(bam, e))
+                results = []
+                for ip in ips:
+                    try:
+                        results.append(runBam(ip))
+                    except Exception as e2:
+                        logger.error("Exception on `{}` {} ({})".format(bam, ip.tredName, e2))
+                        results.append(None)
+            for tred, r in zip(rest, results):
+                if r is not None:
+                    fields[tred] = result_fields(r, depths[tred])
+        for tred in wanted:
+            for k, v in fields.get(tred, {}).items():
+                o["tredCalls"][tred + "." + k] = v
+    return out
 
 
 def vcfstanza(sampleid, bam, tredCalls, ref):
@@ -455,11 +540,49 @@ def write_vcf_json(results, ref, repo, treds, store):
         print("Error writing: {} ({})".format(results.get("samplekey"), e), file=sys.stderr)
 
 
+CHUNK_SAMPLES = int(os.environ.get("TREDSW_CHUNK_SAMPLES", "16"))     # samples per fused device call
+
+
+def locus_costs(repo, task_args, readlen=150):
+    """A-priori cost of every (sample, locus) problem of a task list, flat in task order: the forward cells of the
+    locus' template family (all a scheduler knows before reading the BAMs).  -> (costs, [(sample index, tred)])"""
+    costs, keys = [], []
+    for si, ta in enumerate(task_args):
+        for t in ta[3]:
+            tr = repo[t]
+            P, flank = len(tr.repeat), len(tr.prefix) + len(tr.suffix)
+            mu = -(-readlen // P)
+            costs.append(2.0 * readlen * sum(flank + P * u for u in range(1, mu + 1)))
+            keys.append((si, t))
+    return np.array(costs), keys
+
+
 def _worker(rank, ngpus, task_args, queue):
-    os.environ["TREDSW_DEVICE"] = str(rank)
-    for i in range(rank, len(task_args), ngpus):
-        queue.put((i, run(task_args[i])))
-    queue.put((-1, rank))
+    """One process per GPU.  The (sample, locus) problems are dealt by cost (dist.shard_by_cost: every rank computes
+    the same partition, no communication); a rank ingests only the windows of its own problems and sends back, per
+    chunk of samples, the per-locus fields it produced.  The parent merges them into the per-sample JSON."""
+    try:
+        os.environ["TREDSW_DEVICE"] = str(rank)
+        from .dist import shard_by_cost
+        costs, keys = locus_costs(task_args[0][2], task_args)
+        owner = shard_by_cost(costs, ngpus)
+        mine = {}
+        for (si, t), o in zip(keys, owner):
+            if o == rank:
+                mine.setdefault(si, []).append(t)
+        order = sorted(mine)
+        for c0 in range(0, len(order), CHUNK_SAMPLES):
+            idx = order[c0:c0 + CHUNK_SAMPLES]
+            try:
+                res = run_chunk([task_args[i] for i in idx], only=[mine[i] for i in idx])
+                for i, r in zip(idx, res):
+                    queue.put(("part", i, r, len(mine[i])))
+            except Exception as e:                              # a failed chunk must not hang the parent
+                for i in idx:
+                    queue.put(("part", i, {"samplekey": task_args[i][0], "bam": task_args[i][1], "tredCalls": {},
+                                           "error": repr(e)}, len(mine[i])))
+    finally:
+        queue.put(("done", rank, None, 0))
 
 
 def main(args):
@@ -502,34 +625,56 @@ def main(args):
         os.chdir(cwd)
         return
 
-    ngpus = max(1, min(args.gpus, len(task_args)))
+    def emit(results):
+        if not args.no_output:
+            write_vcf_json(results, ref, repo, treds, None)
+
+    ngpus = max(1, args.gpus)
     if ngpus == 1:
-        for ta in task_args:
-            results = run(ta)
-            if not args.no_output:
-                write_vcf_json(results, ref, repo, treds, None)
+        # chunks of samples: one fused device call per chunk (all loci of all its samples)
+        for c0 in range(0, len(task_args), CHUNK_SAMPLES):
+            for results in run_chunk(task_args[c0:c0 + CHUNK_SAMPLES]):
+                emit(results)
     else:
         import multiprocessing as mp
+        import queue as pyqueue
         ctx = mp.get_context("spawn")
         queue = ctx.Queue()
         procs = [ctx.Process(target=_worker, args=(r, ngpus, task_args, queue)) for r in range(ngpus)]
         for pr in procs:
             pr.start()
-        done, pending, nxt = 0, {}, 0
+        merged = [None] * len(task_args)
+        got = [0] * len(task_args)
+        need = [len(ta[3]) for ta in task_args]
+        done, nxt = 0, 0
         while done < ngpus:
-            i, res = queue.get()
-            if i < 0:
+            try:
+                kind, i, res, n = queue.get(timeout=30)
+            except pyqueue.Empty:
+                # a worker that died without its sentinel (segfault, OOM kill) must not hang the run
+                dead = [pr for pr in procs if not pr.is_alive() and pr.exitcode not in (0, None)]
+                if dead:
+                    raise RuntimeError("worker process(es) died: exit codes {}".format([pr.exitcode for pr in dead]))
+                continue
+            if kind == "done":
                 done += 1
                 continue
-            pending[i] = res
-            while nxt in pending:                      # emit in input order, like Pool.imap
-                if not args.no_output:
-                    write_vcf_json(pending.pop(nxt), ref, repo, treds, None)
-                else:
-                    pending.pop(nxt)
+            if merged[i] is None:
+                merged[i] = {"samplekey": res["samplekey"], "bam": res["bam"], "tredCalls": {}}
+            merged[i]["tredCalls"].update(res["tredCalls"])
+            if "error" in res:
+                logger.error("Sample `{}`: {}".format(res["samplekey"], res["error"]))
+            got[i] += n
+            while nxt < len(task_args) and got[nxt] >= need[nxt]:          # emit in input order, like Pool.imap
+                emit(merged[nxt])
+                merged[nxt] = None
                 nxt += 1
         for pr in procs:
             pr.join()
+        while nxt < len(task_args):                                         # (samples no rank owned a locus of)
+            if merged[nxt] is not None:
+                emit(merged[nxt])
+            nxt += 1
 
     print("Elapsed time={}".format(timedelta(seconds=time.time() - start)), file=sys.stderr)
     os.chdir(cwd)
