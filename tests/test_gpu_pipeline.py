@@ -71,8 +71,9 @@ def test_runBam_equals_batched_run():
     ip = InputParams(bam=bam, READLEN=150, tredName="HD", repo=repo, maxinsert=300, fullsearch=False,
                      gender="Unknown", depth=depth, clip=False, alts=True, repeatpairs=True, log="INFO")
     r = T.runBam(ip)
-    assert r.alleles == [res["HD.1"], res["HD.2"]] and r.CI == res["HD.CI"] and r.PP == res["HD.PP"]
-    assert r.P_h1 == res["HD.P_h1"] and r.P_h1h2 == res["HD.P_h1h2"] and r.label == res["HD.label"]
+    assert r.alleles == [res["HD.1"], res["HD.2"]] and r.CI == res["HD.CI"] and abs(r.PP - res["HD.PP"]) < 1e-12
+    _close(r.P_h1, res["HD.P_h1"], 1e-12); _close(r.P_h1h2, res["HD.P_h1h2"], 1e-12)      # (per-stage vs fused path: summation order)
+    assert r.label == res["HD.label"]
     assert T.counter_s(r.counts["PREF"]) == res["HD.PR"]
 
 
