@@ -183,29 +183,30 @@ def test_threaded_ingest_equals_serial(sample, tredname, bam, repo):
 
 
 def test_run_wiring_without_the_gpu(monkeypatch, repo):
-    """tred.run up to the kernels: pre-steps, threaded ingest, one InputParams per locus with the locus depth
-    (tred.py:195-249); the batched GPU stage is replaced by a recorder."""
+    """tred.run up to the kernels: pre-steps, threaded ingest, one item per locus with the locus depth
+    (tred.py:195-249); the fused device stage (tred.genotype_evidence) is replaced by a recorder."""
     from tredparse_b200 import tred as tredmod
     seen = {}
 
-    def fake_run_batched(ips, evidence=None):
-        seen["ips"], seen["evidence"] = ips, evidence
-        return [None] * len(ips)
-    monkeypatch.setattr(tredmod, "run_batched", fake_run_batched)
+    def fake_genotype_evidence(items, **kw):
+        seen["items"], seen["kw"] = items, kw
+        return [{} for _ in items]
+    monkeypatch.setattr(tredmod, "genotype_evidence", fake_genotype_evidence)
     bam = os.path.join(GOLDEN, "t001.mini.bam")
     names = ["HD", "DM1", "FXS"]
     out = tredmod.run(("t001", bam, repo, names, 300, False, False, True, True, "INFO"))
     assert out["samplekey"] == "t001" and out["bam"] == bam
     calls = out["tredCalls"]
     assert calls["readLen"] == 150 and calls["inferredGender"] == "Female" and calls["depthY"] == 0.0
-    assert not any(k.startswith("HD.") for k in calls)                   # the recorder returned no results
-    ips = seen["ips"]
-    assert [ip.tredName for ip in ips] == names and all(ip.READLEN == 150 and ip.gender == "Female" for ip in ips)
-    assert set(seen["evidence"]) == set(names)
-    hd = seen["evidence"]["HD"]
-    assert ips[0].depth == hd.depth > 5 and hd.nreads > 50
-    assert seen["evidence"]["DM1"].nreads == 0 and ips[1].depth == 0.0  # chr19: nothing in the chr4 mini BAM
-    assert ips[0].kwargs["maxinsert"] == 300 and ips[0].kwargs["fullsearch"] is False
+    assert not any(k.startswith("HD.") for k in calls)                   # the recorder returned no fields
+    items = seen["items"]                                                # (tred, READLEN, gender, depth, evidence)
+    assert [it[0].name for it in items] == names
+    assert all(it[1] == 150 and it[2] == "Female" for it in items)
+    hd, dm1 = items[0], items[1]
+    assert hd[3] == hd[4].depth > 5 and hd[4].nreads > 50
+    assert dm1[4].nreads == 0 and dm1[3] == 0.0                          # chr19: nothing in the chr4 mini BAM
+    assert seen["kw"]["maxinsert"] == 300 and seen["kw"]["fullsearch"] is False
+    assert seen["kw"]["clip"] is False and seen["kw"]["repeatpairs"] is True
 
 
 # ---- corrupt input must not take the process down ---------------------------------------------------------------
