@@ -243,7 +243,10 @@ def load(libssw=None, modules=None):
     if key in _loaded:
         return _loaded[key]
 
-    pkgname = "reftredparse" if not _loaded else "reftredparse_{}".format(len(_loaded))
+    # the full package keeps the name `reftredparse` (the cached code objects import from it by that name); an
+    # ssw-only instance bound to another library (the drop-in tests) imports nothing and takes a numbered name
+    full = any(m != "ssw" for m in modules)
+    pkgname = "reftredparse" if full and "reftredparse" not in sys.modules else "reftredparse_{}".format(len(_loaded) + 1)
     scratch = tempfile.mkdtemp(prefix="refssw_")
     os.symlink(libssw, os.path.join(scratch, "libssw.so"))
 
@@ -274,7 +277,7 @@ def load(libssw=None, modules=None):
             mod.__dict__.update(_py2div=_py2div, range=_py2range)
             sys.modules[mod.__name__] = mod
             code = _code(name)
-            if pkgname != "reftredparse" and not available():
+            if pkgname != "reftredparse" and name != "ssw" and not available():
                 raise RuntimeError("cached code objects import from `reftredparse` only")
             exec(code, mod.__dict__)
             setattr(pkg, name, mod)
