@@ -388,6 +388,54 @@ int tredsw_bam_region_depth(tredsw_bam *bam, int32_t tid, int64_t start, int64_t
  * first first_n + 1 records of the file. */
 int tredsw_bam_read_length(tredsw_bam *bam, int32_t first_n, int32_t *max_out, int32_t *min_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * (D) BAM ingest on the GPU for a whole batch of (sample, locus) problems (csrc/bgzf_gpu.cu): the host reads only
+ * the COMPRESSED BGZF blocks behind the BAI chunks of the requested windows; raw-DEFLATE decoding (one thread per
+ * block, CRC-32 checked), the record walk, read selection (tredparse/bam_parser.py:194-243), PEextractor
+ * (:316-369, pairing by query name) and the pileup depth (:404-411) run on the device and leave rbuf / roff /
+ * read_problem / pe_lens in device memory in the layout of tredsw_cohort (TREDSW_DEVICE_PTRS) — same reads,
+ * order, pair lists and depth as tredsw_bam_extract_locus query by query.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tredsw_ingest_batch tredsw_ingest_batch;
+
+#define TREDSW_INGEST_NO_NAMES 1u    /* do not collect read names */
+#define TREDSW_INGEST_NO_CRC 2u      /* skip the CRC-32 check of the inflated blocks */
+
+typedef struct {                /* where problem p's share of the flat buffers starts */
+    int64_t read0, base0, name0;
+    int64_t off_global, off_target;   /* into pe_lens: n_global values, then n_target values */
+} tredsw_problem_span;
+
+typedef struct {
+    int32_t nproblems, nreads;
+    int64_t nbases, name_bytes, n_pe_lens;
+    /* device memory, valid until tredsw_ingest_batch_free */
+    const int8_t *d_rbuf; const int64_t *d_roff; const int32_t *d_read_problem; const int32_t *d_pe_lens;
+    /* page-locked host copies of the same */
+    const int8_t *h_rbuf; const int64_t *h_roff; const int32_t *h_pe_lens; const char *h_names;
+    const tredsw_locus_summary *summaries;   /* per problem: counts and depth as tredsw_bam_extract_locus reports them */
+    const tredsw_problem_span *spans;
+    const int32_t *status;      /* per problem: 0 ok; 1 its sample could not be staged (I/O, index, BGZF framing), 2 a block
+                                   failed to inflate or its CRC-32 differs, 3 corrupt records — no evidence is reported for
+                                   such a problem: read it with tredsw_bam_extract_locus (which has zlib behind it) */
+    int64_t n_blocks, n_records, comp_bytes, inflated_bytes;
+    double ms_host_stage, ms_total;
+} tredsw_ingest_view;
+
+/* queries[i] belongs to bams[sample_of[i]]; problems are numbered like the queries.  The handles are only read
+ * (index, file descriptor with pread): one handle may serve several batches, but not from two threads at once. */
+int tredsw_ingest_batch_run(tredsw_ctx *ctx, tredsw_bam *const *bams, const int32_t *sample_of,
+                            const tredsw_locus_query *queries, int32_t nqueries, uint32_t flags,
+                            tredsw_ingest_batch **out);
+int tredsw_ingest_batch_view(const tredsw_ingest_batch *batch, tredsw_ingest_view *view);
+void tredsw_ingest_batch_free(tredsw_ingest_batch *batch);
+/* TEST INFRASTRUCTURE: the same pipeline with every kernel body executed serially on the host (the bodies are
+ * __host__ __device__, csrc/ingest_device.cuh), so that the CPU test-suite can compare the device logic with the
+ * host reader bit for bit.  The d_* pointers of its view are host pointers.  The package never calls it. */
+int tredsw_ingest_batch_emulate(tredsw_bam *const *bams, const int32_t *sample_of, const tredsw_locus_query *queries,
+                                int32_t nqueries, uint32_t flags, tredsw_ingest_batch **out);
+int tredsw_inflate_raw_device_code(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
+
 #ifdef __cplusplus
 }
 #endif

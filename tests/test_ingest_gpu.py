@@ -1,0 +1,188 @@
+"""GPU BAM ingest (csrc/bgzf_gpu.cu, csrc/ingest_device.cuh): BGZF inflate, record walk, read selection, pairing
+by name and depth for a whole batch of (sample, locus) problems — against the host reader
+(tredsw_bam_extract_locus, itself pinned to the Python reader and the reference's BAMs in test_ingest.py).
+
+CPU tests run the SAME per-thread bodies through the serial host backend (tredsw_ingest_batch_emulate: test
+infrastructure); the `gpu` tests run the kernels and compare with the host reader problem by problem."""
+import os
+import random
+import shutil
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def repo():
+    from tredparse_b200.meta import TREDsRepo
+    return TREDsRepo()
+
+
+def _queries(handles, repo, names, readlen=150, alts=True):
+    from tredparse_b200 import ingest
+    qs, so, keep, key = [], [], [], []
+    for si, h in enumerate(handles):
+        for n in names:
+            q = ingest.locus_query(h, repo[n], readlen, alts=repo[n].alt if alts else ())
+            if q is None:
+                continue
+            qs.append(q[0]); keep.append(q[1]); so.append(si); key.append((si, n))
+    return qs, so, keep, key
+
+
+def _same(ev, ref):
+    return (np.array_equal(ev.reads, ref.reads) and np.array_equal(ev.roff, ref.roff)
+            and np.array_equal(ev.global_lens, ref.global_lens) and np.array_equal(ev.target_lens, ref.target_lens)
+            and ev.depth == ref.depth and ev.n_unmapped == ref.n_unmapped and ev.names == ref.names)
+
+
+def _check_batch(ctx, paths, repo, names, alts=True, readlen=150):
+    from tredparse_b200 import ingest
+    hs = [ingest.BamIngest(p) for p in paths]
+    try:
+        qs, so, keep, key = _queries(hs, repo, names, readlen, alts)
+        with ingest.IngestBatch(ctx, hs, so, qs, keep=keep) as b:
+            assert b.nproblems == len(key) and not b.status.any()
+            total = 0
+            for i, (si, n) in enumerate(key):
+                ref = hs[si].extract_locus(repo[n], readlen, alts=repo[n].alt if alts else (), want_names=True)
+                assert _same(b.evidence(i), ref), (paths[si], n)
+                total += ref.nreads
+            st = b.stats()
+            assert st["blocks"] > 0 and st["records"] > 0
+            return total
+    finally:
+        for h in hs:
+            h.close()
+
+
+def _write_sample(path, repo, names, sample, seed):
+    from tredparse_b200 import simulate, bamio
+    sam = bamio.AlignmentFile(os.path.join(GOLDEN, "t001.mini.bam"))
+    refs = list(zip(sam.references, sam.lengths))
+    sam.close()
+    simulate.write_sample_bam(path, repo, names, refs, sample, 150, seed)
+
+
+def _raw_deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+# ---- CPU: the device code, executed serially on the host -----------------------------------------------------
+def test_device_decoder_on_every_block_type():
+    """stored / fixed / dynamic blocks, long distances, runs, every window size, empty input, and refusal of
+    truncated or corrupted streams (the __host__ __device__ decoder behind inflate_kernel)."""
+    from tredparse_b200 import _lib, ingest
+    lib = _lib.load()
+    ingest._bind_batch(lib)
+    rng = random.Random(5)
+    cases = [b"", b"a", b"ab" * 40000, bytes(rng.getrandbits(8) for _ in range(20000)),
+             b"".join(bytes([rng.choice(b"ACGT")]) for _ in range(65536)),
+             bytes(rng.choice(b"IIIIIHHGF#") for _ in range(30000)), open(__file__, "rb").read(), bytes(65536)]
+    for data in cases:
+        for level, strategy in ((0, 0), (1, 0), (6, 0), (9, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            raw = _raw_deflate(data, level, strategy)
+            out = np.zeros(len(data) + 16, np.uint8)
+            assert lib.tredsw_inflate_raw_device_code(raw, len(raw), out.ctypes.data, len(data)) == 0
+            assert bytes(out[:len(data)]) == data
+            if len(data) > 100:
+                # wrong inflated size, truncation, and bit flips must be refused or yield different bytes — never crash
+                assert lib.tredsw_inflate_raw_device_code(raw, len(raw), out.ctypes.data, len(data) - 1) != 0
+                assert lib.tredsw_inflate_raw_device_code(raw[:len(raw) // 2], len(raw) // 2, out.ctypes.data, len(data)) != 0
+                for _ in range(20):
+                    bad = bytearray(raw)
+                    bad[rng.randrange(len(bad))] ^= 1 << rng.randrange(8)
+                    rc = lib.tredsw_inflate_raw_device_code(bytes(bad), len(bad), out.ctypes.data, len(data))
+                    assert rc != 0 or zlib.crc32(bytes(out[:len(data)])) != zlib.crc32(data) or bytes(out[:len(data)]) == data
+
+
+def test_emulated_pipeline_equals_host_reader_on_the_fixtures(repo):
+    paths = [os.path.join(GOLDEN, "t001.mini.bam"), os.path.join(GOLDEN, "t002.mini.bam")]
+    assert _check_batch(None, paths, repo, repo.names) > 100
+    assert _check_batch(None, paths[:1], repo, ["HD"], alts=False) > 50
+    assert _check_batch(None, paths, repo, ["HD", "DM1", "SCA17"], readlen=101) > 50
+
+
+def test_emulated_pipeline_on_the_reference_bams(repo):
+    ref = [p for p in ("/root/reference/tests/t001.bam", "/root/reference/tests/t002.bam") if os.path.exists(p)]
+    if not ref:
+        pytest.skip("reference tree not mounted")
+    assert _check_batch(None, ref, repo, repo.names) > 200
+
+
+def test_emulated_pipeline_on_a_synthetic_whole_sample_bam(repo, tmp_path):
+    """~30x at every catalogue locus: thousands of pair candidates per problem (pairing tables, ordered compaction)."""
+    names = ["HD", "DM1", "FXS", "SCA10"]
+    path = str(tmp_path / "s.bam")
+    _write_sample(path, repo, names, 3, 11)
+    assert _check_batch(None, [path], repo, names) > 200
+
+
+def test_corrupt_input_is_reported_per_problem_not_as_evidence(repo, tmp_path):
+    """a flipped byte inside a BGZF block / a truncated file: status != 0 for the problems of that sample, the other
+    sample of the batch is untouched (the caller reads flagged problems with the host reader)."""
+    from tredparse_b200 import ingest
+    good = os.path.join(GOLDEN, "t001.mini.bam")
+    for how in ("flip", "truncate"):
+        bad = str(tmp_path / (how + ".bam"))
+        data = bytearray(open(good, "rb").read())
+        if how == "flip":
+            data[len(data) // 2] ^= 0x55
+        else:
+            data = data[:len(data) // 2]
+        open(bad, "wb").write(bytes(data))
+        shutil.copy(good + ".bai", bad + ".bai")
+        hs = [ingest.BamIngest(good), ingest.BamIngest(bad)]
+        qs, so, keep, key = _queries(hs, repo, ["HD"])
+        with ingest.IngestBatch(None, hs, so, qs, keep=keep) as b:
+            assert b.status[0] == 0 and b.status[1] != 0
+            assert _same(b.evidence(0), hs[0].extract_locus(repo["HD"], 150, alts=repo["HD"].alt, want_names=True))
+        for h in hs:
+            h.close()
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_ingest_equals_host_reader_on_the_fixtures(repo):
+    from tredparse_b200 import _lib
+    ctx = _lib.default_context(0)
+    paths = [os.path.join(GOLDEN, "t001.mini.bam"), os.path.join(GOLDEN, "t002.mini.bam")]
+    assert _check_batch(ctx, paths, repo, repo.names) > 100
+    assert _check_batch(ctx, paths, repo, ["HD", "DM1"], alts=False) > 50
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_on_synthetic_whole_sample_bams(repo, tmp_path):
+    from tredparse_b200 import _lib
+    ctx = _lib.default_context(0)
+    names = [n for n in repo.names][:12]
+    paths = []
+    for s in range(3):
+        p = str(tmp_path / "s{}.bam".format(s))
+        _write_sample(p, repo, names, s, 21)
+        paths.append(p)
+    assert _check_batch(ctx, paths, repo, names) > 1000
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_flags_corrupt_blocks(repo, tmp_path):
+    from tredparse_b200 import _lib, ingest
+    ctx = _lib.default_context(0)
+    good = os.path.join(GOLDEN, "t001.mini.bam")
+    bad = str(tmp_path / "flip.bam")
+    data = bytearray(open(good, "rb").read())
+    data[len(data) // 2] ^= 0x55
+    open(bad, "wb").write(bytes(data))
+    shutil.copy(good + ".bai", bad + ".bai")
+    hs = [ingest.BamIngest(good), ingest.BamIngest(bad)]
+    qs, so, keep, key = _queries(hs, repo, ["HD"])
+    with ingest.IngestBatch(ctx, hs, so, qs, keep=keep) as b:
+        assert b.status[0] == 0 and b.status[1] != 0
+        assert _same(b.evidence(0), hs[0].extract_locus(repo["HD"], 150, alts=repo["HD"].alt, want_names=True))
+    for h in hs:
+        h.close()

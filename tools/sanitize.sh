@@ -6,7 +6,6 @@ mkdir -p gpurun_out
 for tool in memcheck racecheck synccheck initcheck; do
   extra=""
   [ $tool = memcheck ] && extra="--leak-check no"
-  [ $tool = initcheck ] && extra="--track-unused-memory no"
   log=gpurun_out/r2_sanitize_$tool.txt
   timeout ${SANITIZE_TIMEOUT:-1500} compute-sanitizer --tool $tool $extra --print-limit 20 \
       python tools/sanitize_target.py ${SANITIZE_WHAT:-smoke cohort flags stress} > $log.full 2>&1

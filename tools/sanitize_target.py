@@ -28,7 +28,10 @@ def main():
         b = cohort.CohortBatch(probs)
         a = b.run_host(ctx=ctx, want_reads=True, want_hist=True, want_post=True)
         b.to_device(0)
+        import torch
+        torch.cuda.synchronize()
         b.run_device(ctx)
+        torch.cuda.synchronize()                 # (ctx owns its stream)
         got = b.calls_from_device()
         assert np.asarray(a["calls"]).tobytes() == got.tobytes(), "device-resident != host-buffer calls"
     if "flags" in which:

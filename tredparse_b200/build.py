@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtredsw.so")
-SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu", "ingest.cpp"]
+SOURCES = ["capi.cu", "sw_pairs.cu", "sw_family.cu", "grid.cu", "cohort.cu", "ingest.cpp", "bgzf_gpu.cu"]
 INCLUDE = os.path.abspath(os.path.join(HERE, "..", "include"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(CSRC, os.path.splitext(s)[0] + ".o")
-        cmd = [nvcc_path(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-c",
+        cmd = [nvcc_path(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC", "-c",
                os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd += ["-Xptxas", "-v"]

@@ -195,3 +195,142 @@ class BamIngest:
         pr.global_lens, pr.target_lens = ev.global_lens, ev.target_lens
         pr.alleles, pr.names = None, None
         return pr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Batched ingest on the GPU (csrc/bgzf_gpu.cu): compressed BGZF blocks in, flat cohort buffers out
+# ---------------------------------------------------------------------------------------------------------
+INGEST_NO_NAMES, INGEST_NO_CRC = 1, 2
+
+
+class ProblemSpan(ctypes.Structure):
+    """tredsw_problem_span (include/tredsw.h)"""
+    _fields_ = [(n, ctypes.c_int64) for n in ("read0", "base0", "name0", "off_global", "off_target")]
+
+
+class IngestView(ctypes.Structure):
+    """tredsw_ingest_view (include/tredsw.h)"""
+    _fields_ = [("nproblems", ctypes.c_int32), ("nreads", ctypes.c_int32), ("nbases", ctypes.c_int64),
+                ("name_bytes", ctypes.c_int64), ("n_pe_lens", ctypes.c_int64),
+                ("d_rbuf", ctypes.c_void_p), ("d_roff", ctypes.c_void_p), ("d_read_problem", ctypes.c_void_p),
+                ("d_pe_lens", ctypes.c_void_p),
+                ("h_rbuf", ctypes.c_void_p), ("h_roff", ctypes.c_void_p), ("h_pe_lens", ctypes.c_void_p),
+                ("h_names", ctypes.c_void_p),
+                ("summaries", ctypes.POINTER(LocusSummary)), ("spans", ctypes.POINTER(ProblemSpan)),
+                ("status", ctypes.POINTER(ctypes.c_int32)),
+                ("n_blocks", ctypes.c_int64), ("n_records", ctypes.c_int64), ("comp_bytes", ctypes.c_int64),
+                ("inflated_bytes", ctypes.c_int64), ("ms_host_stage", ctypes.c_double), ("ms_total", ctypes.c_double)]
+
+
+def _bind_batch(lib):
+    if getattr(lib, "_ingest_batch_bound", False):
+        return
+    lib.tredsw_ingest_batch_run.restype = ctypes.c_int
+    lib.tredsw_ingest_batch_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                            ctypes.POINTER(LocusQuery), ctypes.c_int32, ctypes.c_uint32,
+                                            ctypes.POINTER(ctypes.c_void_p)]
+    lib.tredsw_ingest_batch_emulate.restype = ctypes.c_int
+    lib.tredsw_ingest_batch_emulate.argtypes = lib.tredsw_ingest_batch_run.argtypes[1:]
+    lib.tredsw_ingest_batch_view.restype = ctypes.c_int
+    lib.tredsw_ingest_batch_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(IngestView)]
+    lib.tredsw_ingest_batch_free.restype = None
+    lib.tredsw_ingest_batch_free.argtypes = [ctypes.c_void_p]
+    lib.tredsw_inflate_raw_device_code.restype = ctypes.c_int
+    lib.tredsw_inflate_raw_device_code.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
+    lib._ingest_batch_bound = True
+
+
+def locus_query(handle, tred, readlen, alts=(), pad=SPAN):
+    """(LocusQuery, keep-alive array) of one locus on one open BAM; None when the contig is unknown."""
+    tid = handle.tid(tred.chr)
+    if tid < 0:
+        return None
+    rows = [(t, int(s), int(e)) for (t, s, e) in ((handle.tid(c), s, e) for (c, s, e) in alts) if t >= 0]
+    arr = np.ascontiguousarray(np.array(rows, dtype=np.int32).reshape(-1, 3))
+    q = LocusQuery(tid=tid, repeat_start=tred.repeat_start, repeat_end=tred.repeat_end, readlen=readlen, pad=pad,
+                   pe_window=DNAPE_ELONGATE, flankmatch=FLANKMATCH, span=SPAN, n_alts=len(rows),
+                   alts=arr.ctypes.data if len(rows) else None)
+    return q, arr
+
+
+class IngestBatch:
+    """The evidence of many (sample, locus) problems extracted on the GPU in one pass.
+
+        batch = IngestBatch(ctx, handles, sample_of, queries)      # handles: [BamIngest], queries: [LocusQuery]
+        batch.status[i] == 0        problem i is good; otherwise read it with BamIngest.extract_locus
+        batch.evidence(i)           LocusEvidence (host copies), identical to BamIngest.extract_locus
+        batch.view.d_rbuf ...       device buffers in the tredsw_cohort layout (valid until close())
+
+    ``ctx=None`` runs the serial host emulation of the device code — test infrastructure only."""
+
+    def __init__(self, ctx, handles, sample_of, queries, keep=(), want_names=True, check_crc=True):
+        self.lib = _lib.load()
+        _bind(self.lib)
+        _bind_batch(self.lib)
+        n = len(queries)
+        self._keep = (list(keep), list(handles))
+        hs = (ctypes.c_void_p * max(1, len(handles)))(*[h.handle for h in handles])
+        so = np.ascontiguousarray(np.asarray(sample_of, dtype=np.int32))
+        qs = (LocusQuery * max(1, n))(*queries)
+        flags = (0 if want_names else INGEST_NO_NAMES) | (0 if check_crc else INGEST_NO_CRC)
+        out = ctypes.c_void_p()
+        if ctx is None:
+            rc = self.lib.tredsw_ingest_batch_emulate(hs, so.ctypes.data, qs, n, flags, ctypes.byref(out))
+        else:
+            rc = self.lib.tredsw_ingest_batch_run(ctx.handle, hs, so.ctypes.data, qs, n, flags, ctypes.byref(out))
+        _lib.check(rc, "tredsw_ingest_batch_run")
+        self.handle = out
+        self.view = IngestView()
+        _lib.check(self.lib.tredsw_ingest_batch_view(self.handle, ctypes.byref(self.view)), "tredsw_ingest_batch_view")
+        v = self.view
+        self.nproblems, self.nreads = int(v.nproblems), int(v.nreads)
+        self.status = np.ctypeslib.as_array(v.status, shape=(max(1, n),))[:n].copy() if n else np.zeros(0, np.int32)
+        self.summaries = [v.summaries[i] for i in range(n)]
+        self.spans = [v.spans[i] for i in range(n)]
+        as_np = lambda ptr, ct, m: (np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(m,)) if m and ptr
+                                    else np.zeros(0, dtype=ct))
+        self.h_rbuf = as_np(v.h_rbuf, ctypes.c_int8, int(v.nbases))
+        self.h_roff = as_np(v.h_roff, ctypes.c_int64, self.nreads + 1)
+        self.h_pe_lens = as_np(v.h_pe_lens, ctypes.c_int32, int(v.n_pe_lens))
+        self.h_names = ctypes.string_at(v.h_names, int(v.name_bytes)) if v.h_names and v.name_bytes else b""
+        self.want_names = want_names
+
+    def evidence(self, i):
+        s, sp = self.summaries[i], self.spans[i]
+        ev = LocusEvidence()
+        r0, b0 = int(sp.read0), int(sp.base0)
+        ev.reads = self.h_rbuf[b0:b0 + int(s.nbases)].copy()
+        ev.roff = (self.h_roff[r0:r0 + s.nreads + 1] - b0).astype(np.int64)
+        ev.global_lens = self.h_pe_lens[int(sp.off_global):int(sp.off_global) + s.n_global].copy()
+        ev.target_lens = self.h_pe_lens[int(sp.off_target):int(sp.off_target) + s.n_target].copy()
+        ev.depth = float(s.depth)
+        ev.n_unmapped = int(s.n_unmapped)
+        if self.want_names:
+            raw = self.h_names[int(sp.name0):int(sp.name0) + int(s.name_bytes)]
+            ev.names = raw.decode("latin-1").split("\0")[:-1]
+        else:
+            ev.names = None
+        return ev
+
+    def stats(self):
+        v = self.view
+        return {"blocks": int(v.n_blocks), "records": int(v.n_records), "compressed_bytes": int(v.comp_bytes),
+                "inflated_bytes": int(v.inflated_bytes), "ms_host_stage": float(v.ms_host_stage),
+                "ms_total": float(v.ms_total)}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.tredsw_ingest_batch_free(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
