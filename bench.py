@@ -784,9 +784,12 @@ def _main(args):
                 dt = time.perf_counter() - t0
                 fb = {"value": len(bams) * nloci / dt, "unit": UNIT, "samples": len(bams), "loci": nloci, "seconds": dt,
                       "bam_mb_per_sample": os.path.getsize(bams[0]) / 1e6, "host_threads": T.INGEST_THREADS,
-                      "what": "tred.run_chunk on synthetic whole-sample BAMs (+-10 kb windows, ~35x, 30 loci): BGZF inflate + "
-                              "record parsing + read selection + pair lengths + depth on host threads (csrc/ingest.cpp), then "
-                              "ONE fused device call for all loci of all samples; pre-steps (gender, read length) included",
+                      "gpu_ingest": bool(T.GPU_INGEST),
+                      "what": "tred.run_chunk on synthetic whole-sample BAMs (+-10 kb windows, ~35x, 30 loci): the host reads the "
+                              "compressed BGZF blocks; inflate (one warp per block, CRC-32 checked) + record walk + read selection "
+                              "+ pairing by name + depth on the GPU (csrc/bgzf_gpu.cu), then ONE fused device call for all loci of "
+                              "all samples and the reference's JSON fields assembled on the host; pre-steps (gender, read length) "
+                              "included",
                       "setup_write_bams_s": t_bams}
                 if ref_pool is not None:
                     jobs = [("s{:04d}".format(i), p, list(names)) for i, p in enumerate(bams)]

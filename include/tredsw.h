@@ -368,6 +368,8 @@ tredsw_bam *tredsw_bam_clone(tredsw_bam *bam);
 void tredsw_bam_close(tredsw_bam *bam);
 int32_t tredsw_bam_nref(tredsw_bam *bam);
 int32_t tredsw_bam_tid(tredsw_bam *bam, const char *contig);     /* -1 when unknown */
+/* signature of the reference dictionary (names + lengths, in order): equal signatures = equal contig numbering */
+uint64_t tredsw_bam_header_signature(tredsw_bam *bam);
 /* names may be NULL (not wanted).  Reads are written in the reference's order: window reads in file
  * order, then the alt-region reads. */
 int tredsw_bam_extract_locus(tredsw_bam *bam, const tredsw_locus_query *q, int8_t *rbuf, int64_t rbuf_cap,
@@ -419,7 +421,9 @@ typedef struct {
                                    failed to inflate or its CRC-32 differs, 3 corrupt records — no evidence is reported for
                                    such a problem: read it with tredsw_bam_extract_locus (which has zlib behind it) */
     int64_t n_blocks, n_records, comp_bytes, inflated_bytes;
-    double ms_host_stage, ms_total;
+    double ms_host_stage, ms_total;   /* host time: compressed bytes staged; whole call */
+    double ms_marks[4];         /* host time at the four synchronisation points: blocks inflated + records counted,
+                                   records selected, pairs formed, results copied */
 } tredsw_ingest_view;
 
 /* queries[i] belongs to bams[sample_of[i]]; problems are numbered like the queries.  The handles are only read

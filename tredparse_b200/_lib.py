@@ -30,6 +30,7 @@ EXPORTS = [
     # native BAM ingest
     "tredsw_bam_open", "tredsw_bam_close", "tredsw_bam_nref", "tredsw_bam_tid", "tredsw_bam_extract_locus",
     "tredsw_bam_region_depth", "tredsw_bam_read_length", "tredsw_bam_clone", "tredsw_bam_inflate_stats", "tredsw_inflate_raw",
+    "tredsw_bam_header_signature",
     # BAM ingest on the GPU (batched); *_emulate / *_device_code run the device code on the host for the CPU tests
     "tredsw_ingest_batch_run", "tredsw_ingest_batch_view", "tredsw_ingest_batch_free", "tredsw_ingest_batch_emulate",
     "tredsw_inflate_raw_device_code",

@@ -262,16 +262,21 @@ class PEextractor:
 class BamReadLen:
     """Read length of a BAM: longest of the first ~100 reads (bam_parser.py:372-391)."""
 
-    def __init__(self, bamfile, logger):
+    def __init__(self, bamfile, logger, ing=None):
+        """ing: an open ``ingest.BamIngest`` on the same file to use instead of opening another one"""
         self.bamfile = bamfile
         self.logger = logger
+        self.ing = ing
 
     @property
     def readlen(self, firstN=100):
         try:                                   # native reader (csrc/ingest.cpp); needs the .bai next to the BAM
             from .ingest import BamIngest
-            with BamIngest(os.path.abspath(self.bamfile)) as ing:
-                rmax, rmin = ing.read_length(firstN)
+            if self.ing is not None:
+                rmax, rmin = self.ing.read_length(firstN)
+            else:
+                with BamIngest(os.path.abspath(self.bamfile)) as ing:
+                    rmax, rmin = ing.read_length(firstN)
             if rmin != rmax:
                 self.logger.debug("Read length: min={}bp max={}bp".format(rmin, rmax))
             return rmax
@@ -294,10 +299,12 @@ class BamDepth:
     """Average depth of a region, for the repeat-only read model and for gender inference
     (bam_parser.py:394-429)."""
 
-    def __init__(self, bamfile, ref, logger):
+    def __init__(self, bamfile, ref, logger, ing=None):
+        """ing: an open ``ingest.BamIngest`` on the same file to use instead of opening another one"""
         self.bamfile = bamfile
         self.logger = logger
         self.ref = ref
+        self.ing = ing
 
     def region_depth(self, chr, start, end, verbose=False):
         sam = read_alignment(self.bamfile)
@@ -327,17 +334,18 @@ class BamDepth:
                 if len(regions) >= N:
                     break
         depths = []
-        ing = None
-        try:
-            from .ingest import BamIngest
-            ing = BamIngest(os.path.abspath(self.bamfile))
-        except Exception:
-            ing = None
+        ing, own = self.ing, False
+        if ing is None:
+            try:
+                from .ingest import BamIngest
+                ing, own = BamIngest(os.path.abspath(self.bamfile)), True
+            except Exception:
+                ing = None
         try:
             for c, start, end in regions:
                 depths.append(ing.region_depth(c, start, end) if ing is not None else self.region_depth(c, start, end))
         finally:
-            if ing is not None:
+            if own:
                 ing.close()
         self.logger.debug("Y depths (first {} regions): {}".format(N, np.array(depths)))
         return float(np.median(depths))

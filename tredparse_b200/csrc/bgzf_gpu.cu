@@ -26,11 +26,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -98,6 +100,16 @@ __global__ void for_each_warp_kernel(int64_t n, F f) {
     if (i < n) f(i, (int)(threadIdx.x & 31));
 }
 
+// one warp per item with WALK_WINDOW bytes of shared memory per warp: f(item, lane, window)
+constexpr int WALK_WARPS = 4;
+template <class Tag, class F>
+__global__ void __launch_bounds__(32 * WALK_WARPS) for_each_warp_window_kernel(int64_t n, F f) {
+    __shared__ __align__(16) uint32_t win[WALK_WARPS][WALK_WINDOW / 4 + 4];
+    const int w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * WALK_WARPS + w;
+    if (i < n) f(i, (int)(threadIdx.x & 31), win[w]);
+}
+
 // exclusive scan of uint32 -> uint32 (n + 1 outputs, out[n] = total), three phases over tiles of SCAN_TILE elements
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
 __device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {     // SCAN_THREADS threads
@@ -152,6 +164,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 // ---------------------------------------------------------------------------------------------------------------
 // backends
 // ---------------------------------------------------------------------------------------------------------------
+// Page-locked host blocks are expensive to create (~0.3 ms per MB) and a batch needs a few tens of MB of them: freed
+// blocks are kept and handed out again (best fit), so consecutive batches of a cohort allocate nothing.
+struct PinnedPool {
+    struct Block { void *p; size_t cap; bool used; };
+    std::mutex mu;
+    std::vector<Block> blocks;
+    void *get(size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (!blocks[i].used && blocks[i].cap >= bytes && (best < 0 || blocks[i].cap < blocks[best].cap)) best = i;
+        if (best >= 0 && blocks[best].cap <= 4 * bytes + (1 << 16)) { blocks[best].used = true; return blocks[best].p; }
+        void *p = nullptr;
+        const size_t cap = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        blocks.push_back(Block{p, cap, true});
+        return p;
+    }
+    void put(void *p) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (Block &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+};
+PinnedPool &pinned_pool() { static PinnedPool *pool = new PinnedPool(); return *pool; }
+
 struct CudaBackend {
     static constexpr bool on_device = true;
     cudaStream_t stream;
@@ -169,8 +206,8 @@ struct CudaBackend {
         return p;
     }
     void *alloc_host(size_t bytes) {                   // page-locked host memory
-        void *p = nullptr;
-        if (fail(cudaHostAlloc(&p, bytes + 64, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+        void *p = pinned_pool().get(bytes + 64);
+        if (!p) { fail(cudaErrorMemoryAllocation, "cudaHostAlloc"); return nullptr; }
         pinned.push_back(p);
         return p;
     }
@@ -187,6 +224,11 @@ struct CudaBackend {
         if (n <= 0 || rc) return;
         for_each_warp_kernel<Tag><<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(n, f);
         fail(cudaGetLastError(), "for_each_warp launch");
+    }
+    template <class Tag, class F> void for_each_warp_window(int64_t n, F f) {
+        if (n <= 0 || rc) return;
+        for_each_warp_window_kernel<Tag><<<(unsigned)((n + WALK_WARPS - 1) / WALK_WARPS), 32 * WALK_WARPS, 0, stream>>>(n, f);
+        fail(cudaGetLastError(), "for_each_warp_window launch");
     }
     void inflate(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int nblocks, uint8_t *status, int check_crc) {
         if (nblocks <= 0 || rc) return;
@@ -216,7 +258,7 @@ struct CudaBackend {
         for (void *p : dev) cudaFreeAsync(p, stream);
         dev.clear();
         cudaStreamSynchronize(stream);
-        for (void *p : pinned) cudaFreeHost(p);
+        for (void *p : pinned) pinned_pool().put(p);
         pinned.clear();
     }
 };
@@ -233,6 +275,7 @@ struct HostBackend {                                   // serial emulation of th
     void sync() {}
     template <class Tag, class F> void for_each(int64_t n, F f) { for (int64_t i = 0; i < n && !rc; ++i) f(i); }
     template <class Tag, class F> void for_each_warp(int64_t n, F f) { for (int64_t i = 0; i < n && !rc; ++i) f(i, 0); }
+    template <class Tag, class F> void for_each_warp_window(int64_t n, F f) { for (int64_t i = 0; i < n && !rc; ++i) f(i, 0, nullptr); }
     void inflate(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int nblocks, uint8_t *status, int check_crc) {
         std::vector<uint32_t> crct(1024);
         for (int i = 0; i < 256; ++i) crc_tables(crct.data(), i);
@@ -273,7 +316,7 @@ struct tredsw_ingest_batch {
                                                     // BGZF framing), 2 a block failed to inflate, 3 corrupt records
     std::vector<tredsw_problem_span> spans;
     tredsw_ingest_view view;
-    double ms_host_stage = 0, ms_total = 0;
+    double ms_host_stage = 0, ms_total = 0, ms_marks[4] = {0, 0, 0, 0};
     long long n_blocks = 0, n_records = 0;
     long long comp_bytes = 0, inflated_bytes = 0;
 };
@@ -324,12 +367,20 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
         sp.problems.push_back(i);
     }
     std::vector<ProblemParams> params(nq);
-    for (int s = 0; s < nsamples; ++s) {
+    // the samples are independent: their plans (index queries), reads (pread) and BGZF framing go to host threads
+    const int nthreads = std::max(1, std::min({nsamples, (int)std::thread::hardware_concurrency(), 16}));
+    auto parallel_samples = [&](auto &&body) {
+        if (nthreads <= 1) { for (int s = 0; s < nsamples; ++s) body(s); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back([&, t]() { for (int s = t; s < nsamples; s += nthreads) body(s); });
+        for (auto &th : pool) th.join();
+    };
+    parallel_samples([&](int s) {
         SamplePlan &sp = plans[s];
-        if (!sp.bam) continue;
+        if (!sp.bam) return;
         const int fd = fileno(sp.bam->bgzf.fh);
-        const off_t fsz = lseek(fd, 0, SEEK_END);
-        sp.file_size = fsz > 0 ? (int64_t)fsz : 0;
+        struct stat st;
+        sp.file_size = fstat(fd, &st) == 0 ? (int64_t)st.st_size : 0;
         std::vector<std::pair<int64_t, int64_t>> raw;
         for (int p : sp.problems) {
             const tredsw_locus_query &q = queries[p];
@@ -366,7 +417,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
             if (!sp.ranges.empty() && r.first <= sp.ranges.back().second) sp.ranges.back().second = std::max(sp.ranges.back().second, r.second);
             else sp.ranges.push_back(r);
         }
-    }
+    });
     // ---- (2) read the compressed bytes of every range into page-locked memory, parse the BGZF framing ----------
     int64_t comp_total = 0;
     for (SamplePlan &sp : plans) {
@@ -380,20 +431,23 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     }
     uint8_t *h_comp = static_cast<uint8_t *>(be.alloc_host((size_t)comp_total + 16));
     if (be.rc) return be.rc;
-    std::vector<BlockDesc> blocks;
     std::vector<Chunk> chunks;
     std::vector<Fetch> fetches;
     std::vector<int32_t> fetch_first(nq + 1, 0);
-    int64_t ibuf_total = 0;
+    // (offsets into ibuf are relative to the sample's first block until the samples are laid out one after the other)
     struct LoadedBlock { int64_t coffset; int64_t out_off; uint32_t isize; int64_t run_end; };
     std::vector<std::vector<LoadedBlock>> loaded(nsamples);
-    for (int s = 0; s < nsamples; ++s) {
+    std::vector<std::vector<BlockDesc>> sample_blocks(nsamples);
+    std::vector<int64_t> sample_inflated(nsamples, 0);
+    std::vector<const char *> sample_error(nsamples, nullptr);
+    parallel_samples([&](int s) {
         SamplePlan &sp = plans[s];
-        if (!sp.bam) continue;
+        if (!sp.bam) return;
         const int fd = fileno(sp.bam->bgzf.fh);
         bool ok = true;
         const char *why = "";
         std::vector<LoadedBlock> &lb = loaded[s];
+        int64_t cursor = 0;
         for (size_t r = 0; r < sp.ranges.size() && ok; ++r) {
             uint8_t *dst = h_comp + sp.range_comp_off[r];
             int64_t got = 0;
@@ -426,17 +480,26 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
                 if (isize > 65536) { ok = false; why = "BGZF block larger than 64 KiB"; break; }
                 BlockDesc d;
                 d.in_off = sp.range_comp_off[r] + o + 12 + xlen;
-                d.out_off = ibuf_total; d.clen = (uint32_t)clen; d.isize = isize; d.crc = crc; d.pad_ = 0;
-                blocks.push_back(d);
-                lb.push_back(LoadedBlock{sp.ranges[r].first + o, ibuf_total, isize, 0});
-                ibuf_total += isize;
+                d.out_off = cursor; d.clen = (uint32_t)clen; d.isize = isize; d.crc = crc; d.pad_ = 0;
+                sample_blocks[s].push_back(d);
+                lb.push_back(LoadedBlock{sp.ranges[r].first + o, cursor, isize, 0});
+                cursor += isize;
                 o += bsize + 1;
             }
-            for (size_t k = first_block; k < lb.size(); ++k) lb[k].run_end = ibuf_total;
+            for (size_t k = first_block; k < lb.size(); ++k) lb[k].run_end = cursor;
         }
-        if (!ok) {
-            for (int p : sp.problems) if (!out->status[p]) out->status[p] = 1;
-            tredsw_set_error("%s: %s", sp.bam->path.c_str(), why);
+        sample_inflated[s] = cursor;
+        if (!ok) sample_error[s] = why;
+    });
+    std::vector<BlockDesc> blocks;
+    int64_t ibuf_total = 0;
+    for (int s = 0; s < nsamples; ++s) {
+        for (BlockDesc &d : sample_blocks[s]) { d.out_off += ibuf_total; blocks.push_back(d); }
+        for (LoadedBlock &b : loaded[s]) { b.out_off += ibuf_total; b.run_end += ibuf_total; }
+        ibuf_total += sample_inflated[s];
+        if (sample_error[s]) {
+            for (int p : plans[s].problems) if (!out->status[p]) out->status[p] = 1;
+            tredsw_set_error("%s: %s", plans[s].bam->path.c_str(), sample_error[s]);
         }
     }
     // fetches and chunks, problem-major (= output order): the window first, then the alt regions in order
@@ -505,10 +568,11 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     {
         const uint8_t *ibuf = d_ibuf; const Fetch *fe = d_fetches; const Chunk *ch = d_chunks;
         uint32_t *fcount = d_fcount, *ferr = d_ferr;
-        be.template for_each<WalkCountTag>(nfetch, [=] __host__ __device__(int64_t i) {
+        const int64_t ibuf_len = ((ibuf_total + 16) / 16) * 16;               // (allocated: ibuf_total + 16 + slack)
+        be.template for_each_warp_window<WalkCountTag>(nfetch, [=] __host__ __device__(int64_t i, int lane, uint32_t *win) {
             uint32_t n = 0;
-            const bool ok = walk_fetch(ibuf, fe[i], ch, [&](int64_t) { ++n; });
-            fcount[i] = n; ferr[i] = ok ? 0u : 1u;
+            const bool ok = walk_fetch_lanes(ibuf, ibuf_len, fe[i], ch, lane, win, [&](int64_t) { ++n; });
+            if (lane == 0) { fcount[i] = n; ferr[i] = ok ? 0u : 1u; }
         });
     }
     be.scan(d_fcount, nfetch, d_fbase);
@@ -516,6 +580,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     uint32_t *h_ferr = static_cast<uint32_t *>(be.alloc_host(sizeof(uint32_t) * (size_t)(nfetch + 1)));
     be.download(h_ferr, d_ferr, sizeof(uint32_t) * (size_t)nfetch);
     be.sync();                                                                                  // sync 1
+    out->ms_marks[0] = now_ms() - t_begin;
     if (be.rc) return be.rc;
     {
         // blocks the decoder refused or whose CRC differs: the problems reading them are reported (the caller
@@ -555,10 +620,14 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
         const uint8_t *ibuf = d_ibuf; const Fetch *fe = d_fetches; const Chunk *ch = d_chunks;
         const uint32_t *fbase = d_fbase;
         int64_t *rpos = d_rpos; int32_t *rfetch = d_rfetch;
-        be.template for_each<WalkFillTag>(nfetch, [=] __host__ __device__(int64_t i) {
+        const int64_t ibuf_len = ((ibuf_total + 16) / 16) * 16;
+        be.template for_each_warp_window<WalkFillTag>(nfetch, [=] __host__ __device__(int64_t i, int lane, uint32_t *win) {
             uint32_t k = fbase[i];                               // (a fetch flagged by the count pass yields the same prefix)
             const uint32_t stop = fbase[i + 1];
-            walk_fetch(ibuf, fe[i], ch, [&](int64_t p) { if (k < stop) { rpos[k] = p; rfetch[k] = (int32_t)i; ++k; } });
+            walk_fetch_lanes(ibuf, ibuf_len, fe[i], ch, lane, win, [&](int64_t p) {
+                if (k < stop && lane == 0) { rpos[k] = p; rfetch[k] = (int32_t)i; }
+                ++k;
+            });
         });
         // ---- (5) per-record selection --------------------------------------------------------------------------------
         const ProblemParams *pp = d_params; ProblemCounts *pc = d_counts;
@@ -591,6 +660,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     be.download(h_psum, d_psum, sizeof(ProblemSummary) * (size_t)nq);
     be.download(h_counts, d_counts, sizeof(ProblemCounts) * (size_t)nq);
     be.sync();                                                                                  // sync 2
+    out->ms_marks[1] = now_ms() - t_begin;
     if (be.rc) return be.rc;
     const int64_t nreads = (int64_t)h_psum[nq - 1].read0 + h_psum[nq - 1].nreads;
     const int64_t nbases = (int64_t)h_psum[nq - 1].base0 + h_psum[nq - 1].nbases;
@@ -683,6 +753,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     }
     be.download(h_pcnt, d_pcnt, sizeof(uint32_t) * 2 * (size_t)nq);
     be.sync();                                                                                  // sync 3
+    out->ms_marks[2] = now_ms() - t_begin;
     if (be.rc) return be.rc;
     std::vector<int64_t> pe_off(2 * (size_t)nq);
     int64_t n_pe_lens = 0;
@@ -715,6 +786,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     be.download(h_pelens, d_pelens, sizeof(int32_t) * (size_t)n_pe_lens);
     if (want_names) be.download(h_names, d_names, (size_t)name_bytes);
     be.sync();                                                                                  // sync 4
+    out->ms_marks[3] = now_ms() - t_begin;
     if (be.rc) return be.rc;
 
     for (int p = 0; p < nq; ++p) {
@@ -737,6 +809,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     v.n_blocks = out->n_blocks; v.n_records = out->n_records; v.comp_bytes = out->comp_bytes; v.inflated_bytes = out->inflated_bytes;
     out->ms_total = now_ms() - t_begin;
     v.ms_host_stage = out->ms_host_stage; v.ms_total = out->ms_total;
+    for (int k = 0; k < 4; ++k) v.ms_marks[k] = out->ms_marks[k];
     return TREDSW_OK;
 }
 

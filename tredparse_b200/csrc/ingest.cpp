@@ -127,6 +127,16 @@ tredsw_bam *tredsw_bam_clone(tredsw_bam *src) {
 void tredsw_bam_close(tredsw_bam *b) { delete b; }
 
 // BGZF blocks inflated by this handle so far: by the library's own decoder / by zlib (the fallback).
+// A signature of the reference dictionary (names and lengths in order): handles with equal signatures number their
+// contigs alike, so per-locus queries built for one sample of a cohort can be reused for the next.
+uint64_t tredsw_bam_header_signature(tredsw_bam *b) {
+    if (!b) return 0;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) { const unsigned char *c = (const unsigned char *)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+    for (size_t i = 0; i < b->names.size(); ++i) { mix(b->names[i].c_str(), b->names[i].size() + 1); mix(&b->lengths[i], sizeof(b->lengths[i])); }
+    return h ? h : 1;
+}
+
 void tredsw_bam_inflate_stats(tredsw_bam *b, int64_t *own, int64_t *zlib_blocks) {
     if (own) *own = b ? b->bgzf.n_fast : 0;
     if (zlib_blocks) *zlib_blocks = b ? b->bgzf.n_zlib : 0;

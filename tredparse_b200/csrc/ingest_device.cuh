@@ -391,40 +391,75 @@ enum : uint32_t { ERR_WALK = 1u, ERR_RECORD = 2u };
 // Follows the record chain of every chunk of the fetch exactly like tredsw_bam::fetch (ingest_internal.h) and calls
 // sink(position) for every record that fetch would parse and hand to its overlap test.  Returns false when the chain
 // leaves the loaded bytes or a block_size is implausible (corrupt file / index): the caller flags the problem.
-// The chain is one dependent load per record; the records are contiguous, so the lines a few records ahead are
-// requested into L1 while the current header is decoded (L2 latency per record -> L1 latency).
-TG_HD void prefetch_ahead(const uint8_t *ibuf, int64_t p, int64_t run_end) {
-#if defined(__CUDA_ARCH__)
-    constexpr int64_t AHEAD = 1536;
+// The chain is one dependent load per record, and the inflated bytes of a batch do not fit the L2: read through
+// `Reader`, which on the device is a 4 KB window of the record stream in shared memory that the 32 lanes of a warp
+// refill together (one memory round trip per ~12 records instead of one per record); every lane follows the chain
+// redundantly on the same bytes (uniform control flow).  On the host the reader loads directly.
+struct DirectReader {
+    const uint8_t *ibuf;
+    TG_HD void head(int64_t p, int32_t *bs, int32_t *tid, int32_t *pos) { *bs = ld_i32(ibuf, p); *tid = ld_i32(ibuf, p + 4); *pos = ld_i32(ibuf, p + 8); }
+};
+constexpr int WALK_WINDOW = 4096;                    // bytes per warp
+#if defined(__CUDACC__)
+struct WindowReader {
+    const uint8_t *ibuf; int64_t ibuf_len;           // (allocated length, a multiple of 16)
+    uint32_t *win; int lane; int64_t base;
+    __device__ __forceinline__ void refill(int64_t p) {
+        base = p & ~(int64_t)15;
+        __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int64_t q = p + AHEAD + 128 * k;
-        if (q < run_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(ibuf + q));
+        for (int k = 0; k < WALK_WINDOW / 512; ++k) {
+            const int64_t a = base + 16 * (lane + 32 * k);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (a + 16 <= ibuf_len) v = *reinterpret_cast<const uint4 *>(ibuf + a);
+            reinterpret_cast<uint4 *>(win)[lane + 32 * k] = v;
+        }
+        __syncwarp();
     }
-#else
-    (void)ibuf; (void)p; (void)run_end;
+    __device__ __forceinline__ uint32_t word(int64_t p) const {      // 32 bits at byte p (inside the window)
+        const int o = (int)(p - base);
+        const uint32_t lo = win[o >> 2];
+        const unsigned sh = (unsigned)(o & 3) * 8u;
+        return sh ? __funnelshift_r(lo, win[(o >> 2) + 1], sh) : lo;
+    }
+    __device__ __forceinline__ void head(int64_t p, int32_t *bs, int32_t *tid, int32_t *pos) {
+        if (p < base || p + 16 > base + WALK_WINDOW) refill(p);
+        *bs = (int32_t)word(p); *tid = (int32_t)word(p + 4); *pos = (int32_t)word(p + 8);
+    }
+};
 #endif
-}
 
-template <class Sink>
-TG_HD bool walk_fetch(const uint8_t *ibuf, const Fetch &f, const Chunk *chunks, Sink &&sink) {
+template <class Reader, class Sink>
+TG_HD bool walk_fetch(Reader &rd, const Fetch &f, const Chunk *chunks, Sink &&sink) {
     for (int c = f.chunk_begin; c < f.chunk_end; ++c) {
         int64_t p = chunks[c].begin;
         const int64_t end = chunks[c].end, run_end = chunks[c].run_end;
         while (p < end) {
             if (p + 12 > run_end) return false;
-            const int32_t bs = ld_i32(ibuf, p);
+            int32_t bs, tid, pos;
+            rd.head(p, &bs, &tid, &pos);
             if (bs < 32 || bs > (64 << 20) || p + 4 + (int64_t)bs > run_end) return false;
-            const int32_t tid = ld_i32(ibuf, p + 4), pos = ld_i32(ibuf, p + 8);
             const int64_t here = p;
             p += 4 + (int64_t)bs;
-            prefetch_ahead(ibuf, p, run_end);
             if (tid != f.tid) { if (tid >= 0 && tid < f.tid) continue; return true; }
             if ((int64_t)pos >= f.end) return true;
             sink(here);
         }
     }
     return true;
+}
+// one warp (device) / one thread (host) per fetch; `win`: WALK_WINDOW bytes of shared memory of this warp
+template <class Sink>
+TG_HD bool walk_fetch_lanes(const uint8_t *ibuf, int64_t ibuf_len, const Fetch &f, const Chunk *chunks, int lane,
+                            uint32_t *win, Sink &&sink) {
+#if defined(__CUDA_ARCH__)
+    WindowReader rd{ibuf, ibuf_len, win, lane, (int64_t)-(1ll << 40)};
+    return walk_fetch(rd, f, chunks, sink);
+#else
+    (void)ibuf_len; (void)lane; (void)win;
+    DirectReader rd{ibuf};
+    return walk_fetch(rd, f, chunks, sink);
+#endif
 }
 
 // ---- one record ----------------------------------------------------------------------------------------------------

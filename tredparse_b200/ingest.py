@@ -50,6 +50,8 @@ def _bind(lib):
     lib.tredsw_bam_nref.argtypes = [ctypes.c_void_p]
     lib.tredsw_bam_tid.restype = ctypes.c_int32
     lib.tredsw_bam_tid.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.tredsw_bam_header_signature.restype = ctypes.c_uint64
+    lib.tredsw_bam_header_signature.argtypes = [ctypes.c_void_p]
     lib.tredsw_bam_extract_locus.restype = ctypes.c_int
     lib.tredsw_bam_extract_locus.argtypes = [ctypes.c_void_p, ctypes.POINTER(LocusQuery), ctypes.c_void_p,
                                              ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
@@ -72,9 +74,19 @@ class LocusEvidence:
     def nreads(self):
         return len(self.roff) - 1
 
+    _TO_BASES = bytes.maketrans(bytes(range(5)), b"ACGTN")
+
+    def read_string(self, i):
+        return self.reads[self.roff[i]:self.roff[i + 1]].tobytes().translate(self._TO_BASES).decode("ascii")
+
+    def read_text(self):
+        """all reads as one string of bases (read i = text[roff[i]:roff[i + 1]])"""
+        return self.reads.tobytes().translate(self._TO_BASES).decode("ascii")
+
     def read_strings(self):
-        lut = np.array(list("ACGTN"))
-        return ["".join(lut[self.reads[self.roff[i]:self.roff[i + 1]]]) for i in range(self.nreads)]
+        text = self.read_text()
+        off = self.roff.tolist()
+        return [text[off[i]:off[i + 1]] for i in range(self.nreads)]
 
 
 class BamIngest:
@@ -120,8 +132,21 @@ class BamIngest:
         except Exception:
             pass
 
+    _TIDS = {}          # header signature -> {contig: tid}: the samples of a cohort share one reference dictionary
+
+    @property
+    def signature(self):
+        sig = getattr(self, "_signature", None)
+        if sig is None:
+            sig = self._signature = int(self.lib.tredsw_bam_header_signature(self.handle))
+        return sig
+
     def tid(self, contig):
-        return int(self.lib.tredsw_bam_tid(self.handle, contig.encode()))
+        tids = BamIngest._TIDS.setdefault(self.signature, {})
+        t = tids.get(contig)
+        if t is None:
+            t = tids[contig] = int(self.lib.tredsw_bam_tid(self.handle, contig.encode()))
+        return t
 
     def region_depth(self, contig, start, end):
         """``BamDepth.region_depth`` (bam_parser.py:404-411) on the native reader."""
@@ -219,7 +244,8 @@ class IngestView(ctypes.Structure):
                 ("summaries", ctypes.POINTER(LocusSummary)), ("spans", ctypes.POINTER(ProblemSpan)),
                 ("status", ctypes.POINTER(ctypes.c_int32)),
                 ("n_blocks", ctypes.c_int64), ("n_records", ctypes.c_int64), ("comp_bytes", ctypes.c_int64),
-                ("inflated_bytes", ctypes.c_int64), ("ms_host_stage", ctypes.c_double), ("ms_total", ctypes.c_double)]
+                ("inflated_bytes", ctypes.c_int64), ("ms_host_stage", ctypes.c_double), ("ms_total", ctypes.c_double),
+                ("ms_marks", ctypes.c_double * 4)]
 
 
 def _bind_batch(lib):
@@ -240,16 +266,28 @@ def _bind_batch(lib):
     lib._ingest_batch_bound = True
 
 
+_QUERIES = {}           # (header signature, locus, readlen, pad, alts) -> (LocusQuery, keep-alive array)
+
+
 def locus_query(handle, tred, readlen, alts=(), pad=SPAN):
-    """(LocusQuery, keep-alive array) of one locus on one open BAM; None when the contig is unknown."""
+    """(LocusQuery, keep-alive array) of one locus on one open BAM; None when the contig is unknown.  Queries depend
+    on the BAM only through its reference dictionary, so they are built once per dictionary."""
+    key = (handle.signature, tred.chr, tred.repeat_start, tred.repeat_end, readlen, pad, tuple(alts))
+    hit = _QUERIES.get(key)
+    if hit is not None:
+        return hit if hit else None
     tid = handle.tid(tred.chr)
     if tid < 0:
+        _QUERIES[key] = ()
         return None
     rows = [(t, int(s), int(e)) for (t, s, e) in ((handle.tid(c), s, e) for (c, s, e) in alts) if t >= 0]
     arr = np.ascontiguousarray(np.array(rows, dtype=np.int32).reshape(-1, 3))
     q = LocusQuery(tid=tid, repeat_start=tred.repeat_start, repeat_end=tred.repeat_end, readlen=readlen, pad=pad,
                    pe_window=DNAPE_ELONGATE, flankmatch=FLANKMATCH, span=SPAN, n_alts=len(rows),
                    alts=arr.ctypes.data if len(rows) else None)
+    if len(_QUERIES) > 100000:
+        _QUERIES.clear()
+    _QUERIES[key] = (q, arr)
     return q, arr
 
 
@@ -316,7 +354,7 @@ class IngestBatch:
         v = self.view
         return {"blocks": int(v.n_blocks), "records": int(v.n_records), "compressed_bytes": int(v.comp_bytes),
                 "inflated_bytes": int(v.inflated_bytes), "ms_host_stage": float(v.ms_host_stage),
-                "ms_total": float(v.ms_total)}
+                "ms_total": float(v.ms_total), "ms_marks": [float(x) for x in v.ms_marks]}
 
     def close(self):
         if getattr(self, "handle", None):

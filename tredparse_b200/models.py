@@ -73,13 +73,21 @@ class NoiseModel:
 def mean_std(a):
     if not len(a):
         return ""
-    a = np.array(a)
+    a = np.asarray(a)
     return "{:.0f}+/-{:.0f}bp".format(a.mean(), a.std())
 
 
 def histogram(a, bins=40):
+    """``np.histogram(a, bins=bins, range=(0, SPAN))`` as "edge:count" pairs (tredparse/models.py histogram).  Integer
+    inputs (pair distances) take an exact integer path — same counts, without numpy's generic machinery."""
     if not len(a):
         return ""
+    a = np.asarray(a)
+    if a.dtype.kind in "iu" and SPAN % bins == 0:
+        w = SPAN // bins
+        a = a[(a >= 0) & (a <= SPAN)]
+        ar = np.bincount(np.minimum(a // w, bins - 1), minlength=bins)
+        return ",".join("{}:{}".format(w * k, n) for k, n in enumerate(ar.tolist()))
     ar, br = np.histogram(a, bins=bins, range=(0, SPAN))
     return ",".join("{}:{}".format(int(b), n) for (n, b) in zip(ar, br))
 

@@ -255,13 +255,15 @@ def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeat
             raise RuntimeError("likelihood arena overflow")          # (run_host repeats the call; not expected)
         rows = out["reads"][r0:r0 + ev.nreads]
         r0 += ev.nreads
-        seqs, names = ev.read_strings(), ev.names or [""] * ev.nreads
-        details = [{"tag": TAGNAME[int(t)], "h": int(h), "id": names[k], "seq": seqs[k]}
-                   for k, (t, h) in enumerate(rows[:, :2]) if int(t) in TAGNAME]
+        names = ev.names or [""] * ev.nreads
+        tags, hs = rows[:, 0].tolist(), rows[:, 1].tolist()
+        text, off = ev.read_text(), ev.roff.tolist()
+        details = [{"tag": TAGNAME[t], "h": hs[k], "id": names[k], "seq": text[off[k]:off[k + 1]]}
+                   for k, t in enumerate(tags) if t in TAGNAME]
         hist = out["hist"][i]
         cs = lambda row: ";".join("{}|{}".format(k, int(v)) for k, v in enumerate(row) if v)
         missing = c["alleles"][0] < 0
-        g, t = [int(x) for x in ev.global_lens], [int(x) for x in ev.target_lens]
+        g, t = np.asarray(ev.global_lens), np.asarray(ev.target_lens)
         results.append({
             "1": c["alleles"][0], "2": c["alleles"][1], "FR": cs(hist[0]), "PR": cs(hist[1]), "RR": cs(hist[2]),
             "DP": depth, "FDP": c["FDP"], "PDP": c["PDP"], "RDP": c["RDP"], "PEDP": len(t),
@@ -334,21 +336,68 @@ def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None,
     return evidence, depths
 
 
-def presteps(bam, repo, tredNames, logger):
+GPU_INGEST = os.environ.get("TREDSW_GPU_INGEST", "1") != "0"
+
+
+def ingest_chunk_gpu(samples, ctx=None):
+    """Evidence of every (sample, locus) of a chunk through the GPU ingest (csrc/bgzf_gpu.cu): the host reads the
+    compressed BGZF blocks behind the windows, the device inflates them, walks the records and applies the
+    selection / pairing / depth rules — same evidence as ``ingest_loci`` locus by locus.
+    :param samples: [(key, run-argument tuple, wanted TRED names, READLEN, open ingest.BamIngest)]
+    :return: {key: ({tredName: LocusEvidence}, {tredName: depth})} — loci the device path could not serve (contig
+             missing, a block the decoder refused, corrupt records) are left out: the caller reads them with the
+             host reader."""
+    from . import _lib
+    from .ingest import IngestBatch, locus_query
+    handles, qs, so, keep, key = [], [], [], [], []
+    try:
+        for k, arg, wanted, READLEN, h in samples:
+            samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
+            if h is None:
+                continue
+            handles.append(h)
+            for t in wanted:
+                xtred = repo[t]
+                alt = ()
+                if alts and not clip:
+                    alt = [(c[3:] if "nochr" in repo.ref else c, s, e) for (c, s, e) in xtred.alt] if "nochr" in repo.ref else xtred.alt
+                q = locus_query(h, xtred, READLEN, alts=alt)
+                if q is None:
+                    continue
+                qs.append(q[0]); keep.append(q[1]); so.append(len(handles) - 1); key.append((k, t))
+        got = {}
+        if not qs:
+            return got
+        ctx = ctx or _lib.default_context()
+        with IngestBatch(ctx, handles, so, qs, keep=keep) as b:
+            for i, (k, t) in enumerate(key):
+                if b.status[i]:
+                    logger.debug("GPU ingest handed {} / {} back (status {})".format(k, t, int(b.status[i])))
+                    continue
+                ev = b.evidence(i)
+                e, d = got.setdefault(k, ({}, {}))
+                e[t], d[t] = ev, ev.depth
+        return got
+    except Exception as e:
+        logger.error("GPU ingest failed ({}); reading with the host reader".format(e))
+        return {}
+
+
+def presteps(bam, repo, tredNames, logger, ing=None):
     """The per-sample pre-steps of tred.run (tred.py:195-223): gender from the chrY depth — only when an X-linked
     locus is requested; 'Unknown' / -1 when the lookup fails — and the read length (150 when it cannot be read).
     They decide ploidy (bam_parser.py:58-61) and the number of templates (:73), so they gate parity on real BAMs."""
     gender, ydepth = "Unknown", -1
     if any(repo[tred].is_xlinked for tred in tredNames):
         try:
-            ydepth = BamDepth(bam, repo.ref, logger).get_Y_depth()
+            ydepth = BamDepth(bam, repo.ref, logger, ing=ing).get_Y_depth()
             gender = "Male" if ydepth > 1 else "Female"
         except Exception:
             pass
         logger.debug("Inferred gender: {} (depthY={})".format(gender, ydepth))
     READLEN = 150
     try:
-        READLEN = BamReadLen(bam, logger).readlen
+        READLEN = BamReadLen(bam, logger, ing=ing).readlen
     except Exception:
         pass
     logger.debug("Read length: {}bp".format(READLEN))
@@ -380,19 +429,60 @@ def run_chunk(args, only=None):
     :param only: optional list, per sample, of the TRED names to process (a rank's share of a sharded cohort);
                  the other requested names of that sample are left out of its tredCalls
     :return: list of {"samplekey", "bam", "tredCalls"}"""
-    out, items, where = [], [], []
+    out, items, where, todo = [], [], [], []
     for si, arg in enumerate(args):
         samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
         tredCalls = {"inferredGender": "Unknown", "depthY": -1}
         out.append({"samplekey": samplekey, "bam": bam, "tredCalls": tredCalls, "_fields": {}, "_names": list(tredNames)})
-        if check_bam(bam) is None:
+    # per sample: one native handle (validity check, pre-steps, GPU ingest), the pre-steps (gender looks at every
+    # requested locus); the samples are dealt to host threads
+    def pre(si):
+        samplekey, bam, repo, tredNames = args[si][:4]
+        ing = None
+        try:
+            from .ingest import BamIngest
+            ing = BamIngest(bam_path(bam))
+        except Exception as e:
+            logger.debug("native BAM ingest unavailable for `{}` ({})".format(bam, e))
+            if check_bam(bam) is None:
+                return None
+        return ing, presteps(bam, repo, tredNames, logger, ing=ing)
+    if len(args) > 1 and INGEST_THREADS > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(INGEST_THREADS, len(args))) as pool:
+            pres = list(pool.map(pre, range(len(args))))
+    else:
+        pres = [pre(si) for si in range(len(args))]
+    wanted_of, handle_of = {}, {}
+    for si, ps in enumerate(pres):
+        if ps is None:
             continue
-        tredCalls.update(presteps(bam, repo, tredNames, logger))          # (gender looks at every requested locus)
-        gender, READLEN = tredCalls["inferredGender"], tredCalls["readLen"]
-        wanted = [t for t in tredNames if only is None or t in only[si]]
-        out[-1]["_names"] = wanted
-        evidence, depths = ingest_loci(bam, repo, wanted, READLEN, alts, clip, logger, want_names=True)
-        out[-1].update(_depths=depths, _gender=gender, _readlen=READLEN)
+        todo.append(si)
+        handle_of[si] = ps[0]
+        out[si]["tredCalls"].update(ps[1])
+        tredNames = args[si][3]
+        wanted_of[si] = [t for t in tredNames if only is None or t in only[si]]
+        out[si]["_names"] = wanted_of[si]
+    # evidence: the GPU ingest for every (sample, locus) of the chunk in one pass; the host reader for what it
+    # hands back (no index, corrupt blocks, unknown contig) or when it is switched off (TREDSW_GPU_INGEST=0)
+    try:
+        got = ingest_chunk_gpu([(si, args[si], wanted_of[si], out[si]["tredCalls"]["readLen"], handle_of[si])
+                                for si in todo]) if GPU_INGEST else {}
+    finally:
+        for h in handle_of.values():
+            if h is not None:
+                h.close()
+    for si in todo:
+        samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = args[si]
+        gender, READLEN = out[si]["tredCalls"]["inferredGender"], out[si]["tredCalls"]["readLen"]
+        wanted = wanted_of[si]
+        evidence, depths = got.get(si, ({}, {}))
+        rest = [t for t in wanted if t not in depths]
+        if rest:
+            ev2, d2 = ingest_loci(bam, repo, rest, READLEN, alts, clip, logger, want_names=True)
+            evidence.update(ev2)
+            depths.update(d2)
+        out[si].update(_depths=depths, _gender=gender, _readlen=READLEN)
         for t in wanted:
             if t in evidence:
                 items.append((repo[t], READLEN, gender, depths[t], evidence[t]))
