@@ -186,3 +186,29 @@ def test_gpu_ingest_flags_corrupt_blocks(repo, tmp_path):
         assert _same(b.evidence(0), hs[0].extract_locus(repo["HD"], 150, alts=repo["HD"].alt, want_names=True))
     for h in hs:
         h.close()
+
+
+@pytest.mark.gpu
+def test_run_chunk_is_served_by_the_gpu_ingest_and_equals_the_host_reader_path(repo, tmp_path, monkeypatch):
+    """tred.run_chunk on whole-sample BAMs: every locus comes from the GPU ingest (the host reader is not called),
+    and the JSON fields equal those of the same run with the host reader (TREDSW_GPU_INGEST=0 behaviour)."""
+    from tredparse_b200 import tred as T
+    names = [n for n in repo.names][:10]
+    paths = []
+    for s in range(2):
+        p = str(tmp_path / "s{}.bam".format(s))
+        _write_sample(p, repo, names, s, 31)
+        paths.append(p)
+    tasks = [("s{}".format(i), p, repo, list(names), 300, False, False, True, True, "INFO") for i, p in enumerate(paths)]
+    monkeypatch.setattr(T, "GPU_INGEST", False)
+    host = T.run_chunk(tasks)
+    monkeypatch.setattr(T, "GPU_INGEST", True)
+
+    def no_host_reader(*a, **k):
+        raise AssertionError("the host reader was called although the GPU ingest can serve every locus")
+    monkeypatch.setattr(T, "ingest_loci", no_host_reader)
+    gpu = T.run_chunk(tasks)
+    assert len(gpu) == len(host) == 2
+    for a, b in zip(gpu, host):
+        assert a["tredCalls"].keys() == b["tredCalls"].keys() and len(a["tredCalls"]) > 20 * len(names)
+        assert a["tredCalls"] == b["tredCalls"]
