@@ -65,7 +65,7 @@ __host__ __device__ inline void crc_tables_ext(uint32_t *t, int i) {    // after
 }
 
 // status: 0 ok, 1 the decoder refused the stream, 2 CRC-32 / length mismatch
-__global__ void __launch_bounds__(INFLATE_THREADS)
+__global__ void __launch_bounds__(INFLATE_THREADS, 8)
 inflate_kernel(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int nblocks, uint8_t *status, int check_crc) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem);
@@ -83,7 +83,7 @@ inflate_kernel(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int 
     if (d.isize > 0) {
         const TabRef tr{tabs + warp, INFLATE_WARPS};
         if (!inflate_block<32>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, lane)) st = 1;
-        else if (check_crc && crc32_bytes(crct, ibuf + d.out_off, (int64_t)d.isize) != d.crc) st = 2;
+        else if (check_crc && crc32_warp(crct, ibuf + d.out_off, (int64_t)d.isize, lane) != d.crc) st = 2;
     }
     if (lane == 0) status[b] = st;
 }
@@ -288,7 +288,15 @@ struct HostBackend {                                   // serial emulation of th
             if (d.isize > 0) {
                 const TabRef tr{tabs.data(), 1};
                 if (!inflate_block<1>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, 0)) st = 1;
-                else if (check_crc && crc32_bytes(crct.data(), ibuf + d.out_off, (int64_t)d.isize) != d.crc) st = 2;
+                else if (check_crc) {                          // segmented like the 32 lanes of the device
+                    uint32_t parts[32];
+                    for (int l = 0; l < 32; ++l) {
+                        int64_t sb, sl;
+                        crc_segment<32>((int64_t)d.isize, l, &sb, &sl);
+                        parts[l] = crc32_bytes(crct.data(), ibuf + d.out_off + sb, sl);
+                    }
+                    if (crc_fold_serial<32>(parts, (int64_t)d.isize) != d.crc) st = 2;
+                }
             }
             status[b] = st;
         }

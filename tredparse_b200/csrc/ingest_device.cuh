@@ -21,6 +21,13 @@
 #define TG_HD inline
 #endif
 
+// (statistics hooks of an offline tool; empty in the library)
+#ifndef TG_STAT_LIT
+#define TG_STAT_LIT()
+#define TG_STAT_MATCH(len, dist)
+#define TG_STAT_DBLOCK()
+#endif
+
 namespace tredsw_gi {
 
 // ---- memory helpers ----------------------------------------------------------------------------------------------
@@ -291,6 +298,7 @@ TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_
                 for (int k = 288 + ndist; k < 320; ++k) lens[k] = 0;
                 nlit = 288; ndist = 32;
             }
+            TG_STAT_DBLOCK();
             if (!build_table(lens, nlit, 0, lit, LIT_ROOT, LIT_CAP, sub_need)) return false;
             if (!build_table(lens + 288, ndist, 1, dist, DIST_ROOT, DIST_CAP, sub_need)) return false;
             for (;;) {
@@ -307,6 +315,7 @@ TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_
                     if (op >= out_len) return false;
                     if (lane == 0) out[op] = (uint8_t)pay;
                     ++op;
+                    TG_STAT_LIT();
                     continue;
                 }
                 if (kind == K_END) break;
@@ -328,6 +337,7 @@ TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_
                 if (ds < 4) distance = 1 + ds;
                 else { const int eb = (int)(ds >> 1) - 1; distance = ((2 + (ds & 1u)) << eb) + 1 + br.take(eb); }
                 if ((int64_t)distance > op || (int64_t)length > out_len - op) return false;
+                TG_STAT_MATCH(length, distance);
                 uint8_t *dst = out + op;
                 const uint8_t *src = dst - distance;
                 lanes_sync<NL>();                                  // the bytes before `op` are visible to every lane
@@ -356,6 +366,58 @@ TG_HD uint32_t crc32_bytes(const uint32_t *t, const uint8_t *p, int64_t n) {
     for (; i < n; ++i) c = t[(c ^ p[i]) & 0xffu] ^ (c >> 8);
     return c ^ 0xffffffffu;
 }
+
+// CRC-32 of a block by NL lanes: every lane takes a contiguous segment (lane 0 the first n - (NL-1) * (n / NL) bytes,
+// the others n / NL bytes each), and the segment CRCs are combined with zlib's crc32_combine identity
+//     crc(A || B) = x^(8 |B|) * crc(A) + crc(B)     (polynomials over GF(2) modulo the CRC polynomial, reflected)
+// in a tree: at level k the right-hand operand of every pair is 2^k whole segments long.
+TG_HD uint32_t crc_multmodp(uint32_t a, uint32_t b) {          // a != 0
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1u)) == 0) break; }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xedb88320u : b >> 1;
+    }
+    return p;
+}
+TG_HD uint32_t crc_x8n_modp(uint64_t n) {                     // x^(8 n)
+    uint32_t sq = 0x40000000u;                                  // x^1
+    for (int k = 0; k < 3; ++k) sq = crc_multmodp(sq, sq);      // x^8
+    uint32_t p = 1u << 31;                                      // x^0
+    while (n) { if (n & 1u) p = crc_multmodp(sq, p); n >>= 1; if (n) sq = crc_multmodp(sq, sq); }
+    return p;
+}
+template <int NL>
+TG_HD void crc_segment(int64_t n, int lane, int64_t *begin, int64_t *len) {
+    const int64_t L = n / NL, first = n - (NL - 1) * L;
+    *begin = lane == 0 ? 0 : first + (int64_t)(lane - 1) * L;
+    *len = lane == 0 ? first : L;
+}
+// serial form of the tree (host / tests): parts[i] = CRC of lane i's segment
+template <int NL>
+TG_HD uint32_t crc_fold_serial(uint32_t *parts, int64_t n) {
+    uint32_t op = crc_x8n_modp((uint64_t)(n / NL));
+    for (int s = 1; s < NL; s <<= 1) {
+        for (int i = 0; i + s < NL; i += 2 * s) parts[i] = crc_multmodp(op, parts[i]) ^ parts[i + s];
+        op = crc_multmodp(op, op);
+    }
+    return parts[0];
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t crc32_warp(const uint32_t *t, const uint8_t *p, int64_t n, int lane) {
+    int64_t b, len;
+    crc_segment<32>(n, lane, &b, &len);
+    uint32_t c = crc32_bytes(t, p + b, len);
+    uint32_t op = crc_x8n_modp((uint64_t)(n / 32));
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t q = __shfl_down_sync(0xffffffffu, c, s);
+        if ((lane & (2 * s - 1)) == 0) c = crc_multmodp(op, c) ^ q;
+        op = crc_multmodp(op, op);
+    }
+    return __shfl_sync(0xffffffffu, c, 0);
+}
+#endif
 
 // ---- batch description (host-built, read-only on the device) ----------------------------------------------------------
 struct BlockDesc {              // one BGZF block of the batch
