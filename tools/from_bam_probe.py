@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--host-ingest", action="store_true")
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--chunk", type=int, default=8)
     a = ap.parse_args()
     if a.host_ingest:
         os.environ["TREDSW_GPU_INGEST"] = "0"
@@ -34,14 +35,14 @@ def main():
     times = []
     for _ in range(a.reps):
         t = time.perf_counter()
-        T.run_chunk(tasks)
+        list(T.run_chunks(tasks, chunk=a.chunk))
         times.append(time.perf_counter() - t)
     print(json.dumps({"samples": a.samples, "loci": len(names), "seconds": times,
                       "loci_per_s": a.samples * len(names) / min(times), "gpu_ingest": T.GPU_INGEST}))
     if a.profile:
         pr = cProfile.Profile()
         pr.enable()
-        T.run_chunk(tasks)
+        list(T.run_chunks(tasks, chunk=a.chunk))
         pr.disable()
         s = io.StringIO()
         pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(35)

@@ -77,6 +77,9 @@ def mean_std(a):
     return "{:.0f}+/-{:.0f}bp".format(a.mean(), a.std())
 
 
+_HIST_FORMATS = {}
+
+
 def histogram(a, bins=40):
     """``np.histogram(a, bins=bins, range=(0, SPAN))`` as "edge:count" pairs (tredparse/models.py histogram).  Integer
     inputs (pair distances) take an exact integer path — same counts, without numpy's generic machinery."""
@@ -85,9 +88,13 @@ def histogram(a, bins=40):
     a = np.asarray(a)
     if a.dtype.kind in "iu" and SPAN % bins == 0:
         w = SPAN // bins
-        a = a[(a >= 0) & (a <= SPAN)]
+        if a.min() < 0 or a.max() > SPAN:
+            a = a[(a >= 0) & (a <= SPAN)]
         ar = np.bincount(np.minimum(a // w, bins - 1), minlength=bins)
-        return ",".join("{}:{}".format(w * k, n) for k, n in enumerate(ar.tolist()))
+        fmt = _HIST_FORMATS.get(bins)
+        if fmt is None:
+            fmt = _HIST_FORMATS[bins] = ",".join("{}:%d".format(w * k) for k in range(bins))
+        return fmt % tuple(ar.tolist())
     ar, br = np.histogram(a, bins=bins, range=(0, SPAN))
     return ",".join("{}:{}".format(int(b), n) for (n, b) in zip(ar, br))
 

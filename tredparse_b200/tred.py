@@ -422,13 +422,11 @@ def run(arg):
     return run_chunk([arg])[0]
 
 
-def run_chunk(args, only=None):
-    """Several samples at once: per-sample pre-steps and native ingest on the host (threads), then the loci of ALL
-    the samples through ONE fused device call.  Same results as ``run`` sample by sample.
-    :param args: list of ``run`` argument tuples (same maxinsert / fullsearch / clip / repeatpairs for all)
-    :param only: optional list, per sample, of the TRED names to process (a rank's share of a sharded cohort);
-                 the other requested names of that sample are left out of its tredCalls
-    :return: list of {"samplekey", "bam", "tredCalls"}"""
+def prepare_chunk(args, only=None, ctx=None):
+    """First half of ``run_chunk``: per-sample pre-steps and the evidence of every (sample, locus) — the GPU ingest,
+    the host reader for what it hands back.  Touches no state of the genotyping context, so the next chunk can be
+    prepared (on ``ctx``, a context of its own) while the previous one is genotyped.
+    :return: an opaque state for ``finish_chunk``"""
     out, items, where, todo = [], [], [], []
     for si, arg in enumerate(args):
         samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
@@ -467,7 +465,7 @@ def run_chunk(args, only=None):
     # hands back (no index, corrupt blocks, unknown contig) or when it is switched off (TREDSW_GPU_INGEST=0)
     try:
         got = ingest_chunk_gpu([(si, args[si], wanted_of[si], out[si]["tredCalls"]["readLen"], handle_of[si])
-                                for si in todo]) if GPU_INGEST else {}
+                                for si in todo], ctx=ctx) if GPU_INGEST else {}
     finally:
         for h in handle_of.values():
             if h is not None:
@@ -487,12 +485,20 @@ def run_chunk(args, only=None):
             if t in evidence:
                 items.append((repo[t], READLEN, gender, depths[t], evidence[t]))
                 where.append((si, t))
+    return args, out, items, where
+
+
+def finish_chunk(state, ctx=None):
+    """Second half of ``run_chunk``: ONE fused device call for the loci of all the samples of the chunk, then the
+    reference's per-locus JSON fields.
+    :return: list of {"samplekey", "bam", "tredCalls"}"""
+    args, out, items, where = state
     if not args:
         return []
     _, _, repo, _, maxinsert, fullsearch, clip, alts, repeatpairs, log = args[0]
     # loci whose evidence came from the native one-pass ingest: the fused device pipeline, all of them in one call
     try:
-        res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
+        res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs, ctx=ctx)
         for (si, t), r in zip(where, res):
             out[si]["_fields"][t] = r
     except Exception as e:
@@ -526,6 +532,68 @@ def run_chunk(args, only=None):
             for k, v in fields.get(tred, {}).items():
                 o["tredCalls"][tred + "." + k] = v
     return out
+
+
+def run_chunk(args, only=None):
+    """Several samples at once: per-sample pre-steps, then the evidence of every (sample, locus) of the chunk in one
+    pass of the GPU ingest, then the loci of ALL the samples through ONE fused device call.  Same results as ``run``
+    sample by sample.
+    :param args: list of ``run`` argument tuples (same maxinsert / fullsearch / clip / repeatpairs for all)
+    :param only: optional list, per sample, of the TRED names to process (a rank's share of a sharded cohort);
+                 the other requested names of that sample are left out of its tredCalls
+    :return: list of {"samplekey", "bam", "tredCalls"}"""
+    return finish_chunk(prepare_chunk(args, only))
+
+
+def run_chunks(args, only=None, chunk=None, isolate=False):
+    """``run_chunk`` over a long list of samples, ``chunk`` samples at a time, two stages deep: a helper thread
+    prepares chunk k + 1 (file reads and the GPU ingest, on a context and stream of its own; the C calls release the
+    GIL) while this thread genotypes chunk k and assembles its JSON fields.  Yields the per-sample results in order.
+    isolate: a chunk that raises yields {"samplekey", "bam", "tredCalls": {}, "error"} for its samples instead of
+    ending the run."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import _lib
+    chunk = chunk or CHUNK_SAMPLES
+    spans = [(c0, min(len(args), c0 + chunk)) for c0 in range(0, len(args), chunk)]
+    if not spans:
+        return
+    ictx = None
+    if GPU_INGEST and len(spans) > 1:
+        try:
+            ictx = _lib.Context(_lib.default_context().device)
+        except Exception:
+            ictx = None
+
+    def prep(k):
+        a, b = spans[k]
+        return prepare_chunk(args[a:b], None if only is None else only[a:b], ctx=ictx)
+    try:
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(prep, 0)
+            for k in range(len(spans)):
+                try:
+                    state, err = fut.result(), None
+                except Exception as e:
+                    if not isolate:
+                        raise
+                    state, err = None, e
+                if k + 1 < len(spans):
+                    fut = pool.submit(prep, k + 1)
+                if err is None:
+                    try:
+                        results = finish_chunk(state)
+                    except Exception as e:
+                        if not isolate:
+                            raise
+                        err = e
+                if err is not None:
+                    a, b = spans[k]
+                    results = [{"samplekey": x[0], "bam": x[1], "tredCalls": {}, "error": repr(err)} for x in args[a:b]]
+                for r in results:
+                    yield r
+    finally:
+        if ictx is not None:
+            ictx.close()
 
 
 def vcfstanza(sampleid, bam, tredCalls, ref):
@@ -661,16 +729,9 @@ def _worker(rank, ngpus, task_args, queue):
             if o == rank:
                 mine.setdefault(si, []).append(t)
         order = sorted(mine)
-        for c0 in range(0, len(order), CHUNK_SAMPLES):
-            idx = order[c0:c0 + CHUNK_SAMPLES]
-            try:
-                res = run_chunk([task_args[i] for i in idx], only=[mine[i] for i in idx])
-                for i, r in zip(idx, res):
-                    queue.put(("part", i, r, len(mine[i])))
-            except Exception as e:                              # a failed chunk must not hang the parent
-                for i in idx:
-                    queue.put(("part", i, {"samplekey": task_args[i][0], "bam": task_args[i][1], "tredCalls": {},
-                                           "error": repr(e)}, len(mine[i])))
+        got = run_chunks([task_args[i] for i in order], only=[mine[i] for i in order], isolate=True)
+        for i, r in zip(order, got):                                # (a failed chunk must not hang the parent)
+            queue.put(("part", i, r, len(mine[i])))
     finally:
         queue.put(("done", rank, None, 0))
 
@@ -722,9 +783,8 @@ def main(args):
     ngpus = max(1, args.gpus)
     if ngpus == 1:
         # chunks of samples: one fused device call per chunk (all loci of all its samples)
-        for c0 in range(0, len(task_args), CHUNK_SAMPLES):
-            for results in run_chunk(task_args[c0:c0 + CHUNK_SAMPLES]):
-                emit(results)
+        for results in run_chunks(task_args):
+            emit(results)
     else:
         import multiprocessing as mp
         import queue as pyqueue
