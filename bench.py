@@ -269,6 +269,21 @@ def reference_tasks(nsamples):
     return tasks, keys, len(names)
 
 
+def _ref_one_thread():
+    """Pool initializer: one BLAS / OpenMP thread per worker process.  The pool already runs one process per core; with
+    the libraries' default (one thread per core in EVERY process) the numpy / scipy calls of the reference
+    oversubscribe the host 16-fold and the arm runs ~4x slower — and torchrun exports OMP_NUM_THREADS=1 while a plain
+    `python bench.py` does not, which made the arm differ by that factor between N = 1 and N > 1 (round-1 verdict)."""
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        import threadpoolctl
+        global _REF_LIMIT
+        _REF_LIMIT = threadpoolctl.threadpool_limits(limits=1)
+    except Exception:
+        pass
+
+
 def _ref_warm(_):
     from oracle import refdrive
     refdrive.reference()
@@ -285,7 +300,7 @@ class ReferencePool:
         if not refdrive.usable():
             raise RuntimeError("the reference package is not loadable here (oracle/_ref/ not built)")
         self.cores = cores
-        self.pool = mp.get_context("fork").Pool(processes=cores)
+        self.pool = mp.get_context("fork").Pool(processes=cores, initializer=_ref_one_thread)
         self.pool.map(_ref_warm, range(cores * 2), chunksize=1)
 
     def run(self, tasks):
