@@ -8,7 +8,7 @@ for tool in memcheck racecheck synccheck initcheck; do
   [ $tool = memcheck ] && extra="--leak-check no"
   log=gpurun_out/r2_sanitize_$tool.txt
   timeout ${SANITIZE_TIMEOUT:-1500} compute-sanitizer --tool $tool $extra --print-limit 20 \
-      python tools/sanitize_target.py ${SANITIZE_WHAT:-smoke cohort flags stress} > $log.full 2>&1
+      python tools/sanitize_target.py ${SANITIZE_WHAT:-smoke cohort flags stress ingest} > $log.full 2>&1
   echo "exit code $?" >> $log.full
   # keep the summary: every sanitizer line, the target's own last line and the exit code
   grep -E "^=========|sanitize_target|exit code|Error|Traceback" $log.full | head -200 > $log
