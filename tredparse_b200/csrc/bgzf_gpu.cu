@@ -79,10 +79,11 @@ inflate_kernel(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int 
     if (b >= nblocks) return;
     const BlockDesc d = blocks[b];
     uint8_t lens[320], sub_need[1 << LIT_ROOT];
+    uint16_t sub_base[1 << LIT_ROOT];
     uint8_t st = 0;
     if (d.isize > 0) {
-        const TabRef tr{tabs + warp, INFLATE_WARPS};
-        if (!inflate_block<32>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, lane)) st = 1;
+        const TabRef tr{tabs + warp, INFLATE_WARPS, lane == 0};
+        if (!inflate_block<32>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, sub_base, lane)) st = 1;
         else if (check_crc && crc32_warp(crct, ibuf + d.out_off, (int64_t)d.isize, lane) != d.crc) st = 2;
     }
     if (lane == 0) status[b] = st;
@@ -282,12 +283,13 @@ struct HostBackend {                                   // serial emulation of th
         for (int i = 0; i < 256; ++i) crc_tables_ext(crct.data(), i);
         std::vector<uint16_t> tabs(TAB_ENTRIES);
         uint8_t lens[320], sub_need[1 << LIT_ROOT];
+        uint16_t sub_base[1 << LIT_ROOT];
         for (int b = 0; b < nblocks; ++b) {
             const BlockDesc &d = blocks[b];
             uint8_t st = 0;
             if (d.isize > 0) {
-                const TabRef tr{tabs.data(), 1};
-                if (!inflate_block<1>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, 0)) st = 1;
+                const TabRef tr{tabs.data(), 1, true};
+                if (!inflate_block<1>(comp + d.in_off, (int64_t)d.clen, ibuf + d.out_off, (int64_t)d.isize, tr, lens, sub_need, sub_base, 0)) st = 1;
                 else if (check_crc) {                          // segmented like the 32 lanes of the device
                     uint32_t parts[32];
                     for (int l = 0; l < 32; ++l) {
@@ -884,8 +886,9 @@ int tredsw_inflate_raw_device_code(const uint8_t *in, int64_t in_len, uint8_t *o
     if (in_len > 0) memcpy(padded.data() + 4, in, (size_t)in_len);
     std::vector<uint16_t> tabs(TAB_ENTRIES);
     uint8_t lens[320], sub_need[1 << LIT_ROOT];
+    uint16_t sub_base[1 << LIT_ROOT];
     // (offset 4 + a caller-chosen misalignment would also work: the reader handles any start address)
-    return inflate_block<1>(padded.data() + 4, in_len, out, out_len, TabRef{tabs.data(), 1}, lens, sub_need, 0) ? 0 : 1;
+    return inflate_block<1>(padded.data() + 4, in_len, out, out_len, TabRef{tabs.data(), 1, true}, lens, sub_need, sub_base, 0) ? 0 : 1;
 }
 
 }  // extern "C"

@@ -93,8 +93,9 @@ TG_HD uint32_t ld_u16(const uint8_t *base, int64_t off) { return (uint32_t)base[
 //          bits 7..15 payload (literal byte, length / distance / code-length symbol, sub-table offset / 2)
 struct TabRef {
     uint16_t *p; int stride;
+    bool writer;                // the lanes that share a table all compute its entries; one of them stores them
     TG_HD uint32_t get(uint32_t i) const { return p[(size_t)i * stride]; }
-    TG_HD void set(uint32_t i, uint32_t v) const { p[(size_t)i * stride] = (uint16_t)v; }
+    TG_HD void set(uint32_t i, uint32_t v) const { if (writer) p[(size_t)i * stride] = (uint16_t)v; }
 };
 enum : uint32_t { K_INVALID = 0, K_LITERAL = 1, K_LENGTH = 2, K_END = 3, K_SUB = 4, K_SYMBOL = 5 };
 constexpr int LIT_ROOT = 9, DIST_ROOT = 6, PRE_ROOT = 7;
@@ -106,7 +107,7 @@ TG_HD uint32_t mk_entry(uint32_t kind, uint32_t payload, uint32_t bits) { return
 
 // which: 0 literal / length alphabet, 1 distance alphabet, 2 code-length alphabet
 TG_HD bool build_table(const uint8_t *lens, int nsyms, int which, const TabRef &tab, int root_bits, int cap,
-                       uint8_t *sub_need /* 1 << root_bits bytes of scratch */) {
+                       uint8_t *sub_need /* 1 << root_bits bytes of scratch */, uint16_t *sub_base /* likewise, 16-bit */) {
     int count[16];
     for (int l = 0; l < 16; ++l) count[l] = 0;
     for (int s = 0; s < nsyms; ++s) { if (lens[s] > 15) return false; ++count[lens[s]]; }
@@ -142,6 +143,7 @@ TG_HD bool build_table(const uint8_t *lens, int nsyms, int which, const TabRef &
         const int size = 1 << sub_need[prefix];
         if (top + size > cap) return false;
         tab.set(prefix, mk_entry(K_SUB, (uint32_t)top >> 1, sub_need[prefix]));    // (top is even: sizes are powers of two)
+        sub_base[prefix] = (uint16_t)top;
         for (int i = 0; i < size; ++i) tab.set(top + i, 0);
         top += size;
     }
@@ -165,9 +167,8 @@ TG_HD bool build_table(const uint8_t *lens, int nsyms, int which, const TabRef &
             for (uint32_t i = r; i < (uint32_t)root_size; i += 1u << l) tab.set(i, e);
         } else {
             const uint32_t prefix = r & (uint32_t)(root_size - 1);
-            const uint32_t sub = tab.get(prefix);
-            if (((sub >> 4) & 7u) != K_SUB) return false;
-            const uint32_t base = (sub >> 7) << 1, sub_bits = sub & 15u, rem = (uint32_t)(l - root_bits);
+            if (!sub_need[prefix]) return false;
+            const uint32_t base = sub_base[prefix], sub_bits = sub_need[prefix], rem = (uint32_t)(l - root_bits);
             const uint32_t e = kind == K_INVALID ? 0u : mk_entry(kind, payload, rem);
             for (uint32_t i = r >> root_bits; i < (1u << sub_bits); i += 1u << rem) tab.set(base + i, e);
         }
@@ -225,9 +226,9 @@ TG_HD uint8_t ld_written(const uint8_t *p) {
 // of it can be fetched independently.
 template <int NL>
 TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len, const TabRef &tabs,
-                         uint8_t *lens /* 320 */, uint8_t *sub_need /* 512 */, int lane) {
-    const TabRef lit = tabs, dist = TabRef{tabs.p + (size_t)LIT_CAP * tabs.stride, tabs.stride},
-                 pre = TabRef{tabs.p + (size_t)(LIT_CAP + DIST_CAP) * tabs.stride, tabs.stride};
+                         uint8_t *lens /* 320 */, uint8_t *sub_need /* 512 */, uint16_t *sub_base /* 512 */, int lane) {
+    const TabRef lit = tabs, dist = TabRef{tabs.p + (size_t)LIT_CAP * tabs.stride, tabs.stride, tabs.writer},
+                 pre = TabRef{tabs.p + (size_t)(LIT_CAP + DIST_CAP) * tabs.stride, tabs.stride, tabs.writer};
     BitReader br;
     br.init(in, in_len);
     int64_t op = 0;
@@ -274,7 +275,9 @@ TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_
                     else o = 7 - ((i - 5) >> 1);                            // i = 5, 7, 9 ... -> 7, 6, 5, ...
                     plens[o] = (uint8_t)br.take(3);
                 }
-                if (!build_table(plens, 19, 2, pre, PRE_ROOT, PRE_CAP, sub_need)) return false;
+                lanes_sync<NL>();                                  // nobody still reads the previous block's tables
+                if (!build_table(plens, 19, 2, pre, PRE_ROOT, PRE_CAP, sub_need, sub_base)) return false;
+                lanes_sync<NL>();
                 int i = 0;
                 while (i < nlit + ndist) {
                     if (br.overrun()) return false;
@@ -299,8 +302,10 @@ TG_HD bool inflate_block(const uint8_t *in, int64_t in_len, uint8_t *out, int64_
                 nlit = 288; ndist = 32;
             }
             TG_STAT_DBLOCK();
-            if (!build_table(lens, nlit, 0, lit, LIT_ROOT, LIT_CAP, sub_need)) return false;
-            if (!build_table(lens + 288, ndist, 1, dist, DIST_ROOT, DIST_CAP, sub_need)) return false;
+            lanes_sync<NL>();
+            if (!build_table(lens, nlit, 0, lit, LIT_ROOT, LIT_CAP, sub_need, sub_base)) return false;
+            if (!build_table(lens + 288, ndist, 1, dist, DIST_ROOT, DIST_CAP, sub_need, sub_base)) return false;
+            lanes_sync<NL>();                                      // the tables are visible to every lane
             for (;;) {
                 if (br.overrun()) return false;
                 br.refill();                                      // >= 33 bits: code 15 + extra 5
