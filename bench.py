@@ -63,7 +63,8 @@ def parse_args():
     p.add_argument("--depth", type=int, default=3, help="host-buffer calls kept in flight by the e2e pipeline")
     p.add_argument("--streams", type=int, default=3, help="streams the device-resident steps alternate over "
                    "(the tail of one step's persistent SW kernel overlaps the head of the next step)")
-    p.add_argument("--transfer", default="packed4", choices=("bytes", "packed4"),
+    p.add_argument("--no-numa", action="store_true", help="do not bind the ranks to the cores next to their GPUs")
+    p.add_argument("--transfer", default="auto", choices=("auto", "bytes", "packed4"),
                    help="e2e leg: copy the reads as ingest leaves them (one byte per base, pinned), or pack them to "
                         "4 bit/base on the host first (inside the timed region) — less PCIe traffic, more host work")
     p.add_argument("--from-bam", type=int, default=32, help="samples of the from-BAM leg (N = 1 only; 0 = skip): synthetic "
@@ -484,6 +485,12 @@ def _main(args):
     names = distinct_loci(repo)
     nloci = len(names)
     W, K = max(args.warmup, 3), args.steps
+    # several ranks on one host: each next to its GPU (the staging buffers of the e2e leg are first-touched here)
+    numa = tdist.bind_to_gpu_numa(local_rank) if world > 1 and not args.no_numa else None
+    if args.transfer == "auto":
+        # packing the reads to 4 bit/base halves the PCIe bytes but costs host cores: it pays with one GPU per host
+        # (+10 % where PCIe is the slower side), not with 4-8 ranks sharing the cores (measured: profiles/)
+        args.transfer = "packed4" if world == 1 else "bytes"
 
     # ---- the cohort and this rank's share of it (no communication: every rank computes the same partition) ---
     t_gen = time.perf_counter()
@@ -705,7 +712,7 @@ def _main(args):
             "e2e": {"value": nprob / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                     "ms_per_step": 1e3 * t_e2e / len(timed), "calls_in_flight": depth,
-                    "transfer": args.transfer,
+                    "transfer": args.transfer, "numa": numa,
                     "includes": ("per step: native packing of the batch's base codes (1 byte/base as ingest leaves them -> "
                                  "4 bit/base, {} host threads), ".format(pack_threads) if packing else
                                  "per step: the batch's reads as ingest leaves them (1 byte/base, no host-side repacking), ") +
