@@ -119,7 +119,6 @@ tredsw_bam *tredsw_bam_clone(tredsw_bam *src) {
     if (!b->bgzf.fh) { tredsw_set_error("cannot open %s", src->path.c_str()); delete b; return nullptr; }
     b->names = src->names; b->lengths = src->lengths; b->tid_of = src->tid_of;
     b->index_ptr = src->index_ptr; b->has_index = src->has_index;
-    b->bgzf.image = src->bgzf.image;                     // blocks inflated ahead on the GPU are shared too
     b->first_record = src->first_record; b->path = src->path;
     return b;
 }

@@ -1,5 +1,5 @@
-// ingest_internal.h — the BGZF / BAI / BAM-record reader of the native ingest, shared by ingest.cpp (host paths) and
-// bgzf_gpu.cu (which inflates the BGZF blocks of a set of locus windows on the GPU ahead of the host-side parse).
+// ingest_internal.h — the BGZF / BAI / BAM-record reader of the native ingest: the host paths of ingest.cpp, and the
+// handle (file descriptor, reference dictionary, BAI chunk queries) the GPU ingest of bgzf_gpu.cu stages its blocks from.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -21,23 +21,10 @@ void tredsw_set_error(const char *fmt, ...);
 
 namespace tredsw_ingest {
 
-// Inflated BGZF blocks prefetched by the GPU decoder (bgzf_gpu.cu): file offset of a block -> its inflated bytes.
-// Shared (read-only) by a handle and its clones; blocks that are not in it are read and inflated on the host.
-struct BlockImage {
-    struct Ent { const unsigned char *p; uint32_t len; int64_t next; };
-    std::unordered_map<int64_t, Ent> map;
-    void *mem = nullptr;                       // page-locked host buffer holding the bytes
-    void (*release)(void *) = nullptr;
-    long long n_blocks = 0, n_failed = 0;
-    ~BlockImage() { if (mem && release) release(mem); }
-};
-
 struct Bgzf {
     FILE *fh = nullptr;
     std::vector<unsigned char> cbuf, block;
-    const unsigned char *cur = nullptr;               // inflated bytes of the current block (in `block` or in the image)
-    std::shared_ptr<const BlockImage> image;          // blocks inflated ahead on the GPU
-    long long n_image = 0;                            // blocks served from it
+    const unsigned char *cur = nullptr;               // inflated bytes of the current block
     int64_t block_coffset = -1, next_coffset = 0;
     size_t pos = 0;
     z_stream zs;
@@ -52,10 +39,6 @@ struct Bgzf {
 
     bool load(int64_t coffset) {
         blen = 0; pos = 0; block_coffset = coffset; next_coffset = coffset;
-        if (image) {
-            auto it = image->map.find(coffset);
-            if (it != image->map.end()) { cur = it->second.p; blen = it->second.len; next_coffset = it->second.next; ++n_image; return true; }
-        }
         if (fseeko(fh, coffset, SEEK_SET) != 0) return fail("seek failed");
         unsigned char head[18];
         const size_t nhead = fread(head, 1, 18, fh);
