@@ -331,26 +331,29 @@ def posteriors(post, nproblems):
     """Entry list of tredsw_genotype_batch_ex -> per problem {"P_h1": {...}, "P_h2": {...}, "P_h1h2": {...}} with the
     reference's keys ("15", "15,41") and values (models.py:304-317)."""
     out = [{"P_h1": {}, "P_h2": {}, "P_h1h2": {}} for _ in range(nproblems)]
-    totals = {int(e["problem"]): float(e["p"]) for e in post[post["kind"] == _lib.POST_JOINT_TOTAL]}
-    for e in post:
-        k, p = int(e["kind"]), int(e["problem"])
+    if not len(post):
+        return out
+    kinds, probs = post["kind"].tolist(), post["problem"].tolist()
+    a, b, p = post["a"].tolist(), post["b"].tolist(), post["p"].tolist()
+    totals = {pr: v for k, pr, v in zip(kinds, probs, p) if k == _lib.POST_JOINT_TOTAL}
+    for k, pr, x, y, v in zip(kinds, probs, a, b, p):
         if k == _lib.POST_H1:
-            out[p]["P_h1"][str(int(e["a"]))] = float(e["p"])
+            out[pr]["P_h1"][str(x)] = v
         elif k == _lib.POST_H2:
-            out[p]["P_h2"][str(int(e["a"]))] = float(e["p"])
+            out[pr]["P_h2"][str(x)] = v
         elif k == _lib.POST_JOINT:
-            out[p]["P_h1h2"]["{},{}".format(int(e["a"]), int(e["b"]))] = float(e["p"]) / totals[p]
+            out[pr]["P_h1h2"]["{},{}".format(x, y)] = v / totals[pr]
     return out
 
 
 def decode_call(call, period=None):
     """tredsw_call record -> dict with the reference's field names."""
-    missing = call["allele1"] < 0
-    return {"alleles": [int(call["allele1"]), int(call["allele2"])],
-            "CI": "" if missing else "{}-{}|{}-{}".format(*[int(x) for x in call["ci"]]),
-            "PP": -1 if missing else float(call["pp"]), "label": LABELS.get(int(call["label"]), "error"),
-            "FDP": int(call["fdp"]), "PDP": int(call["pdp"]), "RDP": int(call["rdp"]),
-            "lik": float(call["lik"]), "n_points": int(call["n_points"]), "run_pe": bool(call["run_pe"])}
+    a1, a2, ci, label, n_points, fdp, pdp, rdp, run_pe, pp, lik = call.tolist() if hasattr(call, "tolist") else call
+    missing = a1 < 0
+    return {"alleles": [a1, a2],
+            "CI": "" if missing else "{}-{}|{}-{}".format(*ci),
+            "PP": -1 if missing else pp, "label": LABELS.get(label, "error"),
+            "FDP": fdp, "PDP": pdp, "RDP": rdp, "lik": lik, "n_points": n_points, "run_pe": bool(run_pe)}
 
 
 def shard(n_items, rank, world):

@@ -71,10 +71,18 @@ class NoiseModel:
 
 
 def mean_std(a):
-    if not len(a):
+    """"mean+/-stdbp" of the pair distances (tredparse/models.py mean_std: a.mean(), a.std()) — the same reductions
+    numpy's mean / std perform (float64 pairwise sums, population variance), called without their wrappers."""
+    n = len(a)
+    if not n:
         return ""
     a = np.asarray(a)
-    return "{:.0f}+/-{:.0f}bp".format(a.mean(), a.std())
+    if a.dtype.kind not in "iuf" or a.ndim != 1:
+        return "{:.0f}+/-{:.0f}bp".format(a.mean(), a.std())
+    m = np.add.reduce(a, dtype=np.float64) / n
+    x = a - m
+    np.multiply(x, x, out=x)
+    return "{:.0f}+/-{:.0f}bp".format(m, math.sqrt(np.add.reduce(x) / n))
 
 
 _HIST_FORMATS = {}

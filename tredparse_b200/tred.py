@@ -249,8 +249,13 @@ def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeat
     out = batch.run_host(ctx=ctx, want_reads=True, want_hist=True, want_post=True)
     post = cohort.posteriors(out["post"], len(problems))
     results, r0 = [], 0
+    calls = out["calls"].tolist()                                    # (plain tuples: no numpy scalars in the loop)
+
+    def cs(row):                                                     # "units|count;..." of one histogram row
+        nz = np.flatnonzero(row).tolist()
+        return ";".join(["{}|{}".format(k, v) for k, v in zip(nz, row[nz].tolist())]) if nz else ""
     for i, (tred, readlen, gender, depth, ev) in enumerate(items):
-        c = cohort.decode_call(out["calls"][i])
+        c = cohort.decode_call(calls[i])
         if c["n_points"] < 0:
             raise RuntimeError("likelihood arena overflow")          # (run_host repeats the call; not expected)
         rows = out["reads"][r0:r0 + ev.nreads]
@@ -261,7 +266,6 @@ def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeat
         details = [{"tag": TAGNAME[t], "h": hs[k], "id": names[k], "seq": text[off[k]:off[k + 1]]}
                    for k, t in enumerate(tags) if t in TAGNAME]
         hist = out["hist"][i]
-        cs = lambda row: ";".join("{}|{}".format(k, int(v)) for k, v in enumerate(row) if v)
         missing = c["alleles"][0] < 0
         g, t = np.asarray(ev.global_lens), np.asarray(ev.target_lens)
         results.append({
