@@ -270,7 +270,8 @@ typedef struct {
     int64_t n_pe_lens;
     int32_t nreads;
     int32_t nproblems;
-    int32_t max_read_len;       /* upper bound on read length (required) */
+    int32_t max_read_len;       /* upper bound on read length (required; checked against roff for host buffers —
+                                   with TREDSW_DEVICE_PTRS a longer read is skipped: it gets the "no tag" record) */
     int32_t nfamilies;
     /* the following three are always HOST pointers (small, shape decisions are made on the host) */
     const tredsw_family *families;

@@ -208,3 +208,12 @@ def test_host_pipeline_keeps_order_and_results(problems):
         got_packed = [o["calls"].tobytes() for o in pipe.map(batches, packed=True)]
         assert pipe.launches > 0
     assert got == want and got_packed == want
+
+
+def test_a_read_longer_than_max_read_len_is_an_error_not_lost_evidence(problems):
+    """host buffers: tredsw_genotype_batch checks roff against max_read_len instead of skipping the read"""
+    from tredparse_b200 import cohort, _lib
+    batch = cohort.CohortBatch(problems[:2])
+    batch.max_read_len = 100                       # the reads are 150 bp
+    with pytest.raises(_lib.TredswError, match="max_read_len"):
+        batch.run_host()

@@ -190,3 +190,35 @@ def test_json_and_vcf_writers(tmp_path, repo, capsys):
     f = vcf[-1].split("\t")
     assert f[8] == "GT:GB:FR:PR:RR:DP:FDP:PDP:RDP:PEDP:CI:PP:LABEL" and f[9].startswith("1/2:15/41:15|4:6|1::29.3:4:1:0:13:")
     assert T.counter_s({15: 4, 6: 1}) == "6|1;15|4"
+
+
+def test_run_chunks_keeps_order_prefetches_and_isolates_failures(monkeypatch):
+    """tred.run_chunks: chunk k + 1 is prepared while chunk k is finished, results come back in input order, and with
+    isolate=True a chunk that raises yields error records for its samples instead of ending the run."""
+    import threading
+    from tredparse_b200 import tred as T
+    log, lock = [], threading.Lock()
+
+    def fake_prepare(args, only=None, ctx=None):
+        with lock:
+            log.append(("prep", args[0][0]))
+        if args[0][0] == "s4":
+            raise RuntimeError("boom")
+        return list(args)
+
+    def fake_finish(state, ctx=None):
+        with lock:
+            log.append(("fin", state[0][0]))
+        return [{"samplekey": a[0], "bam": a[1], "tredCalls": {"x": 1}} for a in state]
+    monkeypatch.setattr(T, "prepare_chunk", fake_prepare)
+    monkeypatch.setattr(T, "finish_chunk", fake_finish)
+    monkeypatch.setattr(T, "GPU_INGEST", False)
+    args = [("s{}".format(i), "b{}".format(i)) for i in range(7)]
+    got = list(T.run_chunks(args, chunk=2, isolate=True))
+    assert [r["samplekey"] for r in got] == ["s{}".format(i) for i in range(7)]
+    assert "error" in got[4] and "error" in got[5] and "boom" in got[4]["error"] and got[4]["tredCalls"] == {}
+    assert all("error" not in got[i] for i in (0, 1, 2, 3, 6))
+    # chunk 1 (s2) is prepared before chunk 0 (s0) is finished: two stages deep
+    assert log.index(("prep", "s2")) < log.index(("fin", "s2")) and ("fin", "s4") not in log
+    with pytest.raises(RuntimeError):
+        list(T.run_chunks(args, chunk=2))

@@ -374,9 +374,20 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     if (c->norepeatpairs && c->nreads > 0 && !c->read_name) { tredsw_set_error("norepeatpairs needs read_name"); return TREDSW_ERR_ARG; }
     if (c->nproblems <= 0 || c->nreads < 0 || c->nfamilies <= 0 || !c->families || !c->loci || !c->step_pmf ||
         c->max_read_len <= 0 || c->maxinsert < 1) { tredsw_set_error("bad cohort descriptor"); return TREDSW_ERR_ARG; }
+    const bool dev = dev_ptrs(flags);
+    if (!dev && c->nreads > 0) {
+        // host buffers can be checked: a read longer than max_read_len would be skipped by the kernels (their row
+        // buffers are sized by it), i.e. silently lose evidence
+        if (!c->roff || !c->rbuf || !c->read_problem || !c->problems) { tredsw_set_error("null input buffer"); return TREDSW_ERR_ARG; }
+        int64_t longest = 0;
+        for (int32_t i = 0; i < c->nreads; ++i) { const int64_t l = c->roff[i + 1] - c->roff[i]; longest = l > longest ? l : longest; }
+        if (longest > c->max_read_len) {
+            tredsw_set_error("a read of %lld bases exceeds max_read_len = %d", (long long)longest, c->max_read_len);
+            return TREDSW_ERR_ARG;
+        }
+    }
     std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const bool dev = dev_ptrs(flags);
     ctx->mark(8);
     ctx->wait_before_sw = nullptr; ctx->record_sw_end = false;
     const int nr = c->nreads, np_ = c->nproblems, nf = c->nfamilies;
