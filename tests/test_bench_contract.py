@@ -49,3 +49,28 @@ def test_reference_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     own = _line("r1_bench.json")
     assert (d["metric"], d["unit"], d["higher_is_better"]) == (own["metric"], own["unit"], own["higher_is_better"])
+
+
+@pytest.mark.parametrize("name", ["r2_bench.json", "r2_bench_2gpu.json", "r2_bench_4gpu.json", "r2_bench_8gpu.json",
+                                  "r2_bench_cohort10000.json"])
+def test_round2_lines(name):
+    """this round's lines: per-run roofline counters (not literals), distinct batches, the reference's own code as the
+    CPU arm with a call-by-call parity check, the from-BAM leg"""
+    d = _line(name)
+    assert BASE <= set(d) and d["metric"] == "loci genotyped/sec" and d["value"] > 1e6 * d["n_gpus"]
+    assert d["scaling"] == ("strong" if "cohort10000" in name else "weak")
+    r = d["roofline"]
+    assert r["calibration"] == "current" and 0.5 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 2.0 < r["alu_lane_instr_per_executed_cell"] < 4.0 and r["traffic"] > 1e9
+    assert "nothing is replayed" in d["config"]["l2"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 5e7 and 0 < e["value"] < d["value"] and e["transfer"] in ("bytes", "packed4")
+    if name == "r2_bench.json":
+        b = d["cpu_baseline"]
+        assert b["kind"] == "reference" and b["identical_to_gpu"].startswith("390/390")
+        s = d["roofline_grid_stress"]
+        assert s["points"] == 32032000 and s["kernel_ms"] < 0.6 and s["traffic"] < 8 * s["points"]
+        f = d["from_bam"]
+        assert f["gpu_ingest"] is True and f["value"] > 10 * 355 and f["reference"]["identical_to_gpu"].startswith("240/240")
+        ref = _line("r2_bench_reference.json")
+        assert ref["impl"] == "reference" and abs(ref["value"] / b["value"] - 1) < 0.15      # the arm is repeatable

@@ -12,7 +12,7 @@ python tools/calibrate.py merge gpurun_out/r2_cal.csv gpurun_out/r2_cal_stats.js
 python bench.py > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err; tail -c 600 gpurun_out/r2_bench_$tag.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_$tag.json 2>> gpurun_out/r2_bench_$tag.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_$tag.csv \
-    python bench.py --steps 2 --warmup 1 > /dev/null 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --from-bam 0 > /dev/null 2>&1
 python - <<PY
 import json
 d=json.load(open("gpurun_out/r2_bench_$tag.json"))
