@@ -321,12 +321,12 @@ class ReferencePool:
 
 
 def cpu_sample_size(args, cores, nloci, passes=1):
-    """Whole samples worth ~12 s of wall time per pass at the ~2 loci/s/core of the reference's Python + ssw.c
+    """Whole samples worth ~10 s of wall time per pass at the ~5 loci/s/core of the reference's Python + ssw.c
     path (fewer per pass when many passes are asked for, so that the run ends within minutes)."""
     if args.cpu_sample:
         return max(1, args.cpu_sample)
-    seconds = min(12.0, 150.0 / max(1, passes))
-    return max(1, min(24, int(round(seconds * 2.0 * cores / nloci))))
+    seconds = min(10.0, 150.0 / max(1, passes))
+    return max(1, min(32, int(round(seconds * 5.0 * cores / nloci))))
 
 
 def ssw_c_loop_ceiling(tasks, cores, max_pairs=40000):
