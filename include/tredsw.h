@@ -74,6 +74,9 @@ uint32_t cigar_int_to_len(uint32_t cigar_int);
 #define TREDSW_ERR_IO (-4)       /* BAM ingest: truncated / corrupt file, read error (never partial evidence) */
 
 #define TREDSW_DEVICE_PTRS 1u    /* all buffer arguments are device pointers; enqueue only */
+#define TREDSW_DEVICE_INPUTS 64u /* tredsw_genotype_batch[_ex]: rbuf, roff, read_problem and pe_lens are device pointers
+                                    (e.g. a tredsw_ingest_view); `problems`, `read_name` and all outputs are host
+                                    buffers; tredsw_cohort.n_bases is required; returns with the outputs valid */
 #define TREDSW_SCORE2 2u         /* also produce score2 / ref_end2 exactly like ssw.c (ghost rows) */
 #define TREDSW_NO_BEGIN 4u       /* skip the reverse pass (ref_begin/query_begin = -1), flag==0 of ssw_align */
 #define TREDSW_CIGAR 8u          /* also produce CIGARs (banded_sw restatement) */

@@ -207,7 +207,25 @@ def test_run_chunk_is_served_by_the_gpu_ingest_and_equals_the_host_reader_path(r
     def no_host_reader(*a, **k):
         raise AssertionError("the host reader was called although the GPU ingest can serve every locus")
     monkeypatch.setattr(T, "ingest_loci", no_host_reader)
+    # ... and the fused call runs on the ingest's device buffers (no batch assembled on the host, no second upload)
+    from tredparse_b200 import cohort
+    used = {"ingest": 0, "host": 0}
+    run_host = cohort.CohortBatch.run_host
+
+    def counted_host(self, *a, **k):
+        used["ingest" if k.get("device_view") is not None else "host"] += 1
+        return run_host(self, *a, **k)
+    monkeypatch.setattr(cohort.CohortBatch, "run_host", counted_host)
     gpu = T.run_chunk(tasks)
+    assert used == {"ingest": 1, "host": 0}
+    for flags in ((True, True, False), (False, True, True)):          # --useclippedreads; --norepeatpairs (name ids)
+        t2 = [x[:6] + flags + x[9:] for x in tasks]
+        monkeypatch.setattr(T, "DEVICE_HANDOFF", False)
+        a = T.run_chunk(t2)
+        monkeypatch.setattr(T, "DEVICE_HANDOFF", True)
+        b = T.run_chunk(t2)
+        assert [r["tredCalls"] for r in a] == [r["tredCalls"] for r in b]
+    assert used == {"ingest": 3, "host": 2}
     assert len(gpu) == len(host) == 2
     for a, b in zip(gpu, host):
         assert a["tredCalls"].keys() == b["tredCalls"].keys() and len(a["tredCalls"]) > 20 * len(names)

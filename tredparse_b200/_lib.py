@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtredsw.so")
 
 DEVICE_PTRS, SCORE2, NO_BEGIN, CIGAR, FORCE_WORD = 1, 2, 4, 8, 16
+DEVICE_INPUTS = 64      # tredsw_genotype_batch: bulk evidence in device memory, problems + outputs on the host
 
 TAG_NAMES = {0: None, 1: "FULL", 2: "PREF", 3: "POST", 4: "REPT", 5: "HANG"}
 

@@ -189,7 +189,8 @@ class CohortBatch:
         return c
 
     # ---- host buffers through the C ABI (H2D + kernels + D2H inside the call) -------------------------
-    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False, packed=False, want_post=False):
+    def run_host(self, ctx=None, want_reads=False, want_hist=False, want_stats=False, packed=False, want_post=False,
+                 device_view=None):
         """want_post: also return the sparsified posteriors (``posteriors()`` turns them into the reference's
         P_h1 / P_h2 / P_h1h2 dicts)."""
         ctx = ctx or _lib.default_context()
@@ -210,13 +211,19 @@ class CohortBatch:
             flags_in = (IN_READS_PACKED4 if "rbuf" in bufs else 0) | (IN_PE_LENS_I16 if "pe_lens" in bufs else 0)
         else:
             rbuf, pe, flags_in = self.rbuf, self.pe_lens, 0
-        c = self._descriptor(rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
-                             self.problems.ctypes.data, pe.ctypes.data, flags_in)
+        call_flags = 0
+        if device_view is not None:
+            # the bulk evidence is an ingest.IngestBatch's device buffers (TREDSW_DEVICE_INPUTS)
+            v, call_flags = device_view, _lib.DEVICE_INPUTS
+            c = self._descriptor(v.d_rbuf, v.d_roff, v.d_read_problem, self.problems.ctypes.data, v.d_pe_lens, 0)
+        else:
+            c = self._descriptor(rbuf.ctypes.data, self.roff.ctypes.data, self.read_problem.ctypes.data,
+                                 self.problems.ctypes.data, pe.ctypes.data, flags_in)
         post_cap = max(4096, 64 * self.nproblems) if want_post else 0
         n_post = np.zeros(1, dtype=np.int64)
         for attempt in range(4):
             post = np.zeros(post_cap, dtype=_lib.POSTERIOR_DTYPE) if want_post else None
-            rc = ctx.lib.tredsw_genotype_batch_ex(ctx.handle, ctypes.byref(c), 0, _lib.ptr(calls), _lib.ptr(read_out),
+            rc = ctx.lib.tredsw_genotype_batch_ex(ctx.handle, ctypes.byref(c), call_flags, _lib.ptr(calls), _lib.ptr(read_out),
                                                   _lib.ptr(hist), self.hist_units, _lib.ptr(stats), _lib.ptr(post),
                                                   post_cap, _lib.ptr(n_post) if want_post else None)
             if rc == 0 and want_post and int(n_post[0]) > post_cap:
@@ -227,8 +234,8 @@ class CohortBatch:
         _lib.check(rc, "tredsw_genotype_batch")
         n_rbuf = (len(self.rbuf) + 1) // 2 if (flags_in & IN_READS_PACKED4) else self.rbuf.nbytes   # bytes the call copies
         n_pe = len(self.pe_lens) * (2 if (flags_in & IN_PE_LENS_I16) else 4)
-        self.h2d_bytes = (n_rbuf + self.roff.nbytes + self.read_problem.nbytes + self.problems.nbytes +
-                          n_pe + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes)
+        bulk = 0 if device_view is not None else n_rbuf + self.roff.nbytes + self.read_problem.nbytes + n_pe
+        self.h2d_bytes = bulk + self.problems.nbytes + self.families.nbytes + self.loci.nbytes + self.step_pmf.nbytes
         self.d2h_bytes = calls.nbytes + (read_out.nbytes if want_reads else 0) + (hist.nbytes if want_hist else 0)
         out = {"calls": calls}
         if want_reads:
@@ -266,6 +273,42 @@ class CohortBatch:
         rc = ctx.lib.tredsw_genotype_batch(ctx.handle, ctypes.byref(c), _lib.DEVICE_PTRS, d["calls"].data_ptr(),
                                            None, None, 0, None)
         _lib.check(rc, "tredsw_genotype_batch")
+
+    # ---- evidence that is already in device memory (the GPU ingest's buffers) ------------------------------
+    @classmethod
+    def from_ingest(cls, ing, family_of, ploidy, depth, family_keys, names=None, **kw):
+        """A batch over the flat buffers an ``ingest.IngestBatch`` left in HBM (problem i of the batch = problem i of
+        the ingest): nothing is concatenated or copied, only the 40-byte problem records are built.
+        family_of: index into family_keys per problem; names: per problem read names (only without repeatpairs)."""
+        self = cls([], family_keys=family_keys, **kw)
+        n = ing.nproblems
+        summ, span = ing.summary_table, ing.span_table
+        P = np.zeros(n, dtype=PROBLEM_DTYPE)
+        P["family"], P["ploidy"], P["depth"] = family_of, ploidy, depth
+        P["n_global"], P["n_target"] = summ["n_global"], summ["n_target"]
+        P["off_global"], P["off_target"] = span["off_global"], span["off_target"]
+        self.nproblems, self.problems = n, P
+        self.rbuf, self.roff, self.pe_lens = ing.h_rbuf, ing.h_roff, ing.h_pe_lens        # (host copies: sizes only)
+        self.read_problem = None
+        self.nreads = ing.nreads
+        self.max_read_len = max(1, int(np.diff(ing.h_roff).max())) if ing.nreads else 1
+        self.read_name = None
+        if not self.repeatpairs and not self.clip:
+            if names is None:
+                raise ValueError("repeatpairs=False needs the read names of every problem")
+            ids = []
+            for nm in names:
+                seen = {}
+                ids.append(np.array([seen.setdefault(x, len(seen)) for x in nm], dtype=np.int32))
+            self.read_name = np.ascontiguousarray(np.concatenate(ids) if ids else np.zeros(0, np.int32), dtype=np.int32)
+        self._ingest = ing
+        return self
+
+    def run_ingest(self, ctx, want_reads=False, want_hist=False, want_post=False):
+        """``tredsw_genotype_batch_ex`` with TREDSW_DEVICE_INPUTS on the ingest's device buffers: the evidence stays
+        where the ingest left it, the problem records and the outputs are host buffers.  Same dict as ``run_host``."""
+        return self.run_host(ctx=ctx, want_reads=want_reads, want_hist=want_hist, want_post=want_post,
+                             device_view=self._ingest.view)
 
     def calls_from_device(self):
         calls = self._dev["calls"].cpu().numpy().view(CALL_DTYPE)

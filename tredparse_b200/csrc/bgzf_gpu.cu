@@ -200,17 +200,28 @@ struct CudaBackend {
         if (rc == TREDSW_OK) { tredsw_set_error("%s failed: %s", what, cudaGetErrorString(e)); rc = TREDSW_ERR_CUDA; }
         return true;
     }
-    void *alloc(size_t bytes) {                        // device memory (with slack for the word-wise readers)
+    // keep = true: a result buffer (lives until the batch is freed); otherwise an intermediate of the pipeline
+    // (released as soon as the results are complete: the inflated stream alone is 8x the compressed bytes)
+    std::vector<void *> dev_keep, pinned_keep;
+    void *alloc(size_t bytes, bool keep = false) {     // device memory (with slack for the word-wise readers)
         void *p = nullptr;
         if (fail(cudaMallocAsync(&p, bytes + 64, stream), "cudaMallocAsync")) return nullptr;
-        dev.push_back(p);
+        (keep ? dev_keep : dev).push_back(p);
         return p;
     }
-    void *alloc_host(size_t bytes) {                   // page-locked host memory
+    void *alloc_host(size_t bytes, bool keep = false) {   // page-locked host memory
         void *p = pinned_pool().get(bytes + 64);
         if (!p) { fail(cudaErrorMemoryAllocation, "cudaHostAlloc"); return nullptr; }
-        pinned.push_back(p);
+        (keep ? pinned_keep : pinned).push_back(p);
         return p;
+    }
+    bool quiesced = false;                             // the pipeline has run to its last synchronisation
+    void release_intermediates() {                     // (after a synchronisation: nothing is in flight)
+        for (void *p : dev) cudaFreeAsync(p, stream);
+        dev.clear();
+        for (void *p : pinned) pinned_pool().put(p);
+        pinned.clear();
+        quiesced = true;
     }
     void upload(void *dst, const void *src, size_t bytes) { if (bytes && dst) fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(H2D)"); }
     void download(void *dst, const void *src, size_t bytes) { if (bytes && dst) fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(D2H)"); }
@@ -257,10 +268,14 @@ struct CudaBackend {
     }
     void release() {
         for (void *p : dev) cudaFreeAsync(p, stream);
-        dev.clear();
-        cudaStreamSynchronize(stream);
+        for (void *p : dev_keep) cudaFreeAsync(p, stream);
+        dev.clear(); dev_keep.clear();
+        // a finished batch has nothing in flight (and its stream may be busy with the NEXT batch by now: waiting for it
+        // would stall the thread that frees this one); an aborted one may still have copies into the pinned buffers
+        if (!quiesced) cudaStreamSynchronize(stream);
         for (void *p : pinned) pinned_pool().put(p);
-        pinned.clear();
+        for (void *p : pinned_keep) pinned_pool().put(p);
+        pinned.clear(); pinned_keep.clear();
     }
 };
 
@@ -268,8 +283,15 @@ struct HostBackend {                                   // serial emulation of th
     static constexpr bool on_device = false;
     std::vector<void *> mem;
     int rc = TREDSW_OK;
-    void *alloc(size_t bytes) { void *p = calloc(bytes + 64, 1); if (!p) { rc = TREDSW_ERR_ARG; tredsw_set_error("out of memory"); } mem.push_back(p); return p; }
-    void *alloc_host(size_t bytes) { return alloc(bytes); }
+    std::vector<void *> mem_keep;
+    void *alloc(size_t bytes, bool keep = false) {
+        void *p = calloc(bytes + 64, 1);
+        if (!p) { rc = TREDSW_ERR_ARG; tredsw_set_error("out of memory"); }
+        (keep ? mem_keep : mem).push_back(p);
+        return p;
+    }
+    void *alloc_host(size_t bytes, bool keep = false) { return alloc(bytes, keep); }
+    void release_intermediates() { for (void *p : mem) free(p); mem.clear(); }
     void upload(void *dst, const void *src, size_t bytes) { if (bytes && dst) memcpy(dst, src, bytes); }
     void download(void *dst, const void *src, size_t bytes) { if (bytes && dst) memcpy(dst, src, bytes); }
     void fill(void *dst, int byte, size_t bytes) { if (bytes && dst) memset(dst, byte, bytes); }
@@ -304,7 +326,7 @@ struct HostBackend {                                   // serial emulation of th
         }
     }
     void scan(const uint32_t *in, int64_t n, uint32_t *out) { uint32_t s = 0; for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; } out[n > 0 ? n : 0] = s; }
-    void release() { for (void *p : mem) free(p); mem.clear(); }
+    void release() { for (void *p : mem) free(p); for (void *p : mem_keep) free(p); mem.clear(); mem_keep.clear(); }
 };
 
 struct ProblemSummary {         // device -> host after the selection pass
@@ -687,9 +709,9 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
         if (h_counts[p].error && !out->status[p]) out->status[p] = 3;
     }
     const int64_t nslots = tab_off[nq];
-    int8_t *d_rbuf = static_cast<int8_t *>(be.alloc((size_t)nbases + 16));
-    int64_t *d_roff = static_cast<int64_t *>(be.alloc(sizeof(int64_t) * (size_t)(nreads + 1)));
-    int32_t *d_rprob = static_cast<int32_t *>(be.alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(1, nreads)));
+    int8_t *d_rbuf = static_cast<int8_t *>(be.alloc((size_t)nbases + 16, true));
+    int64_t *d_roff = static_cast<int64_t *>(be.alloc(sizeof(int64_t) * (size_t)(nreads + 1), true));
+    int32_t *d_rprob = static_cast<int32_t *>(be.alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(1, nreads), true));
     char *d_names = want_names ? static_cast<char *>(be.alloc((size_t)name_bytes + 16)) : nullptr;
     uint32_t *d_elist = static_cast<uint32_t *>(be.alloc(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nreads)));
     uint32_t *d_plist = static_cast<uint32_t *>(be.alloc(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, npe)));
@@ -771,12 +793,12 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
         pe_off[2 * p] = n_pe_lens; n_pe_lens += h_pcnt[2 * p];
         pe_off[2 * p + 1] = n_pe_lens; n_pe_lens += h_pcnt[2 * p + 1];
     }
-    int32_t *d_pelens = static_cast<int32_t *>(be.alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_pe_lens)));
+    int32_t *d_pelens = static_cast<int32_t *>(be.alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_pe_lens), true));
     int64_t *d_peoff = static_cast<int64_t *>(be.alloc(sizeof(int64_t) * 2 * (size_t)nq));
-    int8_t *h_rbuf = static_cast<int8_t *>(be.alloc_host((size_t)nbases + 16));
-    int64_t *h_roff = static_cast<int64_t *>(be.alloc_host(sizeof(int64_t) * (size_t)(nreads + 1)));
-    int32_t *h_pelens = static_cast<int32_t *>(be.alloc_host(sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_pe_lens)));
-    char *h_names = want_names ? static_cast<char *>(be.alloc_host((size_t)name_bytes + 16)) : nullptr;
+    int8_t *h_rbuf = static_cast<int8_t *>(be.alloc_host((size_t)nbases + 16, true));
+    int64_t *h_roff = static_cast<int64_t *>(be.alloc_host(sizeof(int64_t) * (size_t)(nreads + 1), true));
+    int32_t *h_pelens = static_cast<int32_t *>(be.alloc_host(sizeof(int32_t) * (size_t)std::max<int64_t>(1, n_pe_lens), true));
+    char *h_names = want_names ? static_cast<char *>(be.alloc_host((size_t)name_bytes + 16, true)) : nullptr;
     if (be.rc) return be.rc;
     be.upload(d_peoff, pe_off.data(), sizeof(int64_t) * 2 * (size_t)nq);
     {
@@ -817,6 +839,7 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     v.h_rbuf = h_rbuf; v.h_roff = h_roff; v.h_pe_lens = h_pelens; v.h_names = h_names;
     v.summaries = out->summaries.data(); v.spans = out->spans.data(); v.status = out->status.data();
     v.n_blocks = out->n_blocks; v.n_records = out->n_records; v.comp_bytes = out->comp_bytes; v.inflated_bytes = out->inflated_bytes;
+    be.release_intermediates();            // compressed bytes, inflated stream, record arrays, tables: only results stay
     out->ms_total = now_ms() - t_begin;
     v.ms_host_stage = out->ms_host_stage; v.ms_total = out->ms_total;
     for (int k = 0; k < 4; ++k) v.ms_marks[k] = out->ms_marks[k];

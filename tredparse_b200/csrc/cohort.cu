@@ -375,7 +375,11 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     if (c->nproblems <= 0 || c->nreads < 0 || c->nfamilies <= 0 || !c->families || !c->loci || !c->step_pmf ||
         c->max_read_len <= 0 || c->maxinsert < 1) { tredsw_set_error("bad cohort descriptor"); return TREDSW_ERR_ARG; }
     const bool dev = dev_ptrs(flags);
-    if (!dev && c->nreads > 0) {
+    // TREDSW_DEVICE_INPUTS: the bulk evidence (rbuf, roff, read_problem, pe_lens) already lies in device memory — e.g.
+    // where tredsw_ingest_batch_run left it — while `problems`, `read_name` and every output are host buffers that
+    // travel through the page-locked staging of the host mode (the call returns when the outputs are valid)
+    const bool dev_in = dev || (flags & TREDSW_DEVICE_INPUTS) != 0;
+    if (!dev_in && c->nreads > 0) {
         // host buffers can be checked: a read longer than max_read_len would be skipped by the kernels (their row
         // buffers are sized by it), i.e. silently lose evidence
         if (!c->roff || !c->rbuf || !c->read_problem || !c->problems) { tredsw_set_error("null input buffer"); return TREDSW_ERR_ARG; }
@@ -408,15 +412,15 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     const int32_t *d_rname = c->read_name;
     const tredsw_family *d_fam; const tredsw_locus *d_loci;
     const bool packed4 = (c->input_flags & TREDSW_IN_READS_PACKED4) != 0, pe16 = (c->input_flags & TREDSW_IN_PE_LENS_I16) != 0;
-    if (dev && packed4 && c->n_bases <= 0 && nr > 0) { tredsw_set_error("n_bases is required for packed reads in device memory"); return TREDSW_ERR_ARG; }
-    const int64_t nbases = nr > 0 ? (dev ? c->n_bases : c->roff[nr]) : 0;
+    if (dev_in && c->n_bases <= 0 && nr > 0 && (packed4 || !dev)) { tredsw_set_error("n_bases is required for reads in device memory"); return TREDSW_ERR_ARG; }
+    const int64_t nbases = nr > 0 ? (dev_in ? c->n_bases : c->roff[nr]) : 0;
     const uint32_t *unpack_src = nullptr; int64_t unpack_words = 0;
     const int16_t *widen_src = nullptr;
     if (packed4 && nr > 0) {
         // rbuf holds nibbles: bring the packed words to the device, expand into the byte-per-base buffer
         const int64_t nwords = (nbases + 7) / 8;
         const uint32_t *d_pk = reinterpret_cast<const uint32_t *>(c->rbuf);
-        if (!dev) {
+        if (!dev_in) {
             if ((rc = ctx->d_pk.ensure((size_t)nwords * 4))) return rc;
             CUDA_TRY(cudaMemcpyAsync(ctx->d_pk.p, c->rbuf, (size_t)(nbases + 1) / 2, cudaMemcpyHostToDevice, ctx->stream));
             d_pk = ctx->d_pk.as<uint32_t>();
@@ -425,15 +429,14 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
         unpack_src = d_pk; unpack_words = nwords;            // launched below, once every input copy is queued
         d_rbuf = ctx->d_q.as<int8_t>();
     }
-    if (!dev) {
-        if (nr > 0) {
-            if (!packed4 && (rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
-            if ((rc = stage_in(ctx, ctx->d_qoff, c->roff, (size_t)nr + 1, 0u, &d_roff))) return rc;
-            if ((rc = stage_in(ctx, ctx->d_qidx, c->read_problem, (size_t)nr, 0u, &d_rp))) return rc;
-            if (c->norepeatpairs && (rc = stage_in(ctx, ctx->d_tidx, c->read_name, (size_t)nr, 0u, &d_rname))) return rc;
-        }
-        if ((rc = stage_in(ctx, ctx->d_prob, c->problems, (size_t)np_, 0u, &d_prob))) return rc;
+    if (!dev_in && nr > 0) {
+        if (!packed4 && (rc = stage_in(ctx, ctx->d_q, c->rbuf, (size_t)c->roff[nr], 0u, &d_rbuf))) return rc;
+        if ((rc = stage_in(ctx, ctx->d_qoff, c->roff, (size_t)nr + 1, 0u, &d_roff))) return rc;
+        if ((rc = stage_in(ctx, ctx->d_qidx, c->read_problem, (size_t)nr, 0u, &d_rp))) return rc;
     }
+    // (name ids and problem records are made by host code in either mode)
+    if (!dev && nr > 0 && c->norepeatpairs && (rc = stage_in(ctx, ctx->d_tidx, c->read_name, (size_t)nr, 0u, &d_rname))) return rc;
+    if (!dev && (rc = stage_in(ctx, ctx->d_prob, c->problems, (size_t)np_, 0u, &d_prob))) return rc;
     // the small per-call tables (always host pointers) travel through the context's page-locked staging buffer
     const size_t b_step = (size_t)nf * NSTEP * sizeof(double);
     size_t hoff[3];
@@ -453,7 +456,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
     int32_t *d_ipool = ctx->d_ipool.as<int32_t>();
     if (c->n_pe_lens > 0 && pe16) {
         const int16_t *d16 = reinterpret_cast<const int16_t *>(c->pe_lens);
-        if (!dev) {
+        if (!dev_in) {
             if ((rc = ctx->d_pe16.ensure((size_t)c->n_pe_lens * sizeof(int16_t)))) return rc;
             CUDA_TRY(cudaMemcpyAsync(ctx->d_pe16.p, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
             d16 = ctx->d_pe16.as<int16_t>();
@@ -461,7 +464,7 @@ extern "C" int tredsw_genotype_batch_ex(tredsw_ctx *ctx, const tredsw_cohort *c,
         widen_src = d16;
     } else if (c->n_pe_lens > 0)
         CUDA_TRY(cudaMemcpyAsync(d_ipool, c->pe_lens, (size_t)c->n_pe_lens * sizeof(int32_t),
-                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+                                 dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
 
     const int64_t n_dpool = (int64_t)np_ * KDE_SPAN + (int64_t)nf * NSTEP;
     if ((rc = ctx->d_dpool.ensure((size_t)n_dpool * sizeof(double)))) return rc;

@@ -233,6 +233,12 @@ class ProblemSpan(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("read0", "base0", "name0", "off_global", "off_target")]
 
 
+SUMMARY_DTYPE = np.dtype([("nreads", "<i4"), ("n_unmapped", "<i4"), ("n_global", "<i4"), ("n_target", "<i4"),
+                          ("nbases", "<i8"), ("name_bytes", "<i8"), ("depth", "<f8"), ("overflow", "<i4"), ("reserved_", "<i4")])
+SPAN_DTYPE = np.dtype([(n, "<i8") for n in ("read0", "base0", "name0", "off_global", "off_target")])
+assert SUMMARY_DTYPE.itemsize == ctypes.sizeof(LocusSummary) and SPAN_DTYPE.itemsize == ctypes.sizeof(ProblemSpan)
+
+
 class IngestView(ctypes.Structure):
     """tredsw_ingest_view (include/tredsw.h)"""
     _fields_ = [("nproblems", ctypes.c_int32), ("nreads", ctypes.c_int32), ("nbases", ctypes.c_int64),
@@ -325,6 +331,10 @@ class IngestBatch:
         self.status = np.ctypeslib.as_array(v.status, shape=(max(1, n),))[:n].copy() if n else np.zeros(0, np.int32)
         self.summaries = [v.summaries[i] for i in range(n)]
         self.spans = [v.spans[i] for i in range(n)]
+        raw = lambda ptr, dt: (np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)),
+                                                      shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt))
+        self.summary_table = raw(v.summaries, SUMMARY_DTYPE)      # the same records as numpy tables
+        self.span_table = raw(v.spans, SPAN_DTYPE)
         as_np = lambda ptr, ct, m: (np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(m,)) if m and ptr
                                     else np.zeros(0, dtype=ct))
         self.h_rbuf = as_np(v.h_rbuf, ctypes.c_int8, int(v.nbases))
@@ -333,14 +343,16 @@ class IngestBatch:
         self.h_names = ctypes.string_at(v.h_names, int(v.name_bytes)) if v.h_names and v.name_bytes else b""
         self.want_names = want_names
 
-    def evidence(self, i):
+    def evidence(self, i, copy=True):
+        """copy=False: views into the batch's page-locked buffers (valid until close())"""
         s, sp = self.summaries[i], self.spans[i]
         ev = LocusEvidence()
         r0, b0 = int(sp.read0), int(sp.base0)
-        ev.reads = self.h_rbuf[b0:b0 + int(s.nbases)].copy()
+        own = (lambda a: a.copy()) if copy else (lambda a: a)
+        ev.reads = own(self.h_rbuf[b0:b0 + int(s.nbases)])
         ev.roff = (self.h_roff[r0:r0 + s.nreads + 1] - b0).astype(np.int64)
-        ev.global_lens = self.h_pe_lens[int(sp.off_global):int(sp.off_global) + s.n_global].copy()
-        ev.target_lens = self.h_pe_lens[int(sp.off_target):int(sp.off_target) + s.n_target].copy()
+        ev.global_lens = own(self.h_pe_lens[int(sp.off_global):int(sp.off_global) + s.n_global])
+        ev.target_lens = own(self.h_pe_lens[int(sp.off_target):int(sp.off_target) + s.n_target])
         ev.depth = float(s.depth)
         ev.n_unmapped = int(s.n_unmapped)
         if self.want_names:

@@ -225,29 +225,48 @@ def run_batched(ips, evidence=None):
 TAGNAME = {1: "FULL", 2: "PREF", 3: "POST", 4: "REPT"}
 
 
-def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeatpairs=True, ctx=None):
+def genotype_evidence(items, maxinsert=300, fullsearch=False, clip=False, repeatpairs=True, ctx=None, device_batch=None):
     """The fused device path for loci whose evidence came from the native ingest: ONE ``tredsw_genotype_batch_ex``
     call (Smith-Waterman + classification -> tallies -> candidate ranges -> KDE -> likelihood grid -> call / CI / PP
     / label -> sparse posteriors) over any number of (sample, locus) problems, then the reference's per-locus
     result fields (tred.py:251-275) assembled from what comes back.
     :param items: list of (tred, READLEN, gender, depth, ingest.LocusEvidence)
+    :param device_batch: the ``ingest.IngestBatch`` the items came from, problem i = item i: its buffers are consumed
+                         where they lie in device memory (no batch is assembled on the host, nothing is uploaded again)
     :return: list of dicts keyed like the ``<T>.xxx`` entries of tredCalls, without the prefix."""
-    from . import cohort
+    from . import cohort, _lib
     from .simulate import Problem
     if not items:
         return []
-    problems = []
-    for tred, readlen, gender, depth, ev in items:
-        pr = Problem()
-        pr.tred, pr.readlen = tred, readlen
-        pr.ploidy = 1 if (gender == "Male" and tred.is_xlinked) else tred.ploidy
-        pr.depth, pr.reads, pr.roff = depth, ev.reads, ev.roff
-        pr.global_lens, pr.target_lens = ev.global_lens, ev.target_lens
-        pr.alleles, pr.names = None, ev.names
-        problems.append(pr)
-    batch = cohort.CohortBatch(problems, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
-    out = batch.run_host(ctx=ctx, want_reads=True, want_hist=True, want_post=True)
-    post = cohort.posteriors(out["post"], len(problems))
+    ploidy_of = lambda tred, gender: 1 if (gender == "Male" and tred.is_xlinked) else tred.ploidy
+    out = None
+    if device_batch is not None:
+        keys, fam_of = {}, []
+        for tred, readlen, gender, depth, ev in items:
+            fam_of.append(keys.setdefault((tred.name, readlen), len(keys)))
+        family_keys = [None] * len(keys)
+        for (tred, readlen, gender, depth, ev), f in zip(items, fam_of):
+            family_keys[f] = (tred, readlen)
+        batch = cohort.CohortBatch.from_ingest(
+            device_batch, np.array(fam_of, dtype=np.int32),
+            np.array([ploidy_of(it[0], it[2]) for it in items], dtype=np.int32),
+            np.array([it[3] for it in items], dtype=np.float64), family_keys,
+            names=None if (repeatpairs or clip) else [it[4].names for it in items],
+            maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
+        out = batch.run_ingest(ctx or _lib.default_context(), want_reads=True, want_hist=True, want_post=True)
+    if out is None:
+        problems = []
+        for tred, readlen, gender, depth, ev in items:
+            pr = Problem()
+            pr.tred, pr.readlen = tred, readlen
+            pr.ploidy = ploidy_of(tred, gender)
+            pr.depth, pr.reads, pr.roff = depth, ev.reads, ev.roff
+            pr.global_lens, pr.target_lens = ev.global_lens, ev.target_lens
+            pr.alleles, pr.names = None, ev.names
+            problems.append(pr)
+        batch = cohort.CohortBatch(problems, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs)
+        out = batch.run_host(ctx=ctx, want_reads=True, want_hist=True, want_post=True)
+    post = cohort.posteriors(out["post"], len(items))
     results, r0 = [], 0
     calls = out["calls"].tolist()                                    # (plain tuples: no numpy scalars in the loop)
 
@@ -341,13 +360,17 @@ def ingest_loci(bam, repo, tredNames, READLEN, alts, clip, logger, threads=None,
 
 
 GPU_INGEST = os.environ.get("TREDSW_GPU_INGEST", "1") != "0"
+DEVICE_HANDOFF = os.environ.get("TREDSW_DEVICE_HANDOFF", "1") != "0"     # genotype from the ingest's device buffers
 
 
-def ingest_chunk_gpu(samples, ctx=None):
+def ingest_chunk_gpu(samples, ctx=None, keep_batch=None):
     """Evidence of every (sample, locus) of a chunk through the GPU ingest (csrc/bgzf_gpu.cu): the host reads the
     compressed BGZF blocks behind the windows, the device inflates them, walks the records and applies the
     selection / pairing / depth rules — same evidence as ``ingest_loci`` locus by locus.
     :param samples: [(key, run-argument tuple, wanted TRED names, READLEN, open ingest.BamIngest)]
+    :param keep_batch: a list; when every problem of the batch is good, (IngestBatch, [(key, tredName)]) is appended
+                       and the batch stays open (the evidence objects are views into it): the caller genotypes from
+                       its device buffers and closes it
     :return: {key: ({tredName: LocusEvidence}, {tredName: depth})} — loci the device path could not serve (contig
              missing, a block the decoder refused, corrupt records) are left out: the caller reads them with the
              host reader."""
@@ -373,14 +396,23 @@ def ingest_chunk_gpu(samples, ctx=None):
         if not qs:
             return got
         ctx = ctx or _lib.default_context()
-        with IngestBatch(ctx, handles, so, qs, keep=keep) as b:
+        b = IngestBatch(ctx, handles, so, qs, keep=keep)
+        try:
+            hold = keep_batch is not None and not b.status.any()
             for i, (k, t) in enumerate(key):
                 if b.status[i]:
                     logger.debug("GPU ingest handed {} / {} back (status {})".format(k, t, int(b.status[i])))
                     continue
-                ev = b.evidence(i)
+                ev = b.evidence(i, copy=not hold)
                 e, d = got.setdefault(k, ({}, {}))
                 e[t], d[t] = ev, ev.depth
+            if hold:
+                # every problem is good: the caller may genotype straight from the batch's device buffers
+                keep_batch.append((b, key))
+                b = None
+        finally:
+            if b is not None:
+                b.close()
         return got
     except Exception as e:
         logger.error("GPU ingest failed ({}); reading with the host reader".format(e))
@@ -467,9 +499,10 @@ def prepare_chunk(args, only=None, ctx=None):
         out[si]["_names"] = wanted_of[si]
     # evidence: the GPU ingest for every (sample, locus) of the chunk in one pass; the host reader for what it
     # hands back (no index, corrupt blocks, unknown contig) or when it is switched off (TREDSW_GPU_INGEST=0)
+    kept = []
     try:
         got = ingest_chunk_gpu([(si, args[si], wanted_of[si], out[si]["tredCalls"]["readLen"], handle_of[si])
-                                for si in todo], ctx=ctx) if GPU_INGEST else {}
+                                for si in todo], ctx=ctx, keep_batch=kept if DEVICE_HANDOFF else None) if GPU_INGEST else {}
     finally:
         for h in handle_of.values():
             if h is not None:
@@ -489,24 +522,52 @@ def prepare_chunk(args, only=None, ctx=None):
             if t in evidence:
                 items.append((repo[t], READLEN, gender, depths[t], evidence[t]))
                 where.append((si, t))
-    return args, out, items, where
+    # the fused call can run on the ingest's device buffers when the items are exactly the problems of the batch
+    device_batch = None
+    if kept:
+        b, key = kept[0]
+        if key == where:
+            device_batch = b
+        else:                                   # (some locus came from the host reader: assemble the batch on the host)
+            items = [(it[0], it[1], it[2], it[3], _own_evidence(it[4])) for it in items]
+            b.close()
+    return args, out, items, where, device_batch
+
+
+def _own_evidence(ev):
+    """a LocusEvidence whose arrays no longer point into an IngestBatch"""
+    for name in ("reads", "global_lens", "target_lens"):
+        setattr(ev, name, np.array(getattr(ev, name)))
+    return ev
 
 
 def finish_chunk(state, ctx=None):
     """Second half of ``run_chunk``: ONE fused device call for the loci of all the samples of the chunk, then the
     reference's per-locus JSON fields.
     :return: list of {"samplekey", "bam", "tredCalls"}"""
-    args, out, items, where = state
+    args, out, items, where, device_batch = state
     if not args:
         return []
     _, _, repo, _, maxinsert, fullsearch, clip, alts, repeatpairs, log = args[0]
-    # loci whose evidence came from the native one-pass ingest: the fused device pipeline, all of them in one call
+    # loci whose evidence came from the ingest: the fused device pipeline, all of them in one call — on the ingest's
+    # own device buffers when the whole chunk came from the GPU ingest, else from a batch assembled on the host
     try:
-        res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs, ctx=ctx)
+        res = None
+        if device_batch is not None:
+            try:
+                res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip,
+                                        repeatpairs=repeatpairs, ctx=ctx, device_batch=device_batch)
+            except Exception as e:
+                logger.error("Device hand-off failed ({}); assembling the batch on the host".format(e))
+        if res is None:
+            res = genotype_evidence(items, maxinsert=maxinsert, fullsearch=fullsearch, clip=clip, repeatpairs=repeatpairs, ctx=ctx)
         for (si, t), r in zip(where, res):
             out[si]["_fields"][t] = r
     except Exception as e:
         logger.error("Fused run failed ({}); falling back to the per-stage path".format(e))
+    finally:
+        if device_batch is not None:
+            device_batch.close()
     for o, arg in zip(out, args):
         samplekey, bam, repo, tredNames, maxinsert, fullsearch, clip, alts, repeatpairs, log = arg
         fields, depths = o.pop("_fields"), o.pop("_depths", {})
