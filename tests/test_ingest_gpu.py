@@ -230,3 +230,44 @@ def test_run_chunk_is_served_by_the_gpu_ingest_and_equals_the_host_reader_path(r
     for a, b in zip(gpu, host):
         assert a["tredCalls"].keys() == b["tredCalls"].keys() and len(a["tredCalls"]) > 20 * len(names)
         assert a["tredCalls"] == b["tredCalls"]
+
+
+def test_device_decoder_differential_fuzz_against_zlib():
+    """randomised streams with shallow, deep (Fibonacci-weighted: 15-bit codes, sub-tables) and degenerate Huffman
+    trees, every zlib strategy / level / memLevel: the device decoder returns zlib's input, byte for byte"""
+    from tredparse_b200 import _lib, ingest
+    lib = _lib.load()
+    ingest._bind_batch(lib)
+    rng = random.Random(123)
+    nrng = np.random.default_rng(5)
+
+    def gen(kind, n):
+        if kind == 0:
+            return bytes(nrng.integers(0, 256, n, dtype=np.uint8))
+        if kind == 1:
+            return bytes(np.minimum(nrng.geometric(rng.choice([0.3, 0.5, 0.7, 0.9]), n) - 1, 255).astype(np.uint8))
+        if kind == 2:
+            return bytes(np.minimum(nrng.zipf(rng.choice([1.2, 1.5, 2.0]), n), 255).astype(np.uint8))
+        if kind == 3:
+            unit = bytes(nrng.integers(0, 4, rng.randint(1, 300), dtype=np.uint8))
+            b = bytearray(unit * (n // len(unit) + 1))[:n]
+            for _ in range(n // 50):
+                b[rng.randrange(n)] = rng.randrange(256)
+            return bytes(b)
+        if kind == 4:
+            f, syms = [1, 1], []
+            while len(f) < 24:
+                f.append(f[-1] + f[-2])
+            for i, c in enumerate(f):
+                syms += [i] * min(c, 4000)
+            rng.shuffle(syms)
+            return bytes(syms[:n])
+        return b"ACGT"[rng.randrange(4):][:1] * n
+    for _ in range(400):
+        data = gen(rng.randrange(6), rng.choice([1, 2, 10, 100, 1000, 5000, 20000, 65536]))
+        c = zlib.compressobj(rng.choice([1, 4, 6, 9]), zlib.DEFLATED, -15, rng.choice([1, 5, 8, 9]),
+                             rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        raw = c.compress(data) + c.flush()
+        out = np.zeros(len(data) + 16, np.uint8)
+        assert lib.tredsw_inflate_raw_device_code(raw, len(raw), out.ctypes.data, len(data)) == 0
+        assert bytes(out[:len(data)]) == data
