@@ -698,6 +698,15 @@ int run_pipeline(B &be, tredsw_ingest_batch *out, tredsw_bam *const *bams, const
     const int64_t nbases = (int64_t)h_psum[nq - 1].base0 + h_psum[nq - 1].nbases;
     const int64_t name_bytes = (int64_t)h_psum[nq - 1].name0 + h_psum[nq - 1].name_bytes;
     const int64_t npe = (int64_t)h_psum[nq - 1].pe0 + h_psum[nq - 1].npe;
+    {
+        // the scans are 32-bit: a batch whose selected bytes do not fit them (only a corrupt file gets there) is refused
+        unsigned long long total64 = 0;
+        for (int p = 0; p < nq; ++p) total64 += h_counts[p].bytes64;
+        if (total64 != (unsigned long long)nbases + (unsigned long long)name_bytes || total64 >= (1ull << 31)) {
+            tredsw_set_error("implausible amount of selected read data (%llu bytes): corrupt input?", total64);
+            return TREDSW_ERR_IO;
+        }
+    }
     // per-problem pairing tables (power-of-two slots, load <= 1/2)
     std::vector<uint32_t> tab_off(nq + 1, 0), tab_mask(nq, 0);
     for (int p = 0; p < nq; ++p) {

@@ -448,9 +448,11 @@ struct ProblemParams {          // windows of one locus (extract_locus_impl)
 };
 struct ProblemCounts {          // accumulated by the record kernel
     unsigned long long depth_sum;
+    unsigned long long bytes64; // selected bases + name bytes in 64 bits: guards the 32-bit scans against a wrap
     int32_t n_unmapped;
     uint32_t error;             // bit 0 walk (record chain), bit 1 record fields
 };
+constexpr int32_t MAX_SELECTED_READ = 1 << 20;      // a "read" longer than this is a corrupt record, not evidence
 
 enum : uint32_t { ERR_WALK = 1u, ERR_RECORD = 2u };
 
@@ -598,7 +600,11 @@ TG_HD RecOut select_record(const uint8_t *ibuf, int64_t p, const Fetch &f, const
     } else {
         emit = r.next_tid == q.tid && (int64_t)r.next_pos >= q.win_s && (int64_t)r.next_pos <= q.win_e;
     }
-    if (emit) { o.emit = 1; o.bases = (uint32_t)r.l_seq; o.name_bytes = (uint32_t)(r.l_name > 0 ? r.l_name : 1); }
+    if (emit && r.l_seq > MAX_SELECTED_READ) { atomic_or_u32(&cnt->error, ERR_RECORD); emit = false; }
+    if (emit) {
+        o.emit = 1; o.bases = (uint32_t)r.l_seq; o.name_bytes = (uint32_t)(r.l_name > 0 ? r.l_name : 1);
+        atomic_add_u64(&cnt->bytes64, (unsigned long long)o.bases + o.name_bytes);
+    }
     return o;
 }
 
