@@ -195,6 +195,7 @@ struct CudaBackend {
     cudaStream_t stream;
     std::vector<void *> dev, pinned;
     int rc = TREDSW_OK;
+    long long launches = 0;                            // kernels launched by this batch
     bool fail(cudaError_t e, const char *what) {
         if (e == cudaSuccess) return false;
         if (rc == TREDSW_OK) { tredsw_set_error("%s failed: %s", what, cudaGetErrorString(e)); rc = TREDSW_ERR_CUDA; }
@@ -230,16 +231,19 @@ struct CudaBackend {
     template <class Tag, class F> void for_each(int64_t n, F f) {
         if (n <= 0 || rc) return;
         for_each_kernel<Tag><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, f);
+        ++launches;
         fail(cudaGetLastError(), "for_each launch");
     }
     template <class Tag, class F> void for_each_warp(int64_t n, F f) {
         if (n <= 0 || rc) return;
         for_each_warp_kernel<Tag><<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(n, f);
+        ++launches;
         fail(cudaGetLastError(), "for_each_warp launch");
     }
     template <class Tag, class F> void for_each_warp_window(int64_t n, F f) {
         if (n <= 0 || rc) return;
         for_each_warp_window_kernel<Tag><<<(unsigned)((n + WALK_WARPS - 1) / WALK_WARPS), 32 * WALK_WARPS, 0, stream>>>(n, f);
+        ++launches;
         fail(cudaGetLastError(), "for_each_warp_window launch");
     }
     void inflate(const uint8_t *comp, uint8_t *ibuf, const BlockDesc *blocks, int nblocks, uint8_t *status, int check_crc) {
@@ -252,6 +256,7 @@ struct CudaBackend {
             attr_set[devid] = true;
         }
         inflate_kernel<<<(nblocks + INFLATE_WARPS - 1) / INFLATE_WARPS, INFLATE_THREADS, INFLATE_SMEM, stream>>>(comp, ibuf, blocks, nblocks, status, check_crc);
+        ++launches;
         fail(cudaGetLastError(), "inflate launch");
     }
     // out[0..n] = exclusive prefix sums of in[0..n)
@@ -264,6 +269,7 @@ struct CudaBackend {
         scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, stream>>>(in, n, tiles);
         scan_tiles_kernel<<<1, SCAN_THREADS, 0, stream>>>(tiles, ntiles, out + n);
         scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, stream>>>(in, n, tiles, out);
+        launches += 3;
         fail(cudaGetLastError(), "scan launch");
     }
     void release() {
@@ -878,8 +884,8 @@ int tredsw_ingest_batch_run(tredsw_ctx *ctx, tredsw_bam *const *bams, const int3
     int rc;
     try { rc = run_pipeline(b->cuda, b.get(), bams, sample_of, queries, nqueries, flags); }
     catch (const std::exception &e) { tredsw_set_error("tredsw_ingest_batch_run: %s", e.what()); rc = TREDSW_ERR_IO; }
+    ctx->launches += b->cuda.launches;
     if (rc) { b->cuda.release(); return rc; }
-    ctx->launches += 0;
     *out = b.release();
     return TREDSW_OK;
 }
