@@ -301,6 +301,10 @@ class ReferencePool:
         if not refdrive.usable():
             raise RuntimeError("the reference package is not loadable here (oracle/_ref/ not built)")
         self.cores = cores
+        # the workers bind the reference's own ssw.c (oracle/_ref/libssw_ref.so) through its ssw_wrap.py; load it in
+        # this process too, so that whoever watches the loaded libraries of the arm sees it (the workers are forks)
+        import ctypes
+        self._libssw = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libssw_ref.so"))
         self.pool = mp.get_context("fork").Pool(processes=cores, initializer=_ref_one_thread)
         self.pool.map(_ref_warm, range(cores * 2), chunksize=1)
 
