@@ -5,10 +5,11 @@
 // only reads COMPRESSED bytes (the BGZF blocks behind the BAI chunks of every requested window, each block once per
 // sample) into page-locked memory; everything else runs on the device:
 //
-//   inflate_kernel        one thread per BGZF block: raw-DEFLATE decoder with its Huffman tables in shared memory
-//                         (16-bit entries, strided per thread), CRC-32 of the inflated block checked on the device;
-//   walk (count, fill)    one thread per indexed fetch (the locus window, every alt region) follows the record chain
-//                         of its BAI chunks exactly like tredsw_bam::fetch;
+//   inflate_kernel        one warp per BGZF block: raw-DEFLATE decoder with its Huffman tables in shared memory
+//                         (16-bit entries); the 32 lanes decode the same bits and share the copying (literals by
+//                         lane 0, the bytes of a match dealt to the lanes); CRC-32 of the inflated block by 32 lanes;
+//   walk (count, fill)    one warp per indexed fetch (the locus window, every alt region) follows the record chain
+//                         of its BAI chunks exactly like tredsw_bam::fetch, through a 4 KB shared-memory window;
 //   select                one thread per record: CIGAR span / clips, the read-selection rules of
 //                         BamParser.parse (bam_parser.py:194-243), the pileup depth of BamDepth.region_depth
 //                         (:404-411), the pair candidates of PEextractor (:316-369);

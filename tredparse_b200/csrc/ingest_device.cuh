@@ -8,9 +8,11 @@
 // item, the same rule set as the host reader in ingest.cpp (`extract_locus_impl`, `tredsw_bam::fetch`,
 // `read_record`), which the tests use as its oracle.
 //
-// Every body is `__host__ __device__` and touches memory only through plain loads / stores and the three atomic
-// wrappers below: the kernels of bgzf_gpu.cu call them with one thread per item, and a serial host loop over the
-// same bodies (tredsw_ingest_batch_emulate: test infrastructure) lets the CPU suite check the device logic bit for bit.
+// Every body is `__host__ __device__` and touches memory only through plain loads / stores and the atomic wrappers
+// below: the kernels of bgzf_gpu.cu call them with one thread (or one warp: NL = 32 lanes, `lane`) per item, and a
+// serial host loop over the same bodies with NL = 1 (tredsw_ingest_batch_emulate: test infrastructure) lets the CPU
+// suite check the device logic bit for bit.  Only the warp-level plumbing (shuffles of the CRC tree, the shared-memory
+// window of the record walk) is device-only; the GPU tests cover it against the same oracle.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -85,10 +87,9 @@ TG_HD uint32_t ld_u32(const uint8_t *base, int64_t off) {
 TG_HD int32_t ld_i32(const uint8_t *base, int64_t off) { return (int32_t)ld_u32(base, off); }
 TG_HD uint32_t ld_u16(const uint8_t *base, int64_t off) { return (uint32_t)base[off] | ((uint32_t)base[off + 1] << 8); }
 
-// ---- raw DEFLATE (RFC 1951), one thread per BGZF block ----------------------------------------------------------------
-// Huffman tables of 16-bit entries, reached through a strided reference: stride 1 on the host, the thread count of the
-// CTA on the device (entry i of thread t at [i * stride + t] in shared memory: lanes that look up the same index read
-// neighbouring half-words).
+// ---- raw DEFLATE (RFC 1951), one warp (device) / one thread (host) per BGZF block -------------------------------------
+// Huffman tables of 16-bit entries, reached through a strided reference: stride 1 on the host, the warp count of the
+// CTA on the device (entry i of warp w at [i * stride + w] in shared memory; the lanes of a warp read the same entry).
 //   entry: bits 0..3 code bits to consume (sub-table pointer: index bits of the sub-table), bits 4..6 kind,
 //          bits 7..15 payload (literal byte, length / distance / code-length symbol, sub-table offset / 2)
 struct TabRef {
