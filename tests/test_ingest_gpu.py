@@ -271,3 +271,40 @@ def test_device_decoder_differential_fuzz_against_zlib():
         out = np.zeros(len(data) + 16, np.uint8)
         assert lib.tredsw_inflate_raw_device_code(raw, len(raw), out.ctypes.data, len(data)) == 0
         assert bytes(out[:len(data)]) == data
+
+
+def test_problem_records_built_from_an_ingest_batch_equal_the_host_assembled_batch(repo):
+    """cohort.CohortBatch.from_ingest (the device hand-off: no concatenation, only the 40-byte problem records) against
+    the batch assembled from the per-problem evidence — records, sizes, family tables, name ids (emulated ingest)"""
+    from tredparse_b200 import ingest, cohort
+    from tredparse_b200.simulate import Problem
+    paths = [os.path.join(GOLDEN, "t001.mini.bam"), os.path.join(GOLDEN, "t002.mini.bam")]
+    hs = [ingest.BamIngest(p) for p in paths]
+    names = ["HD", "DM1", "SCA17", "AR"]
+    qs, so, keep, key = _queries(hs, repo, names)
+    with ingest.IngestBatch(None, hs, so, qs, keep=keep) as b:
+        evs = [b.evidence(i) for i in range(len(key))]
+        problems, fam_keys, fam_of = [], [], []
+        for (si, n), ev in zip(key, evs):
+            pr = Problem()
+            pr.tred, pr.readlen, pr.ploidy, pr.depth = repo[n], 150, repo[n].ploidy, ev.depth
+            pr.reads, pr.roff, pr.global_lens, pr.target_lens, pr.alleles, pr.names = ev.reads, ev.roff, ev.global_lens, ev.target_lens, None, ev.names
+            problems.append(pr)
+            if (repo[n], 150) not in fam_keys:
+                fam_keys.append((repo[n], 150))
+            fam_of.append(fam_keys.index((repo[n], 150)))
+        for kw in ({}, {"repeatpairs": False}):
+            host = cohort.CohortBatch(problems, **kw)
+            dev = cohort.CohortBatch.from_ingest(b, np.array(fam_of, np.int32), np.array([p.ploidy for p in problems], np.int32),
+                                                 np.array([p.depth for p in problems]), fam_keys,
+                                                 names=[ev.names for ev in evs], **kw)
+            assert dev.problems.tobytes() == host.problems.tobytes()
+            assert (dev.nproblems, dev.nreads, dev.max_read_len) == (host.nproblems, host.nreads, host.max_read_len)
+            assert len(dev.rbuf) == len(host.rbuf) and len(dev.pe_lens) == len(host.pe_lens)
+            assert np.array_equal(dev.rbuf, host.rbuf) and np.array_equal(dev.roff, host.roff) and np.array_equal(dev.pe_lens, host.pe_lens)
+            assert dev.families.tobytes() == host.families.tobytes() and dev.loci.tobytes() == host.loci.tobytes()
+            assert (dev.read_name is None) == (host.read_name is None)
+            if host.read_name is not None:
+                assert np.array_equal(dev.read_name, host.read_name)
+    for h in hs:
+        h.close()
