@@ -308,3 +308,83 @@ def test_problem_records_built_from_an_ingest_batch_equal_the_host_assembled_bat
                 assert np.array_equal(dev.read_name, host.read_name)
     for h in hs:
         h.close()
+
+
+def _bam_with_a_corrupt_record(dst):
+    """t001.mini.bam with ONE record whose l_seq does not fit its block_size, inside a BGZF block that is otherwise
+    valid: the block is re-deflated, its CRC-32 recomputed, and a padding subfield keeps its size (and thus every
+    virtual offset of the .bai) unchanged — corruption that only record-level checks can see."""
+    import bisect
+    import struct
+    src = os.path.join(GOLDEN, "t001.mini.bam")
+    data = open(src, "rb").read()
+    blocks, o = [], 0
+    while o < len(data):
+        xlen = struct.unpack_from("<H", data, o + 10)[0]
+        bsize = struct.unpack_from("<H", data, o + 16)[0] + 1
+        blocks.append((o, xlen, bsize))
+        o += bsize
+    inflated, offs = b"", []
+    for (o, xlen, bsize) in blocks:
+        offs.append(len(inflated))
+        inflated += zlib.decompress(data[o + 12 + xlen:o + bsize - 8], -15)
+    p = 4
+    p += 4 + struct.unpack_from("<i", inflated, p)[0]
+    n_ref = struct.unpack_from("<i", inflated, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        p += 4 + struct.unpack_from("<i", inflated, p)[0] + 4
+    recs = []
+    while p + 4 <= len(inflated):
+        recs.append(p)
+        p += 4 + struct.unpack_from("<i", inflated, p)[0]
+    for ri in range(len(recs) // 2, len(recs)):
+        bi = bisect.bisect_right(offs, recs[ri]) - 1
+        o, xlen, bsize = blocks[bi]
+        raw = bytearray(inflated[offs[bi]:offs[bi + 1] if bi + 1 < len(offs) else len(inflated)])
+        local = recs[ri] - offs[bi]
+        if local + 300 > len(raw):
+            continue
+        struct.pack_into("<i", raw, local + 4 + 16, 0x7fffff00)                    # l_seq far beyond block_size
+        for k in range(local + 120, local + 260):
+            raw[k] = raw[local + 120]                                              # (more compressible: room for padding)
+        for lvl, ml in ((9, 8), (9, 9), (8, 8)):
+            c = zlib.compressobj(lvl, zlib.DEFLATED, -15, ml)
+            cd = c.compress(bytes(raw)) + c.flush()
+            pad = (bsize - 12 - xlen - 8) - len(cd)
+            if pad == 0 or pad >= 4:
+                extra = data[o + 12:o + 12 + xlen] + (b"ZZ" + struct.pack("<H", pad - 4) + b"\0" * (pad - 4) if pad else b"")
+                hdr = bytearray(data[o:o + 12])
+                struct.pack_into("<H", hdr, 10, len(extra))
+                blk = bytes(hdr) + extra + cd + struct.pack("<II", zlib.crc32(bytes(raw)) & 0xffffffff, len(raw))
+                assert len(blk) == bsize
+                open(dst, "wb").write(data[:o] + blk + data[o + bsize:])
+                shutil.copy(src + ".bai", dst + ".bai")
+                return
+    raise AssertionError("could not craft the file")
+
+
+def _corrupt_record_case(ctx, repo, tmp_path):
+    from tredparse_b200 import ingest, _lib
+    bad = str(tmp_path / "corrupt_record.bam")
+    _bam_with_a_corrupt_record(bad)
+    good = os.path.join(GOLDEN, "t001.mini.bam")
+    hs = [ingest.BamIngest(good), ingest.BamIngest(bad)]
+    with pytest.raises(_lib.TredswError, match="corrupt BAM record"):          # the host reader refuses the file ...
+        hs[1].extract_locus(repo["HD"], 150, alts=repo["HD"].alt, want_names=True)
+    qs, so, keep, key = _queries(hs, repo, ["HD"])
+    with ingest.IngestBatch(ctx, hs, so, qs, keep=keep) as b:                  # ... and the device code flags the problem
+        assert b.status[0] == 0 and b.status[1] == 3
+        assert _same(b.evidence(0), hs[0].extract_locus(repo["HD"], 150, alts=repo["HD"].alt, want_names=True))
+    for h in hs:
+        h.close()
+
+
+def test_a_corrupt_record_inside_a_valid_block_is_flagged_emulated(repo, tmp_path):
+    _corrupt_record_case(None, repo, tmp_path)
+
+
+@pytest.mark.gpu
+def test_a_corrupt_record_inside_a_valid_block_is_flagged_on_the_gpu(repo, tmp_path):
+    from tredparse_b200 import _lib
+    _corrupt_record_case(_lib.default_context(0), repo, tmp_path)
