@@ -921,7 +921,7 @@ void tredsw_ingest_batch_free(tredsw_ingest_batch *b) {
 
 // The block decoder on its own (test hook, host execution of the device code): 0 iff `in` inflates to out_len bytes.
 int tredsw_inflate_raw_device_code(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len) {
-    std::vector<uint8_t> padded((size_t)in_len + 16, 0);      // the bit reader loads whole words
+    std::vector<uint8_t> padded((size_t)in_len + 4 + 32, 0);  // the bit reader loads whole words, up to 16 bytes behind a corrupt stream
     if (in_len > 0) memcpy(padded.data() + 4, in, (size_t)in_len);
     std::vector<uint16_t> tabs(TAB_ENTRIES);
     uint8_t lens[320], sub_need[1 << LIT_ROOT];

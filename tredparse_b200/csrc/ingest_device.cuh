@@ -177,8 +177,9 @@ TG_HD bool build_table(const uint8_t *lens, int nsyms, int which, const TabRef &
     return true;
 }
 
-// LSB-first bit reader over aligned 32-bit words (the compressed bytes may start at any address; up to 7 bytes
-// behind the end of the input are read and never used)
+// LSB-first bit reader over aligned 32-bit words (the compressed bytes may start at any address).  A valid stream
+// reads at most 7 bytes behind the end of its input; a corrupt one is stopped by overrun() at the next symbol, by
+// when it may have read up to 16 bytes behind it — the buffers are allocated with that slack; the bytes are never used
 struct BitReader {
     const uint32_t *w0, *w, *wlimit;
     uint64_t buf; int cnt; int mis;
