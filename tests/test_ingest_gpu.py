@@ -388,3 +388,68 @@ def test_a_corrupt_record_inside_a_valid_block_is_flagged_emulated(repo, tmp_pat
 def test_a_corrupt_record_inside_a_valid_block_is_flagged_on_the_gpu(repo, tmp_path):
     from tredparse_b200 import _lib
     _corrupt_record_case(_lib.default_context(0), repo, tmp_path)
+
+
+_STAGE_FUZZ = r"""
+import os, sys, random, shutil
+sys.path.insert(0, {root!r})
+import numpy as np
+from tredparse_b200 import ingest, _lib
+from tredparse_b200.meta import TREDsRepo
+repo = TREDsRepo()
+good = open({bam!r}, "rb").read()
+bai = open({bam!r} + ".bai", "rb").read()
+rng = random.Random(11)
+ok = flagged = refused = 0
+for trial in range(120):
+    bad, ix = bytearray(good), bytearray(bai)
+    how = trial % 4
+    if how == 0:                                           # bytes anywhere in the file: headers, payloads, footers
+        for _ in range(rng.randrange(1, 6)):
+            p = rng.randrange(len(bad)); bad[p] = rng.randrange(256)
+    elif how == 1:                                         # truncated file
+        bad = bad[:rng.randrange(100, len(bad))]
+    elif how == 2:                                         # damaged index: chunk offsets point anywhere
+        for _ in range(rng.randrange(1, 6)):
+            p = rng.randrange(8, len(ix)); ix[p] = rng.randrange(256)
+    else:                                                  # BGZF framing fields (XLEN, BSIZE, ISIZE) of some block
+        off = 0
+        for _ in range(rng.randrange(0, 25)):
+            nxt = off + int.from_bytes(bad[off + 16:off + 18], "little") + 1
+            if nxt + 28 >= len(bad): break
+            off = nxt
+        p = off + rng.choice([10, 11, 16, 17]); bad[p] = rng.randrange(256)
+    p2 = os.path.join({tmp!r}, "bad.bam")
+    open(p2, "wb").write(bytes(bad)); open(p2 + ".bai", "wb").write(bytes(ix))
+    try:
+        h = ingest.BamIngest(p2)
+    except Exception:
+        refused += 1
+        continue
+    try:
+        qs = [ingest.locus_query(h, repo[n], 150, alts=repo[n].alt) for n in ("HD", "SCA17")]
+        qs = [q for q in qs if q is not None]
+        with ingest.IngestBatch(None, [h], [0] * len(qs), [q[0] for q in qs], keep=[q[1] for q in qs]) as b:
+            for i in range(len(qs)):
+                if b.status[i]:
+                    flagged += 1
+                else:
+                    ev = b.evidence(i); assert ev.nreads == len(ev.roff) - 1 and ev.roff[-1] == len(ev.reads)
+                    ok += 1
+    except _lib.TredswError:
+        refused += 1
+    finally:
+        h.close()
+print("survived", ok, flagged, refused)
+"""
+
+
+def test_damaged_files_and_indexes_do_not_take_the_ingest_down(tmp_path):
+    """the host staging (BAI chunks -> block ranges -> BGZF framing) and the device code (emulated) on damaged BAMs and
+    damaged .bai files: every outcome is a result, a per-problem flag or a TredswError — never a crash"""
+    import subprocess
+    import sys
+    code = _STAGE_FUZZ.format(root=ROOT, bam=os.path.join(GOLDEN, "t001.mini.bam"), tmp=str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
+    assert "survived" in r.stdout
